@@ -1,0 +1,111 @@
+"""Per-layer parity of the tcgen05 conv kernels (through the C-ABI) against fp32 torch ops on the same
+16-bit-rounded operands.  Tolerances: the only differences are fp32 summation order and the final 16-bit
+store (fp16: 2^-11 per element, bf16: 2^-8)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests._pkg import load
+
+pytestmark = pytest.mark.gpu
+
+# (name, transposed, ks, stride, cin0, cin1, cout, (W,H,D))
+CASES = [
+    ("k3s1_16_16", 0, 3, 1, 16, 0, 16, (24, 16, 8)),
+    ("k3s1_1_16", 0, 3, 1, 1, 0, 16, (16, 16, 16)),
+    ("k3s1_cat16_16", 0, 3, 1, 16, 16, 16, (20, 12, 8)),
+    ("k3s1_cat32_32", 0, 3, 1, 32, 32, 32, (16, 8, 8)),
+    ("k3s2_16_32", 0, 3, 2, 16, 0, 32, (32, 16, 16)),
+    ("k3s1_64_64", 0, 3, 1, 64, 0, 64, (16, 8, 8)),
+    ("k3s1_cat128_128", 0, 3, 1, 128, 128, 128, (8, 8, 4)),
+    ("k3s2_128_256", 0, 3, 2, 128, 0, 256, (8, 8, 8)),
+    ("k3s1_256_256_tiny", 0, 3, 1, 256, 0, 256, (5, 6, 5)),
+    ("k1_16_2", 0, 1, 1, 16, 0, 2, (24, 16, 8)),
+    ("k1_256_6", 0, 1, 1, 256, 0, 6, (10, 12, 10)),
+    ("ct_32_16", 1, 2, 2, 32, 0, 16, (12, 8, 8)),
+    ("ct_256_256", 1, 2, 2, 256, 0, 256, (5, 6, 5)),
+    ("k3s1_odd_24_40", 0, 3, 1, 24, 0, 40, (13, 7, 9)),
+    ("k3s2_odd", 0, 3, 2, 16, 0, 16, (14, 10, 6)),
+    ("k3s1_320", 0, 3, 1, 32, 0, 320, (8, 8, 4)),
+]
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def make(case, seed=0):
+    name, tr, ks, st, c0, c1, co, (W, H, D) = case
+    g = torch.Generator().manual_seed(seed)
+    x0 = torch.randn(c0, D, H, W, generator=g).half().float()
+    x1 = torch.randn(c1, D, H, W, generator=g).half().float() if c1 else None
+    cin = c0 + c1
+    kk = 2 if tr else ks
+    shape = (cin, co, kk, kk, kk) if tr else (co, cin, kk, kk, kk)
+    w = (torch.randn(shape, generator=g) / (cin * kk ** 3) ** 0.5)
+    b = torch.randn(co, generator=g)
+    return x0, x1, w, b
+
+
+def ref_forward(case, x0, x1, w, b):
+    name, tr, ks, st, c0, c1, co, _ = case
+    x = x0 if x1 is None else torch.cat([x0, x1], 0)
+    x = x[None].cuda()
+    if tr:
+        return F.conv_transpose3d(x, w.cuda(), b.cuda(), stride=2)[0]
+    return F.conv3d(x, w.cuda(), b.cuda(), stride=st, padding=(ks - 1) // 2)[0]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_forward(case):
+    m = load()
+    x0, x1, w, b = make(case)
+    wh = w.half().float()
+    y_ref = ref_forward(case, x0, x1, wh, b).cpu().numpy()
+    y, stats = m.conv_forward(x0.numpy(), w.numpy(), b.numpy(), None if x1 is None else x1.numpy(),
+                              transposed=bool(case[1]), ks=case[2], stride=case[3], want_stats=True)
+    assert np.isfinite(y).all()
+    assert rel(y, y_ref) < 6e-4, rel(y, y_ref)
+    if not case[1]:
+        v = y_ref.reshape(y_ref.shape[0], -1).astype(np.float64)
+        np.testing.assert_allclose(stats[0], v.sum(1), rtol=2e-3, atol=2e-2 * np.sqrt(v.shape[1]))
+        np.testing.assert_allclose(stats[1], (v * v).sum(1), rtol=2e-3)
+    yp = m.conv_forward(x0.numpy(), w.numpy(), b.numpy(), None if x1 is None else x1.numpy(),
+                        transposed=bool(case[1]), ks=case[2], stride=case[3], planar_fp32=True) if not case[1] else None
+    if yp is not None:
+        assert rel(yp, y_ref) < 2e-5, rel(yp, y_ref)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_backward(case):
+    m = load()
+    name, tr, ks, st, c0, c1, co, _ = case
+    x0, x1, w, b = make(case, 1)
+    x = (x0 if x1 is None else torch.cat([x0, x1], 0))[None].cuda().requires_grad_(True)
+    wq = w.bfloat16().float().cuda().requires_grad_(True)   # dgrad runs on the bf16 weight pack
+    y = F.conv_transpose3d(x, wq, None, stride=2) if tr else F.conv3d(x, wq, None, stride=st, padding=(ks - 1) // 2)
+    g = torch.Generator().manual_seed(7)
+    dy = torch.randn(y.shape[1:], generator=g).bfloat16().float()
+    y.backward(dy[None].cuda())
+    gx_ref = x.grad[0].cpu().numpy()
+    gw_ref = wq.grad.cpu().numpy()
+    gx0, gx1, gw = m.conv_backward(x0.numpy(), w.numpy(), dy.numpy(), None if x1 is None else x1.numpy(),
+                                   transposed=bool(tr), ks=ks, stride=st)
+    assert rel(gx0, gx_ref[:c0]) < 4e-3, rel(gx0, gx_ref[:c0])
+    if c1:
+        assert rel(gx1, gx_ref[c0:]) < 4e-3, rel(gx1, gx_ref[c0:])
+    assert rel(gw, gw_ref) < 2e-4, rel(gw, gw_ref)
+    # accumulate form (skip connections add two data gradients into one tensor)
+    init = np.random.default_rng(0).standard_normal(x0.shape).astype(np.float32)
+    init = torch.from_numpy(init).bfloat16().float().numpy()
+    gx0a, _, _ = m.conv_backward(x0.numpy(), w.numpy(), dy.numpy(), None if x1 is None else x1.numpy(),
+                                 transposed=bool(tr), ks=ks, stride=st, gx0_init=init)
+    assert rel(gx0a, gx_ref[:c0] + init) < 6e-3

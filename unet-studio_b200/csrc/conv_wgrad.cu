@@ -1,0 +1,339 @@
+// Weight-gradient GEMM on tcgen05 / TMEM (sm_100a): replaces autograd's conv3d / conv_transpose3d
+// weight gradients (reference: total_loss.backward(), /root/reference/train.cpp:706).
+//
+//   dW[n][m][tap] += sum_{v in lattice} T[v*tstride + tap][m] * U[v][n]            (see u3d.h)
+//
+// The reduction dimension K is the voxel lattice, so both operands are MN-major in their natural
+// NDHWC order: a voxel's channel vector is one 16-byte-chunked row.  Each smem stage holds 64 voxels:
+//   A (M side): 16 chunks x 64 voxels x 16 B  — M = 128 rows = (tap group) x (channels), i.e. several
+//               taps of the same K-block are stacked along M so that 16-channel layers still fill
+//               the 128-row MMA;
+//   B (N side): ntile/8 chunks x 64 voxels x 16 B.
+// Canonical SWIZZLE_NONE MN-major layout: 8 voxels x 16 B = one core matrix (LBO = 128 B between
+// K groups, SBO = 1024 B between channel chunks).  Work item = (problem, M tile, N tile, K split);
+// results are reduced across K splits with fp32 atomics straight into the reference-layout
+// gradient tensor (summation order across CTAs is not fixed; see DESIGN.md "determinism").
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "u3d.h"
+
+namespace u3d {
+namespace {
+
+constexpr int kThreads = 288;
+constexpr int kLag = 2;
+constexpr int kMaxProb = 8;
+constexpr int kKB = 64;  // voxels per stage
+
+struct WParams {
+    WgradProblem probs[kMaxProb];
+    int nprob;
+    int total_items;
+    int stages;
+    int t_fmt, u_fmt;
+    int ntile_max;
+    int tmem_cols;
+    uint32_t off_b, off_bars;
+};
+
+struct WItem {
+    int pi, mt, nt, ks;
+};
+
+__device__ __forceinline__ WItem decode_witem(const WParams& p, int item) {
+    int pi = 0;
+#pragma unroll 1
+    for (int i = 1; i < p.nprob; ++i)
+        if (item >= p.probs[i].item_base) pi = i;
+    const WgradProblem& P = p.probs[pi];
+    int local = item - P.item_base;
+    WItem w;
+    w.pi = pi;
+    w.ks = local % P.ksplit;
+    local /= P.ksplit;
+    w.nt = local % P.ntiles;
+    w.mt = local / P.ntiles;
+    return w;
+}
+
+// channels per M tile and channel tiles per tap
+__device__ __forceinline__ int cpt_of(const WgradProblem& P) { return P.t_c <= 128 ? P.t_c : 128; }
+
+__device__ __forceinline__ void kblock_range(const WgradProblem& P, int ks, int& kb0, int& kb1) {
+    const int K = P.ld * P.lh * P.lw;
+    const int kblocks = (K + kKB - 1) / kKB;
+    const int per = (kblocks + P.ksplit - 1) / P.ksplit;
+    kb0 = ks * per;
+    kb1 = min(kblocks, kb0 + per);
+    if (kb0 > kb1) kb0 = kb1;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_constant__ WParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const uint32_t a_stage_bytes = 16u * kKB * 16u;                      // 16 KB
+    const uint32_t b_stage_bytes = uint32_t(p.ntile_max / 8) * kKB * 16u;
+    const uint32_t sA = smem_u32(smem);
+    const uint32_t sB = sA + p.off_b;
+    const uint32_t bars = sA + p.off_bars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * S + 4));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 128);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp >= 4 && warp < 8) {
+        // ===================================== producers =====================================
+        const int t = threadIdx.x - 128;
+        const int v = t & 63, h = t >> 6;
+        int stage = 0, phase = 0, lag_stage = 0;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const WItem w = decode_witem(p, item);
+            const WgradProblem& P = p.probs[w.pi];
+            const int K = P.ld * P.lh * P.lw;
+            const int cpt = cpt_of(P);
+            const int ctiles = (P.t_c + cpt - 1) / cpt;
+            const int tapgrp = w.mt / ctiles, ctile = w.mt % ctiles;
+            const int tap0 = tapgrp * P.tg;
+            const int ntap_here = min(P.tg, P.ntaps - tap0);
+            const int nchunks_n = P.ntile / 8;
+            int kb0, kb1;
+            kblock_range(P, w.ks, kb0, kb1);
+#pragma unroll 1
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                mbar_wait(empty_bar(stage), phase ^ 1, 0x500u | stage);
+                const int vg = kb * kKB + v;
+                const bool vv = vg < K;
+                int lx = 0, ly = 0, lz = 0;
+                if (vv) {
+                    lx = vg % P.lw;
+                    const int q = vg / P.lw;
+                    ly = q % P.lh;
+                    lz = q / P.lh;
+                }
+                // ---- A: tapped tensor, 8 chunks per thread
+                const uint32_t a_dst = sA + stage * a_stage_bytes + v * 16u;
+#pragma unroll 1
+                for (int mc = h; mc < 16; mc += 2) {
+                    const int row0 = mc * 8;
+                    const int tl = row0 / cpt;
+                    const int c = row0 - tl * cpt + ctile * 128;
+                    bool ok = vv && tl < ntap_here && c < P.t_c;
+                    const uint8_t* src = static_cast<const uint8_t*>(P.T);
+                    if (ok) {
+                        const ConvTap tp = P.taps[tap0 + tl];
+                        const int iz = lz * P.tstride + tp.dz, iy = ly * P.tstride + tp.dy, ix = lx * P.tstride + tp.dx;
+                        ok = (unsigned)iz < (unsigned)P.t_d && (unsigned)iy < (unsigned)P.t_h && (unsigned)ix < (unsigned)P.t_w;
+                        if (ok) src += (size_t((iz * P.t_h + iy) * P.t_w + ix) * P.t_cp + P.t_coff + c) * 2;
+                    }
+                    cp_async16(a_dst + mc * (kKB * 16u), src, ok ? 16u : 0u);
+                }
+                // ---- B: untapped tensor
+                const uint32_t b_dst = sB + stage * b_stage_bytes + v * 16u;
+                const uint8_t* ub = static_cast<const uint8_t*>(P.U);
+                const uint8_t* usrc = vv ? ub + (size_t(vg) * P.u_cp + P.u_coff + w.nt * P.ntile) * 2 : ub;
+#pragma unroll 1
+                for (int nc = h; nc < nchunks_n; nc += 2)
+                    cp_async16(b_dst + nc * (kKB * 16u), vv ? usrc + nc * 16 : ub, vv ? 16u : 0u);
+                cp_async_commit();
+                if (it >= kLag) {
+                    cp_async_wait<kLag>();
+                    fence_proxy_async();
+                    mbar_arrive(full_bar(lag_stage));
+                    if (++lag_stage == S) lag_stage = 0;
+                }
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        const uint32_t rem = it < (uint32_t)kLag ? it : (uint32_t)kLag;
+        for (uint32_t j = 0; j < rem; ++j) {
+            mbar_arrive(full_bar(lag_stage));
+            if (++lag_stage == S) lag_stage = 0;
+        }
+    } else if (warp == 8) {
+        // ===================================== MMA issuer ====================================
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            uint32_t acc_cnt = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const WItem w = decode_witem(p, item);
+                const WgradProblem& P = p.probs[w.pi];
+                int kb0, kb1;
+                kblock_range(P, w.ks, kb0, kb1);
+                if (kb0 >= kb1) continue;  // empty split: no accumulator is produced (epilogue skips it too)
+                const int acc = acc_cnt & 1;
+                mbar_wait(tempty_bar(acc), ((acc_cnt >> 1) & 1) ^ 1, 0x600u | acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * p.ntile_max);
+                const uint32_t idesc = umma_idesc(128, P.ntile, p.t_fmt, p.u_fmt, 1, 1);
+#pragma unroll 1
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar(stage), phase, 0x700u | stage);
+                    tc_fence_after();
+                    const uint32_t a0 = sA + stage * a_stage_bytes;
+                    const uint32_t b0 = sB + stage * b_stage_bytes;
+#pragma unroll
+                    for (int j = 0; j < kKB / 16; ++j) {
+                        const uint64_t adesc = umma_smem_desc(a0 + j * 256u, 128u, kKB * 16u);
+                        const uint64_t bdesc = umma_smem_desc(b0 + j * 256u, 128u, kKB * 16u);
+                        umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));
+                ++acc_cnt;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================== epilogue ======================================
+        const int r = threadIdx.x;
+        uint32_t acc_cnt = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const WItem w = decode_witem(p, item);
+            const WgradProblem& P = p.probs[w.pi];
+            int kb0, kb1;
+            kblock_range(P, w.ks, kb0, kb1);
+            if (kb0 >= kb1) continue;
+            const int cpt = cpt_of(P);
+            const int ctiles = (P.t_c + cpt - 1) / cpt;
+            const int tapgrp = w.mt / ctiles, ctile = w.mt % ctiles;
+            const int tap0 = tapgrp * P.tg;
+            const int ntap_here = min(P.tg, P.ntaps - tap0);
+            const int tl = r / cpt;
+            const int c = r - tl * cpt + ctile * 128;
+            const bool rv = tl < ntap_here && c < P.t_creal;
+            const int acc = acc_cnt & 1;
+            mbar_wait(tfull_bar(acc), (acc_cnt >> 1) & 1, 0x800u | acc);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(acc * p.ntile_max);
+            float* dwrow = nullptr;
+            if (rv) dwrow = P.dw + size_t(P.w_moff + c) * P.w_ktaps + P.tap_ref[tap0 + tl];
+            const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
+#pragma unroll 1
+            for (int c0 = 0; c0 < P.ntile; c0 += 16) {
+                float v[16];
+                tmem_ld16(t_row + c0, v);
+                if (rv) {
+                    const int n0 = w.nt * P.ntile + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < P.u_creal) atomicAdd(dwrow + size_t(P.w_noff + n0 + j) * nstride, v[j]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            ++acc_cnt;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace
+
+unsigned int read_device_error_wgrad() {
+    unsigned int v = 0;
+    cudaMemcpyFromSymbol(&v, g_dev_error, sizeof(v));
+    return v;
+}
+
+int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch& cfg, WgradProblem*, cudaStream_t stream) {
+    if (probs.empty()) return 0;
+    if (probs.size() > kMaxProb) {
+        set_error("conv_wgrad_launch: too many problems");
+        return 1;
+    }
+    WParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.nprob = int(probs.size());
+    kp.t_fmt = cfg.t_bf16;
+    kp.u_fmt = cfg.u_bf16;
+    const int sms = device_sm_count();
+    int base_items = 0;
+    int ntile_max = 16;
+    for (size_t i = 0; i < probs.size(); ++i) {
+        WgradProblem& P = kp.probs[i];
+        P = probs[i];
+        if (P.t_c % 16 || P.u_c % 16 || P.t_c < 16 || P.u_c < 16 || P.ntaps < 1 || P.ntaps > 27) {
+            set_error("conv_wgrad_launch: bad problem shape");
+            return 1;
+        }
+        const int cpt = P.t_c <= 128 ? P.t_c : 128;
+        P.tg = P.t_c <= 128 ? 128 / P.t_c : 1;
+        const int ctiles = (P.t_c + cpt - 1) / cpt;
+        P.mtiles = ((P.ntaps + P.tg - 1) / P.tg) * ctiles;
+        int nt = std::min(P.u_c, 256);
+        while (P.u_c % nt) nt -= 16;
+        P.ntile = nt;
+        P.ntiles = P.u_c / nt;
+        ntile_max = std::max(ntile_max, nt);
+        base_items += P.mtiles * P.ntiles;
+    }
+    int items = 0;
+    for (int i = 0; i < kp.nprob; ++i) {
+        WgradProblem& P = kp.probs[i];
+        const long long K = 1LL * P.ld * P.lh * P.lw;
+        const int kblocks = int((K + kKB - 1) / kKB);
+        int ks = std::max(1, (2 * sms + base_items - 1) / base_items);
+        ks = std::min(ks, std::max(1, kblocks / 4));
+        // make sure no split is empty
+        while (ks > 1 && (ks - 1) * ((kblocks + ks - 1) / ks) >= kblocks) --ks;
+        P.ksplit = ks;
+        P.item_base = items;
+        items += P.mtiles * P.ntiles * ks;
+    }
+    kp.total_items = items;
+    kp.ntile_max = ntile_max;
+    int cols = 32;
+    while (cols < 2 * ntile_max) cols <<= 1;
+    kp.tmem_cols = cols;
+    const size_t a_stage = size_t(16) * kKB * 16, b_stage = size_t(ntile_max / 8) * kKB * 16;
+    int stages = int((200 * 1024) / (a_stage + b_stage));
+    stages = std::min(stages, 8);
+    kp.stages = stages;
+    kp.off_b = uint32_t(stages * a_stage);
+    kp.off_bars = uint32_t(kp.off_b + stages * b_stage);
+    const size_t smem = kp.off_bars + 8 * (2 * stages + 4) + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = std::max(1, std::min(items, sms));
+    conv_wgrad_kernel<<<grid, kThreads, smem, stream>>>(kp);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace u3d

@@ -1,0 +1,113 @@
+// Layout kernels: reference NCDHW fp32 <-> internal NDHWC 16-bit (channels padded to 16), and the
+// weight pack from the reference parameter layout (tensorN order/shape, /root/reference/main.cpp:193-204)
+// into the canonical UMMA B-operand blobs consumed by conv_igemm.cu.
+#include <string>
+
+#include "common.cuh"
+#include "plan.h"
+
+namespace u3d {
+namespace {
+
+template <bool BF16>
+__global__ void pack_act_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, int Cp, long long V) {
+    const long long total = V * (Cp / 8);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long vox = i % V;
+        const int chunk = int(i / V);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = chunk * 8 + j;
+            f[j] = c < C ? in[(long long)c * V + vox] : 0.f;
+        }
+        uint4 q;
+        q.x = pack2<BF16>(f[0], f[1]);
+        q.y = pack2<BF16>(f[2], f[3]);
+        q.z = pack2<BF16>(f[4], f[5]);
+        q.w = pack2<BF16>(f[6], f[7]);
+        out[vox * (Cp / 8) + chunk] = q;
+    }
+}
+
+template <bool BF16>
+__global__ void unpack_act_kernel(const uint4* __restrict__ in, float* __restrict__ out, int C, int Cp, long long V) {
+    const long long total = V * (Cp / 8);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long vox = i % V;
+        const int chunk = int(i / V);
+        const uint4 q = in[vox * (Cp / 8) + chunk];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2<BF16>(w[j]);
+            const int c = chunk * 8 + 2 * j;
+            if (c < C) out[(long long)c * V + vox] = f.x;
+            if (c + 1 < C) out[(long long)(c + 1) * V + vox] = f.y;
+        }
+    }
+}
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackDesc d) {
+    const int nch = d.nch[0] + d.nch[1];
+    const long long total = (long long)d.ntaps * nch * d.ntiles * d.ntile * d.kc;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int k8 = int(r % 8); r /= 8;
+        const int n = int(r % d.ntile); r /= d.ntile;
+        const int kg = int(r % (d.kc / 8)); r /= (d.kc / 8);
+        const int nt = int(r % d.ntiles); r /= d.ntiles;
+        const int ch = int(r % nch); r /= nch;
+        const int tap = int(r);
+        const int s = ch < d.nch[0] ? 0 : 1;
+        const int kk = (ch - (s ? d.nch[0] : 0)) * d.kc + kg * 8 + k8;
+        const int nn = nt * d.ntile + n;
+        float v = 0.f;
+        if (kk < d.k_real[s] && nn < d.n_real) {
+            const int kidx = d.k_off[s] + kk, nidx = d.n_off + nn;
+            const long long a = d.n_is_A ? nidx : kidx, b = d.n_is_A ? kidx : nidx;
+            v = d.w[(a * d.dimB + b) * d.ktaps + d.tap_ref[tap]];
+        }
+        if (d.out_bf16)
+            static_cast<__nv_bfloat16*>(d.out)[i] = __float2bfloat16_rn(v);
+        else
+            static_cast<__half*>(d.out)[i] = __float2half_rn(v);
+    }
+}
+
+inline int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148LL * 16;
+    return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int pack_weights_launch(const PackDesc& d, cudaStream_t stream) {
+    const long long total = (long long)pack_bytes(d) / 2;
+    pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(d);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int pack_act_launch(const float* in, void* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream) {
+    const long long total = V * (Cp / 8);
+    if (bf16)
+        pack_act_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(in, static_cast<uint4*>(out), C, Cp, V);
+    else
+        pack_act_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(in, static_cast<uint4*>(out), C, Cp, V);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int unpack_act_launch(const void* in, float* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream) {
+    const long long total = V * (Cp / 8);
+    if (bf16)
+        unpack_act_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), out, C, Cp, V);
+    else
+        unpack_act_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), out, C, Cp, V);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace u3d

@@ -1,0 +1,225 @@
+#include "plan.h"
+
+#include <cstring>
+
+namespace u3d {
+
+int choose_kc(int c0p, int c1p) {
+    auto ok = [&](int k) { return c0p % k == 0 && c1p % k == 0; };
+    if (ok(64)) return 64;
+    if (ok(32)) return 32;
+    return 16;
+}
+
+void choose_ntile(int np, int& ntile, int& ntiles) {
+    int nt = np < 256 ? np : 256;
+    while (np % nt) nt -= 16;
+    ntile = nt;
+    ntiles = np / nt;
+}
+
+size_t pack_bytes(const PackDesc& d) {
+    return size_t(d.ntaps) * (d.nch[0] + d.nch[1]) * d.ntiles * d.ntile * d.kc * 2;
+}
+
+static void zero_problem(ConvProblem& P) { std::memset(&P, 0, sizeof(P)); }
+
+static void init_pack(PackDesc& k) {
+    std::memset(&k, 0, sizeof(k));
+}
+
+void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc) {
+    probs.clear();
+    packs.clear();
+    const int c0p = pad16(g.cin[0]), c1p = g.cin[1] ? pad16(g.cin[1]) : 0;
+    kc = choose_kc(c0p, c1p);
+    int ntile, ntiles;
+    choose_ntile(pad16(g.cout), ntile, ntiles);
+    if (!g.transposed) {
+        ConvProblem P;
+        zero_problem(P);
+        PackDesc K;
+        init_pack(K);
+        P.c0p = c0p; P.c1p = c1p;
+        P.nch0 = c0p / kc; P.nch1 = c1p / kc;
+        P.in_d = g.in_d; P.in_h = g.in_h; P.in_w = g.in_w;
+        P.istride = g.stride;
+        P.ntaps = g.ks * g.ks * g.ks;
+        const int pad = (g.ks - 1) / 2;
+        int t = 0;
+        for (int kz = 0; kz < g.ks; ++kz)
+            for (int ky = 0; ky < g.ks; ++ky)
+                for (int kx = 0; kx < g.ks; ++kx, ++t) {
+                    P.taps[t] = ConvTap{int8_t(kz - pad), int8_t(ky - pad), int8_t(kx - pad), 0};
+                    K.tap_ref[t] = t;
+                }
+        P.od = g.out_d; P.oh = g.out_h; P.ow = g.out_w;
+        P.OD = g.out_d; P.OH = g.out_h; P.OW = g.out_w;
+        P.ostep = 1;
+        P.dst_cp = pad16(g.cout);
+        P.ntile = ntile; P.ntiles = ntiles; P.n_real = g.cout;
+        K.dimA = g.cout; K.dimB = g.cin[0] + g.cin[1]; K.ktaps = P.ntaps;
+        K.n_is_A = 1; K.n_off = 0; K.n_real = g.cout; K.ntile = ntile; K.ntiles = ntiles;
+        K.k_off[0] = 0; K.k_real[0] = g.cin[0]; K.nch[0] = P.nch0;
+        K.k_off[1] = g.cin[0]; K.k_real[1] = g.cin[1]; K.nch[1] = P.nch1;
+        K.kc = kc; K.ntaps = P.ntaps;
+        probs.push_back(P);
+        packs.push_back(K);
+    } else {
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b)
+                for (int c = 0; c < 2; ++c) {
+                    ConvProblem P;
+                    zero_problem(P);
+                    PackDesc K;
+                    init_pack(K);
+                    P.c0p = c0p; P.c1p = 0;
+                    P.nch0 = c0p / kc; P.nch1 = 0;
+                    P.in_d = g.in_d; P.in_h = g.in_h; P.in_w = g.in_w;
+                    P.istride = 1;
+                    P.ntaps = 1;
+                    P.taps[0] = ConvTap{0, 0, 0, 0};
+                    P.od = g.in_d; P.oh = g.in_h; P.ow = g.in_w;
+                    P.OD = g.out_d; P.OH = g.out_h; P.OW = g.out_w;
+                    P.ostep = 2; P.ooff_z = a; P.ooff_y = b; P.ooff_x = c;
+                    P.dst_cp = pad16(g.cout);
+                    P.ntile = ntile; P.ntiles = ntiles; P.n_real = g.cout;
+                    K.dimA = g.cin[0]; K.dimB = g.cout; K.ktaps = 8;
+                    K.n_is_A = 0; K.n_off = 0; K.n_real = g.cout; K.ntile = ntile; K.ntiles = ntiles;
+                    K.k_off[0] = 0; K.k_real[0] = g.cin[0]; K.nch[0] = P.nch0;
+                    K.kc = kc; K.ntaps = 1; K.tap_ref[0] = (a * 2 + b) * 2 + c;
+                    probs.push_back(P);
+                    packs.push_back(K);
+                }
+    }
+}
+
+void plan_dgrad(const LayerGeom& g, int src, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc) {
+    probs.clear();
+    packs.clear();
+    const int coutp = pad16(g.cout);
+    kc = choose_kc(coutp, 0);
+    const int n_real = g.cin[src];
+    int ntile, ntiles;
+    choose_ntile(pad16(n_real), ntile, ntiles);
+    const int n_off = src ? g.cin[0] : 0;
+    auto base = [&](ConvProblem& P, PackDesc& K) {
+        zero_problem(P);
+        init_pack(K);
+        P.c0p = coutp; P.nch0 = coutp / kc;
+        P.in_d = g.out_d; P.in_h = g.out_h; P.in_w = g.out_w;  // gathered tensor = dy
+        P.OD = g.in_d; P.OH = g.in_h; P.OW = g.in_w;            // destination = dx
+        P.dst_cp = pad16(n_real);
+        P.ntile = ntile; P.ntiles = ntiles; P.n_real = n_real;
+        K.ntile = ntile; K.ntiles = ntiles; K.n_real = n_real; K.n_off = n_off;
+        K.k_off[0] = 0; K.k_real[0] = g.cout; K.nch[0] = P.nch0;
+        K.kc = kc;
+    };
+    if (!g.transposed && g.stride == 1) {
+        ConvProblem P;
+        PackDesc K;
+        base(P, K);
+        const int pad = (g.ks - 1) / 2;
+        P.istride = 1;
+        P.ntaps = g.ks * g.ks * g.ks;
+        int t = 0;
+        for (int kz = 0; kz < g.ks; ++kz)
+            for (int ky = 0; ky < g.ks; ++ky)
+                for (int kx = 0; kx < g.ks; ++kx, ++t) {
+                    P.taps[t] = ConvTap{int8_t(pad - kz), int8_t(pad - ky), int8_t(pad - kx), 0};
+                    K.tap_ref[t] = t;
+                }
+        P.od = g.in_d; P.oh = g.in_h; P.ow = g.in_w;
+        P.ostep = 1;
+        K.dimA = g.cout; K.dimB = g.cin[0] + g.cin[1]; K.ktaps = P.ntaps; K.n_is_A = 0; K.ntaps = P.ntaps;
+        probs.push_back(P);
+        packs.push_back(K);
+    } else if (!g.transposed) {
+        // stride 2, k3, pad 1:  y[o] = sum_k W[k] x[2o + k - 1]  =>  for x index i = 2j + p:
+        //   p = 0: k = 1 (o = j);   p = 1: k = 0 (o = j + 1), k = 2 (o = j)
+        const int kk[2][2] = {{1, -1}, {0, 2}};
+        const int off[2][2] = {{0, 0}, {1, 0}};
+        const int cnt[2] = {1, 2};
+        for (int pz = 0; pz < 2; ++pz)
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px) {
+                    ConvProblem P;
+                    PackDesc K;
+                    base(P, K);
+                    P.istride = 1;
+                    P.od = (g.in_d - pz + 1) / 2; P.oh = (g.in_h - py + 1) / 2; P.ow = (g.in_w - px + 1) / 2;
+                    if (P.od <= 0 || P.oh <= 0 || P.ow <= 0) continue;
+                    P.ostep = 2; P.ooff_z = pz; P.ooff_y = py; P.ooff_x = px;
+                    int t = 0;
+                    for (int a = 0; a < cnt[pz]; ++a)
+                        for (int b = 0; b < cnt[py]; ++b)
+                            for (int c = 0; c < cnt[px]; ++c, ++t) {
+                                P.taps[t] = ConvTap{int8_t(off[pz][a]), int8_t(off[py][b]), int8_t(off[px][c]), 0};
+                                K.tap_ref[t] = (kk[pz][a] * 3 + kk[py][b]) * 3 + kk[px][c];
+                            }
+                    P.ntaps = t;
+                    K.dimA = g.cout; K.dimB = g.cin[0] + g.cin[1]; K.ktaps = 27; K.n_is_A = 0; K.ntaps = t;
+                    probs.push_back(P);
+                    packs.push_back(K);
+                }
+    } else {
+        // conv_transpose k2 s2:  y[2i + a] = sum_ci x[i] W[ci][co][a]  =>  dx[i] = sum_a sum_co dy[2i + a] W[ci][co][a]
+        ConvProblem P;
+        PackDesc K;
+        base(P, K);
+        P.istride = 2;
+        P.ntaps = 8;
+        int t = 0;
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b)
+                for (int c = 0; c < 2; ++c, ++t) {
+                    P.taps[t] = ConvTap{int8_t(a), int8_t(b), int8_t(c), 0};
+                    K.tap_ref[t] = t;
+                }
+        P.od = g.in_d; P.oh = g.in_h; P.ow = g.in_w;
+        P.ostep = 1;
+        K.dimA = g.cin[0]; K.dimB = g.cout; K.ktaps = 8; K.n_is_A = 1; K.ntaps = 8;
+        probs.push_back(P);
+        packs.push_back(K);
+    }
+}
+
+void plan_wgrad(const LayerGeom& g, int src, WgradProblem& W) {
+    std::memset(&W, 0, sizeof(W));
+    if (!g.transposed) {
+        const int pad = (g.ks - 1) / 2;
+        W.t_cp = pad16(g.cin[src]); W.t_coff = 0; W.t_c = pad16(g.cin[src]); W.t_creal = g.cin[src];
+        W.t_d = g.in_d; W.t_h = g.in_h; W.t_w = g.in_w;
+        W.tstride = g.stride;
+        W.ntaps = g.ks * g.ks * g.ks;
+        int t = 0;
+        for (int kz = 0; kz < g.ks; ++kz)
+            for (int ky = 0; ky < g.ks; ++ky)
+                for (int kx = 0; kx < g.ks; ++kx, ++t) {
+                    W.taps[t] = ConvTap{int8_t(kz - pad), int8_t(ky - pad), int8_t(kx - pad), 0};
+                    W.tap_ref[t] = t;
+                }
+        W.ld = g.out_d; W.lh = g.out_h; W.lw = g.out_w;
+        W.u_cp = pad16(g.cout); W.u_coff = 0; W.u_c = pad16(g.cout); W.u_creal = g.cout;
+        W.w_mtot = g.cin[0] + g.cin[1]; W.w_moff = src ? g.cin[0] : 0; W.w_ktaps = W.ntaps;
+        W.w_ntot = g.cout; W.w_noff = 0;
+    } else {
+        W.t_cp = pad16(g.cout); W.t_coff = 0; W.t_c = pad16(g.cout); W.t_creal = g.cout;
+        W.t_d = g.out_d; W.t_h = g.out_h; W.t_w = g.out_w;
+        W.tstride = 2;
+        W.ntaps = 8;
+        int t = 0;
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b)
+                for (int c = 0; c < 2; ++c, ++t) {
+                    W.taps[t] = ConvTap{int8_t(a), int8_t(b), int8_t(c), 0};
+                    W.tap_ref[t] = t;
+                }
+        W.ld = g.in_d; W.lh = g.in_h; W.lw = g.in_w;
+        W.u_cp = pad16(g.cin[0]); W.u_coff = 0; W.u_c = pad16(g.cin[0]); W.u_creal = g.cin[0];
+        W.w_mtot = g.cout; W.w_moff = 0; W.w_ktaps = 8;
+        W.w_ntot = g.cin[0]; W.w_noff = 0;
+    }
+}
+
+}  // namespace u3d

@@ -1,0 +1,50 @@
+// Host-side planner: turns one reference layer (Conv3d / ConvTranspose3d, unet.cpp:46-72) into the
+// gather-GEMM problems of conv_igemm.cu / conv_wgrad.cu and the weight-pack descriptors of layout.cu.
+#pragma once
+#include "u3d.h"
+
+namespace u3d {
+
+inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+// Generic weight pack (layout.cu): reference fp32 tensor [dimA][dimB][ktaps] -> 16-bit blobs
+// [tap][chunk][ntile][kc/8][ntile rows][8]  (canonical K-major SWIZZLE_NONE B operand).
+struct PackDesc {
+    const float* w;
+    int dimA, dimB, ktaps;
+    int n_is_A;              // 1: output channel n indexes dimA, K indexes dimB; 0: the other way round
+    int n_off, n_real, ntile, ntiles;
+    int k_off[2], k_real[2], nch[2];
+    int kc;
+    int ntaps;
+    int tap_ref[27];
+    void* out;
+    int out_bf16;
+};
+size_t pack_bytes(const PackDesc& d);
+int pack_weights_launch(const PackDesc& d, cudaStream_t stream);
+
+// NCDHW fp32 (reference order, train.cpp:619-621) <-> NDHWC 16-bit with channels zero-padded to Cp
+int pack_act_launch(const float* in, void* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream);
+int unpack_act_launch(const void* in, float* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream);
+
+struct LayerGeom {
+    int transposed;          // 0 = Conv3d (k1 s1 | k3 s1 | k3 s2, pad (k-1)/2), 1 = ConvTranspose3d k2 s2
+    int ks, stride;
+    int cin[2];              // real input channels per source (cin[1] = 0 unless the input is a folded concat)
+    int cout;
+    int in_d, in_h, in_w;
+    int out_d, out_h, out_w;
+};
+
+int choose_kc(int c0p, int c1p);
+void choose_ntile(int np, int& ntile, int& ntiles);
+
+// Forward: fills `probs` (operand/destination pointers left null) and `packs` (one per problem, w/out null).
+void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc);
+// Data gradient wrt source `src` (0/1): dy (cout channels, output extent) -> dx (cin[src] channels, input extent).
+void plan_dgrad(const LayerGeom& g, int src, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc);
+// Weight gradient wrt the channels of source `src`.
+void plan_wgrad(const LayerGeom& g, int src, WgradProblem& prob);
+
+}  // namespace u3d

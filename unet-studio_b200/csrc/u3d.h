@@ -1,0 +1,114 @@
+// Internal host-side declarations shared by the .cu/.cpp files of libunet3d_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace u3d {
+
+void set_error(const std::string& msg);  // thread-local last error (capi.cpp)
+const char* last_error();
+
+// ------------------------------------------------------------------------------------------
+// Implicit-GEMM gather convolution (conv_igemm.cu).  One "problem" computes, for every voxel o of an
+// output lattice (od x oh x ow) and every output channel n:
+//     acc[o][n] = sum_{t < ntaps} sum_{k} src[(o*istride + tap_t)][k] * W_t[n][k]
+// where src voxels outside [0,in_*) read as zero.  The result goes to the voxel
+// (o*ostep + ooff) of the destination tensor.  This one form covers:
+//   conv k3 s1/s2 p1, conv k1           istride = stride, taps = {-1,0,1}^3 or {0}
+//   dgrad of conv k3 s1                 istride = 1, flipped taps, W transposed
+//   dgrad of conv k3 s2                 8 output-parity problems with 1/2/4/8 taps
+//   conv_transpose k2 s2 forward        8 output-parity problems, 1 tap each (ostep = 2)
+//   dgrad of conv_transpose k2 s2       istride = 2, taps = {0,1}^3
+// The channel concat of the decoder (unet.cpp:181) never materialises: K runs over src0's channels
+// then src1's.
+// ------------------------------------------------------------------------------------------
+struct ConvTap {
+    int8_t dz, dy, dx, pad;
+};
+
+enum EpiMode : int {
+    EPI_STORE16 = 0,    // 16-bit NDHWC store (+bias) (+column sum / sum-of-squares partials)
+    EPI_ACCUM16 = 1,    // 16-bit NDHWC read-add-store
+    EPI_PLANAR32 = 2,   // fp32 planar [n][lattice voxel] store (+bias): logits in reference NCDHW order
+};
+
+struct ConvProblem {
+    const void* src0;
+    const void* src1;
+    int c0p, c1p;          // channel pitch (elements) of each source tensor
+    int coff0, coff1;      // first channel used in each source
+    int nch0, nch1;        // number of kc-wide K chunks taken from each source
+    int in_d, in_h, in_w;  // source spatial extent
+    int istride;
+    int ntaps;
+    ConvTap taps[27];
+    int od, oh, ow;        // lattice extent; M = od*oh*ow
+    void* dst;
+    int dst_cp;            // destination channel pitch (EPI_*16) ; unused for planar
+    int dst_coff;          // first destination channel
+    int OD, OH, OW;        // destination tensor extent
+    int ostep, ooff_z, ooff_y, ooff_x;
+    int ntile;             // N per tile (multiple of 16, <= 256)
+    int ntiles;            // number of N tiles
+    int n_real;            // real output channels (<= ntile*ntiles)
+    const void* wpack;     // blobs [tap][chunk][ntile] of ntile x kc 16-bit, canonical K-major interleaved
+    const float* bias;     // n_real entries or nullptr
+    int mtiles;            // ceil(M/128)              (filled by the launcher)
+    int item_base;         // first work item           (filled by the launcher)
+};
+
+struct ConvLaunch {
+    int kc;                // K chunk (16, 32 or 64 channels)
+    int a_bf16, b_bf16;    // operand formats (0 = fp16, 1 = bf16)
+    int out_bf16;          // 16-bit output format
+    EpiMode epi;
+    float* stats_partials; // [grid][2][ntile*ntiles] or nullptr (single-problem launches only)
+    int* stats_grid_out;   // host pointer: receives the grid size used (number of partial rows)
+};
+
+int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, ConvProblem* dev_scratch,
+                      cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------
+// Weight-gradient GEMM (conv_wgrad.cu).  For every tap t of a problem:
+//     dW[nch][mch][t] += sum_{v in lattice} T[(v*tstride + tap_t)][mch] * U[v][nch]
+// T = "tapped" tensor (M side, up to 128 rows = tap-group x channels), U = "untapped" tensor (N side).
+//   conv:        T = layer input x (fp16), U = dy (bf16), dW is [Cout][Cin][k^3]
+//   conv_trans:  T = dy (bf16), U = layer input x (fp16), dW is [Cin][Cout][2^3]
+// ------------------------------------------------------------------------------------------
+struct WgradProblem {
+    const void* T;
+    const void* U;
+    int t_cp, t_coff, t_c;      // pitch, first channel, padded channel count (multiple of 16) on the M side
+    int t_creal;                // real channels on the M side
+    int t_d, t_h, t_w;          // tapped tensor extent
+    int tstride;
+    int ntaps;
+    ConvTap taps[27];
+    int tap_ref[27];            // index of each tap in the reference weight's trailing k^3 dims
+    int ld, lh, lw;             // lattice = untapped tensor extent (K = ld*lh*lw)
+    int u_cp, u_coff, u_c;      // pitch, first channel, padded channel count on the N side
+    int u_creal;
+    float* dw;                  // reference-layout gradient, element (n, m, tap) at (n*w_mtot + w_moff + m)*w_ktaps + tap_ref
+    int w_mtot, w_moff, w_ktaps;
+    int w_ntot, w_noff;         // N-side channel offset inside the reference tensor's leading dim
+    int tg;                     // taps per M tile   (filled by launcher)
+    int mtiles;                 // M tiles          (filled by launcher)
+    int ntile, ntiles;          // N tiling         (filled by launcher)
+    int ksplit;                 // K splits         (filled by launcher)
+    int item_base;
+};
+struct WgradLaunch {
+    int t_bf16, u_bf16;
+};
+int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch& cfg, WgradProblem* dev_scratch,
+                      cudaStream_t stream);
+
+int device_sm_count();
+unsigned int read_device_error();  // first non-zero mbarrier-timeout code of any kernel TU (0 = ok)
+unsigned int read_device_error_wgrad();
+
+}  // namespace u3d

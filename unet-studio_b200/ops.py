@@ -1,0 +1,46 @@
+"""Operator-level bindings (u3d_op_* in include/unet3d_b200.h): one reference layer, host numpy buffers."""
+import ctypes
+
+import numpy as np
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a, t=ctypes.c_float):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def conv_forward(x0, weight, bias=None, x1=None, transposed=False, ks=3, stride=1, want_stats=False, planar_fp32=False):
+    """x0/x1: [C,D,H,W] fp32; weight in the reference layout.  Returns y [Cout,D',H',W'] (and stats [2,Cout])."""
+    from . import lib, check
+    x0 = _f32(x0); x1 = _f32(x1); weight = _f32(weight); bias = _f32(bias)
+    cin0, d, h, w = x0.shape
+    cin1 = 0 if x1 is None else x1.shape[0]
+    cout = weight.shape[1] if transposed else weight.shape[0]
+    if transposed:
+        od, oh, ow = 2 * d, 2 * h, 2 * w
+    else:
+        p = (ks - 1) // 2
+        od, oh, ow = [(n + 2 * p - ks) // stride + 1 for n in (d, h, w)]
+    y = np.empty((cout, od, oh, ow), np.float32)
+    stats = np.zeros((2, cout), np.float64) if want_stats else None
+    check(lib().u3d_op_conv_forward(int(transposed), ks, stride, cin0, cin1, cout, w, h, d, _ptr(x0), _ptr(x1),
+                                    _ptr(weight), _ptr(bias), _ptr(y), _ptr(stats, ctypes.c_double), int(planar_fp32)))
+    return (y, stats) if want_stats else y
+
+
+def conv_backward(x0, weight, dy, x1=None, transposed=False, ks=3, stride=1, gx0_init=None):
+    """Returns (gx0, gx1, gw) of the layer given dy [Cout,D',H',W']."""
+    from . import lib, check
+    x0 = _f32(x0); x1 = _f32(x1); weight = _f32(weight); dy = _f32(dy)
+    cin0, d, h, w = x0.shape
+    cin1 = 0 if x1 is None else x1.shape[0]
+    cout = weight.shape[1] if transposed else weight.shape[0]
+    gx0 = np.array(gx0_init, np.float32, copy=True) if gx0_init is not None else np.empty_like(x0)
+    gx1 = None if x1 is None else np.empty_like(x1)
+    gw = np.empty_like(weight)
+    check(lib().u3d_op_conv_backward(int(transposed), ks, stride, cin0, cin1, cout, w, h, d, _ptr(x0), _ptr(x1),
+                                     _ptr(weight), _ptr(dy), _ptr(gx0), _ptr(gx1), _ptr(gw), int(gx0_init is not None)))
+    return gx0, gx1, gw
