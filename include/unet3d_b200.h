@@ -4,13 +4,22 @@
  * plus the training-step body (train.cpp:628-706,755-766), the inference window loop
  * (evaluate.cpp:223-230) and visual_perception_augmentation (train.hpp:43-48).  Every entry point below
  * cites the reference interface it replaces.  Plain pointers and sizes only; no torch types.
+ * include/unet3d.hpp wraps this ABI in a C++ class with the reference's member names.
  *
- * Conventions: every function returns 0 on success, non-zero on failure; unet3d_last_error() then
- * returns a thread-local message (constructor errors carry the reference's std::runtime_error text,
- * unet.cpp:53,66,88,117).  Nothing throws or aborts.  Host tensors are fp32, NCDHW with x fastest
- * (train.cpp:619-621).  A handle owns its device memory, belongs to one GPU, is not internally locked;
- * distinct handles may be driven from distinct threads (train.cpp:592-600).  The library never keeps a
- * caller pointer past the call (train.cpp:615-621).
+ * Conventions
+ *  - every int function returns 0 on success, non-zero on failure; unet3d_last_error() then returns a
+ *    thread-local message (constructor errors carry the reference's std::runtime_error text,
+ *    unet.cpp:53,66,88,117).  Nothing throws or aborts (the reference turns worker exceptions into
+ *    error_msg + aborted, train.cpp:709-721).
+ *  - tensors are fp32, NCDHW with x fastest (train.cpp:619-621); labels are float-stored integers
+ *    (train.cpp:615-617).  `where` = 0: host pointers (copies happen inside the call, the call returns
+ *    after the results are in the caller's buffers); 1: device pointers on the handle's GPU
+ *    (stream-ordered, call unet3d_sync() before reading).
+ *  - a handle owns its device memory and one CUDA stream, belongs to one GPU, is not internally locked;
+ *    distinct handles may be driven from distinct threads (train.cpp:592-600, validation replica
+ *    train.cpp:834-840).  The library never keeps a caller pointer past the call (train.cpp:615-621).
+ *  - arithmetic: fp16 operands with fp32 accumulation on tcgen05 tensor cores, fp32 statistics, losses,
+ *    parameters, gradients and optimizer state (see DESIGN.md "precision").
  */
 #ifndef UNET3D_B200_H
 #define UNET3D_B200_H
@@ -20,7 +29,85 @@
 extern "C" {
 #endif
 
+typedef struct unet3d unet3d_t;
+
 const char* unet3d_last_error(void);
+
+/* default_feature(out_count), train.cpp:1054-1069.  Returns 0, or the needed buffer size if too small. */
+int unet3d_default_feature(int out_count, char* buf, size_t buflen);
+
+/* UNet3d(in_count, out_count, feature_string), unet.cpp:103-166 (+ create_layer, unet.cpp:24-101).
+ * The module starts in training mode like a fresh torch module. */
+int unet3d_create(int in_count, int out_count, const char* feature_string, int gpu, unet3d_t** out);
+void unet3d_destroy(unet3d_t* h);
+
+/* public fields of UNet3dImpl: in_count, out_count, architecture, dim, voxel_size (unet.hpp:16-18,37-38) */
+int unet3d_in_count(const unet3d_t* h);
+int unet3d_out_count(const unet3d_t* h);
+int unet3d_levels(const unet3d_t* h);                   /* output.size(): number of deep-supervision heads */
+const char* unet3d_architecture(const unet3d_t* h);
+int unet3d_set_dim(unet3d_t* h, int w, int hgt, int d); /* model->dim = {w,h,d} (train.cpp:1131) */
+int unet3d_get_dim(const unet3d_t* h, int dim3[3]);
+int unet3d_set_voxel_size(unet3d_t* h, float x, float y, float z);
+
+/* parameters() in registration order == tensorN order of the .nz model file (main.cpp:193-204,225-231):
+ * native contiguous element order, fp32. */
+int unet3d_param_count(const unet3d_t* h);
+long long unet3d_param_total(const unet3d_t* h);
+int unet3d_param_shape(const unet3d_t* h, int i, int64_t dims[5], int* ndim);
+const char* unet3d_param_name(const unet3d_t* h, int i);   /* named_parameters() key, e.g. "encode0.0.weight" */
+int unet3d_param_decay(const unet3d_t* h, int i);          /* 1 if in the weight-decay group (unet.cpp:252-258) */
+int unet3d_get_param(unet3d_t* h, int i, float* host);
+int unet3d_set_param(unet3d_t* h, int i, const float* host);
+int unet3d_get_grad(unet3d_t* h, int i, float* host);      /* accumulated .grad() of parameter i */
+int unet3d_get_momentum(unet3d_t* h, int i, float* host);  /* SGD momentum_buffer (the .opt file, train.cpp:787) */
+int unet3d_set_momentum(unet3d_t* h, int i, const float* host);
+int unet3d_init_params(unet3d_t* h, uint64_t seed);        /* torch's default init rule, own RNG stream */
+
+/* train(bool) (unet.hpp:58-62) / prepare_for_inference (unet.cpp:7-22): training != 0 -> training mode;
+ * 0 -> eval mode with every BatchNorm3d reduced to y = gamma*x + beta (running stats forced to (0,1), eps 0). */
+int unet3d_set_mode(unet3d_t* h, int training);
+
+/* forward(Tensor{1,in,D,H,W}) -> vector<Tensor> (unet.hpp:51, unet.cpp:168-193).  out_levels[k] receives
+ * results[k] ({1,out,D>>k,H>>k,W>>k}); only the first n_levels heads are computed (inference uses
+ * n_levels = 1, evaluate.cpp:226). */
+int unet3d_forward(unet3d_t* h, const float* in, float* const* out_levels, int n_levels, int where);
+
+/* the inference window loop, evaluate.cpp:223-230: out_windows[i] = forward(in_windows[i])[0] */
+int unet3d_evaluate_windows(unet3d_t* h, const float* const* in_windows, float* const* out_windows, int n_windows, int where);
+
+/* one N=1 micro-batch of the training step body, train.cpp:628-706: forward, calc_losses on every
+ * deep-supervision level (train.cpp:501-552), level weights (1/2^k)/sum, backward.  Gradients ACCUMULATE
+ * across calls until unet3d_step.  loss_out = level-0 {ce, dice, mse} (what the reference logs,
+ * train.cpp:675-681); all_level_losses (optional) = 3 floats per level. */
+int unet3d_train_microbatch(unet3d_t* h, const float* in, const float* label, int collapse_before, int use_ce, int use_dice,
+                            int use_mse, float loss_out[3], float* all_level_losses, int where);
+
+/* validation forward + level-0 calc_losses, no gradient (train.cpp:826-851) */
+int unet3d_validate(unet3d_t* h, const float* in, const float* label, int collapse_before, float loss_out[3], int where);
+
+/* create_optimizer(lr) (unet.cpp:246-277): SGD momentum .99, Nesterov, weight decay 3e-5 | 0 groups */
+int unet3d_create_optimizer(unet3d_t* h, float learning_rate);
+
+/* update, train.cpp:755-766: [sum of the replicas' gradients: ONE ncclAllReduce over the flat gradient
+ * buffer when nccl_comm != NULL, replacing add_gradient_from + the copy_from weight broadcast],
+ * grad /= batch_size, clip_grad_norm_(12), optimizer.step(), zero_grad().  lr = the step's learning rate
+ * (train.cpp:566-571). */
+int unet3d_step(unet3d_t* h, int batch_size, double lr, void* nccl_comm);
+double unet3d_last_grad_norm(const unet3d_t* h);   /* pre-clip global norm of the last step */
+int unet3d_last_step_skipped(const unet3d_t* h);   /* 1 if the fp16 gradient path overflowed and the update was skipped */
+float unet3d_loss_scale(const unet3d_t* h);
+int unet3d_set_loss_scale(unet3d_t* h, float s);
+long long unet3d_launch_count(const unet3d_t* h);  /* kernels launched by this handle so far */
+
+/* copy_from (unet.cpp:195-222): parameters/buffers of identical size, dim, voxel_size; works across GPUs */
+int unet3d_copy_from(unet3d_t* dst, const unet3d_t* src);
+int unet3d_sync(unet3d_t* h);
+
+/* NCCL plumbing for the data-parallel step (bootstrap the 128-byte id through any host channel) */
+int unet3d_nccl_unique_id(void* id128);
+int unet3d_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);
+int unet3d_nccl_comm_destroy(void* comm);
 
 /* ---- operator level (one reference layer, host buffers) — used by the per-layer parity tests ---------
  * Conv3d k1s1|k3s1|k3s2 pad (k-1)/2 (unet.cpp:59-72) or ConvTranspose3d k2s2 (unet.cpp:46-57), input given
@@ -31,10 +118,11 @@ const char* unet3d_last_error(void);
 int u3d_op_conv_forward(int transposed, int ks, int stride, int cin0, int cin1, int cout, int w, int h, int d,
                         const float* x0, const float* x1, const float* weight, const float* bias, float* y,
                         double* stats_sum_sumsq, int planar_fp32);
-/* autograd of the same layer (train.cpp:706): gx0/gx1 data gradients (NULL to skip), gw weight gradient. */
+/* autograd of the same layer (train.cpp:706): gx0/gx1 data gradients (NULL to skip), gw weight gradient.
+ * flags bit 0: accumulate into gx0 (skip connections sum two data gradients). */
 int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0, int cin1, int cout, int w, int h, int d,
                          const float* x0, const float* x1, const float* weight, const float* dy, float* gx0,
-                         float* gx1, float* gw, int accumulate_gx0);
+                         float* gx1, float* gw, int flags);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
 """Per-layer parity of the tcgen05 conv kernels (through the C-ABI) against fp32 torch ops on the same
 16-bit-rounded operands.  Tolerances: the only differences are fp32 summation order and the final 16-bit
-store (fp16: 2^-11 per element, bf16: 2^-8)."""
+store (fp16: 2^-11 per element)."""
 import numpy as np
 import pytest
 import torch
@@ -90,22 +90,22 @@ def test_conv_backward(case):
     name, tr, ks, st, c0, c1, co, _ = case
     x0, x1, w, b = make(case, 1)
     x = (x0 if x1 is None else torch.cat([x0, x1], 0))[None].cuda().requires_grad_(True)
-    wq = w.bfloat16().float().cuda().requires_grad_(True)   # dgrad runs on the bf16 weight pack
+    wq = w.half().float().cuda().requires_grad_(True)   # both gradients run on the fp16 weight pack / activations
     y = F.conv_transpose3d(x, wq, None, stride=2) if tr else F.conv3d(x, wq, None, stride=st, padding=(ks - 1) // 2)
     g = torch.Generator().manual_seed(7)
-    dy = torch.randn(y.shape[1:], generator=g).bfloat16().float()
+    dy = torch.randn(y.shape[1:], generator=g).half().float()
     y.backward(dy[None].cuda())
     gx_ref = x.grad[0].cpu().numpy()
     gw_ref = wq.grad.cpu().numpy()
     gx0, gx1, gw = m.conv_backward(x0.numpy(), w.numpy(), dy.numpy(), None if x1 is None else x1.numpy(),
                                    transposed=bool(tr), ks=ks, stride=st)
-    assert rel(gx0, gx_ref[:c0]) < 4e-3, rel(gx0, gx_ref[:c0])
+    assert rel(gx0, gx_ref[:c0]) < 6e-4, rel(gx0, gx_ref[:c0])
     if c1:
-        assert rel(gx1, gx_ref[c0:]) < 4e-3, rel(gx1, gx_ref[c0:])
-    assert rel(gw, gw_ref) < 2e-4, rel(gw, gw_ref)
+        assert rel(gx1, gx_ref[c0:]) < 6e-4, rel(gx1, gx_ref[c0:])
+    assert rel(gw, gw_ref) < 2e-5, rel(gw, gw_ref)
     # accumulate form (skip connections add two data gradients into one tensor)
     init = np.random.default_rng(0).standard_normal(x0.shape).astype(np.float32)
-    init = torch.from_numpy(init).bfloat16().float().numpy()
+    init = torch.from_numpy(init).half().float().numpy()
     gx0a, _, _ = m.conv_backward(x0.numpy(), w.numpy(), dy.numpy(), None if x1 is None else x1.numpy(),
                                  transposed=bool(tr), ks=ks, stride=st, gx0_init=init)
-    assert rel(gx0a, gx_ref[:c0] + init) < 6e-3
+    assert rel(gx0a, gx_ref[:c0] + init) < 8e-4

@@ -33,10 +33,10 @@ for case in sel:
         import torch.nn.functional as F
         x0, x1, w, b = T.make(case, 1)
         x = (x0 if x1 is None else torch.cat([x0, x1], 0))[None].cuda().requires_grad_(True)
-        wq = w.bfloat16().float().cuda().requires_grad_(True)
+        wq = w.half().float().cuda().requires_grad_(True)
         y = F.conv_transpose3d(x, wq, None, stride=2) if tr else F.conv3d(x, wq, None, stride=st, padding=(ks - 1) // 2)
         g = torch.Generator().manual_seed(7)
-        dy = torch.randn(y.shape[1:], generator=g).bfloat16().float()
+        dy = torch.randn(y.shape[1:], generator=g).half().float()
         y.backward(dy[None].cuda())
         gx_ref = x.grad[0].cpu().numpy(); gw_ref = wq.grad.cpu().numpy()
         gx0, gx1, gw = m.conv_backward(x0.numpy(), w.numpy(), dy.numpy(), None if x1 is None else x1.numpy(),

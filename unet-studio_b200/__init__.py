@@ -32,3 +32,4 @@ def check(rc):
 
 
 from .ops import conv_forward, conv_backward  # noqa: E402,F401
+from .model import UNet3d, default_feature, poly_lr  # noqa: E402,F401

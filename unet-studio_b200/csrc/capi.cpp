@@ -1,13 +1,227 @@
-// C-ABI glue (include/unet3d_b200.h): error string + model-level entry points.
+// C-ABI glue (include/unet3d_b200.h): error string + model-level entry points.  Nothing throws across
+// the boundary: the reference converts worker exceptions into error_msg + aborted (train.cpp:709-721).
+#include <cstring>
+#include <stdexcept>
 #include <string>
 
 #include "../../include/unet3d_b200.h"
-#include "u3d.h"
+#include "model.h"
 
 namespace u3d {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 const char* last_error() { return g_last_error.c_str(); }
+int nccl_unique_id(void* out128);
+int nccl_comm_init(void** comm, int nranks, int rank, const void* id128);
+int nccl_comm_destroy(void* comm);
 }  // namespace u3d
 
-extern "C" const char* unet3d_last_error(void) { return u3d::last_error(); }
+using u3d::Model;
+using u3d::set_error;
+
+struct unet3d {
+    Model* m;
+};
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                   \
+    }                                               \
+    catch (const std::exception& e) {               \
+        set_error(e.what());                        \
+        return 1;                                   \
+    }                                               \
+    catch (...) {                                   \
+        set_error("unknown error");                 \
+        return 1;                                   \
+    }
+#define NEED(h)                                     \
+    if (!(h) || !(h)->m) {                          \
+        set_error("null handle");                   \
+        return 1;                                   \
+    }
+
+extern "C" {
+
+const char* unet3d_last_error(void) { return u3d::last_error(); }
+
+int unet3d_default_feature(int out_count, char* buf, size_t buflen) {
+    const std::string f = u3d::default_feature(out_count);
+    if (!buf || buflen < f.size() + 1) { set_error("buffer too small"); return int(f.size() + 1); }
+    std::memcpy(buf, f.c_str(), f.size() + 1);
+    return 0;
+}
+
+int unet3d_create(int in_count, int out_count, const char* feature_string, int gpu, unet3d_t** out) {
+    GUARD_BEGIN
+    if (!out || !feature_string) { set_error("null argument"); return 1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libunet3d_b200 is a B200 (sm_100a) library and has no CPU fallback");
+        return 1;
+    }
+    if (gpu < 0 || gpu >= ndev) { set_error("invalid gpu index"); return 1; }
+    if (cudaSetDevice(gpu) != cudaSuccess) { set_error("cudaSetDevice failed"); return 1; }
+    unet3d* h = new unet3d{nullptr};
+    try {
+        h->m = new Model(in_count, out_count, feature_string);
+    } catch (...) {
+        delete h;
+        throw;
+    }
+    *out = h;
+    return 0;
+    GUARD_END
+}
+
+void unet3d_destroy(unet3d_t* h) {
+    if (!h) return;
+    delete h->m;
+    delete h;
+}
+
+int unet3d_in_count(const unet3d_t* h) { return h && h->m ? h->m->in_count : -1; }
+int unet3d_out_count(const unet3d_t* h) { return h && h->m ? h->m->out_count : -1; }
+int unet3d_levels(const unet3d_t* h) { return h && h->m ? h->m->n_levels() : -1; }
+const char* unet3d_architecture(const unet3d_t* h) { return h && h->m ? h->m->architecture.c_str() : ""; }
+
+int unet3d_set_dim(unet3d_t* h, int w, int hh, int d) {
+    GUARD_BEGIN NEED(h) return h->m->set_dim(w, hh, d);
+    GUARD_END
+}
+int unet3d_get_dim(const unet3d_t* h, int dim3[3]) {
+    if (!h || !h->m) return 1;
+    for (int k = 0; k < 3; ++k) dim3[k] = h->m->dim[k];
+    return 0;
+}
+int unet3d_set_voxel_size(unet3d_t* h, float x, float y, float z) {
+    if (!h || !h->m) return 1;
+    h->m->voxel_size[0] = x; h->m->voxel_size[1] = y; h->m->voxel_size[2] = z;
+    return 0;
+}
+
+int unet3d_param_count(const unet3d_t* h) { return h && h->m ? int(h->m->params.size()) : -1; }
+long long unet3d_param_total(const unet3d_t* h) {
+    if (!h || !h->m) return -1;
+    long long n = 0;
+    for (auto& p : h->m->params) n += p.numel;
+    return n;
+}
+int unet3d_param_shape(const unet3d_t* h, int i, int64_t dims[5], int* ndim) {
+    if (!h || !h->m || i < 0 || i >= int(h->m->params.size())) { set_error("parameter index out of range"); return 1; }
+    const auto& s = h->m->params[i].shape;
+    *ndim = int(s.size());
+    for (size_t k = 0; k < s.size(); ++k) dims[k] = s[k];
+    return 0;
+}
+const char* unet3d_param_name(const unet3d_t* h, int i) {
+    if (!h || !h->m || i < 0 || i >= int(h->m->params.size())) return "";
+    return h->m->params[i].name.c_str();
+}
+int unet3d_param_decay(const unet3d_t* h, int i) {
+    if (!h || !h->m || i < 0 || i >= int(h->m->params.size())) return -1;
+    return h->m->params[i].decay ? 1 : 0;
+}
+int unet3d_get_param(unet3d_t* h, int i, float* host) {
+    GUARD_BEGIN NEED(h) return h->m->get_flat(h->m->d_params, i, host, 1.f);
+    GUARD_END
+}
+int unet3d_set_param(unet3d_t* h, int i, const float* host) {
+    GUARD_BEGIN NEED(h) return h->m->set_param(i, host);
+    GUARD_END
+}
+int unet3d_get_grad(unet3d_t* h, int i, float* host) {
+    GUARD_BEGIN NEED(h)
+    const float s = h->m->loss_scale > 0.f ? 1.0f / h->m->loss_scale : 1.f;
+    return h->m->get_flat(h->m->d_grads, i, host, s);
+    GUARD_END
+}
+int unet3d_get_momentum(unet3d_t* h, int i, float* host) {
+    GUARD_BEGIN NEED(h) return h->m->get_flat(h->m->d_mom, i, host, 1.f);
+    GUARD_END
+}
+int unet3d_set_momentum(unet3d_t* h, int i, const float* host) {
+    GUARD_BEGIN NEED(h) return h->m->set_momentum(i, host);
+    GUARD_END
+}
+int unet3d_init_params(unet3d_t* h, uint64_t seed) {
+    GUARD_BEGIN NEED(h) return h->m->init_params(seed);
+    GUARD_END
+}
+
+int unet3d_set_mode(unet3d_t* h, int training) {
+    GUARD_BEGIN NEED(h) return h->m->set_mode(training);
+    GUARD_END
+}
+
+int unet3d_forward(unet3d_t* h, const float* in, float* const* out_levels, int n_levels, int where) {
+    GUARD_BEGIN NEED(h) return h->m->forward(in, out_levels, n_levels, where);
+    GUARD_END
+}
+
+int unet3d_evaluate_windows(unet3d_t* h, const float* const* in_windows, float* const* out_windows, int n_windows, int where) {
+    GUARD_BEGIN NEED(h)
+    for (int i = 0; i < n_windows; ++i) {
+        float* outs[1] = {out_windows[i]};
+        if (h->m->forward(in_windows[i], outs, 1, where)) return 1;
+    }
+    return 0;
+    GUARD_END
+}
+
+int unet3d_train_microbatch(unet3d_t* h, const float* in, const float* label, int collapse_before, int use_ce, int use_dice,
+                            int use_mse, float loss_out[3], float* all_level_losses, int where) {
+    GUARD_BEGIN NEED(h)
+    return h->m->train_microbatch(in, label, collapse_before, use_ce, use_dice, use_mse, loss_out, all_level_losses, where);
+    GUARD_END
+}
+
+int unet3d_validate(unet3d_t* h, const float* in, const float* label, int collapse_before, float loss_out[3], int where) {
+    GUARD_BEGIN NEED(h) return h->m->validate(in, label, collapse_before, loss_out, where);
+    GUARD_END
+}
+
+int unet3d_create_optimizer(unet3d_t* h, float learning_rate) {
+    GUARD_BEGIN NEED(h)
+    h->m->optimizer_created = true;
+    h->m->lr0 = learning_rate;
+    return 0;
+    GUARD_END
+}
+
+int unet3d_step(unet3d_t* h, int batch_size, double lr, void* nccl_comm) {
+    GUARD_BEGIN NEED(h) return h->m->step(batch_size, lr, nccl_comm);
+    GUARD_END
+}
+
+double unet3d_last_grad_norm(const unet3d_t* h) { return h && h->m ? h->m->last_grad_norm : -1.0; }
+int unet3d_last_step_skipped(const unet3d_t* h) { return h && h->m ? h->m->last_step_skipped : -1; }
+float unet3d_loss_scale(const unet3d_t* h) { return h && h->m ? h->m->loss_scale : -1.f; }
+int unet3d_set_loss_scale(unet3d_t* h, float s) {
+    if (!h || !h->m) return 1;
+    h->m->loss_scale = s;
+    h->m->loss_scale_max = s;
+    return 0;
+}
+long long unet3d_launch_count(const unet3d_t* h) { return h && h->m ? h->m->launches : -1; }
+
+int unet3d_copy_from(unet3d_t* dst, const unet3d_t* src) {
+    GUARD_BEGIN NEED(dst) NEED(src) return dst->m->copy_from(*src->m);
+    GUARD_END
+}
+
+int unet3d_sync(unet3d_t* h) {
+    GUARD_BEGIN NEED(h) return h->m->sync();
+    GUARD_END
+}
+
+int unet3d_nccl_unique_id(void* id128) {
+    GUARD_BEGIN return u3d::nccl_unique_id(id128);
+    GUARD_END
+}
+int unet3d_nccl_comm_init(void** comm, int nranks, int rank, const void* id128) {
+    GUARD_BEGIN return u3d::nccl_comm_init(comm, nranks, rank, id128);
+    GUARD_END
+}
+int unet3d_nccl_comm_destroy(void* comm) { return u3d::nccl_comm_destroy(comm); }
+
+}  // extern "C"

@@ -148,14 +148,15 @@ extern "C" int u3d_op_conv_forward(int transposed, int ks, int stride, int cin0,
 
 extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0, int cin1, int cout, int w, int h, int d,
                                     const float* x0, const float* x1, const float* weight, const float* dy,
-                                    float* gx0, float* gx1, float* gw, int accumulate_gx0) {
+                                    float* gx0, float* gx1, float* gw, int flags) {
+    const int accumulate_gx0 = flags & 1;
     cudaStream_t s = 0;
     const LayerGeom g = make_geom(transposed, ks, stride, cin0, cin1, cout, w, h, d);
     const long long Vin = 1LL * w * h * d, Vout = 1LL * g.out_w * g.out_h * g.out_d;
     DevBuf dx[2], ddy, dw, dgw, dgx[2];
     OP_CHECK(upload_act(dx[0], x0, cin0, Vin, false, s));
     if (cin1) OP_CHECK(upload_act(dx[1], x1, cin1, Vin, false, s));
-    OP_CHECK(upload_act(ddy, dy, cout, Vout, true, s));
+    OP_CHECK(upload_act(ddy, dy, cout, Vout, false, s));
     const size_t wcount = size_t(cout) * (cin0 + cin1) * (transposed ? 8 : ks * ks * ks);
     if (dw.alloc(wcount * 4) || dgw.alloc(wcount * 4)) { set_error("cudaMalloc failed"); return 1; }
     OP_CUDA(cudaMemcpy(dw.p, weight, wcount * 4, cudaMemcpyHostToDevice));
@@ -169,8 +170,8 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
         std::vector<PackDesc> packs;
         int kc = 0;
         plan_dgrad(g, src, probs, packs, kc);
-        const bool acc = src == 0 && accumulate_gx0;
-        if (acc) OP_CHECK(upload_act(dgx[src], gx[src], cin[src], Vin, true, s));
+        const bool acc = src == 0 && (accumulate_gx0 & 1);
+        if (acc) OP_CHECK(upload_act(dgx[src], gx[src], cin[src], Vin, false, s));
         else {
             if (dgx[src].alloc(size_t(pad16(cin[src])) * Vin * 2)) { set_error("cudaMalloc failed"); return 1; }
             OP_CUDA(cudaMemset(dgx[src].p, 0xff, size_t(pad16(cin[src])) * Vin * 2));
@@ -180,18 +181,18 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
             if (wp[i].alloc(pack_bytes(packs[i]))) { set_error("cudaMalloc failed"); return 1; }
             packs[i].w = static_cast<const float*>(dw.p);
             packs[i].out = wp[i].p;
-            packs[i].out_bf16 = 1;
+            packs[i].out_bf16 = 0;
             OP_CHECK(pack_weights_launch(packs[i], s));
             probs[i].src0 = ddy.p;
             probs[i].dst = dgx[src].p;
             probs[i].wpack = wp[i].p;
         }
         ConvLaunch cfg{};
-        cfg.kc = kc; cfg.a_bf16 = 1; cfg.b_bf16 = 1; cfg.out_bf16 = 1;
+        cfg.kc = kc;
         cfg.epi = acc ? EPI_ACCUM16 : EPI_STORE16;
         OP_CHECK(conv_igemm_launch(probs, cfg, nullptr, s));
         OP_CHECK(finish(s));
-        OP_CHECK(download_act(dgx[src].p, gx[src], cin[src], Vin, true, s));
+        OP_CHECK(download_act(dgx[src].p, gx[src], cin[src], Vin, false, s));
     }
     // weight gradient
     if (gw) {
@@ -206,8 +207,6 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
             wprobs.push_back(W);
         }
         WgradLaunch wc{};
-        wc.t_bf16 = transposed ? 1 : 0;
-        wc.u_bf16 = transposed ? 0 : 1;
         OP_CHECK(conv_wgrad_launch(wprobs, wc, nullptr, s));
         OP_CHECK(finish(s));
         OP_CUDA(cudaMemcpy(gw, dgw.p, wcount * 4, cudaMemcpyDeviceToHost));

@@ -1,0 +1,815 @@
+#include "model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+
+namespace u3d {
+
+#define M_CHECK(x)                  \
+    do {                            \
+        if ((x) != 0) return 1;     \
+    } while (0)
+#define M_CUDA(x)                                                                      \
+    do {                                                                               \
+        cudaError_t e_ = (x);                                                          \
+        if (e_ != cudaSuccess) {                                                       \
+            set_error(std::string(#x) + ": " + cudaGetErrorString(e_));                \
+            return 1;                                                                  \
+        }                                                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// feature string (grammar of unet.cpp:24-101, graph of unet.cpp:103-166)
+// ------------------------------------------------------------------------------------------------
+std::string default_feature(int out_count) {
+    const std::string out = "conv" + std::to_string(out_count) + ",ks1,stride1";
+    auto blk = [](int c, int s) {
+        const std::string cs = std::to_string(c);
+        return "conv" + cs + ",ks3,stride" + std::to_string(s) + "+norm,leaky_relu+conv" + cs + ",ks3,stride1+norm,leaky_relu";
+    };
+    std::string f;
+    f += blk(16, 1) + "\n" + blk(32, 2) + "\n" + blk(64, 2) + "\n" + blk(128, 2) + "\n" + blk(256, 2) + "\n";
+    f += blk(256, 2) + "+conv_trans256,ks2,stride2\n";
+    f += blk(256, 1) + "+" + out + "+conv_trans128,ks2,stride2\n";
+    f += blk(128, 1) + "+" + out + "+conv_trans64,ks2,stride2\n";
+    f += blk(64, 1) + "+" + out + "+conv_trans32,ks2,stride2\n";
+    f += blk(32, 1) + "+" + out + "+conv_trans16,ks2,stride2\n";
+    f += blk(16, 1) + "+" + out;
+    return f;
+}
+
+static std::vector<std::string> split(const std::string& s, char sep) {
+    std::vector<std::string> out;
+    std::string cur;
+    std::istringstream in(s);
+    while (std::getline(in, cur, sep)) out.push_back(cur);
+    return out;
+}
+
+static std::vector<std::string> split_lines(const std::string& s) {
+    std::vector<std::string> out;
+    for (auto& l : split(s, '\n')) {
+        std::string t = l;
+        while (!t.empty() && (t.back() == '\r' || t.back() == ' ')) t.pop_back();
+        if (!t.empty()) out.push_back(t);
+    }
+    return out;
+}
+
+static int to_int(const std::string& s) {
+    try {
+        return std::stoi(s);
+    } catch (...) {
+        throw std::runtime_error("stoi");  // std::stoi's own what() in the reference
+    }
+}
+
+// Appends the modules of one '+'-separated token; returns the output channel count.
+static int create_layer(BlockDef& blk, const std::string& def, int in_c) {
+    std::map<std::string, std::string> kv;
+    for (const auto& arg : split(def, ',')) {
+        const size_t pos = arg.find_first_of("0123456789");
+        if (pos != std::string::npos) kv[arg.substr(0, pos)] = arg.substr(pos);
+        else kv[arg] = "1";
+    }
+    int out_c = in_c;
+    ModuleDef m;
+    if (kv.count("max_pool")) {
+        m.kind = ModuleDef::MAXPOOL; m.cin = m.cout = in_c;
+        blk.mods.push_back(m);
+    } else if (kv.count("upsample")) {
+        m.kind = ModuleDef::UPSAMPLE; m.cin = m.cout = in_c;
+        blk.mods.push_back(m);
+    } else if (kv.count("conv_trans")) {
+        out_c = to_int(kv["conv_trans"]);
+        const int ks = kv.count("ks") ? to_int(kv["ks"]) : 2;
+        const int stride = kv.count("stride") ? to_int(kv["stride"]) : 2;
+        if (ks != 2 || stride != 2) throw std::runtime_error("conv_trans supports only ks2 stride2");
+        m.kind = ModuleDef::CONVT; m.cin = in_c; m.cout = out_c; m.ks = 2; m.stride = 2;
+        blk.mods.push_back(m);
+    } else if (kv.count("conv")) {
+        out_c = to_int(kv["conv"]);
+        const int ks = kv.count("ks") ? to_int(kv["ks"]) : 3;
+        const int stride = kv.count("stride") ? to_int(kv["stride"]) : 1;
+        if (!((ks == 1 && stride == 1) || (ks == 3 && (stride == 1 || stride == 2))))
+            throw std::runtime_error("conv supports only ks1 stride1, ks3 stride1, and ks3 stride2");
+        m.kind = ModuleDef::CONV; m.cin = in_c; m.cout = out_c; m.ks = ks; m.stride = stride;
+        blk.mods.push_back(m);
+    } else if (kv.count("norm")) {
+        m.kind = ModuleDef::NORM; m.cin = m.cout = in_c;
+        blk.mods.push_back(m);
+    } else if (kv.count("bnorm")) {
+        m.kind = ModuleDef::BNORM; m.cin = m.cout = in_c;
+        blk.mods.push_back(m);
+    } else {
+        throw std::runtime_error("unknown layer: " + (kv.empty() ? def : kv.begin()->first));
+    }
+    ModuleDef a;
+    a.cin = a.cout = out_c;
+    if (kv.count("relu")) { a.kind = ModuleDef::RELU; blk.mods.push_back(a); }
+    else if (kv.count("leaky_relu")) { a.kind = ModuleDef::LEAKY; blk.mods.push_back(a); }
+    else if (kv.count("elu")) { a.kind = ModuleDef::ELU; blk.mods.push_back(a); }
+    return out_c;
+}
+
+Model::Model(int in_c, int out_c, const std::string& feature) : in_count(in_c), out_count(out_c), architecture(feature) {
+    const auto lines = split_lines(feature);
+    if (lines.size() < 3) throw std::runtime_error("invalid u-net structure");
+    const size_t enc_count = lines.size() / 2 + 1;
+    std::vector<std::vector<std::string>> enc_tokens, dec_tokens;
+    for (size_t i = 0; i < lines.size(); ++i) (i < enc_count ? enc_tokens : dec_tokens).push_back(split(lines[i], '+'));
+    encoding.resize(enc_tokens.size());
+    int channel = in_c;
+    std::vector<int> skip_channels(enc_tokens.size());
+    for (size_t l = 0; l < enc_tokens.size(); ++l) {
+        encoding[l].name = "encode" + std::to_string(l);
+        for (const auto& tok : enc_tokens[l]) channel = create_layer(encoding[l], tok, channel);
+        skip_channels[l] = channel;
+    }
+    const int n_dec = int(dec_tokens.size());
+    decoding.resize(n_dec);
+    output.resize(n_dec);
+    tail.resize(n_dec);
+    if (dec_tokens.back().empty()) throw std::runtime_error("invalid u-net structure");
+    const std::string out_token = dec_tokens.back().back();
+    for (int level = n_dec - 1; level >= 0; --level) {
+        const auto& tokens = dec_tokens[n_dec - 1 - level];
+        decoding[level].name = "decode" + std::to_string(level);
+        output[level].name = "output" + std::to_string(level);
+        tail[level].name = "decode_tail" + std::to_string(level);
+        bool after_out = false;
+        channel += skip_channels[level];
+        for (const auto& tok : tokens) {
+            if (tok == out_token) {
+                create_layer(output[level], tok, channel);
+                after_out = true;
+                continue;
+            }
+            channel = create_layer(after_out ? tail[level] : decoding[level], tok, channel);
+        }
+    }
+    // registration order == parameters() order == tensorN order (unet.cpp:130,160-164)
+    long long off = 0;
+    auto reg = [&](BlockDef& blk) {
+        for (size_t i = 0; i < blk.mods.size(); ++i) {
+            ModuleDef& m = blk.mods[i];
+            std::vector<std::vector<int64_t>> shapes;
+            if (m.kind == ModuleDef::CONV) shapes = {{m.cout, m.cin, m.ks, m.ks, m.ks}, {m.cout}};
+            else if (m.kind == ModuleDef::CONVT) shapes = {{m.cin, m.cout, 2, 2, 2}, {m.cout}};
+            else if (m.kind == ModuleDef::NORM || m.kind == ModuleDef::BNORM) shapes = {{m.cin}, {m.cin}};
+            else continue;
+            m.p0 = int(params.size());
+            for (int k = 0; k < 2; ++k) {
+                ParamInfo p;
+                p.name = blk.name + "." + std::to_string(i) + (k ? ".bias" : ".weight");
+                p.shape = shapes[k];
+                p.numel = 1;
+                for (auto d : p.shape) p.numel *= d;
+                p.offset = off;
+                off += (p.numel + 3) / 4 * 4;
+                p.decay = !(p.name.find("bias") != std::string::npos || p.shape.size() <= 1);
+                params.push_back(p);
+            }
+            if (m.kind == ModuleDef::BNORM) {
+                m.buf0 = n_buffers;
+                n_buffers += 2;
+            }
+        }
+    };
+    for (auto& b : encoding) reg(b);
+    for (int l = n_dec - 1; l >= 0; --l) {
+        reg(decoding[l]);
+        if (!output[l].mods.empty()) reg(output[l]);
+        if (!tail[l].mods.empty()) reg(tail[l]);
+    }
+    flat_n = off;
+
+    cudaGetDevice(&device);
+    if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess)
+        throw std::runtime_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(cudaGetLastError()) +
+                                 " (libunet3d_b200 needs a CUDA device; there is no CPU fallback)");
+    const size_t fb = size_t(flat_n) * sizeof(float);
+    if (cudaMalloc(&d_params, fb) != cudaSuccess || cudaMalloc(&d_grads, fb) != cudaSuccess || cudaMalloc(&d_mom, fb) != cudaSuccess)
+        throw std::runtime_error("cudaMalloc of the parameter buffers failed");
+    cudaMemsetAsync(d_params, 0, fb, stream);
+    cudaMemsetAsync(d_grads, 0, fb, stream);
+    cudaMemsetAsync(d_mom, 0, fb, stream);
+    // BatchNorm running stats: mean 0, var 1
+    auto bufs = [&](BlockDef& blk) {
+        for (auto& m : blk.mods)
+            if (m.kind == ModuleDef::BNORM)
+                for (int k = 0; k < 2; ++k) {
+                    float* b = nullptr;
+                    cudaMalloc(&b, size_t(m.cin) * 4);
+                    std::vector<float> h(m.cin, k ? 1.f : 0.f);
+                    cudaMemcpy(b, h.data(), size_t(m.cin) * 4, cudaMemcpyHostToDevice);
+                    d_buffers.push_back(b);
+                    buffer_len.push_back(m.cin);
+                }
+    };
+    for (auto& b : encoding) bufs(b);
+    for (int l = n_dec - 1; l >= 0; --l) { bufs(decoding[l]); bufs(output[l]); bufs(tail[l]); }
+    // optimizer work list
+    std::vector<SgdChunk> chunks;
+    for (auto& p : params)
+        for (long long o = 0; o < p.numel; o += 8192)
+            chunks.push_back(SgdChunk{p.offset + o, int(std::min<long long>(8192, p.numel - o)), p.decay ? 3e-5f : 0.f});
+    n_chunks = int(chunks.size());
+    cudaMalloc(&d_chunks, chunks.size() * sizeof(SgdChunk));
+    cudaMemcpy(d_chunks, chunks.data(), chunks.size() * sizeof(SgdChunk), cudaMemcpyHostToDevice);
+    cudaMalloc(&d_status, sizeof(SgdStatus));
+    cudaMalloc(&d_loss_acc, sizeof(double) * 8 * 80);
+    cudaMalloc(&d_losses, sizeof(float) * 8 * 3 * 2);
+}
+
+Model::~Model() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    free_plan();
+    cudaFree(d_params); cudaFree(d_grads); cudaFree(d_mom);
+    for (auto b : d_buffers) cudaFree(b);
+    cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_losses);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int Model::alloc(void** p, size_t bytes) {
+    M_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    owned.push_back(*p);
+    return 0;
+}
+
+void Model::free_plan() {
+    for (void* p : owned) cudaFree(p);
+    owned.clear();
+    tens.clear();
+    steps.clear();
+    logits.clear();
+    dlogits.clear();
+    level_dims.clear();
+    d_in_f32 = d_label = d_partials = d_sums = nullptr;
+    d_scratch = nullptr;
+    planned = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------------
+int Model::init_params(uint64_t seed) {
+    // torch default init rule (kaiming_uniform a=sqrt(5) => U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and
+    // bias; norm gamma 1, beta 0).  Own RNG stream: bit-parity with torch::manual_seed is not a goal, the
+    // parity tests load the reference's dumped tensors through set_param instead.
+    std::mt19937_64 rng(seed);
+    std::vector<float> h(size_t(flat_n), 0.f);
+    for (size_t i = 0; i < params.size(); ++i) {
+        const ParamInfo& p = params[i];
+        float* dst = h.data() + p.offset;
+        if (p.shape.size() == 5) {
+            const double fan_in = double(p.shape[1] * p.shape[2] * p.shape[3] * p.shape[4]);
+            const double bound = 1.0 / std::sqrt(fan_in);
+            std::uniform_real_distribution<double> U(-bound, bound);
+            for (long long k = 0; k < p.numel; ++k) dst[k] = float(U(rng));
+            const ParamInfo& b = params[i + 1];
+            float* bd = h.data() + b.offset;
+            for (long long k = 0; k < b.numel; ++k) bd[k] = float(U(rng));
+            ++i;
+        } else {
+            const bool gamma = p.name.size() >= 6 && p.name.compare(p.name.size() - 6, 6, "weight") == 0;
+            for (long long k = 0; k < p.numel; ++k) dst[k] = gamma ? 1.f : 0.f;
+        }
+    }
+    cudaSetDevice(device);
+    M_CUDA(cudaMemcpyAsync(d_params, h.data(), h.size() * 4, cudaMemcpyHostToDevice, stream));
+    M_CUDA(cudaStreamSynchronize(stream));
+    packs_dirty = true;
+    return 0;
+}
+
+int Model::get_flat(const float* base, int i, float* host, float scale) {
+    if (i < 0 || i >= int(params.size())) { set_error("parameter index out of range"); return 1; }
+    cudaSetDevice(device);
+    M_CUDA(cudaMemcpyAsync(host, base + params[i].offset, size_t(params[i].numel) * 4, cudaMemcpyDeviceToHost, stream));
+    M_CUDA(cudaStreamSynchronize(stream));
+    if (scale != 1.f)
+        for (long long k = 0; k < params[i].numel; ++k) host[k] *= scale;
+    return 0;
+}
+
+int Model::set_param(int i, const float* host) {
+    if (i < 0 || i >= int(params.size())) { set_error("parameter index out of range"); return 1; }
+    cudaSetDevice(device);
+    M_CUDA(cudaMemcpyAsync(d_params + params[i].offset, host, size_t(params[i].numel) * 4, cudaMemcpyHostToDevice, stream));
+    M_CUDA(cudaStreamSynchronize(stream));
+    packs_dirty = true;
+    return 0;
+}
+
+int Model::set_momentum(int i, const float* host) {
+    if (i < 0 || i >= int(params.size())) { set_error("parameter index out of range"); return 1; }
+    cudaSetDevice(device);
+    M_CUDA(cudaMemcpyAsync(d_mom + params[i].offset, host, size_t(params[i].numel) * 4, cudaMemcpyHostToDevice, stream));
+    M_CUDA(cudaStreamSynchronize(stream));
+    mom_initialized = true;
+    return 0;
+}
+
+int Model::set_dim(int w, int h, int d) {
+    if (w <= 0 || h <= 0 || d <= 0) { set_error("invalid dimension"); return 1; }
+    if (w != dim[0] || h != dim[1] || d != dim[2]) {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        free_plan();
+    }
+    dim[0] = w; dim[1] = h; dim[2] = d;
+    return 0;
+}
+
+int Model::set_mode(int train) {
+    if ((train != 0) != training) {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        free_plan();
+    }
+    training = train != 0;
+    return 0;
+}
+
+int Model::sync() {
+    cudaSetDevice(device);
+    M_CUDA(cudaStreamSynchronize(stream));
+    const unsigned int code = read_device_error();
+    if (code) { set_error("device pipeline timeout code " + std::to_string(code)); return 1; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph -> steps
+// ------------------------------------------------------------------------------------------------
+int Model::build_steps() {
+    tens.clear();
+    steps.clear();
+    auto new_ten = [&](int C, int d, int h, int w, bool grad) {
+        Ten t;
+        t.C = C; t.Cp = pad16(C); t.d = d; t.h = h; t.w = w; t.needs_grad = grad;
+        tens.push_back(t);
+        return int(tens.size()) - 1;
+    };
+    int cur = new_ten(in_count, dim[2], dim[1], dim[0], false);
+    bool fail = false;
+    std::string why;
+    auto run_block = [&](const BlockDef& blk, int in_a, int in_b, int head_level) -> int {
+        int x = in_a, x2 = in_b;
+        for (size_t i = 0; i < blk.mods.size() && !fail; ++i) {
+            const ModuleDef& m = blk.mods[i];
+            const Ten a = tens[x];
+            if (x2 >= 0 && m.kind != ModuleDef::CONV) {
+                fail = true;
+                why = "a decoder level must start with a conv token (the channel concat is folded into it)";
+                break;
+            }
+            if (m.kind == ModuleDef::CONV || m.kind == ModuleDef::CONVT) {
+                Step s;
+                s.kind = Step::CONV;
+                s.in0 = x; s.in1 = x2;
+                LayerGeom& g = s.g;
+                g.transposed = m.kind == ModuleDef::CONVT;
+                g.ks = m.ks; g.stride = m.stride;
+                g.cin[0] = a.C; g.cin[1] = x2 >= 0 ? tens[x2].C : 0;
+                g.cout = m.cout;
+                g.in_d = a.d; g.in_h = a.h; g.in_w = a.w;
+                if (x2 >= 0 && (tens[x2].d != a.d || tens[x2].h != a.h || tens[x2].w != a.w)) {
+                    fail = true;
+                    why = "skip connection and up-sampled tensor differ in size (torch::cat would throw): use a grid that is a multiple of 2^levels";
+                    break;
+                }
+                if (g.cin[0] + g.cin[1] != m.cin) { fail = true; why = "internal channel mismatch"; break; }
+                if (g.transposed) { g.out_d = 2 * a.d; g.out_h = 2 * a.h; g.out_w = 2 * a.w; }
+                else {
+                    const int pad = (m.ks - 1) / 2;
+                    g.out_d = (a.d + 2 * pad - m.ks) / m.stride + 1;
+                    g.out_h = (a.h + 2 * pad - m.ks) / m.stride + 1;
+                    g.out_w = (a.w + 2 * pad - m.ks) / m.stride + 1;
+                }
+                if (g.out_d <= 0 || g.out_h <= 0 || g.out_w <= 0) { fail = true; why = "volume too small for the network"; break; }
+                s.p_w = m.p0; s.p_b = m.p0 + 1;
+                const bool next_norm = i + 1 < blk.mods.size() &&
+                                       (blk.mods[i + 1].kind == ModuleDef::NORM || (blk.mods[i + 1].kind == ModuleDef::BNORM && training));
+                s.stats = next_norm && !g.transposed;
+                if (head_level >= 0) {
+                    if (blk.mods.size() != 1) { fail = true; why = "the output token must be a single conv"; break; }
+                    s.head_level = head_level;
+                    s.out = -1;
+                    level_dims[3 * head_level] = g.out_d; level_dims[3 * head_level + 1] = g.out_h; level_dims[3 * head_level + 2] = g.out_w;
+                } else {
+                    s.out = new_ten(m.cout, g.out_d, g.out_h, g.out_w, true);
+                    x = s.out;
+                }
+                x2 = -1;
+                steps.push_back(s);
+            } else if (m.kind == ModuleDef::MAXPOOL || m.kind == ModuleDef::UPSAMPLE) {
+                Step s;
+                s.kind = m.kind == ModuleDef::MAXPOOL ? Step::MAXPOOL : Step::UPSAMPLE;
+                s.in0 = x;
+                if (m.kind == ModuleDef::MAXPOOL) {
+                    if (a.d / 2 <= 0 || a.h / 2 <= 0 || a.w / 2 <= 0) { fail = true; why = "volume too small for max_pool"; break; }
+                    s.out = new_ten(a.C, a.d / 2, a.h / 2, a.w / 2, true);
+                } else
+                    s.out = new_ten(a.C, a.d * 2, a.h * 2, a.w * 2, true);
+                x = s.out;
+                steps.push_back(s);
+            } else {
+                Step s;
+                s.kind = Step::NORMACT;
+                s.in0 = x;
+                auto act_of = [](ModuleDef::Kind k) { return k == ModuleDef::RELU ? ACT_RELU : k == ModuleDef::LEAKY ? ACT_LEAKY : ACT_ELU; };
+                if (m.kind == ModuleDef::NORM || m.kind == ModuleDef::BNORM) {
+                    s.norm = m.kind == ModuleDef::NORM ? 1 : 2;
+                    s.p_g = m.p0;
+                    s.buf0 = m.buf0;
+                    if (i + 1 < blk.mods.size() && blk.mods[i + 1].kind >= ModuleDef::RELU) {
+                        s.act = act_of(blk.mods[i + 1].kind);
+                        ++i;
+                    }
+                    s.stats_from_conv = !steps.empty() && steps.back().kind == Step::CONV && steps.back().stats && steps.back().out == x;
+                } else
+                    s.act = act_of(m.kind);
+                s.out = new_ten(a.C, a.d, a.h, a.w, true);
+                x = s.out;
+                steps.push_back(s);
+            }
+        }
+        return x;
+    };
+    const int E = int(encoding.size());
+    level_dims.assign(3 * output.size(), 0);
+    std::vector<int> skips(E, -1);
+    for (int l = 0; l < E && !fail; ++l) {
+        cur = run_block(encoding[l], cur, -1, -1);
+        if (l < E - 1) skips[l] = cur;
+    }
+    for (int l = E - 2; l >= 0 && !fail; --l) {
+        cur = run_block(decoding[l], skips[l], cur, -1);
+        if (!fail && !output[l].mods.empty()) run_block(output[l], cur, -1, l);
+        if (!fail && !tail[l].mods.empty()) cur = run_block(tail[l], cur, -1, -1);
+    }
+    if (fail) { set_error(why); return 1; }
+    return 0;
+}
+
+int Model::ensure_plan() {
+    cudaSetDevice(device);
+    if (planned && planned_training == training) return 0;
+    free_plan();
+    M_CHECK(build_steps());
+    const bool tr = training;
+    size_t max_bytes = 0;
+    int max_cp = 16;
+    for (auto& t : tens) {
+        M_CHECK(alloc(&t.p, t.bytes()));
+        if (tr && t.needs_grad) M_CHECK(alloc(&t.grad, t.bytes()));
+        max_bytes = std::max(max_bytes, t.bytes());
+        max_cp = std::max(max_cp, t.Cp);
+    }
+    // padded channels of the network input must be zero; every other tensor is fully written by its producer
+    const long long V0 = tens[0].V();
+    M_CHECK(alloc(reinterpret_cast<void**>(&d_in_f32), size_t(in_count) * V0 * 4));
+    M_CHECK(alloc(reinterpret_cast<void**>(&d_label), size_t(V0) * 4));
+    const int rows = std::max(reduce_rows_max(), device_sm_count());
+    M_CHECK(alloc(reinterpret_cast<void**>(&d_partials), size_t(rows) * 2 * std::max(max_cp, 512) * 4));
+    M_CHECK(alloc(reinterpret_cast<void**>(&d_sums), size_t(2) * max_cp * 4));
+    if (tr) {
+        M_CHECK(alloc(&d_scratch, max_bytes));
+        scratch_bytes = max_bytes;
+    }
+    const int L = int(output.size());
+    logits.assign(L, nullptr);
+    dlogits.assign(L, nullptr);
+    const int ocp = pad16(out_count);
+    for (int l = 0; l < L; ++l) {
+        const long long v = 1LL * level_dims[3 * l] * level_dims[3 * l + 1] * level_dims[3 * l + 2];
+        if (v == 0) continue;
+        M_CHECK(alloc(reinterpret_cast<void**>(&logits[l]), size_t(out_count) * v * 4));
+        if (tr) M_CHECK(alloc(&dlogits[l], size_t(ocp) * v * 2));
+    }
+    for (auto& s : steps) {
+        if (s.kind == Step::CONV) {
+            plan_forward(s.g, s.fprobs, s.fpacks, s.fkc);
+            for (size_t i = 0; i < s.fprobs.size(); ++i) {
+                void* blob = nullptr;
+                M_CHECK(alloc(&blob, pack_bytes(s.fpacks[i])));
+                s.pack_bufs.push_back(blob);
+                s.fpacks[i].w = param_ptr(s.p_w);
+                s.fpacks[i].out = blob;
+                s.fpacks[i].out_bf16 = 0;
+                ConvProblem& P = s.fprobs[i];
+                P.src0 = tens[s.in0].p;
+                P.c0p = tens[s.in0].Cp;
+                if (s.in1 >= 0) { P.src1 = tens[s.in1].p; P.c1p = tens[s.in1].Cp; }
+                P.dst = s.head_level >= 0 ? static_cast<void*>(logits[s.head_level]) : tens[s.out].p;
+                P.wpack = blob;
+                P.bias = param_ptr(s.p_b);
+            }
+            if (tr) {
+                void* dy = s.head_level >= 0 ? dlogits[s.head_level] : tens[s.out].grad;
+                const int ins[2] = {s.in0, s.in1};
+                for (int src = 0; src < 2; ++src) {
+                    if (ins[src] < 0) continue;
+                    WgradProblem W;
+                    plan_wgrad(s.g, src, W);
+                    if (!s.g.transposed) { W.T = tens[ins[src]].p; W.t_cp = tens[ins[src]].Cp; W.U = dy; }
+                    else { W.T = dy; W.U = tens[s.in0].p; W.u_cp = tens[s.in0].Cp; }
+                    W.dw = grad_ptr(s.p_w);
+                    s.wg.push_back(W);
+                    if (!tens[ins[src]].needs_grad) continue;
+                    Step::DG& D = s.dg[src];
+                    plan_dgrad(s.g, src, D.probs, D.packs, D.kc);
+                    for (size_t i = 0; i < D.probs.size(); ++i) {
+                        void* blob = nullptr;
+                        M_CHECK(alloc(&blob, pack_bytes(D.packs[i])));
+                        s.pack_bufs.push_back(blob);
+                        D.packs[i].w = param_ptr(s.p_w);
+                        D.packs[i].out = blob;
+                        D.packs[i].out_bf16 = 0;
+                        D.probs[i].src0 = dy;
+                        D.probs[i].dst = tens[ins[src]].grad;
+                        D.probs[i].dst_cp = tens[ins[src]].Cp;
+                        D.probs[i].wpack = blob;
+                    }
+                }
+            }
+        } else if (s.kind == Step::NORMACT) {
+            if (s.norm) {
+                M_CHECK(alloc(reinterpret_cast<void**>(&s.mean), size_t(tens[s.in0].Cp) * 4));
+                M_CHECK(alloc(reinterpret_cast<void**>(&s.rstd), size_t(tens[s.in0].Cp) * 4));
+            }
+        } else if (s.kind == Step::MAXPOOL) {
+            M_CHECK(alloc(reinterpret_cast<void**>(&s.idx), tens[s.out].V() * tens[s.out].Cp * sizeof(int)));
+        }
+    }
+    grad_written.assign(tens.size(), 0);
+    if (loss_scale == 0.f) {
+        int e = int(std::floor(std::log2(double(std::max<long long>(V0, 1))))) - 2;
+        e = std::max(4, std::min(e, 24));
+        loss_scale = std::ldexp(1.f, e);
+    }
+    planned = true;
+    planned_training = tr;
+    packs_dirty = true;
+    return 0;
+}
+
+int Model::repack() {
+    if (!packs_dirty) return 0;
+    for (auto& s : steps) {
+        if (s.kind != Step::CONV) continue;
+        for (auto& k : s.fpacks) { M_CHECK(pack_weights_launch(k, stream)); ++launches; }
+        for (int src = 0; src < 2; ++src)
+            for (auto& k : s.dg[src].packs) { M_CHECK(pack_weights_launch(k, stream)); ++launches; }
+    }
+    packs_dirty = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward (unet.cpp:168-193)
+// ------------------------------------------------------------------------------------------------
+int Model::run_forward(int levels_wanted) {
+    for (auto& s : steps) {
+        if (s.kind == Step::CONV) {
+            if (s.head_level >= levels_wanted) continue;
+            ConvLaunch cfg{};
+            cfg.kc = s.fkc;
+            cfg.epi = s.head_level >= 0 ? EPI_PLANAR32 : EPI_STORE16;
+            int rows = 0;
+            cfg.stats_grid_out = &rows;
+            if (s.stats) cfg.stats_partials = d_partials;
+            M_CHECK(conv_igemm_launch(s.fprobs, cfg, nullptr, stream));
+            ++launches;
+            if (s.stats) { last_stat_rows = rows; last_stat_ntot = s.fprobs[0].ntile * s.fprobs[0].ntiles; }
+        } else if (s.kind == Step::NORMACT) {
+            const Ten& a = tens[s.in0];
+            const float* gamma = s.norm ? param_ptr(s.p_g) : nullptr;
+            const float* beta = s.norm ? param_ptr(s.p_g + 1) : nullptr;
+            if (s.norm == 1 || (s.norm == 2 && training)) {
+                int rows = last_stat_rows, ntot = last_stat_ntot;
+                if (!s.stats_from_conv) {
+                    M_CHECK(channel_stats_launch(a.p, a.V(), a.C, a.Cp, d_partials, &rows, stream));
+                    ntot = a.Cp;
+                    ++launches;
+                }
+                float* rm = (s.norm == 2) ? d_buffers[s.buf0] : nullptr;
+                float* rv = (s.norm == 2) ? d_buffers[s.buf0 + 1] : nullptr;
+                M_CHECK(finalize_stats_launch(d_partials, rows, ntot, a.C, double(a.V()), s.norm == 1 ? 1e-5f : 0.f, s.mean, s.rstd,
+                                              rm, rv, 0.1f, stream));
+                M_CHECK(norm_act_fwd_launch(a.p, tens[s.out].p, a.V(), a.C, a.Cp, 1, s.act, s.mean, s.rstd, gamma, beta, stream));
+                launches += 2;
+            } else {
+                // no norm, or BatchNorm after prepare_for_inference (mean 0, var 1, eps 0 => y = gamma*x + beta; unet.cpp:7-22)
+                M_CHECK(norm_act_fwd_launch(a.p, tens[s.out].p, a.V(), a.C, a.Cp, s.norm ? 1 : 0, s.act, nullptr, nullptr, gamma, beta, stream));
+                ++launches;
+            }
+        } else if (s.kind == Step::MAXPOOL) {
+            const Ten& o = tens[s.out];
+            M_CHECK(maxpool_fwd_launch(tens[s.in0].p, o.p, s.idx, o.Cp, o.d, o.h, o.w, stream));
+            ++launches;
+        } else {
+            const Ten& a = tens[s.in0];
+            M_CHECK(upsample_fwd_launch(a.p, tens[s.out].p, a.Cp, a.d, a.h, a.w, stream));
+            ++launches;
+        }
+    }
+    return 0;
+}
+
+int Model::upload_input(const float* in, int where) {
+    const long long V0 = tens[0].V();
+    const float* src = in;
+    if (where == 0) {
+        M_CUDA(cudaMemcpyAsync(d_in_f32, in, size_t(in_count) * V0 * 4, cudaMemcpyHostToDevice, stream));
+        src = d_in_f32;
+    }
+    M_CHECK(pack_act_launch(src, tens[0].p, in_count, tens[0].Cp, V0, false, stream));
+    ++launches;
+    return 0;
+}
+
+int Model::forward(const float* in, float* const* out_levels, int n_levels_wanted, int where) {
+    M_CHECK(ensure_plan());
+    M_CHECK(repack());
+    const int L = int(output.size());
+    if (n_levels_wanted < 1 || n_levels_wanted > L) { set_error("levels wanted out of range"); return 1; }
+    M_CHECK(upload_input(in, where));
+    M_CHECK(run_forward(n_levels_wanted));
+    for (int l = 0; l < n_levels_wanted; ++l) {
+        if (!out_levels || !out_levels[l]) continue;
+        if (!logits[l]) { set_error("undefined deep supervision output at level " + std::to_string(l)); return 1; }
+        const long long v = 1LL * level_dims[3 * l] * level_dims[3 * l + 1] * level_dims[3 * l + 2];
+        M_CUDA(cudaMemcpyAsync(out_levels[l], logits[l], size_t(out_count) * v * 4,
+                               where == 0 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, stream));
+    }
+    if (where == 0) return sync();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (autograd of the step body, train.cpp:706)
+// ------------------------------------------------------------------------------------------------
+int Model::run_backward() {
+    std::fill(grad_written.begin(), grad_written.end(), 0);
+    for (int si = int(steps.size()) - 1; si >= 0; --si) {
+        Step& s = steps[si];
+        if (s.kind == Step::CONV) {
+            const bool head = s.head_level >= 0;
+            if (!head && !grad_written[s.out]) continue;  // output never used downstream
+            const void* dy = head ? dlogits[s.head_level] : tens[s.out].grad;
+            const long long Vout = 1LL * s.g.out_d * s.g.out_h * s.g.out_w;
+            if (!s.stats) {
+                // bias gradient = sum_v dy (a conv feeding a norm has an exactly-zero bias gradient: the norm removes the mean)
+                M_CHECK(colsum_accumulate_launch(dy, Vout, s.g.cout, pad16(s.g.cout), d_partials, grad_ptr(s.p_b), stream));
+                launches += 2;
+            }
+            WgradLaunch wc{};
+            M_CHECK(conv_wgrad_launch(s.wg, wc, nullptr, stream));
+            ++launches;
+            const int ins[2] = {s.in0, s.in1};
+            for (int src = 0; src < 2; ++src) {
+                if (ins[src] < 0 || !tens[ins[src]].needs_grad) continue;
+                ConvLaunch cfg{};
+                cfg.kc = s.dg[src].kc;
+                cfg.epi = grad_written[ins[src]] ? EPI_ACCUM16 : EPI_STORE16;
+                M_CHECK(conv_igemm_launch(s.dg[src].probs, cfg, nullptr, stream));
+                ++launches;
+                grad_written[ins[src]] = 1;
+            }
+        } else {
+            if (!grad_written[s.out]) continue;
+            const Ten& a = tens[s.in0];
+            const Ten& o = tens[s.out];
+            if (!a.needs_grad) continue;
+            void* target = grad_written[s.in0] ? d_scratch : a.grad;
+            if (s.kind == Step::NORMACT) {
+                const float* gamma = s.norm ? param_ptr(s.p_g) : nullptr;
+                const float* beta = s.norm ? param_ptr(s.p_g + 1) : nullptr;
+                M_CHECK(norm_act_bwd_launch(a.p, o.grad, target, a.V(), a.C, a.Cp, s.norm ? 1 : 0, s.act, s.mean, s.rstd, gamma, beta,
+                                            d_partials, d_sums, s.norm ? grad_ptr(s.p_g) : nullptr,
+                                            s.norm ? grad_ptr(s.p_g + 1) : nullptr, stream));
+                launches += s.norm ? 3 : 1;
+            } else if (s.kind == Step::MAXPOOL) {
+                M_CHECK(maxpool_bwd_launch(o.grad, s.idx, target, o.Cp, o.d, o.h, o.w, stream));
+                ++launches;
+            } else {
+                M_CHECK(upsample_bwd_launch(o.grad, target, a.Cp, a.d, a.h, a.w, stream));
+                ++launches;
+            }
+            if (grad_written[s.in0]) {
+                M_CHECK(add16_launch(a.grad, d_scratch, a.V() * (a.Cp / 8), stream));
+                ++launches;
+            }
+            grad_written[s.in0] = 1;
+        }
+    }
+    return 0;
+}
+
+// one N=1 micro-batch: forward, 5-level deep supervision, backward (train.cpp:628-706)
+int Model::train_microbatch(const float* in, const float* label, int collapse_before, int use_ce, int use_dice, int use_mse,
+                            float* loss_out3, float* all_levels, int where) {
+    if (!training) { set_error("train_microbatch needs training mode (unet3d_set_mode(h, 1))"); return 1; }
+    M_CHECK(ensure_plan());
+    M_CHECK(repack());
+    const int L = int(output.size());
+    for (int l = 0; l < L; ++l) {
+        if (!logits[l]) { set_error("undefined deep supervision output at level " + std::to_string(l)); return 1; }
+        if (level_dims[3 * l] != (dim[2] >> l) || level_dims[3 * l + 1] != (dim[1] >> l) || level_dims[3 * l + 2] != (dim[0] >> l) ||
+            ((dim[2] >> l) << l) != dim[2] || ((dim[1] >> l) << l) != dim[1] || ((dim[0] >> l) << l) != dim[0]) {
+            set_error("deep supervision needs level k to be exactly 1/2^k of the grid (train.cpp:645-662)");
+            return 1;
+        }
+    }
+    if (collapse_before < 0 || collapse_before >= std::max(out_count, 1)) { set_error("invalid collapse_before"); return 1; }
+    const long long V0 = tens[0].V();
+    M_CHECK(upload_input(in, where));
+    const float* lab = label;
+    if (where == 0) {
+        M_CUDA(cudaMemcpyAsync(d_label, label, size_t(V0) * 4, cudaMemcpyHostToDevice, stream));
+        lab = d_label;
+    }
+    M_CHECK(run_forward(L));
+    float weight_sum = 0.f;
+    for (int k = 0; k < L; ++k) weight_sum += 1.0f / float(1 << k);
+    const float inv_weight_sum = 1.0f / weight_sum;
+    const bool any = use_ce || use_dice || use_mse;
+    for (int k = 0; k < L; ++k) {
+        LossLevel Q{};
+        Q.logits = logits[k]; Q.label = lab; Q.dlogits = dlogits[k];
+        Q.C = out_count; Q.Cp = pad16(out_count); Q.collapse_before = collapse_before;
+        Q.d = level_dims[3 * k]; Q.h = level_dims[3 * k + 1]; Q.w = level_dims[3 * k + 2];
+        Q.H0 = dim[1]; Q.W0 = dim[0]; Q.shift = k;
+        const float nw = (1.0f / float(1 << k)) * inv_weight_sum;
+        Q.w_ce = (use_ce || !any) ? nw : 0.f;   // "if(!level_loss.defined()) level_loss = ce" (train.cpp:696-697)
+        Q.w_dice = use_dice ? nw : 0.f;
+        Q.w_mse = use_mse ? nw : 0.f;
+        Q.loss_scale = loss_scale;
+        Q.acc = d_loss_acc + 80 * k;
+        Q.out3 = d_losses + 3 * k;
+        M_CHECK(loss_level_launch(Q, stream));
+        launches += 4;
+    }
+    M_CHECK(run_backward());
+    std::vector<float> h(size_t(3) * L);
+    M_CUDA(cudaMemcpyAsync(h.data(), d_losses, h.size() * 4, cudaMemcpyDeviceToHost, stream));
+    M_CHECK(sync());
+    if (loss_out3) std::memcpy(loss_out3, h.data(), 12);
+    if (all_levels) std::memcpy(all_levels, h.data(), h.size() * 4);
+    return 0;
+}
+
+// validation forward + level-0 losses (train.cpp:826-851)
+int Model::validate(const float* in, const float* label, int collapse_before, float* loss_out3, int where) {
+    M_CHECK(ensure_plan());
+    M_CHECK(repack());
+    const long long V0 = tens[0].V();
+    M_CHECK(upload_input(in, where));
+    const float* lab = label;
+    if (where == 0) {
+        M_CUDA(cudaMemcpyAsync(d_label, label, size_t(V0) * 4, cudaMemcpyHostToDevice, stream));
+        lab = d_label;
+    }
+    M_CHECK(run_forward(1));
+    LossLevel Q{};
+    Q.logits = logits[0]; Q.label = lab; Q.dlogits = nullptr;
+    Q.C = out_count; Q.Cp = pad16(out_count); Q.collapse_before = collapse_before;
+    Q.d = level_dims[0]; Q.h = level_dims[1]; Q.w = level_dims[2];
+    Q.H0 = dim[1]; Q.W0 = dim[0]; Q.shift = 0;
+    Q.acc = d_loss_acc; Q.out3 = d_losses;
+    M_CHECK(loss_level_launch(Q, stream));
+    launches += 3;
+    M_CUDA(cudaMemcpyAsync(loss_out3, d_losses, 12, cudaMemcpyDeviceToHost, stream));
+    return sync();
+}
+
+int Model::copy_from(const Model& src) {
+    // unet.cpp:195-222: parameters (and buffers) with identical sizes are copied, others are left alone
+    cudaSetDevice(device);
+    const size_t n = std::min(params.size(), src.params.size());
+    cudaStreamSynchronize(src.stream);
+    for (size_t i = 0; i < n; ++i) {
+        if (params[i].shape != src.params[i].shape) continue;
+        M_CUDA(cudaMemcpyPeerAsync(d_params + params[i].offset, device, src.d_params + src.params[i].offset, src.device,
+                                   size_t(params[i].numel) * 4, stream));
+    }
+    for (size_t i = 0; i < d_buffers.size() && i < src.d_buffers.size(); ++i) {
+        if (buffer_len[i] != src.buffer_len[i]) continue;
+        M_CUDA(cudaMemcpyPeerAsync(d_buffers[i], device, src.d_buffers[i], src.device, size_t(buffer_len[i]) * 4, stream));
+    }
+    for (int k = 0; k < 3; ++k) { voxel_size[k] = src.voxel_size[k]; }
+    M_CHECK(set_dim(src.dim[0], src.dim[1], src.dim[2]));
+    M_CUDA(cudaStreamSynchronize(stream));
+    packs_dirty = true;
+    return 0;
+}
+
+}  // namespace u3d

@@ -1,0 +1,157 @@
+// Host-side UNet3d: feature_string parser, layer graph, memory plan and the forward / backward /
+// optimizer executors that drive the sm_100a kernels.  Mirrors UNet3dImpl (/root/reference/unet.hpp:13-70).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "elementwise.h"
+#include "plan.h"
+
+namespace u3d {
+
+struct ModuleDef {
+    enum Kind { CONV, CONVT, MAXPOOL, UPSAMPLE, NORM, BNORM, RELU, LEAKY, ELU } kind;
+    int cin = 0, cout = 0, ks = 0, stride = 0;
+    int p0 = -1;    // first parameter index (weight|gamma); p0+1 = bias|beta
+    int buf0 = -1;  // BNORM: running_mean index; buf0+1 = running_var
+};
+struct BlockDef {
+    std::string name;
+    std::vector<ModuleDef> mods;
+};
+struct ParamInfo {
+    std::string name;
+    std::vector<int64_t> shape;
+    long long offset = 0;  // element offset in the flat buffers (4-element aligned)
+    long long numel = 0;
+    bool decay = false;    // unet.cpp:252-258
+};
+
+struct Ten {  // NDHWC fp16 activation
+    int C = 0, Cp = 0, d = 0, h = 0, w = 0;
+    void* p = nullptr;
+    void* grad = nullptr;
+    bool needs_grad = false;
+    long long V() const { return 1LL * d * h * w; }
+    size_t bytes() const { return size_t(V()) * Cp * 2; }
+};
+
+struct Step {
+    enum Kind { CONV, NORMACT, MAXPOOL, UPSAMPLE } kind = CONV;
+    int in0 = -1, in1 = -1, out = -1;
+    int head_level = -1;       // >= 0: this conv writes logits[head_level] (fp32 planar)
+    // CONV
+    LayerGeom g{};
+    int p_w = -1, p_b = -1;
+    bool stats = false;        // epilogue emits the statistics of the norm that follows
+    std::vector<ConvProblem> fprobs;
+    std::vector<PackDesc> fpacks;
+    int fkc = 0;
+    struct DG {
+        std::vector<ConvProblem> probs;
+        std::vector<PackDesc> packs;
+        int kc = 0;
+    } dg[2];
+    std::vector<WgradProblem> wg;
+    std::vector<void*> pack_bufs;  // owned device blobs (fwd then dgrad)
+    // NORMACT
+    int norm = 0;              // 0 none, 1 InstanceNorm3d (eps 1e-5), 2 BatchNorm3d (eps 0)
+    int act = ACT_NONE;
+    int p_g = -1;
+    float* mean = nullptr;
+    float* rstd = nullptr;
+    int buf0 = -1;
+    bool stats_from_conv = false;
+    // MAXPOOL
+    int* idx = nullptr;
+};
+
+class Model {
+  public:
+    Model(int in_c, int out_c, const std::string& feature);  // throws std::runtime_error (unet.cpp:53,66,88,117)
+    ~Model();
+
+    // ---- reference-visible state (unet.hpp:16-18,37-38) ----
+    int in_count, out_count;
+    std::string architecture;
+    int dim[3] = {192, 224, 192};  // W, H, D
+    float voxel_size[3] = {1.f, 1.f, 1.f};
+    bool training = true;
+
+    std::vector<BlockDef> encoding, decoding, output, tail;
+    std::vector<ParamInfo> params;
+    int n_buffers = 0;
+    long long flat_n = 0;
+
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    float* d_params = nullptr;
+    float* d_grads = nullptr;
+    float* d_mom = nullptr;
+    std::vector<float*> d_buffers;   // BatchNorm running stats [C] each
+    std::vector<int> buffer_len;
+    int good_steps = 0;
+    float loss_scale_max = 0.f;
+    bool optimizer_created = false;
+    bool mom_initialized = false;
+    float lr0 = 0.f;
+    float loss_scale = 0.f;          // 0 = choose from the volume size at plan time
+    double last_grad_norm = 0.0;
+    int last_step_skipped = 0;
+    long long launches = 0;          // kernels launched by this handle (bench "gpu_launches")
+
+    int init_params(uint64_t seed);
+    int get_flat(const float* base, int i, float* host, float scale);
+    int set_param(int i, const float* host);
+    int set_momentum(int i, const float* host);
+    int set_dim(int w, int h, int d);
+    int set_mode(int train);
+    // where: 0 = host pointers, 1 = device pointers
+    int forward(const float* in, float* const* out_levels, int n_levels, int where);
+    int train_microbatch(const float* in, const float* label, int collapse_before, int use_ce, int use_dice, int use_mse,
+                         float* loss_out3, float* all_levels, int where);
+    int validate(const float* in, const float* label, int collapse_before, float* loss_out3, int where);
+    int step(int batch_size, double lr, void* nccl_comm);
+    int copy_from(const Model& src);
+    int sync();
+    int n_levels() const { return int(output.size()); }
+
+  private:
+    std::vector<Ten> tens;
+    std::vector<Step> steps;
+    std::vector<float*> logits;      // per level, fp32 planar
+    std::vector<void*> dlogits;      // per level, fp16 [v][Cp]
+    std::vector<int> level_dims;     // d,h,w per level
+    bool planned = false, planned_training = false;
+    bool packs_dirty = true;
+    float* d_in_f32 = nullptr;
+    float* d_label = nullptr;
+    float* d_partials = nullptr;
+    float* d_sums = nullptr;
+    void* d_scratch = nullptr;       // gradient staging for multi-consumer tensors
+    size_t scratch_bytes = 0;
+    double* d_loss_acc = nullptr;
+    float* d_losses = nullptr;
+    SgdChunk* d_chunks = nullptr;
+    int n_chunks = 0;
+    SgdStatus* d_status = nullptr;
+    int last_stat_rows = 0, last_stat_ntot = 0;
+    std::vector<char> grad_written;
+    std::vector<void*> owned;        // every cudaMalloc of the plan
+
+    void free_plan();
+    int ensure_plan();
+    int build_steps();
+    int alloc(void** p, size_t bytes);
+    int repack();
+    int run_forward(int levels_wanted);
+    int run_backward();
+    int upload_input(const float* in, int where);
+    float* param_ptr(int i) { return d_params + params[i].offset; }
+    float* grad_ptr(int i) { return d_grads + params[i].offset; }
+};
+
+std::string default_feature(int out_count);  // train.cpp:1054-1069
+
+}  // namespace u3d

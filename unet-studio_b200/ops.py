@@ -31,7 +31,7 @@ def conv_forward(x0, weight, bias=None, x1=None, transposed=False, ks=3, stride=
     return (y, stats) if want_stats else y
 
 
-def conv_backward(x0, weight, dy, x1=None, transposed=False, ks=3, stride=1, gx0_init=None):
+def conv_backward(x0, weight, dy, x1=None, transposed=False, ks=3, stride=1, gx0_init=None, want_gx=True, want_gw=True):
     """Returns (gx0, gx1, gw) of the layer given dy [Cout,D',H',W']."""
     from . import lib, check
     x0 = _f32(x0); x1 = _f32(x1); weight = _f32(weight); dy = _f32(dy)
@@ -41,6 +41,8 @@ def conv_backward(x0, weight, dy, x1=None, transposed=False, ks=3, stride=1, gx0
     gx0 = np.array(gx0_init, np.float32, copy=True) if gx0_init is not None else np.empty_like(x0)
     gx1 = None if x1 is None else np.empty_like(x1)
     gw = np.empty_like(weight)
+    flags = int(gx0_init is not None)
     check(lib().u3d_op_conv_backward(int(transposed), ks, stride, cin0, cin1, cout, w, h, d, _ptr(x0), _ptr(x1),
-                                     _ptr(weight), _ptr(dy), _ptr(gx0), _ptr(gx1), _ptr(gw), int(gx0_init is not None)))
+                                     _ptr(weight), _ptr(dy), _ptr(gx0) if want_gx else None,
+                                     _ptr(gx1) if want_gx else None, _ptr(gw) if want_gw else None, flags))
     return gx0, gx1, gw
