@@ -103,6 +103,9 @@ long long unet3d_launch_count(const unet3d_t* h);  /* kernels launched by this h
 /* copy_from (unet.cpp:195-222): parameters/buffers of identical size, dim, voxel_size; works across GPUs */
 int unet3d_copy_from(unet3d_t* dst, const unet3d_t* src);
 int unet3d_sync(unet3d_t* h);
+/* CUDA-event timer on the handle's own stream (the stream every kernel of the handle is launched on) */
+int unet3d_timer_start(unet3d_t* h);
+int unet3d_timer_stop(unet3d_t* h, float* ms);
 
 /* NCCL plumbing for the data-parallel step (bootstrap the 128-byte id through any host channel) */
 int unet3d_nccl_unique_id(void* id128);

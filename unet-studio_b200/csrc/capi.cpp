@@ -209,6 +209,15 @@ int unet3d_copy_from(unet3d_t* dst, const unet3d_t* src) {
     GUARD_END
 }
 
+int unet3d_timer_start(unet3d_t* h) {
+    GUARD_BEGIN NEED(h) return h->m->timer_start();
+    GUARD_END
+}
+int unet3d_timer_stop(unet3d_t* h, float* ms) {
+    GUARD_BEGIN NEED(h) return h->m->timer_stop(ms);
+    GUARD_END
+}
+
 int unet3d_sync(unet3d_t* h) {
     GUARD_BEGIN NEED(h) return h->m->sync();
     GUARD_END

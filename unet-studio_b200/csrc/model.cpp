@@ -337,6 +337,21 @@ int Model::set_mode(int train) {
     return 0;
 }
 
+int Model::timer_start() {
+    cudaSetDevice(device);
+    if (!ev0) { M_CUDA(cudaEventCreate(&ev0)); M_CUDA(cudaEventCreate(&ev1)); }
+    M_CUDA(cudaEventRecord(ev0, stream));
+    return 0;
+}
+int Model::timer_stop(float* ms) {
+    cudaSetDevice(device);
+    if (!ev0) { set_error("timer_stop without timer_start"); return 1; }
+    M_CUDA(cudaEventRecord(ev1, stream));
+    M_CUDA(cudaEventSynchronize(ev1));
+    M_CUDA(cudaEventElapsedTime(ms, ev0, ev1));
+    return 0;
+}
+
 int Model::sync() {
     cudaSetDevice(device);
     M_CUDA(cudaStreamSynchronize(stream));

@@ -115,6 +115,9 @@ class Model {
     int step(int batch_size, double lr, void* nccl_comm);
     int copy_from(const Model& src);
     int sync();
+    int timer_start();            // CUDA events on this handle's stream
+    int timer_stop(float* ms);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n_levels() const { return int(output.size()); }
 
   private:

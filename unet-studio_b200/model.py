@@ -186,6 +186,30 @@ class UNet3d:
         check(self._lib.unet3d_copy_from(self._h, other._h))
         self.dim = other.dim
 
+    def timer_start(self):
+        from . import check
+        check(self._lib.unet3d_timer_start(self._h))
+
+    def timer_stop(self):
+        from . import check
+        ms = ctypes.c_float()
+        check(self._lib.unet3d_timer_stop(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def device_forward(self, x_dev_ptr, out_dev_ptrs):
+        """forward with device-resident fp32 NCDHW buffers (raw pointers); stream-ordered, no sync."""
+        from . import check
+        n = len(out_dev_ptrs)
+        ptrs = (_F * n)(*[ctypes.cast(p, _F) for p in out_dev_ptrs])
+        check(self._lib.unet3d_forward(self._h, ctypes.cast(x_dev_ptr, _F), ptrs, n, 1))
+
+    def device_train_microbatch(self, x_dev_ptr, label_dev_ptr, collapse_before=0, use_ce=True, use_dice=True, use_mse=True):
+        from . import check
+        out = np.zeros(3, np.float32)
+        check(self._lib.unet3d_train_microbatch(self._h, ctypes.cast(x_dev_ptr, _F), ctypes.cast(label_dev_ptr, _F),
+                                                int(collapse_before), int(use_ce), int(use_dice), int(use_mse), _fp(out), None, 1))
+        return out
+
     def sync(self):
         from . import check
         check(self._lib.unet3d_sync(self._h))
