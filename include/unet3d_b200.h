@@ -36,6 +36,11 @@ const char* unet3d_last_error(void);
 /* default_feature(out_count), train.cpp:1054-1069.  Returns 0, or the needed buffer size if too small. */
 int unet3d_default_feature(int out_count, char* buf, size_t buflen);
 
+/* Host-only structure query (no GPU needed): parses the feature_string exactly like the constructor and
+ * writes {"levels": L, "params": [{"name","shape","decay"}...]} (tensorN order) as JSON.  Same error
+ * behaviour as unet3d_create.  Returns 0, 1 on a parse error, or the needed size if the buffer is too small. */
+int unet3d_describe(int in_count, int out_count, const char* feature_string, char* json, size_t json_len);
+
 /* UNet3d(in_count, out_count, feature_string), unet.cpp:103-166 (+ create_layer, unet.cpp:24-101).
  * The module starts in training mode like a fresh torch module. */
 int unet3d_create(int in_count, int out_count, const char* feature_string, int gpu, unet3d_t** out);
@@ -126,6 +131,10 @@ int u3d_op_conv_forward(int transposed, int ks, int stride, int cin0, int cin1, 
 int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0, int cin1, int cout, int w, int h, int d,
                          const float* x0, const float* x1, const float* weight, const float* dy, float* gx0,
                          float* gx1, float* gw, int flags);
+
+/* MaxPool3d(2,2) (unet.cpp:38-39): values and torch-convention int64 argmax indices (flat D*H*W input offset,
+ * first maximum in d,h,w scan order, NaN propagates) — bit-exact against torch.max_pool3d(return_indices). */
+int u3d_op_maxpool_forward(int c, int w, int h, int d, const float* x, float* y, int64_t* indices);
 
 #ifdef __cplusplus
 }

@@ -31,5 +31,5 @@ def check(rc):
         raise U3DError(lib().unet3d_last_error().decode(errors="replace"))
 
 
-from .ops import conv_forward, conv_backward  # noqa: E402,F401
+from .ops import conv_forward, conv_backward, maxpool_forward  # noqa: E402,F401
 from .model import UNet3d, default_feature, poly_lr  # noqa: E402,F401

@@ -51,6 +51,24 @@ int unet3d_default_feature(int out_count, char* buf, size_t buflen) {
     return 0;
 }
 
+int unet3d_describe(int in_count, int out_count, const char* feature_string, char* json, size_t json_len) {
+    GUARD_BEGIN
+    if (!feature_string) { set_error("null argument"); return 1; }
+    Model m(in_count, out_count, feature_string, true);
+    std::string o = "{\"levels\": " + std::to_string(m.n_levels()) + ", \"params\": [";
+    for (size_t i = 0; i < m.params.size(); ++i) {
+        const auto& p = m.params[i];
+        o += std::string(i ? "," : "") + "{\"name\": \"" + p.name + "\", \"shape\": [";
+        for (size_t k = 0; k < p.shape.size(); ++k) o += std::string(k ? "," : "") + std::to_string(p.shape[k]);
+        o += "], \"decay\": " + std::string(p.decay ? "1" : "0") + "}";
+    }
+    o += "]}";
+    if (!json || json_len < o.size() + 1) { set_error("buffer too small"); return int(o.size() + 1); }
+    std::memcpy(json, o.c_str(), o.size() + 1);
+    return 0;
+    GUARD_END
+}
+
 int unet3d_create(int in_count, int out_count, const char* feature_string, int gpu, unet3d_t** out) {
     GUARD_BEGIN
     if (!out || !feature_string) { set_error("null argument"); return 1; }

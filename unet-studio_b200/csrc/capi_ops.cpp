@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../include/unet3d_b200.h"
+#include "elementwise.h"
 #include "plan.h"
 
 namespace u3d {
@@ -211,5 +212,25 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
         OP_CHECK(finish(s));
         OP_CUDA(cudaMemcpy(gw, dgw.p, wcount * 4, cudaMemcpyDeviceToHost));
     }
+    return 0;
+}
+
+// MaxPool3d(2,2) with argmax (unet.cpp:38-39): y [C][D/2][H/2][W/2] and torch-style int64 indices (flat D*H*W offset)
+extern "C" int u3d_op_maxpool_forward(int c, int w, int h, int d, const float* x, float* y, int64_t* indices) {
+    cudaStream_t s = 0;
+    const long long Vin = 1LL * w * h * d;
+    const int ow = w / 2, oh = h / 2, od = d / 2;
+    const long long Vout = 1LL * ow * oh * od;
+    const int cp = pad16(c);
+    DevBuf dx, dy, didx;
+    OP_CHECK(upload_act(dx, x, c, Vin, false, s));
+    if (dy.alloc(size_t(cp) * Vout * 2) || didx.alloc(size_t(cp) * Vout * 4)) { set_error("cudaMalloc failed"); return 1; }
+    OP_CHECK(maxpool_fwd_launch(dx.p, dy.p, static_cast<int*>(didx.p), cp, od, oh, ow, s));
+    OP_CHECK(finish(s));
+    OP_CHECK(download_act(dy.p, y, c, Vout, false, s));
+    std::vector<int> hi(size_t(cp) * Vout);
+    OP_CUDA(cudaMemcpy(hi.data(), didx.p, hi.size() * 4, cudaMemcpyDeviceToHost));
+    for (int ch = 0; ch < c; ++ch)
+        for (long long v = 0; v < Vout; ++v) indices[size_t(ch) * Vout + v] = hi[size_t(v) * cp + ch];
     return 0;
 }

@@ -26,7 +26,6 @@ namespace u3d {
 namespace {
 
 constexpr int kThreads = 288;
-constexpr int kLag = 2;       // cp.async groups kept in flight per producer thread
 constexpr int kMaxProb = 8;
 
 struct KParams {
@@ -73,7 +72,8 @@ __device__ __forceinline__ void halve_step(float (&a)[16], float (&q)[16], int l
     }
 }
 
-template <bool OUT_BF16, int EPI>
+// LAG = cp.async groups each producer thread keeps in flight (memory-level parallelism of the gather)
+template <int EPI, int LAG>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 for (int g = 0; g < 8; ++g)
                     if (g * 8 < kc) cp_async16(dst + g * 2048u, src + g * 16, nb);
                 cp_async_commit();
-                if (it >= kLag) {
-                    cp_async_wait<kLag>();
+                if (it >= LAG) {
+                    cp_async_wait<LAG>();
                     fence_proxy_async();
                     mbar_arrive(full_bar(lag_stage));
                     if (++lag_stage == S) lag_stage = 0;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
         cp_async_wait<0>();
         fence_proxy_async();
-        const uint32_t rem = it < (uint32_t)kLag ? it : (uint32_t)kLag;
+        const uint32_t rem = it < (uint32_t)LAG ? it : (uint32_t)LAG;
         for (uint32_t j = 0; j < rem; ++j) {
             mbar_arrive(full_bar(lag_stage));
             if (++lag_stage == S) lag_stage = 0;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                             const uint32_t ow_[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float2 f = unpack2<OUT_BF16>(ow_[j]);
+                                const float2 f = unpack2<false>(ow_[j]);
                                 v[2 * j] += f.x;
                                 v[2 * j + 1] += f.y;
                             }
@@ -270,14 +270,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                     }
                     if (rv) {
                         uint4 q0, q1;
-                        q0.x = pack2<OUT_BF16>(v[0], v[1]);
-                        q0.y = pack2<OUT_BF16>(v[2], v[3]);
-                        q0.z = pack2<OUT_BF16>(v[4], v[5]);
-                        q0.w = pack2<OUT_BF16>(v[6], v[7]);
-                        q1.x = pack2<OUT_BF16>(v[8], v[9]);
-                        q1.y = pack2<OUT_BF16>(v[10], v[11]);
-                        q1.z = pack2<OUT_BF16>(v[12], v[13]);
-                        q1.w = pack2<OUT_BF16>(v[14], v[15]);
+                        q0.x = pack2<false>(v[0], v[1]);
+                        q0.y = pack2<false>(v[2], v[3]);
+                        q0.z = pack2<false>(v[4], v[5]);
+                        q0.w = pack2<false>(v[6], v[7]);
+                        q1.x = pack2<false>(v[8], v[9]);
+                        q1.y = pack2<false>(v[10], v[11]);
+                        q1.z = pack2<false>(v[12], v[13]);
+                        q1.w = pack2<false>(v[14], v[15]);
                         out[0] = q0;
                         out[1] = q1;
                     }
@@ -320,16 +320,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
 int g_sm_count = 0;
 
-template <bool OUT_BF16, int EPI>
+template <int EPI, int LAG>
 int launch_t(const KParams& kp, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<OUT_BF16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<EPI, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    conv_igemm_kernel<OUT_BF16, EPI><<<grid, kThreads, smem, stream>>>(kp);
+    conv_igemm_kernel<EPI, LAG><<<grid, kThreads, smem, stream>>>(kp);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <int EPI>
+int launch_lag(const KParams& kp, int grid, size_t smem, cudaStream_t stream) {
+    if (kp.stages >= 16) return launch_t<EPI, 14>(kp, grid, smem, stream);
+    if (kp.stages >= 8) return launch_t<EPI, 6>(kp, grid, smem, stream);
+    return launch_t<EPI, 2>(kp, grid, smem, stream);
 }
 
 }  // namespace
@@ -385,10 +392,10 @@ int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& c
     while (cols < 2 * ntile_max) cols <<= 1;
     kp.tmem_cols = cols;
     const size_t a_stage = size_t(128) * cfg.kc * 2, b_stage = size_t(ntile_max) * cfg.kc * 2;
-    const size_t fixed = size_t(2) * ntot_max * 4 + 8 * (2 * 8 + 4) + 16 + 256;
+    const size_t fixed = size_t(2) * ntot_max * 4 + 8 * (2 * 32 + 4) + 16 + 256;
     int stages = int((200 * 1024 - fixed) / (a_stage + b_stage));
-    stages = std::min(stages, 8);
-    if (stages < kLag + 1) {
+    stages = std::min(stages, 32);
+    if (stages < 4) {
         set_error("conv_igemm_launch: tile too large for the smem ring");
         return 1;
     }
@@ -400,10 +407,9 @@ int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& c
     kp.stats = (cfg.epi == EPI_STORE16 && probs.size() == 1) ? cfg.stats_partials : nullptr;
     const int grid = std::max(1, std::min(items, device_sm_count()));
     if (cfg.stats_grid_out) *cfg.stats_grid_out = grid;
-    if (cfg.epi == EPI_PLANAR32) return launch_t<false, EPI_PLANAR32>(kp, grid, smem, stream);
-    if (cfg.epi == EPI_STORE16)
-        return cfg.out_bf16 ? launch_t<true, EPI_STORE16>(kp, grid, smem, stream) : launch_t<false, EPI_STORE16>(kp, grid, smem, stream);
-    return cfg.out_bf16 ? launch_t<true, EPI_ACCUM16>(kp, grid, smem, stream) : launch_t<false, EPI_ACCUM16>(kp, grid, smem, stream);
+    if (cfg.epi == EPI_PLANAR32) return launch_lag<EPI_PLANAR32>(kp, grid, smem, stream);
+    if (cfg.epi == EPI_STORE16) return launch_lag<EPI_STORE16>(kp, grid, smem, stream);
+    return launch_lag<EPI_ACCUM16>(kp, grid, smem, stream);
 }
 
 }  // namespace u3d

@@ -24,7 +24,6 @@ namespace u3d {
 namespace {
 
 constexpr int kThreads = 288;
-constexpr int kLag = 2;
 constexpr int kMaxProb = 8;
 constexpr int kKB = 64;  // voxels per stage
 
@@ -71,6 +70,7 @@ __device__ __forceinline__ void kblock_range(const WgradProblem& P, int ks, int&
     if (kb0 > kb1) kb0 = kb1;
 }
 
+template <int LAG>
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_constant__ WParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                 for (int nc = h; nc < nchunks_n; nc += 2)
                     cp_async16(b_dst + nc * (kKB * 16u), vv ? usrc + nc * 16 : ub, vv ? 16u : 0u);
                 cp_async_commit();
-                if (it >= kLag) {
-                    cp_async_wait<kLag>();
+                if (it >= LAG) {
+                    cp_async_wait<LAG>();
                     fence_proxy_async();
                     mbar_arrive(full_bar(lag_stage));
                     if (++lag_stage == S) lag_stage = 0;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
         }
         cp_async_wait<0>();
         fence_proxy_async();
-        const uint32_t rem = it < (uint32_t)kLag ? it : (uint32_t)kLag;
+        const uint32_t rem = it < (uint32_t)LAG ? it : (uint32_t)LAG;
         for (uint32_t j = 0; j < rem; ++j) {
             mbar_arrive(full_bar(lag_stage));
             if (++lag_stage == S) lag_stage = 0;
@@ -320,18 +320,20 @@ int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch&
     kp.tmem_cols = cols;
     const size_t a_stage = size_t(16) * kKB * 16, b_stage = size_t(ntile_max / 8) * kKB * 16;
     int stages = int((200 * 1024) / (a_stage + b_stage));
-    stages = std::min(stages, 8);
+    stages = std::min(stages, 12);
     kp.stages = stages;
     kp.off_b = uint32_t(stages * a_stage);
     kp.off_bars = uint32_t(kp.off_b + stages * b_stage);
     const size_t smem = kp.off_bars + 8 * (2 * stages + 4) + 16;
     static bool attr_set = false;
     if (!attr_set) {
-        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int grid = std::max(1, std::min(items, sms));
-    conv_wgrad_kernel<<<grid, kThreads, smem, stream>>>(kp);
+    if (stages >= 8) conv_wgrad_kernel<6><<<grid, kThreads, smem, stream>>>(kp);
+    else conv_wgrad_kernel<2><<<grid, kThreads, smem, stream>>>(kp);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -50,16 +50,24 @@ __device__ __forceinline__ float act_grad(float z, int act) {
 // ---------------------------------------------------------------------------------------------
 // statistics finalize: partial rows [rows][2][ntot] -> mean / rstd (and BatchNorm running stats)
 // ---------------------------------------------------------------------------------------------
+// one warp per channel: lanes stride over the partial rows, double accumulation, shuffle reduce
 __global__ void finalize_stats_kernel(const float* __restrict__ partials, int rows, int ntot, int C, double count, float eps,
                                       float* __restrict__ mean, float* __restrict__ rstd, float* running_mean,
                                       float* running_var, float momentum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double a = 0, q = 0;
-    for (int r = 0; r < rows; ++r) {
+    for (int r = lane; r < rows; r += 32) {
         a += partials[size_t(r) * 2 * ntot + c];
         q += partials[size_t(r) * 2 * ntot + ntot + c];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane != 0) return;
     const double m = a / count;
     double var = q / count - m * m;
     if (var < 0) var = 0;
@@ -430,7 +438,7 @@ int channel_stats_launch(const void* x, long long V, int C, int Cp, float* parti
 
 int finalize_stats_launch(const float* partials, int rows, int ntot, int C, double count, float eps, float* mean, float* rstd,
                           float* running_mean, float* running_var, float momentum, cudaStream_t s) {
-    finalize_stats_kernel<<<(C + 127) / 128, 128, 0, s>>>(partials, rows, ntot, C, count, eps, mean, rstd, running_mean,
+    finalize_stats_kernel<<<(C * 32 + 127) / 128, 128, 0, s>>>(partials, rows, ntot, C, count, eps, mean, rstd, running_mean,
                                                           running_var, momentum);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;

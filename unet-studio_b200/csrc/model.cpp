@@ -116,7 +116,8 @@ static int create_layer(BlockDef& blk, const std::string& def, int in_c) {
     return out_c;
 }
 
-Model::Model(int in_c, int out_c, const std::string& feature) : in_count(in_c), out_count(out_c), architecture(feature) {
+Model::Model(int in_c, int out_c, const std::string& feature, bool host_only_)
+    : host_only(host_only_), in_count(in_c), out_count(out_c), architecture(feature) {
     const auto lines = split_lines(feature);
     if (lines.size() < 3) throw std::runtime_error("invalid u-net structure");
     const size_t enc_count = lines.size() / 2 + 1;
@@ -188,6 +189,7 @@ Model::Model(int in_c, int out_c, const std::string& feature) : in_count(in_c), 
     }
     flat_n = off;
 
+    if (host_only) return;
     cudaGetDevice(&device);
     if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess)
         throw std::runtime_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(cudaGetLastError()) +
@@ -227,6 +229,7 @@ Model::Model(int in_c, int out_c, const std::string& feature) : in_count(in_c), 
 }
 
 Model::~Model() {
+    if (host_only) return;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     free_plan();

@@ -69,7 +69,9 @@ struct Step {
 
 class Model {
   public:
-    Model(int in_c, int out_c, const std::string& feature);  // throws std::runtime_error (unet.cpp:53,66,88,117)
+    // throws std::runtime_error (unet.cpp:53,66,88,117); host_only = structure without any device state
+    Model(int in_c, int out_c, const std::string& feature, bool host_only = false);
+    bool host_only = false;
     ~Model();
 
     // ---- reference-visible state (unet.hpp:16-18,37-38) ----

@@ -46,3 +46,14 @@ def conv_backward(x0, weight, dy, x1=None, transposed=False, ks=3, stride=1, gx0
                                      _ptr(weight), _ptr(dy), _ptr(gx0) if want_gx else None,
                                      _ptr(gx1) if want_gx else None, _ptr(gw) if want_gw else None, flags))
     return gx0, gx1, gw
+
+
+def maxpool_forward(x):
+    """x [C,D,H,W] -> (y [C,D/2,H/2,W/2], indices int64 in torch's flat-offset convention)."""
+    from . import lib, check
+    x = _f32(x)
+    c, d, h, w = x.shape
+    y = np.empty((c, d // 2, h // 2, w // 2), np.float32)
+    idx = np.empty(y.shape, np.int64)
+    check(lib().u3d_op_maxpool_forward(c, w, h, d, _ptr(x), _ptr(y), _ptr(idx, ctypes.c_int64)))
+    return y, idx
