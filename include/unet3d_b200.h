@@ -112,6 +112,12 @@ int unet3d_sync(unet3d_t* h);
 int unet3d_timer_start(unet3d_t* h);
 int unet3d_timer_stop(unet3d_t* h, float* ms);
 
+/* Per-launch CUDA-event profile of the two tensor-core kernels on the handle's stream (for the bench roofline):
+ * out6 = {conv_igemm ms, launches, algorithmic FLOPs, conv_wgrad ms, launches, algorithmic FLOPs} since the last reset;
+ * algorithmic FLOPs = 2*Cin*Cout*k^3*V_out per layer. */
+int unet3d_profile(unet3d_t* h, int enable);
+int unet3d_profile_read(unet3d_t* h, double out6[6], int reset);
+
 /* NCCL plumbing for the data-parallel step (bootstrap the 128-byte id through any host channel) */
 int unet3d_nccl_unique_id(void* id128);
 int unet3d_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);

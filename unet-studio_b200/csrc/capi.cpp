@@ -236,6 +236,17 @@ int unet3d_timer_stop(unet3d_t* h, float* ms) {
     GUARD_END
 }
 
+int unet3d_profile(unet3d_t* h, int enable) {
+    GUARD_BEGIN NEED(h)
+    h->m->prof_on = enable != 0;
+    return 0;
+    GUARD_END
+}
+int unet3d_profile_read(unet3d_t* h, double out6[6], int reset) {
+    GUARD_BEGIN NEED(h) return h->m->prof_read(out6, reset);
+    GUARD_END
+}
+
 int unet3d_sync(unet3d_t* h) {
     GUARD_BEGIN NEED(h) return h->m->sync();
     GUARD_END

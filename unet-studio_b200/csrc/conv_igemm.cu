@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < 2 * p.ntot_max; i += kThreads) sstats[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * p.ntot_max; i += kThreads) sstats[i] = 0.f;  // [4 epilogue warps][2][ntot]
     if (warp == 8) {
         tmem_alloc(smem_u32(tmem_ptr_smem), p.tmem_cols);
         tmem_relinquish();
@@ -299,8 +299,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                         if ((lane & 1) == 0) {
                             const int col = n0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
                                             ((lane >> 1) & 1);
-                            atomicAdd(&sstats[col], a[0]);
-                            atomicAdd(&sstats[p.ntot_max + col], q[0]);
+                            // one row per warp and one lane per column: plain adds, fixed order => deterministic
+                            float* ws = sstats + warp * 2 * p.ntot_max;
+                            ws[col] += a[0];
+                            ws[p.ntot_max + col] += q[0];
                         }
                     }
                 }
@@ -310,7 +312,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
         if (p.stats != nullptr) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = r; i < 2 * p.ntot_max; i += 128) p.stats[size_t(blockIdx.x) * 2 * p.ntot_max + i] = sstats[i];
+            for (int i = r; i < 2 * p.ntot_max; i += 128)
+                p.stats[size_t(blockIdx.x) * 2 * p.ntot_max + i] =
+                    ((sstats[i] + sstats[2 * p.ntot_max + i]) + sstats[4 * p.ntot_max + i]) + sstats[6 * p.ntot_max + i];
         }
     }
     tc_fence_before();
@@ -392,7 +396,7 @@ int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& c
     while (cols < 2 * ntile_max) cols <<= 1;
     kp.tmem_cols = cols;
     const size_t a_stage = size_t(128) * cfg.kc * 2, b_stage = size_t(ntile_max) * cfg.kc * 2;
-    const size_t fixed = size_t(2) * ntot_max * 4 + 8 * (2 * 32 + 4) + 16 + 256;
+    const size_t fixed = size_t(8) * ntot_max * 4 + 8 * (2 * 32 + 4) + 16 + 256;
     int stages = int((200 * 1024 - fixed) / (a_stage + b_stage));
     stages = std::min(stages, 32);
     if (stages < 4) {
@@ -402,7 +406,7 @@ int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& c
     kp.stages = stages;
     kp.off_b = uint32_t(stages * a_stage);
     kp.off_stats = uint32_t(kp.off_b + stages * b_stage);
-    kp.off_bars = uint32_t((kp.off_stats + 2 * ntot_max * 4 + 15) & ~15u);
+    kp.off_bars = uint32_t((kp.off_stats + 8 * ntot_max * 4 + 15) & ~15u);
     const size_t smem = kp.off_bars + 8 * (2 * stages + 4) + 16;
     kp.stats = (cfg.epi == EPI_STORE16 && probs.size() == 1) ? cfg.stats_partials : nullptr;
     const int grid = std::max(1, std::min(items, device_sm_count()));

@@ -340,6 +340,42 @@ int Model::set_mode(int train) {
     return 0;
 }
 
+void Model::prof_begin(int kind, double flops) {
+    if (!prof_on) return;
+    if (prof_used + 2 > prof_ev.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        prof_ev.push_back(a);
+        prof_ev.push_back(b);
+        prof_kind.push_back(0);
+        prof_flops.push_back(0);
+    }
+    prof_kind[prof_used / 2] = kind;
+    prof_flops[prof_used / 2] = flops;
+    cudaEventRecord(prof_ev[prof_used], stream);
+}
+void Model::prof_end() {
+    if (!prof_on) return;
+    cudaEventRecord(prof_ev[prof_used + 1], stream);
+    prof_used += 2;
+}
+int Model::prof_read(double out[6], int reset) {
+    cudaSetDevice(device);
+    M_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < 6; ++i) out[i] = 0;
+    for (size_t i = 0; i + 1 < prof_used; i += 2) {
+        float ms = 0.f;
+        M_CUDA(cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]));
+        const int k = prof_kind[i / 2] ? 3 : 0;
+        out[k] += ms;
+        out[k + 1] += 1;
+        out[k + 2] += prof_flops[i / 2];
+    }
+    if (reset) prof_used = 0;
+    return 0;
+}
+
 int Model::timer_start() {
     cudaSetDevice(device);
     if (!ev0) { M_CUDA(cudaEventCreate(&ev0)); M_CUDA(cudaEventCreate(&ev1)); }
@@ -515,6 +551,8 @@ int Model::ensure_plan() {
     for (auto& s : steps) {
         if (s.kind == Step::CONV) {
             plan_forward(s.g, s.fprobs, s.fpacks, s.fkc);
+            s.flops = 2.0 * double(s.g.cin[0] + s.g.cin[1]) * s.g.cout * (s.g.transposed ? 1.0 : double(s.g.ks * s.g.ks * s.g.ks)) *
+                      double(s.g.out_d) * s.g.out_h * s.g.out_w;
             for (size_t i = 0; i < s.fprobs.size(); ++i) {
                 void* blob = nullptr;
                 M_CHECK(alloc(&blob, pack_bytes(s.fpacks[i])));
@@ -604,7 +642,9 @@ int Model::run_forward(int levels_wanted) {
             int rows = 0;
             cfg.stats_grid_out = &rows;
             if (s.stats) cfg.stats_partials = d_partials;
+            prof_begin(0, s.flops);
             M_CHECK(conv_igemm_launch(s.fprobs, cfg, nullptr, stream));
+            prof_end();
             ++launches;
             if (s.stats) { last_stat_rows = rows; last_stat_ntot = s.fprobs[0].ntile * s.fprobs[0].ntiles; }
         } else if (s.kind == Step::NORMACT) {
@@ -690,7 +730,9 @@ int Model::run_backward() {
                 launches += 2;
             }
             WgradLaunch wc{};
+            prof_begin(1, s.flops);
             M_CHECK(conv_wgrad_launch(s.wg, wc, nullptr, stream));
+            prof_end();
             ++launches;
             const int ins[2] = {s.in0, s.in1};
             for (int src = 0; src < 2; ++src) {
@@ -698,7 +740,9 @@ int Model::run_backward() {
                 ConvLaunch cfg{};
                 cfg.kc = s.dg[src].kc;
                 cfg.epi = grad_written[ins[src]] ? EPI_ACCUM16 : EPI_STORE16;
+                prof_begin(0, s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
                 M_CHECK(conv_igemm_launch(s.dg[src].probs, cfg, nullptr, stream));
+                prof_end();
                 ++launches;
                 grad_written[ins[src]] = 1;
             }

@@ -55,6 +55,7 @@ struct Step {
     } dg[2];
     std::vector<WgradProblem> wg;
     std::vector<void*> pack_bufs;  // owned device blobs (fwd then dgrad)
+    double flops = 0;              // algorithmic 2*Cin*Cout*k^3*V_out of this layer
     // NORMACT
     int norm = 0;              // 0 none, 1 InstanceNorm3d (eps 1e-5), 2 BatchNorm3d (eps 0)
     int act = ACT_NONE;
@@ -120,6 +121,15 @@ class Model {
     int timer_start();            // CUDA events on this handle's stream
     int timer_stop(float* ms);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // per-launch CUDA-event profile of the tensor-core kernels (bench.py roofline): kind 0 = conv_igemm, 1 = conv_wgrad
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_kind;
+    std::vector<double> prof_flops;
+    size_t prof_used = 0;
+    void prof_begin(int kind, double flops);
+    void prof_end();
+    int prof_read(double out[6], int reset);   // {conv ms, launches, flops, wgrad ms, launches, flops}
     int n_levels() const { return int(output.size()); }
 
   private:

@@ -210,6 +210,16 @@ class UNet3d:
                                                 int(collapse_before), int(use_ce), int(use_dice), int(use_mse), _fp(out), None, 1))
         return out
 
+    def profile(self, enable=True):
+        from . import check
+        check(self._lib.unet3d_profile(self._h, int(enable)))
+
+    def profile_read(self, reset=True):
+        from . import check
+        out = (ctypes.c_double * 6)()
+        check(self._lib.unet3d_profile_read(self._h, out, int(reset)))
+        return [float(v) for v in out]
+
     def sync(self):
         from . import check
         check(self._lib.unet3d_sync(self._h))
