@@ -118,6 +118,18 @@ int unet3d_timer_stop(unet3d_t* h, float* ms);
 int unet3d_profile(unet3d_t* h, int enable);
 int unet3d_profile_read(unet3d_t* h, double out6[6], int reset);
 
+/* visual_perception_augmentation(options, image, label, is_label, shape, seed) (train.hpp:43-48,
+ * visual_perception_augmentation.cpp:163-438): in place on `image` ({channels,D,H,W} fp32 = tipl::image<3> with the
+ * channels stacked along z) and `label` ({D,H,W} fp32).  options = parallel arrays of option ids (options.txt:1-39)
+ * and values; an id that is not listed reads as 0 like unordered_map::operator[].  The random scalars follow the
+ * reference's draw order from std::mt19937(seed).  where = 0 host pointers, 1 device pointers.
+ * vpa_augment is standalone (own stream on `gpu`, returns when done); unet3d_vpa_augment runs stream-ordered on the
+ * handle's stream so the augmented sample feeds unet3d_train_microbatch(where=1) without leaving HBM. */
+int vpa_augment(const char* const* keys, const float* vals, int n_opts, float* image, float* label, int is_label, int w, int h, int d,
+                int channels, uint64_t seed, int where, int gpu);
+int unet3d_vpa_augment(unet3d_t* h, const char* const* keys, const float* vals, int n_opts, float* image, float* label, int is_label,
+                       int w, int hgt, int d, int channels, uint64_t seed, int where);
+
 /* NCCL plumbing for the data-parallel step (bootstrap the 128-byte id through any host channel) */
 int unet3d_nccl_unique_id(void* id128);
 int unet3d_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);

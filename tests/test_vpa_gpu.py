@@ -1,0 +1,82 @@
+"""visual_perception_augmentation: CUDA path (through the C-ABI) against the CPU restatement of the reference's
+.cpp (oracle/vpa_oracle.py; parity unpinned — TIPL is not vendored, see the oracle header), plus size-independent
+properties at the full 160x192x160 grid."""
+import numpy as np
+import pytest
+
+from oracle import vpa_oracle as VO
+from tests._pkg import load
+
+pytestmark = pytest.mark.gpu
+
+
+def phantom(W, H, D, C=1, seed=0):
+    rng = np.random.default_rng(seed)
+    z, y, x = np.meshgrid(np.arange(D, dtype=np.float32), np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    r = np.sqrt(((z - D / 2) / (0.40 * D)) ** 2 + ((y - H / 2) / (0.38 * H)) ** 2 + ((x - W / 2) / (0.36 * W)) ** 2)
+    lab = ((r < 1).astype(np.float32) + (r < 0.6) + (r < 0.3)).astype(np.float32)
+    img = np.stack([(np.clip(1.1 - r, 0, 1) * (0.6 + 0.4 * c) + 0.05 * rng.random(r.shape)).astype(np.float32) for c in range(C)])
+    img /= img.max()
+    return img, lab
+
+
+def compare(m, options, W, H, D, C, seed, is_label=True):
+    img, lab = phantom(W, H, D, C, seed)
+    ref_i, ref_l = VO.augment(options, img, lab, is_label, (W, H, D), seed)
+    out_i, out_l = m.vpa_augment(img, lab, options, is_label, seed)
+    # trilinear samples: fp32 with a different association / FMA contraction; a voxel may differ visibly only where a
+    # source position sits within rounding of a cell border, a valid/invalid edge or a majority tie
+    bad = np.abs(out_i - ref_i) > 2e-3
+    assert bad.mean() < 2e-3, (seed, bad.mean(), np.abs(out_i - ref_i).max())
+    assert np.median(np.abs(out_i - ref_i)) < 1e-5
+    assert (out_l != ref_l).mean() < 2e-3, (seed, (out_l != ref_l).mean())
+    return out_i, out_l
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_default_options_match_oracle(seed):
+    m = load()
+    compare(m, dict(VO.OPTION_DEFAULTS), 40, 48, 32, 1, seed)
+
+
+@pytest.mark.parametrize("seed", [3, 11])
+def test_everything_on_two_channels(seed):
+    m = load()
+    o = dict(VO.OPTION_DEFAULTS)
+    for k in ("cropping", "truncation_z", "downsample_x", "downsample_y", "downsample_z", "noise", "ambient", "diffuse", "specular",
+              "distortion", "rubber_stamping", "perlin_texture"):
+        o[k] = 4
+    o["zero_background"] = 0
+    compare(m, o, 32, 40, 48, 2, seed)
+
+
+def test_zero_background_and_intensity_label_mode():
+    m = load()
+    o = dict(VO.OPTION_DEFAULTS)
+    o["zero_background"] = 4
+    out_i, out_l = compare(m, o, 32, 32, 32, 1, 5)
+    assert np.all(out_i[0][out_l == 0] == 0)
+    compare(m, dict(VO.OPTION_DEFAULTS), 32, 32, 32, 1, 6, is_label=False)
+
+
+def test_identity_options_give_identity_warp():
+    m = load()
+    o = {"scaling_up": 1.0, "scaling_down": 1.0, "aspect_ratio": 1.0}
+    img, lab = phantom(24, 32, 16)
+    out_i, out_l = m.vpa_augment(img, lab, o, True, 9)
+    np.testing.assert_array_equal(out_l, lab)
+    np.testing.assert_allclose(out_i, img / img.max(), rtol=0, atol=1e-6)
+
+
+def test_full_size_properties():
+    m = load()
+    W, H, D = 160, 192, 160
+    img, lab = phantom(W, H, D, 1, 1)
+    for seed in (0, 1, 2):
+        out_i, out_l = m.vpa_augment(img, lab, None, True, seed)
+        assert np.isfinite(out_i).all() and out_i.min() >= 0.0 and out_i.max() <= 1.0 + 1e-6
+        if out_i.max() > 0:
+            assert abs(out_i.max() - 1.0) < 1e-5
+        assert set(np.unique(out_l)).issubset(set(np.unique(lab)))
+        again_i, again_l = m.vpa_augment(img, lab, None, True, seed)
+        assert np.array_equal(again_i, out_i) and np.array_equal(again_l, out_l)   # same seed -> same sample

@@ -6,6 +6,9 @@
 
 #include "../../include/unet3d_b200.h"
 #include "model.h"
+#include "vpa.h"
+#include <mutex>
+#include <map>
 
 namespace u3d {
 static thread_local std::string g_last_error;
@@ -249,6 +252,78 @@ int unet3d_profile_read(unet3d_t* h, double out6[6], int reset) {
 
 int unet3d_sync(unet3d_t* h) {
     GUARD_BEGIN NEED(h) return h->m->sync();
+    GUARD_END
+}
+
+// ---- visual_perception_augmentation (train.hpp:43-48) ------------------------------------------------------
+namespace {
+struct VpaWs { void* p = nullptr; size_t bytes = 0; cudaStream_t s = nullptr; };
+std::mutex g_vpa_mu;
+std::map<int, VpaWs> g_vpa_ws;
+}  // namespace
+
+static int vpa_impl(const char* const* keys, const float* vals, int n_opts, float* image, float* label, int is_label, int w, int h,
+                    int d, int channels, uint64_t seed, int where, void* ws, cudaStream_t stream, long long* launches) {
+    u3d::VpaPlan plan;
+    if (u3d::vpa_make_plan(keys, vals, n_opts, is_label, w, h, d, channels, seed, plan)) return 1;
+    const size_t V = size_t(w) * h * d;
+    float* dimg = image;
+    float* dlab = label;
+    float* stage = nullptr;
+    if (where == 0) {
+        if (cudaMalloc(&stage, (size_t(channels) + 1) * V * 4) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+        dimg = stage;
+        dlab = stage + size_t(channels) * V;
+        cudaMemcpyAsync(dimg, image, size_t(channels) * V * 4, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(dlab, label, V * 4, cudaMemcpyHostToDevice, stream);
+    }
+    int rc = u3d::vpa_run(plan, dimg, dlab, ws, stream, launches);
+    if (where == 0) {
+        if (!rc) {
+            cudaMemcpyAsync(image, dimg, size_t(channels) * V * 4, cudaMemcpyDeviceToHost, stream);
+            cudaMemcpyAsync(label, dlab, V * 4, cudaMemcpyDeviceToHost, stream);
+        }
+        cudaError_t e = cudaStreamSynchronize(stream);
+        cudaFree(stage);
+        if (!rc && e != cudaSuccess) { set_error(std::string("vpa: ") + cudaGetErrorString(e)); rc = 1; }
+    }
+    return rc;
+}
+
+int vpa_augment(const char* const* keys, const float* vals, int n_opts, float* image, float* label, int is_label, int w, int h, int d,
+                int channels, uint64_t seed, int where, int gpu) {
+    GUARD_BEGIN
+    if (cudaSetDevice(gpu) != cudaSuccess) { set_error("no CUDA device: vpa_augment has no CPU fallback"); return 1; }
+    std::lock_guard<std::mutex> lock(g_vpa_mu);
+    VpaWs& W = g_vpa_ws[gpu];
+    const size_t need = u3d::vpa_workspace_bytes(w, h, d, channels);
+    if (!W.s && cudaStreamCreateWithFlags(&W.s, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return 1; }
+    if (W.bytes < need) {
+        if (W.p) cudaFree(W.p);
+        W.bytes = 0;
+        if (cudaMalloc(&W.p, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+        W.bytes = need;
+    }
+    int rc = vpa_impl(keys, vals, n_opts, image, label, is_label, w, h, d, channels, seed, where, W.p, W.s, nullptr);
+    if (!rc && where != 0 && cudaStreamSynchronize(W.s) != cudaSuccess) { set_error("vpa: kernel failed"); rc = 1; }
+    return rc;
+    GUARD_END
+}
+
+int unet3d_vpa_augment(unet3d_t* h, const char* const* keys, const float* vals, int n_opts, float* image, float* label, int is_label,
+                       int w, int hgt, int d, int channels, uint64_t seed, int where) {
+    GUARD_BEGIN NEED(h)
+    Model* m = h->m;
+    cudaSetDevice(m->device);
+    const size_t need = u3d::vpa_workspace_bytes(w, hgt, d, channels);
+    if (m->vpa_ws_bytes < need) {
+        cudaStreamSynchronize(m->stream);
+        if (m->vpa_ws) cudaFree(m->vpa_ws);
+        m->vpa_ws_bytes = 0;
+        if (cudaMalloc(&m->vpa_ws, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+        m->vpa_ws_bytes = need;
+    }
+    return vpa_impl(keys, vals, n_opts, image, label, is_label, w, hgt, d, channels, seed, where, m->vpa_ws, m->stream, &m->launches);
     GUARD_END
 }
 

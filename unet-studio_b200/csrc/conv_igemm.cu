@@ -397,9 +397,9 @@ int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& c
     kp.tmem_cols = cols;
     const size_t a_stage = size_t(128) * cfg.kc * 2, b_stage = size_t(ntile_max) * cfg.kc * 2;
     const size_t fixed = size_t(8) * ntot_max * 4 + 8 * (2 * 32 + 4) + 16 + 256;
-    int stages = int((200 * 1024 - fixed) / (a_stage + b_stage));
+    int stages = int((214 * 1024 - fixed) / (a_stage + b_stage));
     stages = std::min(stages, 32);
-    if (stages < 4) {
+    if (stages < 3) {
         set_error("conv_igemm_launch: tile too large for the smem ring");
         return 1;
     }

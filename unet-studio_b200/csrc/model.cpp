@@ -234,6 +234,7 @@ Model::~Model() {
     if (stream) cudaStreamSynchronize(stream);
     free_plan();
     cudaFree(d_params); cudaFree(d_grads); cudaFree(d_mom);
+    if (vpa_ws) cudaFree(vpa_ws);
     for (auto b : d_buffers) cudaFree(b);
     cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_losses);
     if (stream) cudaStreamDestroy(stream);

@@ -103,6 +103,8 @@ class Model {
     double last_grad_norm = 0.0;
     int last_step_skipped = 0;
     long long launches = 0;          // kernels launched by this handle (bench "gpu_launches")
+    void* vpa_ws = nullptr;          // augmentation workspace (unet3d_vpa_augment)
+    size_t vpa_ws_bytes = 0;
 
     int init_params(uint64_t seed);
     int get_flat(const float* base, int i, float* host, float scale);
