@@ -151,14 +151,7 @@ def main():
         import torch.distributed as dist
         import ctypes
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        ids = [None]
-        if rank == 0:
-            buf = ctypes.create_string_buffer(128)
-            pkg.check(pkg.lib().unet3d_nccl_unique_id(buf))
-            ids = [bytes(buf.raw)]
-        dist.broadcast_object_list(ids, src=0)
-        comm = ctypes.c_void_p()
-        pkg.check(pkg.lib().unet3d_nccl_comm_init(ctypes.byref(comm), world, rank, ids[0]))
+        comm = pkg.dist.bootstrap_nccl(pkg, dist, world, rank)
 
     def barrier():
         if world > 1:
@@ -173,20 +166,22 @@ def main():
     lr0 = 1e-3
     net.create_optimizer(lr0)
     img, lab = synth_sample(rank)                      # each rank trains on its own sample (data parallel)
-    augment = (not args.no_augment) and hasattr(pkg, "vpa_augment_device")
+    augment = not args.no_augment
     x_host = torch.from_numpy(img).pin_memory()
     l_host = torch.from_numpy(lab).pin_memory()
     x_dev, l_dev = x_host.cuda(), l_host.cuda()
     x_aug, l_aug = torch.empty_like(x_dev), torch.empty_like(l_dev)
+    xa_host, la_host = torch.empty_like(x_host).pin_memory(), torch.empty_like(l_host).pin_memory()
     total_steps = 1000
     step_no = [0]
 
     def one_step_device():
         s = step_no[0]
         xin, lin = x_dev, l_dev
-        if augment:
-            pkg.vpa_augment_device(net, x_dev.data_ptr(), l_dev.data_ptr(), x_aug.data_ptr(), l_aug.data_ptr(), W, H, D, IN_C,
-                                   seed=s * world + rank)
+        if augment:   # augmentation output feeds the step without leaving HBM
+            x_aug.copy_(x_dev); l_aug.copy_(l_dev)
+            torch.cuda.current_stream().synchronize()
+            pkg.vpa_augment_on(net, x_aug.data_ptr(), l_aug.data_ptr(), W, H, D, IN_C, seed=s * world + rank, where=1)
             xin, lin = x_aug, l_aug
         loss = net.device_train_microbatch(xin.data_ptr(), lin.data_ptr())
         net.step(world, pkg.poly_lr(lr0, s, total_steps), comm)
@@ -196,8 +191,10 @@ def main():
     def one_step_host():
         s = step_no[0]
         xin, lin = x_host.numpy(), l_host.numpy()
-        if augment:
-            xin, lin = pkg.vpa_augment_host(net, xin, lin, seed=s * world + rank)
+        if augment:   # drop-in order of train.cpp:459-473 + 615-626: augment host buffers in place, then step on host buffers
+            xa_host.copy_(x_host); la_host.copy_(l_host)
+            pkg.vpa_augment_on(net, xa_host.data_ptr(), la_host.data_ptr(), W, H, D, IN_C, seed=s * world + rank, where=0)
+            xin, lin = xa_host.numpy(), la_host.numpy()
         loss = net.train_microbatch(xin, lin)
         net.step(world, pkg.poly_lr(lr0, s, total_steps), comm)
         step_no[0] += 1
@@ -263,7 +260,8 @@ def main():
                    "l2": "no explicit flush: each step streams > 3 GB of activations, far above the 126 MB L2",
                    "arithmetic": "fp16 operands, fp32 accumulate (tcgen05), fp32 stats/loss/optimizer, loss scale %g" % net.loss_scale()},
         "loss": [float(v) for v in loss],
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (IN_C + 1) * vox * 4, "d2h_bytes_per_step": 15 * 4 + 16},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (2 if augment else 1) * (IN_C + 1) * vox * 4,
+                "d2h_bytes_per_step": ((IN_C + 1) * vox * 4 if augment else 0) + 15 * 4 + 16},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (forward + data-gradient launches)",

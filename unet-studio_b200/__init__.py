@@ -34,3 +34,4 @@ def check(rc):
 from .ops import conv_forward, conv_backward, maxpool_forward  # noqa: E402,F401
 from .model import UNet3d, default_feature, poly_lr  # noqa: E402,F401
 from .vpa import vpa_augment, vpa_augment_on, OPTION_DEFAULTS  # noqa: E402,F401
+from . import dist  # noqa: E402,F401
