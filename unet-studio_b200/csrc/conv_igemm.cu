@@ -34,11 +34,15 @@ struct KParams {
     int total_items;
     int kc;
     int stages;
+    int spg;
     int a_fmt, b_fmt;
     int ntile_max;   // TMEM columns per accumulator buffer
     int ntot_max;    // stats row length
     int tmem_cols;
     uint32_t off_b, off_stats, off_bars;
+    uint32_t off_w;     // resident weight pack (whole layer) when resident_w != 0
+    int resident_w;
+    uint32_t w_bytes;
     float* stats;    // [grid][2][ntot_max] or nullptr
 };
 
@@ -73,15 +77,17 @@ __device__ __forceinline__ void halve_step(float (&a)[16], float (&q)[16], int l
 }
 
 // LAG = cp.async groups each producer thread keeps in flight (memory-level parallelism of the gather)
-template <int EPI, int LAG>
+template <int EPI, int LAG, int KC>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int S = p.stages;
-    const int kc = p.kc;
-    const uint32_t a_stage_bytes = 128u * kc * 2u;
-    const uint32_t b_stage_bytes = uint32_t(p.ntile_max) * kc * 2u;
+    constexpr int kc = KC;
+    const int spg = p.spg;                                   // K steps per smem stage
+    const uint32_t a_sub_bytes = 128u * kc * 2u;
+    const uint32_t a_stage_bytes = a_sub_bytes * spg;
+    const uint32_t b_stage_bytes = uint32_t(p.ntile_max) * kc * 2u * spg;
     const uint32_t sA = smem_u32(smem);
     const uint32_t sB = sA + p.off_b;
     float* sstats = reinterpret_cast<float*>(smem + p.off_stats);
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), 129);
+            mbar_init(full_bar(s), p.resident_w ? 128 : 129);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -119,50 +125,93 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const int r = threadIdx.x - 128;
         int stage = 0, phase = 0, lag_stage = 0;
         uint32_t it = 0;
+        if (p.resident_w && blockIdx.x < p.total_items) {
+            // whole-layer weight pack stays in shared memory for the life of the CTA; it rides in the first cp.async
+            // group, so the first full-barrier arrival also publishes it
+            const uint8_t* wsrc = static_cast<const uint8_t*>(p.probs[0].wpack);
+            for (uint32_t o = r * 16u; o < p.w_bytes; o += 128u * 16u) cp_async16(sA + p.off_w + o, wsrc + o, 16u);
+        }
+        // lane mapping: CPR adjacent lanes fetch the CPR 16-byte chunks of ONE voxel row, so every 32-byte L2 sector a warp
+        // instruction touches is fully used (a row-per-thread mapping reads half of each sector: 2x L2 traffic, measured)
+        constexpr int CPR = KC / 8;          // 16-byte chunks per row
+        constexpr int RSTEP = 128 / CPR;     // rows covered per pass; each thread serves CPR rows
+        const int q = r % CPR, rsub = r / CPR;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const Item w = decode_item(p, item);
             const ConvProblem& P = p.probs[w.pi];
             const int M = P.od * P.oh * P.ow;
-            const int m = w.mt * 128 + r;
-            const bool rv = m < M;
-            int ox = 0, oy = 0, oz = 0;
-            if (rv) {
-                ox = m % P.ow;
-                const int t = m / P.ow;
-                oy = t % P.oh;
-                oz = t / P.oh;
-            }
-            const int bz = oz * P.istride, by = oy * P.istride, bx = ox * P.istride;
-            const int nch = P.nch0 + P.nch1;
-            const int nsteps = P.ntaps * nch;
+            // everything the inner loop needs lives in registers: the asm memory clobbers of cp.async would otherwise make the
+            // compiler re-read each field from parameter space (dependent LDC chains) for every tap
+            const int nch0 = P.nch0, nch = P.nch0 + P.nch1, ntaps = P.ntaps;
+            const int nsteps = ntaps * nch;
+            const int ntiles = P.ntiles;
+            const bool resident = p.resident_w != 0;
             const uint32_t bbytes = uint32_t(P.ntile) * kc * 2u;
             const uint8_t* wbase = static_cast<const uint8_t*>(P.wpack);
-            int tap = 0, ch = 0;
-#pragma unroll 1
-            for (int s = 0; s < nsteps; ++s, ++it) {
-                mbar_wait(empty_bar(stage), phase ^ 1, 0x100u | stage);
-                if (r == 0) {
-                    mbar_arrive_expect_tx(full_bar(stage), bbytes);
-                    bulk_g2s(sB + stage * b_stage_bytes,
-                             wbase + (size_t(tap * nch + ch) * P.ntiles + w.nt) * bbytes, bbytes, full_bar(stage));
-                }
-                const ConvTap tp = P.taps[tap];
-                const int iz = bz + tp.dz, iy = by + tp.dy, ix = bx + tp.dx;
-                const bool valid = rv && (unsigned)iz < (unsigned)P.in_d && (unsigned)iy < (unsigned)P.in_h &&
-                                   (unsigned)ix < (unsigned)P.in_w;
-                const uint8_t* src;
-                if (ch < P.nch0) {
-                    src = static_cast<const uint8_t*>(P.src0);
-                    if (valid) src += (size_t((iz * P.in_h + iy) * P.in_w + ix) * P.c0p + P.coff0 + ch * kc) * 2;
-                } else {
-                    src = static_cast<const uint8_t*>(P.src1);
-                    if (valid) src += (size_t((iz * P.in_h + iy) * P.in_w + ix) * P.c1p + P.coff1 + (ch - P.nch0) * kc) * 2;
-                }
-                const uint32_t dst = sA + stage * a_stage_bytes + r * 16u;
-                const uint32_t nb = valid ? 16u : 0u;
+            const int in_d = P.in_d, in_h = P.in_h, in_w = P.in_w;
+            const uint32_t pitch0 = uint32_t(P.c0p) * 2u, pitch1 = uint32_t(P.c1p) * 2u;
+            const uint8_t* const s0 = static_cast<const uint8_t*>(P.src0) + P.coff0 * 2 + q * 16;
+            const uint8_t* const s1 = static_cast<const uint8_t*>(P.src1) + P.coff1 * 2 + q * 16;
+            uint32_t vmask[CPR];          // bit t: tap t of this row reads inside the volume
+            long long vbase[CPR];
 #pragma unroll
-                for (int g = 0; g < 8; ++g)
-                    if (g * 8 < kc) cp_async16(dst + g * 2048u, src + g * 16, nb);
+            for (int j = 0; j < CPR; ++j) {
+                const int m = w.mt * 128 + rsub + j * RSTEP;
+                const bool rv = m < M;
+                int ox = 0, oy = 0, oz = 0;
+                if (rv) {
+                    ox = m % P.ow;
+                    const int t = m / P.ow;
+                    oy = t % P.oh;
+                    oz = t / P.oh;
+                }
+                const int bz = oz * P.istride, by = oy * P.istride, bx = ox * P.istride;
+                uint32_t vm = 0;
+                if (rv) {
+#pragma unroll 1
+                    for (int t = 0; t < ntaps; ++t) {
+                        const ConvTap tp = P.taps[t];
+                        const bool ok = (unsigned)(bz + tp.dz) < (unsigned)in_d && (unsigned)(by + tp.dy) < (unsigned)in_h &&
+                                        (unsigned)(bx + tp.dx) < (unsigned)in_w;
+                        vm |= (ok ? 1u : 0u) << t;
+                    }
+                }
+                vmask[j] = vm;
+                vbase[j] = (long long)(bz * in_h + by) * in_w + bx;
+            }
+            int tap = 0, ch = 0;
+            const int ngroups = (nsteps + spg - 1) / spg;
+#pragma unroll 1
+            for (int g = 0; g < ngroups; ++g, ++it) {
+                // one stage = up to `spg` consecutive K steps (taps x channel chunks): the barrier wait, the proxy fence and the
+                // arrive are paid once per stage instead of once per 4 KB
+                mbar_wait(empty_bar(stage), phase ^ 1, 0x100u | stage);
+                const int cnt = min(spg, nsteps - g * spg);
+                if (r == 0 && !resident) {
+                    mbar_arrive_expect_tx(full_bar(stage), bbytes * cnt);
+                    const uint32_t bdst = sB + stage * b_stage_bytes;
+                    if (ntiles == 1)
+                        bulk_g2s(bdst, wbase + size_t(g * spg) * bbytes, bbytes * cnt, full_bar(stage));
+                    else
+                        for (int j = 0; j < cnt; ++j)
+                            bulk_g2s(bdst + j * bbytes, wbase + (size_t(g * spg + j) * ntiles + w.nt) * bbytes, bbytes, full_bar(stage));
+                }
+                uint32_t dst = sA + stage * a_stage_bytes + q * 2048u + rsub * 16u;
+#pragma unroll 1
+                for (int j = 0; j < cnt; ++j, dst += a_sub_bytes) {
+                    const long long delta = P.tap_delta[tap];
+                    const bool first = ch < nch0;
+                    const uint32_t pitch = first ? pitch0 : pitch1;
+                    const uint8_t* const sb = (first ? s0 : s1);
+                    const int coff = (first ? ch : ch - nch0) * kc * 2;
+#pragma unroll
+                    for (int i = 0; i < CPR; ++i) {
+                        const bool valid = (vmask[i] >> tap) & 1u;
+                        const uint8_t* src = valid ? sb + (vbase[i] + delta) * pitch + coff : sb;
+                        cp_async16(dst + i * (RSTEP * 16u), src, valid ? 16u : 0u);
+                    }
+                    if (++ch == nch) { ch = 0; ++tap; }
+                }
                 cp_async_commit();
                 if (it >= LAG) {
                     cp_async_wait<LAG>();
@@ -170,7 +219,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                     mbar_arrive(full_bar(lag_stage));
                     if (++lag_stage == S) lag_stage = 0;
                 }
-                if (++ch == nch) { ch = 0; ++tap; }
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
@@ -196,16 +244,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 const uint32_t idesc = umma_idesc(128, P.ntile, p.a_fmt, p.b_fmt, 0, 0);
                 const int nsteps = P.ntaps * (P.nch0 + P.nch1);
                 const uint32_t b_lbo = uint32_t(P.ntile) * 16u;
+                const uint32_t bbytes = uint32_t(P.ntile) * kc * 2u;
+                const int ngroups = (nsteps + spg - 1) / spg;
 #pragma unroll 1
-                for (int s = 0; s < nsteps; ++s) {
+                for (int g = 0; g < ngroups; ++g) {
                     mbar_wait(full_bar(stage), phase, 0x300u | stage);
                     tc_fence_after();
-                    const uint32_t a0 = sA + stage * a_stage_bytes;
-                    const uint32_t b0 = sB + stage * b_stage_bytes;
-                    for (int j = 0; j * 16 < kc; ++j) {
-                        const uint64_t adesc = umma_smem_desc(a0 + j * 4096u, 2048u, 128u);
-                        const uint64_t bdesc = umma_smem_desc(b0 + j * 2u * b_lbo, b_lbo, 128u);
-                        umma_f16(d_tmem, adesc, bdesc, idesc, (s | j) != 0 ? 1u : 0u);
+                    const int cnt = min(spg, nsteps - g * spg);
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint32_t a0 = sA + stage * a_stage_bytes + j * a_sub_bytes;
+                        const uint32_t b0 = p.resident_w ? sA + p.off_w + uint32_t(g * spg + j) * bbytes : sB + stage * b_stage_bytes + j * bbytes;
+                        for (int k = 0; k * 16 < kc; ++k) {
+                            const uint64_t adesc = umma_smem_desc(a0 + k * 4096u, 2048u, 128u);
+                            const uint64_t bdesc = umma_smem_desc(b0 + k * 2u * b_lbo, b_lbo, 128u);
+                            umma_f16(d_tmem, adesc, bdesc, idesc, (g | j | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(empty_bar(stage));
                     if (++stage == S) { stage = 0; phase ^= 1; }
@@ -324,23 +377,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
 int g_sm_count = 0;
 
-template <int EPI, int LAG>
+template <int EPI, int LAG, int KC>
 int launch_t(const KParams& kp, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<EPI, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<EPI, LAG, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    conv_igemm_kernel<EPI, LAG><<<grid, kThreads, smem, stream>>>(kp);
+    conv_igemm_kernel<EPI, LAG, KC><<<grid, kThreads, smem, stream>>>(kp);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
+template <int EPI, int KC>
+int launch_kc(const KParams& kp, int grid, size_t smem, cudaStream_t stream) {
+    if (kp.stages >= 8) return launch_t<EPI, 6, KC>(kp, grid, smem, stream);
+    return launch_t<EPI, 2, KC>(kp, grid, smem, stream);
+}
+
 template <int EPI>
 int launch_lag(const KParams& kp, int grid, size_t smem, cudaStream_t stream) {
-    if (kp.stages >= 16) return launch_t<EPI, 14>(kp, grid, smem, stream);
-    if (kp.stages >= 8) return launch_t<EPI, 6>(kp, grid, smem, stream);
-    return launch_t<EPI, 2>(kp, grid, smem, stream);
+    if (kp.kc == 16) return launch_kc<EPI, 16>(kp, grid, smem, stream);
+    if (kp.kc == 32) return launch_kc<EPI, 32>(kp, grid, smem, stream);
+    return launch_kc<EPI, 64>(kp, grid, smem, stream);
 }
 
 }  // namespace
@@ -384,6 +443,7 @@ int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& c
         }
         const long long M = 1LL * P.od * P.oh * P.ow;
         P.mtiles = int((M + 127) / 128);
+        for (int t = 0; t < P.ntaps; ++t) P.tap_delta[t] = (P.taps[t].dz * P.in_h + P.taps[t].dy) * P.in_w + P.taps[t].dx;
         P.item_base = items;
         items += P.mtiles * P.ntiles;
         ntile_max = std::max(ntile_max, P.ntile);
@@ -395,8 +455,20 @@ int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& c
     int cols = 32;
     while (cols < 2 * ntile_max) cols <<= 1;
     kp.tmem_cols = cols;
-    const size_t a_stage = size_t(128) * cfg.kc * 2, b_stage = size_t(ntile_max) * cfg.kc * 2;
-    const size_t fixed = size_t(8) * ntot_max * 4 + 8 * (2 * 32 + 4) + 16 + 256;
+    kp.spg = std::max(1, 64 / cfg.kc);
+    size_t a_stage = size_t(128) * cfg.kc * 2 * kp.spg, b_stage = size_t(ntile_max) * cfg.kc * 2 * kp.spg;
+    // single-problem, single-N-tile layers whose whole weight pack is small keep it resident in shared memory
+    // (no per-K-step bulk copy: a 512-byte UBLKCP per step costs far more than the MMA it feeds)
+    size_t w_bytes = 0;
+    if (probs.size() == 1 && kp.probs[0].ntiles == 1) {
+        const ConvProblem& P0 = kp.probs[0];
+        w_bytes = size_t(P0.ntaps) * (P0.nch0 + P0.nch1) * P0.ntile * cfg.kc * 2;
+        if (w_bytes > 96 * 1024) w_bytes = 0;
+    }
+    kp.resident_w = w_bytes ? 1 : 0;
+    kp.w_bytes = uint32_t(w_bytes);
+    if (w_bytes) b_stage = 0;
+    const size_t fixed = size_t(8) * ntot_max * 4 + 8 * (2 * 32 + 4) + 16 + 256 + w_bytes;
     int stages = int((214 * 1024 - fixed) / (a_stage + b_stage));
     stages = std::min(stages, 32);
     if (stages < 3) {
@@ -405,7 +477,8 @@ int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& c
     }
     kp.stages = stages;
     kp.off_b = uint32_t(stages * a_stage);
-    kp.off_stats = uint32_t(kp.off_b + stages * b_stage);
+    kp.off_w = uint32_t(kp.off_b + stages * b_stage);
+    kp.off_stats = uint32_t(kp.off_w + w_bytes);
     kp.off_bars = uint32_t((kp.off_stats + 8 * ntot_max * 4 + 15) & ~15u);
     const size_t smem = kp.off_bars + 8 * (2 * stages + 4) + 16;
     kp.stats = (cfg.epi == EPI_STORE16 && probs.size() == 1) ? cfg.stats_partials : nullptr;

@@ -57,6 +57,7 @@ struct ConvProblem {
     const void* wpack;     // blobs [tap][chunk][ntile] of ntile x kc 16-bit, canonical K-major interleaved
     const float* bias;     // n_real entries or nullptr
     int mtiles;            // ceil(M/128)              (filled by the launcher)
+    int tap_delta[27];     // (dz*in_h + dy)*in_w + dx  (filled by the launcher)
     int item_base;         // first work item           (filled by the launcher)
 };
 
