@@ -28,6 +28,12 @@ CASES = [
     ("k3s1_odd_24_40", 0, 3, 1, 24, 0, 40, (13, 7, 9)),
     ("k3s2_odd", 0, 3, 2, 16, 0, 16, (14, 10, 6)),
     ("k3s1_320", 0, 3, 1, 32, 0, 320, (8, 8, 4)),
+    # >= 32768 voxels, K,N <= 32: these go through the halo-block kernel (conv_halo.cu), incl. ragged tile edges
+    ("halo_16_16", 0, 3, 1, 16, 0, 16, (40, 36, 28)),
+    ("halo_cat16_16", 0, 3, 1, 16, 16, 16, (64, 32, 20)),
+    ("halo_32_32", 0, 3, 1, 32, 0, 32, (36, 40, 24)),
+    ("halo_1_16", 0, 3, 1, 1, 0, 16, (48, 32, 24)),
+    ("halo_cat16_16_to32", 0, 3, 1, 12, 9, 24, (33, 35, 30)),
 ]
 
 

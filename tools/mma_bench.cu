@@ -1,0 +1,163 @@
+// Microbenchmark: cycles per tcgen05.mma (kind::f16, M=128, K=16) issued back to back by one thread, as a function of N,
+// of the shared-memory layout (SWIZZLE_NONE interleaved vs SWIZZLE_128B) and of the A-operand strides.
+#include <cstdio>
+#include <cstdint>
+#include "../unet-studio_b200/csrc/common.cuh"
+using namespace u3d;
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= uint64_t((addr & 0x3FFFF) >> 4);
+    d |= uint64_t(1) << 16;                 // LBO (ignored for swizzled K-major)
+    d |= uint64_t((sbo >> 4) & 0x3FFF) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+// mode 0: SWIZZLE_NONE, A LBO=2048 SBO=128 (gather kernel); 1: SWIZZLE_NONE, A LBO=big (halo kernel); 2: SWIZZLE_128B
+__global__ void __launch_bounds__(128, 1) bench(int n, int mode, int iters, int nacc, long long* out, int a_lbo_big) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tptr;
+    const uint32_t sb = smem_u32(smem);
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+    if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tptr), 512); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tptr;
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        const uint32_t idesc = umma_idesc(128, n, 0, 0, 0, 0);
+        const uint32_t a0 = sb, b0 = sb + 128 * 1024;
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            uint64_t ad, bd;
+            const uint32_t shift = (i % 27) * 16u;   // different start address per "tap" like the halo kernel
+            if (mode == 0) { ad = umma_smem_desc(a0 + (i % 8) * 4096u, 2048u, 128u); bd = umma_smem_desc(b0, n * 16u, 128u); }
+            else if (mode == 1) { ad = umma_smem_desc(a0 + shift, a_lbo_big, 128u); bd = umma_smem_desc(b0, n * 16u, 128u); }
+            else { ad = desc_sw128(a0 + (i % 4) * 32u, 1024u); bd = desc_sw128(b0, 1024u); }
+            umma_f16(tm + (i % nacc) * n, ad, bd, idesc, i >= nacc ? 1u : 0u);
+        }
+        long long t1 = clock64();
+        umma_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0, 0xF00);
+        long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    tc_fence_before(); __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
+// lean issue loop: 27 'taps' fully unrolled, descriptors = base + register offset
+__global__ void __launch_bounds__(128, 1) bench_lean(int n, int iters, long long* out, int lbo) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tptr;
+    const uint32_t sb = smem_u32(smem);
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tptr), 512); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tptr;
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        const uint32_t idesc = umma_idesc(128, n, 0, 0, 0, 0);
+        int toff[27];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) toff[k] = ((k / 9) * 10 + (k / 3) % 3) * 34 + k % 3;
+        const uint64_t a_base = umma_smem_desc(sb + 4096, lbo, 128u);
+        const uint64_t b_base = umma_smem_desc(sb + 128 * 1024, n * 16u, 128u);
+        const uint32_t bstep = (n * 32u) >> 4;
+        long long t0 = clock64();
+        for (int i = 0; i < iters / 27; ++i) {
+            const uint64_t a_mt = a_base + uint64_t(i & 7) * 128u;
+            uint64_t bd = b_base;
+            umma_f16_first(tm + (i & 1) * n, a_mt + toff[0], bd, idesc);
+#pragma unroll
+            for (int k = 1; k < 27; ++k) {
+                bd += bstep;
+                umma_f16_acc(tm + (i & 1) * n, a_mt + toff[k], bd, idesc);
+            }
+        }
+        long long t1 = clock64();
+        umma_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0, 0xF00);
+        long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    tc_fence_before(); __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
+// warp-uniform issue loop, MMA guarded by elect.sync (CUTLASS idiom)
+__global__ void __launch_bounds__(128, 1) bench_elect(int n, int iters, long long* out, int lbo) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tptr;
+    const uint32_t sb = smem_u32(smem);
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tptr), 512); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tptr;
+    if (threadIdx.x < 32) {
+        fence_proxy_async();
+        const uint32_t idesc = umma_idesc(128, n, 0, 0, 0, 0);
+        int toff[27];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) toff[k] = ((k / 9) * 10 + (k / 3) % 3) * 34 + k % 3;
+        const uint64_t a_base = umma_smem_desc(sb + 4096, lbo, 128u);
+        const uint64_t b_base = umma_smem_desc(sb + 128 * 1024, n * 16u, 128u);
+        const uint32_t bstep = (n * 32u) >> 4;
+        long long t0 = clock64();
+        for (int i = 0; i < iters / 27; ++i) {
+            const uint64_t a_mt = a_base + uint64_t(i & 7) * 128u;
+            uint64_t bd = b_base;
+            if (elect_one()) umma_f16_first(tm + (i & 1) * n, a_mt + toff[0], bd, idesc);
+#pragma unroll
+            for (int k = 1; k < 27; ++k) {
+                bd += bstep;
+                if (elect_one()) umma_f16_acc(tm + (i & 1) * n, a_mt + toff[k], bd, idesc);
+            }
+        }
+        long long t1 = clock64();
+        if (elect_one()) umma_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0, 0xF00);
+        long long t2 = clock64();
+        if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    tc_fence_before(); __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
+int main() {
+    long long* d; cudaMalloc(&d, 16);
+    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int iters = 4096;
+    for (int mode = 0; mode < 0; ++mode)
+        for (int n : {16, 32, 64, 128, 256})
+            for (int nacc : {1, 2}) {
+                if (nacc * n > 512) continue;
+                bench<<<1, 128, 200 * 1024>>>(n, mode, iters, nacc, d, 35200);
+                cudaError_t e = cudaDeviceSynchronize();
+                long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+                printf("mode %d N %3d nacc %d : issue %.1f cyc/mma, complete %.1f cyc/mma  (%s)\n", mode, n, nacc, double(h[0]) / iters,
+                       double(h[1]) / iters, cudaGetErrorString(e));
+            }
+    cudaFuncSetAttribute(bench_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int n : {16, 32, 64}) {
+        bench_lean<<<1, 128, 200 * 1024>>>(n, 27 * 150, d, 35200);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("lean N %3d : issue %.1f cyc/mma, complete %.1f cyc/mma (%s)\n", n, double(h[0]) / (27 * 150), double(h[1]) / (27 * 150), cudaGetErrorString(e));
+    }
+    cudaFuncSetAttribute(bench_elect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int n : {16, 32, 64}) {
+        bench_elect<<<1, 128, 200 * 1024>>>(n, 27 * 150, d, 35200);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("elect N %3d : issue %.1f cyc/mma, complete %.1f cyc/mma (%s)\n", n, double(h[0]) / (27 * 150), double(h[1]) / (27 * 150), cudaGetErrorString(e));
+    }
+    return 0;
+}

@@ -93,7 +93,7 @@ extern "C" int u3d_op_conv_forward(int transposed, int ks, int stride, int cin0,
     std::vector<ConvProblem> probs;
     std::vector<PackDesc> packs;
     int kc = 0;
-    plan_forward(g, probs, packs, kc);
+    plan_forward(g, probs, packs, kc, (!planar_fp32 && conv_halo_wants_kc16(ks, stride, transposed, pad16(cin0) + (cin1 ? pad16(cin1) : 0), pad16(cout), Vout)) ? 16 : 0);
     DevBuf dx0, dx1, dw, db, dy, dstats, dyf;
     OP_CHECK(upload_act(dx0, x0, cin0, Vin, false, s));
     if (cin1) OP_CHECK(upload_act(dx1, x1, cin1, Vin, false, s));
@@ -125,7 +125,7 @@ extern "C" int u3d_op_conv_forward(int transposed, int ks, int stride, int cin0,
         if (dstats.alloc(size_t(device_sm_count()) * 2 * ntot * 4)) { set_error("cudaMalloc failed"); return 1; }
         cfg.stats_partials = static_cast<float*>(dstats.p);
     }
-    OP_CHECK(conv_igemm_launch(probs, cfg, nullptr, s));
+    OP_CHECK(conv_launch(probs, cfg, s));
     OP_CHECK(finish(s));
     if (planar_fp32)
         OP_CUDA(cudaMemcpy(y, dyf.p, size_t(cout) * Vout * 4, cudaMemcpyDeviceToHost));
@@ -170,7 +170,7 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
         std::vector<ConvProblem> probs;
         std::vector<PackDesc> packs;
         int kc = 0;
-        plan_dgrad(g, src, probs, packs, kc);
+        plan_dgrad(g, src, probs, packs, kc, conv_halo_wants_kc16(ks, stride, transposed, pad16(cout), pad16(cin[src]), Vin) ? 16 : 0);
         const bool acc = src == 0 && (accumulate_gx0 & 1);
         if (acc) OP_CHECK(upload_act(dgx[src], gx[src], cin[src], Vin, false, s));
         else {
@@ -191,7 +191,7 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
         ConvLaunch cfg{};
         cfg.kc = kc;
         cfg.epi = acc ? EPI_ACCUM16 : EPI_STORE16;
-        OP_CHECK(conv_igemm_launch(probs, cfg, nullptr, s));
+        OP_CHECK(conv_launch(probs, cfg, s));
         OP_CHECK(finish(s));
         OP_CHECK(download_act(dgx[src].p, gx[src], cin[src], Vin, false, s));
     }

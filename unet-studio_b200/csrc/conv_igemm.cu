@@ -417,7 +417,9 @@ int device_sm_count() {
 unsigned int read_device_error() {
     unsigned int v = 0;
     cudaMemcpyFromSymbol(&v, g_dev_error, sizeof(v));
-    return v ? v : read_device_error_wgrad();
+    if (v) return v;
+    v = read_device_error_wgrad();
+    return v ? v : read_device_error_halo();
 }
 
 int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, ConvProblem*, cudaStream_t stream) {

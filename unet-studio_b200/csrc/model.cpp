@@ -551,7 +551,12 @@ int Model::ensure_plan() {
     }
     for (auto& s : steps) {
         if (s.kind == Step::CONV) {
-            plan_forward(s.g, s.fprobs, s.fpacks, s.fkc);
+            {
+                const long long vox = 1LL * s.g.out_d * s.g.out_h * s.g.out_w;
+                const bool halo = s.head_level < 0 && conv_halo_wants_kc16(s.g.ks, s.g.stride, s.g.transposed,
+                                                                           pad16(s.g.cin[0]) + (s.g.cin[1] ? pad16(s.g.cin[1]) : 0), pad16(s.g.cout), vox);
+                plan_forward(s.g, s.fprobs, s.fpacks, s.fkc, halo ? 16 : 0);
+            }
             s.flops = 2.0 * double(s.g.cin[0] + s.g.cin[1]) * s.g.cout * (s.g.transposed ? 1.0 : double(s.g.ks * s.g.ks * s.g.ks)) *
                       double(s.g.out_d) * s.g.out_h * s.g.out_w;
             for (size_t i = 0; i < s.fprobs.size(); ++i) {
@@ -582,7 +587,11 @@ int Model::ensure_plan() {
                     s.wg.push_back(W);
                     if (!tens[ins[src]].needs_grad) continue;
                     Step::DG& D = s.dg[src];
-                    plan_dgrad(s.g, src, D.probs, D.packs, D.kc);
+                    {
+                        const long long vox = 1LL * s.g.in_d * s.g.in_h * s.g.in_w;
+                        const bool halo = conv_halo_wants_kc16(s.g.ks, s.g.stride, s.g.transposed, pad16(s.g.cout), pad16(s.g.cin[src]), vox);
+                        plan_dgrad(s.g, src, D.probs, D.packs, D.kc, halo ? 16 : 0);
+                    }
                     for (size_t i = 0; i < D.probs.size(); ++i) {
                         void* blob = nullptr;
                         M_CHECK(alloc(&blob, pack_bytes(D.packs[i])));
@@ -644,7 +653,7 @@ int Model::run_forward(int levels_wanted) {
             cfg.stats_grid_out = &rows;
             if (s.stats) cfg.stats_partials = d_partials;
             prof_begin(0, s.flops);
-            M_CHECK(conv_igemm_launch(s.fprobs, cfg, nullptr, stream));
+            M_CHECK(conv_launch(s.fprobs, cfg, stream));
             prof_end();
             ++launches;
             if (s.stats) { last_stat_rows = rows; last_stat_ntot = s.fprobs[0].ntile * s.fprobs[0].ntiles; }
@@ -742,7 +751,7 @@ int Model::run_backward() {
                 cfg.kc = s.dg[src].kc;
                 cfg.epi = grad_written[ins[src]] ? EPI_ACCUM16 : EPI_STORE16;
                 prof_begin(0, s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
-                M_CHECK(conv_igemm_launch(s.dg[src].probs, cfg, nullptr, stream));
+                M_CHECK(conv_launch(s.dg[src].probs, cfg, stream));
                 prof_end();
                 ++launches;
                 grad_written[ins[src]] = 1;

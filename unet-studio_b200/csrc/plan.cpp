@@ -28,11 +28,11 @@ static void init_pack(PackDesc& k) {
     std::memset(&k, 0, sizeof(k));
 }
 
-void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc) {
+void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc, int force_kc) {
     probs.clear();
     packs.clear();
     const int c0p = pad16(g.cin[0]), c1p = g.cin[1] ? pad16(g.cin[1]) : 0;
-    kc = choose_kc(c0p, c1p);
+    kc = force_kc ? force_kc : choose_kc(c0p, c1p);
     int ntile, ntiles;
     choose_ntile(pad16(g.cout), ntile, ntiles);
     if (!g.transposed) {
@@ -94,11 +94,11 @@ void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vect
     }
 }
 
-void plan_dgrad(const LayerGeom& g, int src, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc) {
+void plan_dgrad(const LayerGeom& g, int src, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc, int force_kc) {
     probs.clear();
     packs.clear();
     const int coutp = pad16(g.cout);
-    kc = choose_kc(coutp, 0);
+    kc = force_kc ? force_kc : choose_kc(coutp, 0);
     const int n_real = g.cin[src];
     int ntile, ntiles;
     choose_ntile(pad16(n_real), ntile, ntiles);

@@ -41,9 +41,9 @@ int choose_kc(int c0p, int c1p);
 void choose_ntile(int np, int& ntile, int& ntiles);
 
 // Forward: fills `probs` (operand/destination pointers left null) and `packs` (one per problem, w/out null).
-void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc);
+void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc, int force_kc = 0);
 // Data gradient wrt source `src` (0/1): dy (cout channels, output extent) -> dx (cin[src] channels, input extent).
-void plan_dgrad(const LayerGeom& g, int src, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc);
+void plan_dgrad(const LayerGeom& g, int src, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc, int force_kc = 0);
 // Weight gradient wrt the channels of source `src`.
 void plan_wgrad(const LayerGeom& g, int src, WgradProblem& prob);
 

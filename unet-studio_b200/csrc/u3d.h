@@ -108,6 +108,12 @@ struct WgradLaunch {
 int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch& cfg, WgradProblem* dev_scratch,
                       cudaStream_t stream);
 
+bool conv_halo_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
+int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
+int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);  // halo or gather kernel
+bool conv_halo_wants_kc16(int ks, int stride, int transposed, int k_channels_padded, int n_channels_padded, long long voxels);
+unsigned int read_device_error_halo();
+
 int device_sm_count();
 unsigned int read_device_error();  // first non-zero mbarrier-timeout code of any kernel TU (0 = ok)
 unsigned int read_device_error_wgrad();
