@@ -232,32 +232,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     } else if (warp == 8) {
         // ===================================== MMA issuer ====================================
         if (lane == 0) {
+            // lean issue loop: every parameter in registers, descriptors advanced by 64-bit adds in 16-byte units
+            // (tools/mma_bench.cu: ~45 clk per MMA this way vs ~200+ when descriptors are rebuilt per MMA)
             int stage = 0, phase = 0;
             uint32_t acc_cnt = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++acc_cnt) {
+            const int total_items = p.total_items, nstride = gridDim.x, ntile_max = p.ntile_max;
+            const bool resident = p.resident_w != 0;
+            const uint64_t a_desc0 = umma_smem_desc(sA, 2048u, 128u);
+            const uint64_t a_stage_u = uint64_t(a_stage_bytes >> 4), a_sub_u = uint64_t(a_sub_bytes >> 4);
+            const uint64_t b_stage_u = uint64_t(b_stage_bytes >> 4);
+            for (int item = blockIdx.x; item < total_items; item += nstride, ++acc_cnt) {
                 const Item w = decode_item(p, item);
                 const ConvProblem& P = p.probs[w.pi];
                 const int acc = acc_cnt & 1;
                 mbar_wait(tempty_bar(acc), ((acc_cnt >> 1) & 1) ^ 1, 0x200u | acc);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + uint32_t(acc * p.ntile_max);
-                const uint32_t idesc = umma_idesc(128, P.ntile, p.a_fmt, p.b_fmt, 0, 0);
+                const int ntile = P.ntile;
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * ntile_max);
+                const uint32_t idesc = umma_idesc(128, ntile, p.a_fmt, p.b_fmt, 0, 0);
                 const int nsteps = P.ntaps * (P.nch0 + P.nch1);
-                const uint32_t b_lbo = uint32_t(P.ntile) * 16u;
-                const uint32_t bbytes = uint32_t(P.ntile) * kc * 2u;
+                const uint32_t b_lbo = uint32_t(ntile) * 16u;
+                const uint64_t b_sub_u = uint64_t((uint32_t(ntile) * kc * 2u) >> 4);   // one K step of weights
+                const uint64_t b_k_u = uint64_t((2u * b_lbo) >> 4);                     // one K=16 slice inside it
+                const uint64_t b_desc0 = umma_smem_desc(resident ? sA + p.off_w : sB, b_lbo, 128u);
                 const int ngroups = (nsteps + spg - 1) / spg;
+                bool first = true;
 #pragma unroll 1
                 for (int g = 0; g < ngroups; ++g) {
                     mbar_wait(full_bar(stage), phase, 0x300u | stage);
                     tc_fence_after();
                     const int cnt = min(spg, nsteps - g * spg);
-                    for (int j = 0; j < cnt; ++j) {
-                        const uint32_t a0 = sA + stage * a_stage_bytes + j * a_sub_bytes;
-                        const uint32_t b0 = p.resident_w ? sA + p.off_w + uint32_t(g * spg + j) * bbytes : sB + stage * b_stage_bytes + j * bbytes;
-                        for (int k = 0; k * 16 < kc; ++k) {
-                            const uint64_t adesc = umma_smem_desc(a0 + k * 4096u, 2048u, 128u);
-                            const uint64_t bdesc = umma_smem_desc(b0 + k * 2u * b_lbo, b_lbo, 128u);
-                            umma_f16(d_tmem, adesc, bdesc, idesc, (g | j | k) != 0 ? 1u : 0u);
+                    uint64_t ad = a_desc0 + uint64_t(stage) * a_stage_u;
+                    uint64_t bd = resident ? b_desc0 + uint64_t(g * spg) * b_sub_u : b_desc0 + uint64_t(stage) * b_stage_u;
+#pragma unroll 1
+                    for (int j = 0; j < cnt; ++j, ad += a_sub_u, bd += b_sub_u) {
+#pragma unroll
+                        for (int k = 0; k < KC / 16; ++k) {
+                            if (first) { umma_f16_first(d_tmem, ad + uint64_t(k) * 256u, bd + uint64_t(k) * b_k_u, idesc); first = false; }
+                            else umma_f16_acc(d_tmem, ad + uint64_t(k) * 256u, bd + uint64_t(k) * b_k_u, idesc);
                         }
                     }
                     umma_commit(empty_bar(stage));

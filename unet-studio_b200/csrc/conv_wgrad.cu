@@ -125,6 +125,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
             const int nchunks_n = P.ntile / 8;
             int kb0, kb1;
             kblock_range(P, w.ks, kb0, kb1);
+            // per-item constants of this thread's 8 A chunks (tap, channel offset, linear voxel delta): the stage loop below only
+            // decodes the voxel once and adds — the producers, not the tensor pipe, were the bound of this kernel
+            const int t_d = P.t_d, t_h = P.t_h, t_w = P.t_w, ts = P.tstride, lw = P.lw, lh = P.lh;
+            const uint32_t t_pitch = uint32_t(P.t_cp) * 2u, u_pitch = uint32_t(P.u_cp) * 2u;
+            const uint8_t* const tbase = static_cast<const uint8_t*>(P.T) + P.t_coff * 2;
+            const uint8_t* const ubase = static_cast<const uint8_t*>(P.U) + (P.u_coff + w.nt * P.ntile) * 2;
+            int cdz[8], cdy[8], cdx[8], ccoff[8];
+            long long cdelta[8];
+            uint32_t cok = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row0 = (h + 2 * i) * 8;
+                const int tl = row0 / cpt;
+                const int c = row0 - tl * cpt + ctile * 128;
+                const bool ok = tl < ntap_here && c < P.t_c;
+                const ConvTap tp = P.taps[ok ? tap0 + tl : 0];
+                cdz[i] = tp.dz; cdy[i] = tp.dy; cdx[i] = tp.dx;
+                cdelta[i] = ((long long)tp.dz * t_h + tp.dy) * t_w + tp.dx;
+                ccoff[i] = c * 2;
+                cok |= (ok ? 1u : 0u) << i;
+            }
 #pragma unroll 1
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 mbar_wait(empty_bar(stage), phase ^ 1, 0x500u | stage);
@@ -132,35 +153,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                 const bool vv = vg < K;
                 int lx = 0, ly = 0, lz = 0;
                 if (vv) {
-                    lx = vg % P.lw;
-                    const int q = vg / P.lw;
-                    ly = q % P.lh;
-                    lz = q / P.lh;
+                    lx = vg % lw;
+                    const int q = vg / lw;
+                    ly = q % lh;
+                    lz = q / lh;
                 }
+                const int bz = lz * ts, by = ly * ts, bx = lx * ts;
+                const long long vbase = ((long long)bz * t_h + by) * t_w + bx;
                 // ---- A: tapped tensor, 8 chunks per thread
-                const uint32_t a_dst = sA + stage * a_stage_bytes + v * 16u;
-#pragma unroll 1
-                for (int mc = h; mc < 16; mc += 2) {
-                    const int row0 = mc * 8;
-                    const int tl = row0 / cpt;
-                    const int c = row0 - tl * cpt + ctile * 128;
-                    bool ok = vv && tl < ntap_here && c < P.t_c;
-                    const uint8_t* src = static_cast<const uint8_t*>(P.T);
-                    if (ok) {
-                        const ConvTap tp = P.taps[tap0 + tl];
-                        const int iz = lz * P.tstride + tp.dz, iy = ly * P.tstride + tp.dy, ix = lx * P.tstride + tp.dx;
-                        ok = (unsigned)iz < (unsigned)P.t_d && (unsigned)iy < (unsigned)P.t_h && (unsigned)ix < (unsigned)P.t_w;
-                        if (ok) src += (size_t((iz * P.t_h + iy) * P.t_w + ix) * P.t_cp + P.t_coff + c) * 2;
-                    }
-                    cp_async16(a_dst + mc * (kKB * 16u), src, ok ? 16u : 0u);
+                const uint32_t a_dst = sA + stage * a_stage_bytes + v * 16u + h * (kKB * 16u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool ok = vv && ((cok >> i) & 1u) && (unsigned)(bz + cdz[i]) < (unsigned)t_d &&
+                                    (unsigned)(by + cdy[i]) < (unsigned)t_h && (unsigned)(bx + cdx[i]) < (unsigned)t_w;
+                    const uint8_t* src = ok ? tbase + (vbase + cdelta[i]) * t_pitch + ccoff[i] : tbase;
+                    cp_async16(a_dst + i * (2u * kKB * 16u), src, ok ? 16u : 0u);
                 }
                 // ---- B: untapped tensor
                 const uint32_t b_dst = sB + stage * b_stage_bytes + v * 16u;
-                const uint8_t* ub = static_cast<const uint8_t*>(P.U);
-                const uint8_t* usrc = vv ? ub + (size_t(vg) * P.u_cp + P.u_coff + w.nt * P.ntile) * 2 : ub;
+                const uint8_t* usrc = vv ? ubase + size_t(vg) * u_pitch : ubase;
 #pragma unroll 1
                 for (int nc = h; nc < nchunks_n; nc += 2)
-                    cp_async16(b_dst + nc * (kKB * 16u), vv ? usrc + nc * 16 : ub, vv ? 16u : 0u);
+                    cp_async16(b_dst + nc * (kKB * 16u), vv ? usrc + nc * 16 : ubase, vv ? 16u : 0u);
                 cp_async_commit();
                 if (it >= LAG) {
                     cp_async_wait<LAG>();
@@ -181,9 +195,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     } else if (warp == 8) {
         // ===================================== MMA issuer ====================================
         if (lane == 0) {
+            // lean issue loop (see conv_halo.cu / tools/mma_bench.cu)
             int stage = 0, phase = 0;
             uint32_t acc_cnt = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const int total_items = p.total_items, nstride = gridDim.x, ntile_max = p.ntile_max;
+            const uint64_t a_desc0 = umma_smem_desc(sA, 128u, kKB * 16u);
+            const uint64_t b_desc0 = umma_smem_desc(sB, 128u, kKB * 16u);
+            const uint64_t a_stage_u = uint64_t(a_stage_bytes >> 4), b_stage_u = uint64_t(b_stage_bytes >> 4);
+            for (int item = blockIdx.x; item < total_items; item += nstride) {
                 const WItem w = decode_witem(p, item);
                 const WgradProblem& P = p.probs[w.pi];
                 int kb0, kb1;
@@ -192,19 +211,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                 const int acc = acc_cnt & 1;
                 mbar_wait(tempty_bar(acc), ((acc_cnt >> 1) & 1) ^ 1, 0x600u | acc);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + uint32_t(acc * p.ntile_max);
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * ntile_max);
                 const uint32_t idesc = umma_idesc(128, P.ntile, p.t_fmt, p.u_fmt, 1, 1);
+                bool first = true;
 #pragma unroll 1
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase, 0x700u | stage);
                     tc_fence_after();
-                    const uint32_t a0 = sA + stage * a_stage_bytes;
-                    const uint32_t b0 = sB + stage * b_stage_bytes;
+                    const uint64_t ad = a_desc0 + uint64_t(stage) * a_stage_u;
+                    const uint64_t bd = b_desc0 + uint64_t(stage) * b_stage_u;
 #pragma unroll
                     for (int j = 0; j < kKB / 16; ++j) {
-                        const uint64_t adesc = umma_smem_desc(a0 + j * 256u, 128u, kKB * 16u);
-                        const uint64_t bdesc = umma_smem_desc(b0 + j * 256u, 128u, kKB * 16u);
-                        umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                        if (first) { umma_f16_first(d_tmem, ad + uint64_t(j) * 16u, bd + uint64_t(j) * 16u, idesc); first = false; }
+                        else umma_f16_acc(d_tmem, ad + uint64_t(j) * 16u, bd + uint64_t(j) * 16u, idesc);
                     }
                     umma_commit(empty_bar(stage));
                     if (++stage == S) { stage = 0; phase ^= 1; }
