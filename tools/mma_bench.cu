@@ -131,6 +131,49 @@ __global__ void __launch_bounds__(128, 1) bench_elect(int n, int iters, long lon
     if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
+// several warps issue MMAs concurrently into different TMEM accumulators
+__global__ void __launch_bounds__(256, 1) bench_multi(int n, int iters, int nwarps, long long* out, int lbo) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar[8];
+    __shared__ uint32_t tptr;
+    const uint32_t sb = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bar[i]), 1); fence_barrier_init(); }
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tptr), 512); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tptr;
+    long long t0 = clock64();
+    if (warp < nwarps && lane == 0) {
+        fence_proxy_async();
+        const uint32_t idesc = umma_idesc(128, n, 0, 0, 0, 0);
+        int toff[27];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) toff[k] = ((k / 9) * 10 + (k / 3) % 3) * 34 + k % 3;
+        const uint64_t a_base = umma_smem_desc(sb + 4096, lbo, 128u);
+        const uint64_t b_base = umma_smem_desc(sb + 128 * 1024, n * 16u, 128u);
+        const uint32_t bstep = (n * 32u) >> 4;
+        const uint32_t d = tm + warp * 2 * n;
+        for (int i = 0; i < iters / 27; ++i) {
+            const uint64_t a_mt = a_base + uint64_t((i + warp) & 7) * 128u;
+            uint64_t bd = b_base;
+            umma_f16_first(d + (i & 1) * n, a_mt + toff[0], bd, idesc);
+#pragma unroll
+            for (int k = 1; k < 27; ++k) {
+                bd += bstep;
+                umma_f16_acc(d + (i & 1) * n, a_mt + toff[k], bd, idesc);
+            }
+        }
+        umma_commit(smem_u32(&bar[warp]));
+        mbar_wait(smem_u32(&bar[warp]), 0, 0xF00);
+    }
+    __syncthreads();
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = t2 - t0; out[1] = t2 - t0; }
+    tc_fence_before(); __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
 int main() {
     long long* d; cudaMalloc(&d, 16);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -152,6 +195,14 @@ int main() {
         long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
         printf("lean N %3d : issue %.1f cyc/mma, complete %.1f cyc/mma (%s)\n", n, double(h[0]) / (27 * 150), double(h[1]) / (27 * 150), cudaGetErrorString(e));
     }
+    cudaFuncSetAttribute(bench_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int n : {16, 32})
+        for (int nw : {1, 2, 4, 8}) {
+            bench_multi<<<1, 256, 200 * 1024>>>(n, 27 * 150, nw, d, 35200);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+            printf("multi N %3d warps %d : %.1f cyc per MMA aggregate (%s)\n", n, nw, double(h[0]) / (27 * 150 * nw), cudaGetErrorString(e));
+        }
     cudaFuncSetAttribute(bench_elect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int n : {16, 32, 64}) {
         bench_elect<<<1, 128, 200 * 1024>>>(n, 27 * 150, d, 35200);

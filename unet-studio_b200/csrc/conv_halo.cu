@@ -145,11 +145,9 @@ __global__ void __launch_bounds__(kHThreads, 1) conv_halo_kernel(const __grid_co
                 else src = ok ? s1 + vox * pitch1 + (cg - ncg0) * 16 : s1;
                 cp_async16(blk + (uint32_t(cg) * p.NP_alloc + pos) * 16u, src, ok ? 16u : 0u);
             }
-            cp_async_commit();
-            cp_async_wait<0>();
-            fence_proxy_async();
-            mbar_arrive(full_bar(buf));
+            cp_async_mbar_arrive(full_bar(buf));
         }
+        cp_async_wait<0>();
     } else if (warp == 12) {
         // ===================================== MMA issuer ====================================
         if (lane == 0) {
@@ -170,6 +168,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv_halo_kernel(const __grid_co
             for (int tile = blockIdx.x; tile < total_tiles; tile += nstride, ++cnt) {
                 const int buf = cnt % nbuf;
                 mbar_wait(full_bar(buf), (cnt / nbuf) & 1, 0xA00u | buf);
+                fence_proxy_async();
                 tc_fence_after();
                 const uint64_t a_tile = umma_smem_desc(sbase + buf * a_buf_bytes + p_first16, lbo_a, 128u);
 #pragma unroll 1

@@ -212,23 +212,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                     }
                     if (++ch == nch) { ch = 0; ++tap; }
                 }
-                cp_async_commit();
-                if (it >= LAG) {
-                    cp_async_wait<LAG>();
-                    fence_proxy_async();
-                    mbar_arrive(full_bar(lag_stage));
-                    if (++lag_stage == S) lag_stage = 0;
-                }
+                // completion is signalled by the copy engine itself: no wait and no proxy fence in the producer (a producer-side
+                // fence.proxy.async waits for the in-flight copies and serialises every stage on a full memory latency)
+                cp_async_mbar_arrive(full_bar(stage));
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
         cp_async_wait<0>();
-        fence_proxy_async();
-        const uint32_t rem = it < (uint32_t)LAG ? it : (uint32_t)LAG;
-        for (uint32_t j = 0; j < rem; ++j) {
-            mbar_arrive(full_bar(lag_stage));
-            if (++lag_stage == S) lag_stage = 0;
-        }
     } else if (warp == 8) {
         // ===================================== MMA issuer ====================================
         if (lane == 0) {
@@ -260,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 #pragma unroll 1
                 for (int g = 0; g < ngroups; ++g) {
                     mbar_wait(full_bar(stage), phase, 0x300u | stage);
+                    fence_proxy_async();   // producers' cp.async (generic proxy) writes -> visible to the MMA's async-proxy reads
                     tc_fence_after();
                     const int cnt = min(spg, nsteps - g * spg);
                     uint64_t ad = a_desc0 + uint64_t(stage) * a_stage_u;

@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     if (warp >= 4 && warp < 8) {
         // ===================================== producers =====================================
         const int t = threadIdx.x - 128;
-        const int v = t & 63, h = t >> 6;
+        // adjacent lanes take the two 16-byte halves of one voxel row so every 32-byte L2 sector a warp touches is fully used
+        const int h = t & 1, v = t >> 1;
         int stage = 0, phase = 0, lag_stage = 0;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -175,23 +176,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
 #pragma unroll 1
                 for (int nc = h; nc < nchunks_n; nc += 2)
                     cp_async16(b_dst + nc * (kKB * 16u), vv ? usrc + nc * 16 : ubase, vv ? 16u : 0u);
-                cp_async_commit();
-                if (it >= LAG) {
-                    cp_async_wait<LAG>();
-                    fence_proxy_async();
-                    mbar_arrive(full_bar(lag_stage));
-                    if (++lag_stage == S) lag_stage = 0;
-                }
+                cp_async_mbar_arrive(full_bar(stage));   // fires when this thread's copies have landed (see conv_igemm.cu)
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
         cp_async_wait<0>();
-        fence_proxy_async();
-        const uint32_t rem = it < (uint32_t)LAG ? it : (uint32_t)LAG;
-        for (uint32_t j = 0; j < rem; ++j) {
-            mbar_arrive(full_bar(lag_stage));
-            if (++lag_stage == S) lag_stage = 0;
-        }
     } else if (warp == 8) {
         // ===================================== MMA issuer ====================================
         if (lane == 0) {
@@ -217,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
 #pragma unroll 1
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase, 0x700u | stage);
+                    fence_proxy_async();
                     tc_fence_after();
                     const uint64_t ad = a_desc0 + uint64_t(stage) * a_stage_u;
                     const uint64_t bd = b_desc0 + uint64_t(stage) * b_stage_u;

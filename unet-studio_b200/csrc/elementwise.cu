@@ -265,16 +265,23 @@ __global__ void norm_act_bwd_apply_kernel(const BwdApplyArgs a) {
     }
 }
 
-// sums partial rows into totals [2][Cp]; optionally accumulates (scaled) into the gamma/beta gradients
+// sums partial rows into totals [2][Cp]; optionally accumulates into the gamma/beta gradients.  One warp per channel.
 __global__ void finalize_bwd_sums_kernel(const float* __restrict__ partials, int rows, int Cp, int C, float* __restrict__ sums,
                                          float* dgamma, float* dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= Cp) return;
     double a = 0, q = 0;
-    for (int r = 0; r < rows; ++r) {
+    for (int r = lane; r < rows; r += 32) {
         a += partials[size_t(r) * 2 * Cp + c];
         q += partials[size_t(r) * 2 * Cp + Cp + c];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane != 0) return;
     sums[c] = float(a);
     sums[Cp + c] = float(q);
     if (c < C) {
@@ -285,11 +292,14 @@ __global__ void finalize_bwd_sums_kernel(const float* __restrict__ partials, int
 
 // per-channel sum of a [V][Cp] tensor added into out[c] (bias gradients of convs without a norm behind them)
 __global__ void finalize_colsum_kernel(const float* __restrict__ partials, int rows, int Cp, int C, float* out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double a = 0;
-    for (int r = 0; r < rows; ++r) a += partials[size_t(r) * 2 * Cp + c];
-    out[c] += float(a);
+    for (int r = lane; r < rows; r += 32) a += partials[size_t(r) * 2 * Cp + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) out[c] += float(a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -463,7 +473,7 @@ int norm_act_bwd_launch(const void* x, const void* dy, void* dx, long long V, in
         r.has_norm = 1; r.act = act; r.mean = mean; r.rstd = rstd; r.gamma = gamma; r.beta = beta; r.partials = partials;
         int rows = 0;
         if (reduce_launch(1, r, &rows, s)) return 1;
-        finalize_bwd_sums_kernel<<<(Cp + 127) / 128, 128, 0, s>>>(partials, rows, Cp, C, sums, dgamma, dbeta);
+        finalize_bwd_sums_kernel<<<(Cp * 32 + 127) / 128, 128, 0, s>>>(partials, rows, Cp, C, sums, dgamma, dbeta);
         U3D_CUDA_CHECK(cudaGetLastError());
     }
     BwdApplyArgs a{};
@@ -478,7 +488,7 @@ int norm_act_bwd_launch(const void* x, const void* dy, void* dx, long long V, in
 int colsum_accumulate_launch(const void* x, long long V, int C, int Cp, float* partials, float* out, cudaStream_t s) {
     int rows = 0;
     if (channel_stats_launch(x, V, C, Cp, partials, &rows, s)) return 1;
-    finalize_colsum_kernel<<<(C + 127) / 128, 128, 0, s>>>(partials, rows, Cp, C, out);
+    finalize_colsum_kernel<<<(C * 32 + 127) / 128, 128, 0, s>>>(partials, rows, Cp, C, out);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
