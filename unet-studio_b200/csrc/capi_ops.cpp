@@ -208,7 +208,7 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
             wprobs.push_back(W);
         }
         WgradLaunch wc{};
-        OP_CHECK(conv_wgrad_launch(wprobs, wc, nullptr, s));
+        OP_CHECK(conv_wgrad_dispatch(wprobs, wc, s, nullptr));
         OP_CHECK(finish(s));
         OP_CUDA(cudaMemcpy(gw, dgw.p, wcount * 4, cudaMemcpyDeviceToHost));
     }

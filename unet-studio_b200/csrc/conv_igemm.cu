@@ -422,7 +422,9 @@ unsigned int read_device_error() {
     cudaMemcpyFromSymbol(&v, g_dev_error, sizeof(v));
     if (v) return v;
     v = read_device_error_wgrad();
-    return v ? v : read_device_error_halo();
+    if (v) return v;
+    v = read_device_error_halo();
+    return v ? v : read_device_error_rows();
 }
 
 int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, ConvProblem*, cudaStream_t stream) {

@@ -741,9 +741,10 @@ int Model::run_backward() {
             }
             WgradLaunch wc{};
             prof_begin(1, s.flops);
-            M_CHECK(conv_wgrad_launch(s.wg, wc, nullptr, stream));
+            int nl = 0;
+            M_CHECK(conv_wgrad_dispatch(s.wg, wc, stream, &nl));
             prof_end();
-            ++launches;
+            launches += nl;
             const int ins[2] = {s.in0, s.in1};
             for (int src = 0; src < 2; ++src) {
                 if (ins[src] < 0 || !tens[ins[src]].needs_grad) continue;

@@ -114,6 +114,12 @@ int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cu
 bool conv_halo_wants_kc16(int ks, int stride, int transposed, int k_channels_padded, int n_channels_padded, long long voxels);
 unsigned int read_device_error_halo();
 
+bool conv_wgrad_rows_eligible(const WgradProblem& P);
+int conv_wgrad_rows_launch(const WgradProblem& P, cudaStream_t stream);
+// row-stacked halo kernel per eligible problem, generic kernel for the rest; *launches = kernels launched
+int conv_wgrad_dispatch(const std::vector<WgradProblem>& probs, const WgradLaunch& cfg, cudaStream_t stream, int* launches);
+unsigned int read_device_error_rows();
+
 int device_sm_count();
 unsigned int read_device_error();  // first non-zero mbarrier-timeout code of any kernel TU (0 = ok)
 unsigned int read_device_error_wgrad();
