@@ -140,6 +140,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank)
+    # libraries (NCCL's version banner, ...) may write to fd 1: keep stdout clean for the ONE JSON line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     import numpy as np
     import torch
@@ -237,6 +244,8 @@ def main():
     else:
         e2e_ms = e2e_s * 1000.0
     if rank != 0:
+        import torch.distributed as dist
+        dist.destroy_process_group()
         return 0
     pk = peaks()
     value = world * args.steps / (ms / 1000.0)
@@ -264,7 +273,7 @@ def main():
                 "d2h_bytes_per_step": ((IN_C + 1) * vox * 4 if augment else 0) + 15 * 4 + 16},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (forward + data-gradient launches)",
+        "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel + conv_igemm_kernel (all forward and data-gradient conv launches)",
                      "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": (achieved / pk["tf_sustained"]) if achieved else None, "peak_source": pk["which"] + " bf16/fp16 sustained",
                      "traffic": ncu_summary.get("conv_igemm_dram_bytes_per_launch"),
@@ -279,7 +288,10 @@ def main():
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the baseline is reported, never fatal
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
-    print(json.dumps(line))
+    emit(line)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
     return 0
 
 
