@@ -174,6 +174,52 @@ __global__ void __launch_bounds__(256, 1) bench_multi(int n, int iters, int nwar
     if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
+// MN-major operands with the strides of conv_wgrad_rows.cu (LBO 128 B, SBO 544 B), 9 accumulators, runtime accumulate flag
+__global__ void __launch_bounds__(128, 1) bench_mn(int n, int iters, long long* out, int variant) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tptr;
+    const uint32_t sb = smem_u32(smem);
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tptr), 512); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tptr;
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        const uint32_t idesc = (variant >= 2) ? umma_idesc(128, n, 0, 0, 0, 0) : umma_idesc(128, n, 0, 0, 1, 1);
+        long long aoff[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) aoff[k] = (long long)((k / 3 - 1) * 10 * 2) * 34 + (k % 3 - 1);
+        const uint64_t a_base = umma_smem_desc(sb + 32768, 128u, 544u);
+        const uint64_t b_base = umma_smem_desc(sb + 150 * 1024, 128u, 512u);
+        bool first = true;
+        long long t0 = clock64();
+        for (int i = 0; i < iters / 18; ++i) {
+            const uint64_t a_row = a_base + uint64_t(i & 15) * 68u;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const uint64_t ad = a_row + uint64_t(aoff[k]) + uint64_t(ks * 16);
+                    const uint64_t bd = b_base + uint64_t(ks * 16);
+                    if (variant == 0) { if (first) umma_f16_first(tm + k * n, ad, bd, idesc); else umma_f16_acc(tm + k * n, ad, bd, idesc); }
+                    else if (variant == 3) umma_f16_acc(tm + k * n, ad, bd, idesc);
+                    else umma_f16(tm + k * n, ad, bd, idesc, first ? 0u : 1u);
+                }
+                first = false;
+            }
+        }
+        long long t1 = clock64();
+        umma_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0, 0xF00);
+        long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    tc_fence_before(); __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
 int main() {
     long long* d; cudaMalloc(&d, 16);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -195,6 +241,14 @@ int main() {
         long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
         printf("lean N %3d : issue %.1f cyc/mma, complete %.1f cyc/mma (%s)\n", n, double(h[0]) / (27 * 150), double(h[1]) / (27 * 150), cudaGetErrorString(e));
     }
+    cudaFuncSetAttribute(bench_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int n : {16, 32})
+        for (int variant : {1, 2, 3}) {
+            bench_mn<<<1, 128, 200 * 1024>>>(n, 18 * 200, d, variant);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+            printf("mn-major N %3d variant %d : issue %.1f cyc/mma, complete %.1f (%s)\n", n, variant, double(h[0]) / (18 * 200), double(h[1]) / (18 * 200), cudaGetErrorString(e));
+        }
     cudaFuncSetAttribute(bench_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int n : {16, 32})
         for (int nw : {1, 2, 4, 8}) {

@@ -25,7 +25,9 @@
 namespace u3d {
 namespace {
 
-constexpr int kRThreads = 416;   // warps 0-3 epilogue, 4-11 producers, 12 MMA
+constexpr int kRIssuers = 3;     // one MMA-issuing warp per dz plane: a single thread's issue loop (~80-120 clk per MMA, measured)
+                                 // is the bound, the hardware accepts one M=128 MMA per ~39 clk from any mix of warps
+constexpr int kRThreads = 32 * (12 + kRIssuers);   // warps 0-3 epilogue, 4-11 producers, 12.. MMA issuers
 constexpr int kRProducers = 256;
 
 struct RParams {
@@ -53,9 +55,9 @@ __global__ void __launch_bounds__(kRThreads, 1) conv_wgrad_rows_kernel(const __g
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(full_bar(b), kRProducers);
-            mbar_init(empty_bar(b), 1);
+            mbar_init(empty_bar(b), kRIssuers);
         }
-        mbar_init(done_bar, 1);
+        mbar_init(done_bar, kRIssuers);
         fence_barrier_init();
     }
     if (warp == 12) {
@@ -119,18 +121,21 @@ __global__ void __launch_bounds__(kRThreads, 1) conv_wgrad_rows_kernel(const __g
             cp_async_mbar_arrive(full_bar(buf));
         }
         cp_async_wait<0>();
-    } else if (warp == 12) {
-        // ===================================== MMA issuer ====================================
+    } else if (warp >= 12) {
+        // ===================================== MMA issuers ===================================
+        const int wi = warp - 12;   // this warp owns the three accumulators of dz = wi - 1
         if (lane == 0 && has_work) {
             const int n = p.n, ncg = p.ncg, ncgy = p.ncgy;
             const uint32_t idesc = umma_idesc(128, n, 0, 0, 1, 1);          // both operands MN-major
             const uint32_t sbo_a = uint32_t(p.HX) * 16u, sbo_b = uint32_t(p.TX) * 16u;
             // offsets in 16-byte units; acc index = (dz+1)*3 + (dx+1)
-            long long aoff[9];
+            long long aoff[3];
+            uint32_t dacc[3];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const int dz = k / 3 - 1, dx = k % 3 - 1;
+            for (int k = 0; k < 3; ++k) {
+                const int dz = wi - 1, dx = k - 1;
                 aoff[k] = (long long)(dz * p.HY * ncg) * p.HX + dx;
+                dacc[k] = tmem_base + uint32_t((wi * 3 + k) * n);
             }
             const uint64_t a_row_u = uint64_t(ncg) * p.HX;                   // one hy row
             const uint64_t a_plane_u = a_row_u * p.HY;                       // one hz plane
@@ -155,11 +160,10 @@ __global__ void __launch_bounds__(kRThreads, 1) conv_wgrad_rows_kernel(const __g
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-                            for (int k = 0; k < 9; ++k) {
+                            for (int k = 0; k < 3; ++k) {
                                 const uint64_t ad = a_row + uint64_t(aoff[k]) + uint64_t(ks * 16);
                                 const uint64_t bd = b_row + uint64_t(ks * 16);
-                                if (first) umma_f16_first(tmem_base + uint32_t(k * n), ad, bd, idesc);
-                                else umma_f16_acc(tmem_base + uint32_t(k * n), ad, bd, idesc);
+                                umma_f16(dacc[k], ad, bd, idesc, first ? 0u : 1u);
                             }
                             first = false;
                         }
