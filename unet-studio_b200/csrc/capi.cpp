@@ -269,9 +269,9 @@ static int vpa_impl(const char* const* keys, const float* vals, int n_opts, floa
     const size_t V = size_t(w) * h * d;
     float* dimg = image;
     float* dlab = label;
-    float* stage = nullptr;
     if (where == 0) {
-        if (cudaMalloc(&stage, (size_t(channels) + 1) * V * 4) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+        // host buffers: stage through the tail of the persistent workspace (no per-call cudaMalloc / cudaFree)
+        float* stage = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + u3d::vpa_workspace_bytes(w, h, d, channels));
         dimg = stage;
         dlab = stage + size_t(channels) * V;
         cudaMemcpyAsync(dimg, image, size_t(channels) * V * 4, cudaMemcpyHostToDevice, stream);
@@ -284,7 +284,6 @@ static int vpa_impl(const char* const* keys, const float* vals, int n_opts, floa
             cudaMemcpyAsync(label, dlab, V * 4, cudaMemcpyDeviceToHost, stream);
         }
         cudaError_t e = cudaStreamSynchronize(stream);
-        cudaFree(stage);
         if (!rc && e != cudaSuccess) { set_error(std::string("vpa: ") + cudaGetErrorString(e)); rc = 1; }
     }
     return rc;
@@ -296,7 +295,7 @@ int vpa_augment(const char* const* keys, const float* vals, int n_opts, float* i
     if (cudaSetDevice(gpu) != cudaSuccess) { set_error("no CUDA device: vpa_augment has no CPU fallback"); return 1; }
     std::lock_guard<std::mutex> lock(g_vpa_mu);
     VpaWs& W = g_vpa_ws[gpu];
-    const size_t need = u3d::vpa_workspace_bytes(w, h, d, channels);
+    const size_t need = u3d::vpa_workspace_bytes(w, h, d, channels) + (size_t(channels) + 1) * size_t(w) * h * d * 4;
     if (!W.s && cudaStreamCreateWithFlags(&W.s, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return 1; }
     if (W.bytes < need) {
         if (W.p) cudaFree(W.p);
@@ -315,7 +314,7 @@ int unet3d_vpa_augment(unet3d_t* h, const char* const* keys, const float* vals, 
     GUARD_BEGIN NEED(h)
     Model* m = h->m;
     cudaSetDevice(m->device);
-    const size_t need = u3d::vpa_workspace_bytes(w, hgt, d, channels);
+    const size_t need = u3d::vpa_workspace_bytes(w, hgt, d, channels) + (size_t(channels) + 1) * size_t(w) * hgt * d * 4;
     if (m->vpa_ws_bytes < need) {
         cudaStreamSynchronize(m->stream);
         if (m->vpa_ws) cudaFree(m->vpa_ws);
