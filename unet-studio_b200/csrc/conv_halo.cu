@@ -197,77 +197,87 @@ __global__ void __launch_bounds__(kHThreads, 1) conv_halo_kernel(const __grid_co
         __syncwarp();
     } else {
         // ===================================== epilogue ======================================
+        // The epilogue paces the kernel (MMA needs ~1200 clk per M tile), so it is kept minimal: per-thread register partial
+        // sums for the norm statistics (one cross-lane butterfly per CTA at the very end instead of one per M tile), voxel
+        // position advanced incrementally (no div/mod), bias in shared memory.
         const int r = threadIdx.x;
         uint32_t acc_cnt = 0;
+        float ssum[32], ssq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ssum[j] = ssq[j] = 0.f;
+        float* sbias = sstats + 8 * p.n;   // [n] after the statistics rows
+        int bias_prob = -1;
+        const int HX = p.HX, HY = p.HY, TX = p.TX, TY = p.TY, TZ = p.TZ, ncols = p.n;
+        const int step_x = 128 % HX, step_y = (128 / HX) % HY, step_z = (128 / HX) / HY;
+        const bool want_stats = p.stats != nullptr;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int pi = tile / p.tiles_per_prob;
             const ConvProblem& P = p.probs[pi];
+            if (pi != bias_prob) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int j = r; j < ncols; j += 128) sbias[j] = (P.bias != nullptr && j < P.n_real) ? __ldg(P.bias + j) : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                bias_prob = pi;
+            }
             int rem = tile - pi * p.tiles_per_prob;
             const int tx = rem % p.tiles_x; rem /= p.tiles_x;
             const int ty = rem % p.tiles_y;
             const int tz = rem / p.tiles_y;
-            const int x0 = tx * p.TX - 1, y0 = ty * p.TY - 1, z0 = tz * p.TZ - 1;
+            const int x0 = tx * TX - 1, y0 = ty * TY - 1, z0 = tz * TZ - 1;
             const int W = P.in_w, H = P.in_h, D = P.in_d;
+            uint8_t* const dst = static_cast<uint8_t*>(P.dst) + P.dst_coff * 2;
+            const uint32_t dst_pitch = uint32_t(P.dst_cp) * 2u;
+            const bool accum = p.epi == EPI_ACCUM16;
+            // halo coordinates of this thread's row in M tile 0, advanced by 128 positions per M tile
+            int pos0 = p.p_first + r;
+            int hx = pos0 % HX;
+            int q0 = pos0 / HX;
+            int hy = q0 % HY, hz = q0 / HY;
 #pragma unroll 1
             for (int mt = 0; mt < p.mtiles; ++mt, ++acc_cnt) {
-                const int pos = p.p_first + mt * 128 + r;
-                const int hx = pos % p.HX;
-                const int q = pos / p.HX;
-                const int hy = q % p.HY, hz = q / p.HY;
                 const int gx = x0 + hx, gy = y0 + hy, gz = z0 + hz;
-                const bool rv = hx >= 1 && hx <= p.TX && hy >= 1 && hy <= p.TY && hz >= 1 && hz <= p.TZ && gx < W && gy < H && gz < D;
+                const bool rv = hx >= 1 && hx <= TX && hy >= 1 && hy <= TY && hz >= 1 && hz <= TZ && gx < W && gy < H && gz < D;
                 const size_t vox = rv ? (size_t(gz) * H + gy) * W + gx : 0;
+                hx += step_x; hy += step_y; hz += step_z;
+                if (hx >= HX) { hx -= HX; ++hy; }
+                if (hy >= HY) { hy -= HY; ++hz; }
                 const int acc = acc_cnt & 1;
                 mbar_wait(tfull_bar(acc), (acc_cnt >> 1) & 1, 0xC00u | acc);
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(acc * p.n);
-#pragma unroll 1
-                for (int c0 = 0; c0 < p.n; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(t_row + c0, v);
-                    if (P.bias != nullptr) {
+                const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(acc * ncols);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < P.n_real) v[j] += __ldg(P.bias + c0 + j);
-                    }
-                    uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.dst) + (vox * P.dst_cp + P.dst_coff + c0) * 2);
-                    if (p.epi == EPI_ACCUM16 && rv) {
-                        const uint4 o0 = out[0], o1 = out[1];
-                        const uint32_t ow_[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    if (c0 < ncols) {
+                        float v[16];
+                        tmem_ld16(t_row + c0, v);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float2 f = unpack2<false>(ow_[j]);
-                            v[2 * j] += f.x;
-                            v[2 * j + 1] += f.y;
+                        for (int j = 0; j < 16; ++j) v[j] += sbias[c0 + j];
+                        uint4* out = reinterpret_cast<uint4*>(dst + vox * dst_pitch + c0 * 2);
+                        if (accum && rv) {
+                            const uint4 o0 = out[0], o1 = out[1];
+                            const uint32_t ow_[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 f = unpack2<false>(ow_[j]);
+                                v[2 * j] += f.x;
+                                v[2 * j + 1] += f.y;
+                            }
                         }
-                    }
-                    if (rv) {
-                        uint4 q0, q1;
-                        q0.x = pack2<false>(v[0], v[1]); q0.y = pack2<false>(v[2], v[3]);
-                        q0.z = pack2<false>(v[4], v[5]); q0.w = pack2<false>(v[6], v[7]);
-                        q1.x = pack2<false>(v[8], v[9]); q1.y = pack2<false>(v[10], v[11]);
-                        q1.z = pack2<false>(v[12], v[13]); q1.w = pack2<false>(v[14], v[15]);
-                        out[0] = q0;
-                        out[1] = q1;
-                    }
-                    if (p.stats != nullptr) {
-                        float a[16], qq[16];
+                        if (rv) {
+                            uint4 q0v, q1v;
+                            q0v.x = pack2<false>(v[0], v[1]); q0v.y = pack2<false>(v[2], v[3]);
+                            q0v.z = pack2<false>(v[4], v[5]); q0v.w = pack2<false>(v[6], v[7]);
+                            q1v.x = pack2<false>(v[8], v[9]); q1v.y = pack2<false>(v[10], v[11]);
+                            q1v.z = pack2<false>(v[12], v[13]); q1v.w = pack2<false>(v[14], v[15]);
+                            out[0] = q0v;
+                            out[1] = q1v;
+                            if (want_stats) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            a[j] = rv ? v[j] : 0.f;
-                            qq[j] = a[j] * a[j];
-                        }
-                        halve_step_h<8, 16>(a, qq, lane);
-                        halve_step_h<4, 8>(a, qq, lane);
-                        halve_step_h<2, 4>(a, qq, lane);
-                        halve_step_h<1, 2>(a, qq, lane);
-                        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-                        qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
-                        if ((lane & 1) == 0) {
-                            const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                            float* ws = sstats + warp * 2 * p.n;
-                            ws[col] += a[0];
-                            ws[p.n + col] += qq[0];
+                                for (int j = 0; j < 16; ++j) {
+                                    ssum[c0 + j] += v[j];
+                                    ssq[c0 + j] = fmaf(v[j], v[j], ssq[c0 + j]);
+                                }
+                            }
                         }
                     }
                 }
@@ -275,7 +285,28 @@ __global__ void __launch_bounds__(kHThreads, 1) conv_halo_kernel(const __grid_co
                 mbar_arrive(tempty_bar(acc));
             }
         }
-        if (p.stats != nullptr) {
+        if (want_stats) {
+            // one butterfly per CTA: per-thread partials -> per-warp column sums -> fixed-order sum over the 4 warps
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                if (c0 < ncols) {
+                    float a[16], qq[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { a[j] = ssum[c0 + j]; qq[j] = ssq[c0 + j]; }
+                    halve_step_h<8, 16>(a, qq, lane);
+                    halve_step_h<4, 8>(a, qq, lane);
+                    halve_step_h<2, 4>(a, qq, lane);
+                    halve_step_h<1, 2>(a, qq, lane);
+                    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+                    qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
+                    if ((lane & 1) == 0) {
+                        const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        float* ws = sstats + warp * 2 * ncols;
+                        ws[col] = a[0];
+                        ws[ncols + col] = qq[0];
+                    }
+                }
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = r; i < 2 * p.n; i += 128)
                 p.stats[size_t(blockIdx.x) * 2 * p.n + i] = ((sstats[i] + sstats[2 * p.n + i]) + sstats[4 * p.n + i]) + sstats[6 * p.n + i];
@@ -337,10 +368,10 @@ int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
     hp.total_tiles = hp.tiles_per_prob * hp.nprob;
     hp.a_buf_bytes = uint32_t(hp.ncg) * hp.NP_alloc * 16u;
     hp.w_bytes = uint32_t(27) * hp.ksteps * hp.n * 32u;
-    hp.nbuf = (hp.nprob == 1 && size_t(2) * hp.a_buf_bytes + hp.w_bytes + 8 * hp.n * 4 + 1024 <= 220 * 1024) ? 2 : 1;
+    hp.nbuf = (hp.nprob == 1 && size_t(2) * hp.a_buf_bytes + hp.w_bytes + 9 * hp.n * 4 + 1024 <= 220 * 1024) ? 2 : 1;
     hp.off_w = hp.nbuf * hp.a_buf_bytes;
     hp.off_stats = hp.off_w + hp.w_bytes;
-    hp.off_bars = uint32_t((hp.off_stats + 8 * hp.n * 4 + 15) & ~15u);
+    hp.off_bars = uint32_t((hp.off_stats + 9 * hp.n * 4 + 15) & ~15u);
     const size_t smem = hp.off_bars + 8 * 9 + 16;
     if (smem > 227 * 1024) { set_error("conv_halo_launch: tile does not fit in shared memory"); return 1; }
     int cols = 32;
