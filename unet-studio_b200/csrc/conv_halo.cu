@@ -25,7 +25,8 @@
 namespace u3d {
 namespace {
 
-constexpr int kHThreads = 416;
+constexpr int kHIssuers = 2;     // MMA-issuing warps: issuer w owns accumulator w (even / odd M tiles)
+constexpr int kHThreads = 32 * (12 + kHIssuers);
 constexpr int kProducers = 256;
 constexpr int kMaxHaloProb = 2;
 
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv_halo_kernel(const __grid_co
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(full_bar(b), kProducers);
-            mbar_init(empty_bar(b), 1);
+            mbar_init(empty_bar(b), kHIssuers);
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 128);
         }
@@ -148,8 +149,9 @@ __global__ void __launch_bounds__(kHThreads, 1) conv_halo_kernel(const __grid_co
             cp_async_mbar_arrive(full_bar(buf));
         }
         cp_async_wait<0>();
-    } else if (warp == 12) {
-        // ===================================== MMA issuer ====================================
+    } else if (warp >= 12) {
+        // ===================================== MMA issuers ===================================
+        const int wi = warp - 12;
         if (lane == 0) {
             // Lean issue loop (measured with tools/mma_bench.cu: ~45 clk per tcgen05.mma when the only per-MMA work is one
             // 64-bit add per descriptor; ~200-380 clk when descriptors are rebuilt and parameters re-read per MMA).
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv_halo_kernel(const __grid_co
 #pragma unroll 1
                 for (int mt = 0; mt < mtiles; ++mt, ++acc_cnt) {
                     const int acc = acc_cnt & 1;
+                    if (acc != wi) continue;
                     mbar_wait(tempty_bar(acc), ((acc_cnt >> 1) & 1) ^ 1, 0xB00u | acc);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + uint32_t(acc * ncols);
