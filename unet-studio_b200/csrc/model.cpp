@@ -361,14 +361,14 @@ void Model::prof_end() {
     cudaEventRecord(prof_ev[prof_used + 1], stream);
     prof_used += 2;
 }
-int Model::prof_read(double out[6], int reset) {
+int Model::prof_read(double out[12], int reset) {
     cudaSetDevice(device);
     M_CUDA(cudaStreamSynchronize(stream));
-    for (int i = 0; i < 6; ++i) out[i] = 0;
+    for (int i = 0; i < 12; ++i) out[i] = 0;
     for (size_t i = 0; i + 1 < prof_used; i += 2) {
         float ms = 0.f;
         M_CUDA(cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]));
-        const int k = prof_kind[i / 2] ? 3 : 0;
+        const int k = 3 * (prof_kind[i / 2] & 3);
         out[k] += ms;
         out[k + 1] += 1;
         out[k + 2] += prof_flops[i / 2];
@@ -652,7 +652,7 @@ int Model::run_forward(int levels_wanted) {
             int rows = 0;
             cfg.stats_grid_out = &rows;
             if (s.stats) cfg.stats_partials = d_partials;
-            prof_begin(0, s.flops);
+            prof_begin(conv_halo_eligible(s.fprobs, cfg) ? 2 : 0, s.flops);
             M_CHECK(conv_launch(s.fprobs, cfg, stream));
             prof_end();
             ++launches;
@@ -740,7 +740,9 @@ int Model::run_backward() {
                 launches += 2;
             }
             WgradLaunch wc{};
-            prof_begin(1, s.flops);
+            bool all_rows = !s.wg.empty();
+            for (const auto& wp : s.wg) all_rows = all_rows && conv_wgrad_rows_eligible(wp);
+            prof_begin(all_rows ? 3 : 1, s.flops);
             int nl = 0;
             M_CHECK(conv_wgrad_dispatch(s.wg, wc, stream, &nl));
             prof_end();
@@ -751,7 +753,7 @@ int Model::run_backward() {
                 ConvLaunch cfg{};
                 cfg.kc = s.dg[src].kc;
                 cfg.epi = grad_written[ins[src]] ? EPI_ACCUM16 : EPI_STORE16;
-                prof_begin(0, s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
+                prof_begin(conv_halo_eligible(s.dg[src].probs, cfg) ? 2 : 0, s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
                 M_CHECK(conv_launch(s.dg[src].probs, cfg, stream));
                 prof_end();
                 ++launches;

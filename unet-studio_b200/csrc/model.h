@@ -123,7 +123,8 @@ class Model {
     int timer_start();            // CUDA events on this handle's stream
     int timer_stop(float* ms);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // per-launch CUDA-event profile of the tensor-core kernels (bench.py roofline): kind 0 = conv_igemm, 1 = conv_wgrad
+    // per-launch CUDA-event profile of the tensor-core kernels (bench.py roofline):
+    // kind 0 = conv_igemm, 1 = conv_wgrad, 2 = conv_halo, 3 = conv_wgrad_rows
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int> prof_kind;
@@ -131,7 +132,7 @@ class Model {
     size_t prof_used = 0;
     void prof_begin(int kind, double flops);
     void prof_end();
-    int prof_read(double out[6], int reset);   // {conv ms, launches, flops, wgrad ms, launches, flops}
+    int prof_read(double out[12], int reset);  // per kind: {ms, launches, algorithmic FLOPs}
     int n_levels() const { return int(output.size()); }
 
   private:
