@@ -34,6 +34,8 @@ CASES = [
     ("halo_32_32", 0, 3, 1, 32, 0, 32, (36, 40, 24)),
     ("halo_1_16", 0, 3, 1, 1, 0, 16, (48, 32, 24)),
     ("halo_cat16_16_to32", 0, 3, 1, 12, 9, 24, (33, 35, 30)),
+    ("halo_cat32_32_k64", 0, 3, 1, 32, 32, 32, (40, 28, 30)),
+    ("halo_64_16_k64", 0, 3, 1, 64, 0, 16, (34, 33, 31)),
 ]
 
 

@@ -328,7 +328,7 @@ unsigned int read_device_error_halo() {
     return v;
 }
 
-// Eligibility: k3 s1 p1 problems (same extent in and out), K <= 32 channels in 16-wide chunks, one N tile of <= 32,
+// Eligibility: k3 s1 p1 problems (same extent in and out), K = 16 | 32 | 64 channels in 16-wide chunks, one N tile of <= 32,
 // 16-bit NDHWC epilogues.  The caller packs the weights with kc = 16 (chunk order = [tap][k16]).
 bool conv_halo_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg) {
     static const bool disabled = std::getenv("U3D_NO_HALO") != nullptr;
@@ -337,7 +337,8 @@ bool conv_halo_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch&
     for (const auto& P : probs) {
         if (P.ntaps != 27 || P.istride != 1 || P.ostep != 1 || P.ntiles != 1 || P.ntile > 32) return false;
         if (P.od != P.in_d || P.oh != P.in_h || P.ow != P.in_w) return false;
-        if (P.c0p + P.c1p > 32 || (P.nch0 + P.nch1) * 16 != P.c0p + P.c1p || P.coff0 || P.coff1) return false;
+        if ((P.c0p + P.c1p) != 16 && (P.c0p + P.c1p) != 32 && (P.c0p + P.c1p) != 64) return false;
+        if ((P.nch0 + P.nch1) * 16 != P.c0p + P.c1p || P.coff0 || P.coff1) return false;
         if (P.ntile != probs[0].ntile || P.c0p + P.c1p != probs[0].c0p + probs[0].c1p) return false;
         if (P.in_d != probs[0].in_d || P.in_h != probs[0].in_h || P.in_w != probs[0].in_w) return false;
         if (1LL * P.in_d * P.in_h * P.in_w < 32768) return false;
@@ -352,7 +353,9 @@ int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
     hp.nprob = int(probs.size());
     for (int i = 0; i < hp.nprob; ++i) hp.probs[i] = probs[i];
     const ConvProblem& P0 = probs[0];
-    hp.TX = 32; hp.TY = 8; hp.TZ = 4;
+    // tile: 32x8x4 outputs for K <= 32 channels; K = 64 needs a smaller block to fit next to the 110 KB of resident weights
+    const int ktot = P0.c0p + P0.c1p;
+    hp.TX = 32; hp.TY = ktot <= 32 ? 8 : 4; hp.TZ = ktot <= 32 ? 4 : 2;
     hp.HX = hp.TX + 2; hp.HY = hp.TY + 2; hp.HZ = hp.TZ + 2;
     hp.NP = hp.HX * hp.HY * hp.HZ;
     hp.p_first = (hp.HY + 1) * hp.HX + 1;
@@ -386,12 +389,14 @@ int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
     if (!attr_set) {
         U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int grid = std::max(1, std::min(hp.total_tiles, device_sm_count()));
     if (cfg.stats_grid_out) *cfg.stats_grid_out = grid;
     if (hp.ksteps == 1) conv_halo_kernel<1><<<grid, kHThreads, smem, stream>>>(hp);
-    else conv_halo_kernel<2><<<grid, kHThreads, smem, stream>>>(hp);
+    else if (hp.ksteps == 2) conv_halo_kernel<2><<<grid, kHThreads, smem, stream>>>(hp);
+    else conv_halo_kernel<4><<<grid, kHThreads, smem, stream>>>(hp);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -405,7 +410,8 @@ int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cu
 // Planner hint: a k3 s1 layer with K <= 32 and N <= 32 channels on a big volume is planned with 16-wide K chunks so that
 // conv_halo_eligible() accepts it.
 bool conv_halo_wants_kc16(int ks, int stride, int transposed, int k_channels_padded, int n_channels_padded, long long voxels) {
-    return !transposed && ks == 3 && stride == 1 && k_channels_padded <= 32 && n_channels_padded <= 32 && voxels >= 32768 &&
+    return !transposed && ks == 3 && stride == 1 && (k_channels_padded == 16 || k_channels_padded == 32 || k_channels_padded == 64) &&
+           n_channels_padded <= 32 && voxels >= 32768 &&
            std::getenv("U3D_NO_HALO") == nullptr;
 }
 
