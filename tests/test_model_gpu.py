@@ -206,3 +206,33 @@ def test_maxpool_indices_bit_exact():
     y, idx = m.maxpool_forward(x.numpy())
     assert np.array_equal(idx, i_ref[0].cpu().numpy())
     np.testing.assert_array_equal(y, y_ref[0].cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["f1_train", "f1_collapse"])
+def test_gradients_match_fp16_emulating_oracle_tightly(name):
+    """Separates implementation correctness from precision: against the oracle evaluated with the SAME fp16 storage points
+    (oracle.Fp16Emulation) the GPU gradients agree ~10x tighter than against the pure-fp32 reference, for every tensor."""
+    m = load()
+    z, meta = golden(name)
+    net = build_from_golden(m, z, meta)
+    net.train(True)
+    net.create_optimizer(meta["lr"])
+    x, lab = z["input"][0:1], z["label"][0:1]
+    net.train_microbatch(x, lab, meta["collapse"], meta["ce"], meta["dice"], meta["mse"])
+    n = net.param_count()
+    onet = O.parse_feature(meta["in_c"], meta["out_c"], str(z["feature"]))
+    P = [torch.from_numpy(z[f"param_{i:03d}"].copy()).requires_grad_(True) for i in range(n)]
+    total, _, _ = O.micro_batch_loss(onet, P, torch.from_numpy(x.copy()), torch.from_numpy(lab.copy()).long(), meta["ce"], meta["dice"],
+                                     meta["mse"], meta["collapse"], emu=O.Fp16Emulation(net.loss_scale()))
+    total.backward()
+    num = den = 0.0
+    worst = 0.0
+    for i in range(n):
+        g = net.get_grad(i)
+        gr = P[i].grad.numpy() if P[i].grad is not None else np.zeros_like(g)
+        num += float(((g - gr).astype(np.float64) ** 2).sum()); den += float((gr.astype(np.float64) ** 2).sum())
+        if np.linalg.norm(gr) > 1e-3 and not onet.param_names[i].endswith(".bias"):
+            worst = max(worst, rel(g, gr))
+    print(name, "vs fp16-emulating oracle: global grad rel err", np.sqrt(num / den), "worst weight tensor", worst)
+    assert np.sqrt(num / den) < 5e-3, np.sqrt(num / den)
+    assert worst < 2e-2, worst
