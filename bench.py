@@ -243,6 +243,35 @@ def main():
         ms, e2e_ms = float(t[0]), float(t[1])
     else:
         e2e_ms = e2e_s * 1000.0
+    # ---------------- inference (BASELINE configs[0]/[4] building block): forward()[0] of one 160x192x160 window per GPU ----------------
+    train_loss_scale = net.loss_scale()
+    del net
+    inf = pkg.UNet3d(IN_C, 1, None, gpu=local_rank)       # skull-strip 1 in / 1 out (cfg 1)
+    inf.init_params(0)
+    inf.set_dim(W, H, D)
+    inf.prepare_for_inference()
+    y_dev = torch.empty(1, 1, D, H, W, device="cuda")
+    y_host = torch.empty(1, 1, D, H, W).pin_memory()
+    for _ in range(3):
+        inf.device_forward(x_dev.data_ptr(), [y_dev.data_ptr()])
+    inf.sync()
+    n_inf = max(args.steps, 5)
+    barrier()
+    inf.timer_start()
+    for _ in range(n_inf):
+        inf.device_forward(x_dev.data_ptr(), [y_dev.data_ptr()])
+    inf_ms = inf.timer_stop()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_inf):                                   # evaluate.cpp:226-229: H2D, forward()[0], D2H
+        inf.forward(x_host.numpy(), n_levels=1, out=[y_host.numpy()])
+    inf_e2e_ms = (time.perf_counter() - t0) * 1000.0
+    barrier()
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([inf_ms, inf_e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        inf_ms, inf_e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -272,11 +301,16 @@ def main():
                    "grid": [W, H, D], "in_count": IN_C, "out_count": OUT_C, "micro_batches_per_gpu_per_step": 1,
                    "global_batch": world, "parallelism": f"dp{world}", "augmentation": bool(augment),
                    "l2": "no explicit flush: each step streams > 3 GB of activations, far above the 126 MB L2",
-                   "arithmetic": "fp16 operands, fp32 accumulate (tcgen05), fp32 stats/loss/optimizer, loss scale %g" % net.loss_scale()},
+                   "arithmetic": "fp16 operands, fp32 accumulate (tcgen05), fp32 stats/loss/optimizer, loss scale %g" % train_loss_scale},
         "loss": [float(v) for v in loss],
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (2 if augment else 1) * (IN_C + 1) * vox * 4,
                 "d2h_bytes_per_step": ((IN_C + 1) * vox * 4 if augment else 0) + 15 * 4 + 16},
         "gpu_launches": int(launches),
+        "inference": {"workload": f"cfg1: UNet3d({IN_C},1,default) forward()[0] of one {W}x{H}x{D} window per GPU (windows sharded, no collective)",
+                      "value": world * n_inf * (W * H * D) / 1e6 / (inf_ms / 1e3), "unit": "Mvoxel/s",
+                      "ms_per_window": inf_ms / n_inf,
+                      "e2e": {"value": world * n_inf * (W * H * D) / 1e6 / (inf_e2e_ms / 1e3), "unit": "Mvoxel/s",
+                              "h2d_bytes_per_window": IN_C * W * H * D * 4, "d2h_bytes_per_window": W * H * D * 4}},
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": dom + " (the tensor-core kernel family with the largest share of the step)",
                      "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",

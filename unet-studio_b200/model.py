@@ -128,7 +128,7 @@ class UNet3d:
         w, h, d = self.dim
         return (1, self.out_count, d >> k, h >> k, w >> k)
 
-    def forward(self, x, n_levels=None):
+    def forward(self, x, n_levels=None, out=None):
         """x: [1,in,D,H,W] fp32 -> list of logits (results[k] of unet.cpp:168-193)."""
         from . import check
         x = np.ascontiguousarray(x, np.float32)
@@ -137,7 +137,7 @@ class UNet3d:
         if (w, h, d) != self.dim:
             self.set_dim(w, h, d)
         n = self.levels if n_levels is None else n_levels
-        outs = [np.empty(self._level_shape(k), np.float32) for k in range(n)]
+        outs = out if out is not None else [np.empty(self._level_shape(k), np.float32) for k in range(n)]
         ptrs = (_F * n)(*[_fp(o) for o in outs])
         check(self._lib.unet3d_forward(self._h, _fp(x), ptrs, n, 0))
         return outs
