@@ -245,8 +245,8 @@ int unet3d_profile(unet3d_t* h, int enable) {
     return 0;
     GUARD_END
 }
-int unet3d_profile_read(unet3d_t* h, double out12[12], int reset) {
-    GUARD_BEGIN NEED(h) return h->m->prof_read(out12, reset);
+int unet3d_profile_read(unet3d_t* h, double out18[18], int reset) {
+    GUARD_BEGIN NEED(h) return h->m->prof_read(out18, reset);
     GUARD_END
 }
 

@@ -404,7 +404,13 @@ int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
 // Single entry point used by the model and the op-level API: halo kernel when the problem set qualifies, gather kernel otherwise.
 int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream) {
     if (conv_halo_eligible(probs, cfg)) return conv_halo_launch(probs, cfg, stream);
+    if (conv_tma_eligible(probs, cfg)) return conv_tma_launch(probs, cfg, stream);
     return conv_igemm_launch(probs, cfg, nullptr, stream);
+}
+
+int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg) {
+    if (conv_halo_eligible(probs, cfg)) return 2;
+    return conv_tma_eligible(probs, cfg) ? 4 : 0;
 }
 
 // Planner hint: a k3 s1 layer with K <= 32 and N <= 32 channels on a big volume is planned with 16-wide K chunks so that

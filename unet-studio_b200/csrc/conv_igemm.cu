@@ -424,6 +424,8 @@ unsigned int read_device_error() {
     v = read_device_error_wgrad();
     if (v) return v;
     v = read_device_error_halo();
+    if (v) return v;
+    v = read_device_error_tma();
     return v ? v : read_device_error_rows();
 }
 

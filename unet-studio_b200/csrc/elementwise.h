@@ -46,6 +46,23 @@ struct LossLevel {
 };
 int loss_level_launch(const LossLevel& L, cudaStream_t s);
 
+// 1x1 output head (Conv3d k1 of the `output` token, unet.cpp:186-187) on CUDA cores for head inputs of <= 32 channels:
+// these levels are bandwidth-bound (2*C*xc FLOP per 32..64 bytes), so the tensor path only adds launches and round trips.
+struct HeadFuse {
+    const void* x;         // head input activations, fp16 NDHWC [v][xcp]
+    int xc, xcp;
+    const float* w;        // [C][xc] fp32 master weights (reference [C,xc,1,1,1])
+    void* dx;              // gradient wrt x, fp16 [v][xcp] (x loss_scale)
+    int dx_accum;          // 0 = store, 1 = read-add-store
+    float* dw;             // [C][xc] fp32 gradient, accumulated atomically (x loss_scale)
+    float* db;             // [C]
+};
+bool head_fwd_supported(int C, int xcp);
+bool head_bwd_supported(int C, int xcp);
+int head_fwd_launch(const void* x, int xc, int xcp, const float* w, const float* b, float* logits, int C, long long nv, cudaStream_t s);
+// loss of one level with the gradient pushed straight through the head (no dlogits tensor); Hd == nullptr = plain loss
+int loss_level_launch(const LossLevel& L, const HeadFuse* Hd, cudaStream_t s);
+
 // ---- optimizer (optim.cu): grad/batch, clip_grad_norm_(12), Nesterov SGD (train.cpp:759-766, unet.cpp:246-277) ----
 struct SgdChunk {
     long long offset;

@@ -149,6 +149,62 @@ __global__ void loss_finalize_kernel(const LossLevel L) {
     L.out3[2] = float(L.acc[2] / n);
 }
 
+// dL/dlogit (x loss_scale) for the ORIGINAL output channels j < L.C of one voxel (un-collapsed), from the softmax `o`
+// and the global Dice sums.  Shared by the stand-alone gradient kernel and the head-fused one.
+template <int MAXC>
+__device__ __forceinline__ void voxel_grad(const LossLevel& L, const Voxel<MAXC>& o, const float* sI, const float* sK, float inv_n,
+                                           float invZ, float (&dlo)[MAXC]) {
+    const int cb = L.collapse_before;
+    const int Cc = cb ? L.C - cb + 1 : L.C;
+    const float eps = 1e-5f;
+    float g[MAXC];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        g[c] = 0.f;
+        if (c < Cc) {
+            const float s = o.s[c];
+            const float p = clampp(s);
+            const float hit = (c == o.t) ? 1.f : 0.f;
+            float G = L.w_mse * o.v * (2.f * p - 2.f * hit) * inv_n;
+            if (c >= 1) {
+                const float den = sK[c] + eps;
+                G -= L.w_dice * invZ * o.v * (2.f * hit * den - (2.f * sI[c] + eps)) / (den * den);
+            }
+            const bool pass = s >= 1e-6f && s <= 1.0f - 1e-6f;  // clamp passes gradient on the closed interval
+            g[c] = pass ? G : 0.f;
+            dot += g[c] * s;
+        }
+    }
+    float dl[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        dl[c] = 0.f;
+        if (c < Cc) {
+            const float hit = (c == o.t) ? 1.f : 0.f;
+            dl[c] = (o.s[c] * (g[c] - dot) + L.w_ce * o.v * (o.s[c] - hit) * inv_n) * L.loss_scale;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+        float v = 0.f;
+        if (j < L.C) {
+            if (cb) {
+                if (j < cb) {
+                    v = dl[0] * o.wi[j];
+                } else {
+#pragma unroll
+                    for (int c = 1; c < MAXC; ++c)
+                        if (c == j - cb + 1) v = dl[c];
+                }
+            } else {
+                v = dl[j];
+            }
+        }
+        dlo[j] = v;
+    }
+}
+
 template <int MAXC>
 __global__ void loss_grad_kernel(const LossLevel L) {
     const long long nv = (long long)L.d * L.h * L.w;
@@ -163,7 +219,6 @@ __global__ void loss_grad_kernel(const LossLevel L) {
     if (threadIdx.x == 0) s_n = float(L.acc[1] > 1.0 ? L.acc[1] : 1.0);
     __syncthreads();
     const float inv_n = 1.f / s_n;
-    const float eps = 1e-5f;
     const float invZ = 1.f / float(Cc - 1 > 1 ? Cc - 1 : 1);
     __half* out = static_cast<__half*>(L.dlogits);
     for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < nv; vox += (long long)gridDim.x * blockDim.x) {
@@ -172,65 +227,185 @@ __global__ void loss_grad_kernel(const LossLevel L) {
         const int y = int(q % L.h), z = int(q / L.h);
         Voxel<MAXC> o;
         eval_voxel<MAXC>(L, vox, x, y, z, o);
-        float g[MAXC];
-        float dot = 0.f;
+        float dlo[MAXC];
+        voxel_grad<MAXC>(L, o, sI, sK, inv_n, invZ, dlo);
+        // 8 channels = one 16-byte store (adjacent threads = adjacent voxels)
+        uint4* row = reinterpret_cast<uint4*>(out + vox * L.Cp);
+        for (int j0 = 0; j0 < L.Cp; j0 += 8) {
+            float val[8];
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-            g[c] = 0.f;
-            if (c < Cc) {
-                const float s = o.s[c];
-                const float p = clampp(s);
-                const float hit = (c == o.t) ? 1.f : 0.f;
-                float G = L.w_mse * o.v * (2.f * p - 2.f * hit) * inv_n;
-                if (c >= 1) {
-                    const float den = sK[c] + eps;
-                    G -= L.w_dice * invZ * o.v * (2.f * hit * den - (2.f * sI[c] + eps)) / (den * den);
-                }
-                const bool pass = s >= 1e-6f && s <= 1.0f - 1e-6f;  // clamp passes gradient on the closed interval
-                g[c] = pass ? G : 0.f;
-                dot += g[c] * s;
+            for (int jj = 0; jj < 8; ++jj) {
+                float v = 0.f;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c == j0 + jj) v = dlo[c];
+                val[jj] = v;
             }
-        }
-        float dl[MAXC];
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-            dl[c] = 0.f;
-            if (c < Cc) {
-                const float hit = (c == o.t) ? 1.f : 0.f;
-                dl[c] = (o.s[c] * (g[c] - dot) + L.w_ce * o.v * (o.s[c] - hit) * inv_n) * L.loss_scale;
-            }
-        }
-        // un-collapse and store: original channel j
-        __half* row = out + vox * L.Cp;
-        for (int j = 0; j < L.Cp; ++j) {
-            float val = 0.f;
-            if (j < L.C) {
-                if (cb) {
-                    if (j < cb) {
-                        float wj = 0.f;
-#pragma unroll
-                        for (int c = 0; c < MAXC; ++c)
-                            if (c == j) wj = o.wi[c];
-                        val = dl[0] * wj;
-                    } else {
-#pragma unroll
-                        for (int c = 1; c < MAXC; ++c)
-                            if (c == j - cb + 1) val = dl[c];
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < MAXC; ++c)
-                        if (c == j) val = dl[c];
-                }
-            }
-            row[j] = __float2half_rn(val);
+            uint4 qv;
+            qv.x = pack2<false>(val[0], val[1]); qv.y = pack2<false>(val[2], val[3]);
+            qv.z = pack2<false>(val[4], val[5]); qv.w = pack2<false>(val[6], val[7]);
+            row[j0 / 8] = qv;
         }
     }
 }
 
+// ---- 1x1 output head fused with the loss gradient (levels whose head input has <= 32 channels: bandwidth-bound) ----
+// forward: logits[c][v] = b[c] + sum_k W[c][k] x[v][k]            (unet.cpp:186-187, Conv3d k1 of the output token)
+template <int XCP>
+__global__ void head_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                float* __restrict__ logits, int C, int xc, long long nv) {
+    __shared__ float sw[kMaxC * XCP];
+    __shared__ float sb[kMaxC];
+    for (int i = threadIdx.x; i < C * XCP; i += blockDim.x) {
+        const int c = i / XCP, k = i % XCP;
+        sw[i] = k < xc ? w[c * xc + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sb[i] = b[i];
+    __syncthreads();
+    for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < nv; vox += (long long)gridDim.x * blockDim.x) {
+        float xv[XCP];
+#pragma unroll
+        for (int g = 0; g < XCP / 8; ++g) {
+            const uint4 q = x[vox * (XCP / 8) + g];
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2<false>(u[j]);
+                xv[g * 8 + 2 * j] = f.x;
+                xv[g * 8 + 2 * j + 1] = f.y;
+            }
+        }
+        for (int c = 0; c < C; ++c) {
+            float acc = sb[c];
+#pragma unroll
+            for (int k = 0; k < XCP; ++k) acc = fmaf(sw[c * XCP + k], xv[k], acc);
+            logits[c * nv + vox] = acc;
+        }
+    }
+}
+
+// backward: dlogits stay in registers; dx[v][k] = sum_c dl[c] W[c][k] (fp16, store or accumulate), dW[c][k] += dl[c] x[v][k],
+// db[c] += dl[c].  Replaces loss_grad + the head's dgrad / wgrad / bias-gradient launches and the dlogits round trip.
+template <int CT, int XCP>
+__global__ void __launch_bounds__(128) loss_grad_head_kernel(const LossLevel L, const HeadFuse Hd) {
+    const long long nv = (long long)L.d * L.h * L.w;
+    const int cb = L.collapse_before;
+    const int Cc = cb ? L.C - cb + 1 : L.C;
+    __shared__ float sI[CT], sK[CT];
+    __shared__ float s_n;
+    __shared__ float sw[CT * XCP];
+    __shared__ float sacc[CT * XCP + CT];
+    for (int i = threadIdx.x; i < CT * XCP; i += blockDim.x) {
+        const int c = i / XCP, k = i % XCP;
+        sw[i] = (c < L.C && k < Hd.xc) ? Hd.w[c * Hd.xc + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < CT * XCP + CT; i += blockDim.x) sacc[i] = 0.f;
+    if (threadIdx.x < CT) {
+        sI[threadIdx.x] = threadIdx.x < Cc ? float(L.acc[3 + 2 * threadIdx.x]) : 0.f;
+        sK[threadIdx.x] = threadIdx.x < Cc ? float(L.acc[4 + 2 * threadIdx.x]) : 0.f;
+    }
+    if (threadIdx.x == 0) s_n = float(L.acc[1] > 1.0 ? L.acc[1] : 1.0);
+    __syncthreads();
+    const float inv_n = 1.f / s_n;
+    const float invZ = 1.f / float(Cc - 1 > 1 ? Cc - 1 : 1);
+    const uint4* xin = static_cast<const uint4*>(Hd.x);
+    uint4* dxo = static_cast<uint4*>(Hd.dx);
+    float aw[CT][XCP], ab[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        ab[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < XCP; ++k) aw[c][k] = 0.f;
+    }
+    for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < nv; vox += (long long)gridDim.x * blockDim.x) {
+        const int x = int(vox % L.w);
+        const long long q = vox / L.w;
+        const int y = int(q % L.h), z = int(q / L.h);
+        Voxel<CT> o;
+        eval_voxel<CT>(L, vox, x, y, z, o);
+        float dlo[CT];
+        voxel_grad<CT>(L, o, sI, sK, inv_n, invZ, dlo);
+#pragma unroll
+        for (int g = 0; g < XCP / 8; ++g) {
+            const uint4 qx = xin[vox * (XCP / 8) + g];
+            const uint32_t u[4] = {qx.x, qx.y, qx.z, qx.w};
+            float xv[8], dv[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2<false>(u[j]);
+                xv[2 * j] = f.x;
+                xv[2 * j + 1] = f.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dv[k] = 0.f;
+            if (Hd.dx_accum) {
+                const uint4 qd = dxo[vox * (XCP / 8) + g];
+                const uint32_t ud[4] = {qd.x, qd.y, qd.z, qd.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack2<false>(ud[j]);
+                    dv[2 * j] = f.x;
+                    dv[2 * j + 1] = f.y;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    dv[k] = fmaf(dlo[c], sw[c * XCP + g * 8 + k], dv[k]);
+                    aw[c][g * 8 + k] = fmaf(dlo[c], xv[k], aw[c][g * 8 + k]);
+                }
+            }
+            uint4 qo;
+            qo.x = pack2<false>(dv[0], dv[1]); qo.y = pack2<false>(dv[2], dv[3]);
+            qo.z = pack2<false>(dv[4], dv[5]); qo.w = pack2<false>(dv[6], dv[7]);
+            dxo[vox * (XCP / 8) + g] = qo;
+        }
+#pragma unroll
+        for (int c = 0; c < CT; ++c) ab[c] += dlo[c];
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+#pragma unroll
+        for (int k = 0; k < XCP; ++k) {
+            const float v = warp_sum(aw[c][k]);
+            if (lane == 0) atomicAdd(&sacc[c * XCP + k], v);
+        }
+        const float vb = warp_sum(ab[c]);
+        if (lane == 0) atomicAdd(&sacc[CT * XCP + c], vb);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CT * XCP; i += blockDim.x) {
+        const int c = i / XCP, k = i % XCP;
+        if (c < L.C && k < Hd.xc) atomicAdd(Hd.dw + c * Hd.xc + k, sacc[i]);
+    }
+    for (int i = threadIdx.x; i < CT; i += blockDim.x)
+        if (i < L.C) atomicAdd(Hd.db + i, sacc[CT * XCP + i]);
+}
+
 }  // namespace
 
-int loss_level_launch(const LossLevel& L, cudaStream_t s) {
+bool head_fwd_supported(int C, int xcp) { return C >= 1 && C <= kMaxC && (xcp == 16 || xcp == 32); }
+bool head_bwd_supported(int C, int xcp) {
+    if (xcp != 16 && xcp != 32) return false;
+    const int ct = C <= 2 ? 2 : C <= 4 ? 4 : 8;
+    return C <= 8 && ct * xcp <= 128;
+}
+
+int head_fwd_launch(const void* x, int xc, int xcp, const float* w, const float* b, float* logits, int C, long long nv, cudaStream_t s) {
+    if (!head_fwd_supported(C, xcp)) { set_error("head_fwd_launch: unsupported shape"); return 1; }
+    long long g = (nv + 255) / 256;
+    const int grid = int(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+    if (xcp == 16) head_fwd_kernel<16><<<grid, 256, 0, s>>>(static_cast<const uint4*>(x), w, b, logits, C, xc, nv);
+    else head_fwd_kernel<32><<<grid, 256, 0, s>>>(static_cast<const uint4*>(x), w, b, logits, C, xc, nv);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int loss_level_launch(const LossLevel& L, cudaStream_t s) { return loss_level_launch(L, nullptr, s); }
+
+int loss_level_launch(const LossLevel& L, const HeadFuse* Hd, cudaStream_t s) {
     if (L.C > kMaxC || L.C < 1) {
         set_error("loss head supports 1..32 output channels");
         return 1;
@@ -246,7 +421,17 @@ int loss_level_launch(const LossLevel& L, cudaStream_t s) {
     if (L.C <= 8) loss_reduce_kernel<8><<<grid, 256, 0, s>>>(L);
     else loss_reduce_kernel<kMaxC><<<grid, 256, 0, s>>>(L);
     loss_finalize_kernel<<<1, 32, 0, s>>>(L);
-    if (L.dlogits != nullptr) {
+    if (Hd != nullptr) {
+        if (!head_bwd_supported(L.C, Hd->xcp)) { set_error("loss_level_launch: unsupported fused head shape"); return 1; }
+        long long gh = (nv + 127) / 128;
+        const int gridh = int(gh < 1 ? 1 : (gh > 148 * 8 ? 148 * 8 : gh));
+        const int ct = L.C <= 2 ? 2 : L.C <= 4 ? 4 : 8;
+        if (ct == 2 && Hd->xcp == 16) loss_grad_head_kernel<2, 16><<<gridh, 128, 0, s>>>(L, *Hd);
+        else if (ct == 2) loss_grad_head_kernel<2, 32><<<gridh, 128, 0, s>>>(L, *Hd);
+        else if (ct == 4 && Hd->xcp == 16) loss_grad_head_kernel<4, 16><<<gridh, 128, 0, s>>>(L, *Hd);
+        else if (ct == 4) loss_grad_head_kernel<4, 32><<<gridh, 128, 0, s>>>(L, *Hd);
+        else loss_grad_head_kernel<8, 16><<<gridh, 128, 0, s>>>(L, *Hd);
+    } else if (L.dlogits != nullptr) {
         if (L.C <= 8) loss_grad_kernel<8><<<grid, 256, 0, s>>>(L);
         else loss_grad_kernel<kMaxC><<<grid, 256, 0, s>>>(L);
     }

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <sstream>
@@ -361,14 +362,14 @@ void Model::prof_end() {
     cudaEventRecord(prof_ev[prof_used + 1], stream);
     prof_used += 2;
 }
-int Model::prof_read(double out[12], int reset) {
+int Model::prof_read(double out[18], int reset) {
     cudaSetDevice(device);
     M_CUDA(cudaStreamSynchronize(stream));
-    for (int i = 0; i < 12; ++i) out[i] = 0;
+    for (int i = 0; i < 18; ++i) out[i] = 0;
     for (size_t i = 0; i + 1 < prof_used; i += 2) {
         float ms = 0.f;
         M_CUDA(cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]));
-        const int k = 3 * (prof_kind[i / 2] & 3);
+        const int k = 3 * std::min(prof_kind[i / 2], 5);
         out[k] += ms;
         out[k + 1] += 1;
         out[k + 2] += prof_flops[i / 2];
@@ -549,6 +550,17 @@ int Model::ensure_plan() {
         M_CHECK(alloc(reinterpret_cast<void**>(&logits[l]), size_t(out_count) * v * 4));
         if (tr) M_CHECK(alloc(&dlogits[l], size_t(ocp) * v * 2));
     }
+    head_step.assign(L, -1);
+    for (size_t si = 0; si < steps.size(); ++si) {
+        Step& s = steps[si];
+        if (s.kind == Step::CONV && s.head_level >= 0) {
+            head_step[s.head_level] = int(si);
+            static const bool nofuse = std::getenv("U3D_NO_HEAD_FUSE") != nullptr;
+            const int xcp = tens[s.in0].Cp;
+            s.head_fwd_fused = !nofuse && s.g.ks == 1 && s.in1 < 0 && !s.g.transposed && head_fwd_supported(s.g.cout, xcp);
+            s.head_bwd_fused = s.head_fwd_fused && tr && tens[s.in0].needs_grad && head_bwd_supported(s.g.cout, xcp);
+        }
+    }
     for (auto& s : steps) {
         if (s.kind == Step::CONV) {
             {
@@ -646,13 +658,19 @@ int Model::run_forward(int levels_wanted) {
     for (auto& s : steps) {
         if (s.kind == Step::CONV) {
             if (s.head_level >= levels_wanted) continue;
+            if (s.head_fwd_fused) {
+                const Ten& a = tens[s.in0];
+                M_CHECK(head_fwd_launch(a.p, a.C, a.Cp, param_ptr(s.p_w), param_ptr(s.p_b), logits[s.head_level], s.g.cout, a.V(), stream));
+                ++launches;
+                continue;
+            }
             ConvLaunch cfg{};
             cfg.kc = s.fkc;
             cfg.epi = s.head_level >= 0 ? EPI_PLANAR32 : EPI_STORE16;
             int rows = 0;
             cfg.stats_grid_out = &rows;
             if (s.stats) cfg.stats_partials = d_partials;
-            prof_begin(conv_halo_eligible(s.fprobs, cfg) ? 2 : 0, s.flops);
+            prof_begin(conv_kernel_kind(s.fprobs, cfg), s.flops);
             M_CHECK(conv_launch(s.fprobs, cfg, stream));
             prof_end();
             ++launches;
@@ -727,8 +745,12 @@ int Model::forward(const float* in, float* const* out_levels, int n_levels_wante
 // ------------------------------------------------------------------------------------------------
 int Model::run_backward() {
     std::fill(grad_written.begin(), grad_written.end(), 0);
+    // fused heads: the loss-gradient kernel (launched before this function) already stored dL/dx of the head input
+    for (const Step& s : steps)
+        if (s.kind == Step::CONV && s.head_bwd_fused) grad_written[s.in0] = 1;
     for (int si = int(steps.size()) - 1; si >= 0; --si) {
         Step& s = steps[si];
+        if (s.kind == Step::CONV && s.head_bwd_fused) continue;
         if (s.kind == Step::CONV) {
             const bool head = s.head_level >= 0;
             if (!head && !grad_written[s.out]) continue;  // output never used downstream
@@ -753,7 +775,7 @@ int Model::run_backward() {
                 ConvLaunch cfg{};
                 cfg.kc = s.dg[src].kc;
                 cfg.epi = grad_written[ins[src]] ? EPI_ACCUM16 : EPI_STORE16;
-                prof_begin(conv_halo_eligible(s.dg[src].probs, cfg) ? 2 : 0, s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
+                prof_begin(conv_kernel_kind(s.dg[src].probs, cfg), s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
                 M_CHECK(conv_launch(s.dg[src].probs, cfg, stream));
                 prof_end();
                 ++launches;
@@ -830,7 +852,17 @@ int Model::train_microbatch(const float* in, const float* label, int collapse_be
         Q.loss_scale = loss_scale;
         Q.acc = d_loss_acc + 80 * k;
         Q.out3 = d_losses + 3 * k;
-        M_CHECK(loss_level_launch(Q, stream));
+        HeadFuse Hd{};
+        const Step* hs = head_step[k] >= 0 ? &steps[head_step[k]] : nullptr;
+        if (hs && hs->head_bwd_fused) {
+            const Ten& a = tens[hs->in0];
+            Hd.x = a.p; Hd.xc = a.C; Hd.xcp = a.Cp;
+            Hd.w = param_ptr(hs->p_w);
+            Hd.dx = a.grad; Hd.dx_accum = 0;
+            Hd.dw = grad_ptr(hs->p_w); Hd.db = grad_ptr(hs->p_b);
+            M_CHECK(loss_level_launch(Q, &Hd, stream));
+        } else
+            M_CHECK(loss_level_launch(Q, stream));
         launches += 4;
     }
     M_CHECK(run_backward());

@@ -41,6 +41,8 @@ struct Step {
     enum Kind { CONV, NORMACT, MAXPOOL, UPSAMPLE } kind = CONV;
     int in0 = -1, in1 = -1, out = -1;
     int head_level = -1;       // >= 0: this conv writes logits[head_level] (fp32 planar)
+    bool head_fwd_fused = false;   // head on CUDA cores (head_fwd_kernel) instead of the tensor path
+    bool head_bwd_fused = false;   // head dgrad/wgrad/bias gradient fused into the loss-gradient kernel
     // CONV
     LayerGeom g{};
     int p_w = -1, p_b = -1;
@@ -124,7 +126,7 @@ class Model {
     int timer_stop(float* ms);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // per-launch CUDA-event profile of the tensor-core kernels (bench.py roofline):
-    // kind 0 = conv_igemm, 1 = conv_wgrad, 2 = conv_halo, 3 = conv_wgrad_rows
+    // kind 0 = conv_igemm, 1 = conv_wgrad, 2 = conv_halo, 3 = conv_wgrad_rows, 4 = conv_tma
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int> prof_kind;
@@ -132,7 +134,7 @@ class Model {
     size_t prof_used = 0;
     void prof_begin(int kind, double flops);
     void prof_end();
-    int prof_read(double out[12], int reset);  // per kind: {ms, launches, algorithmic FLOPs}
+    int prof_read(double out[18], int reset);  // per kind: {ms, launches, algorithmic FLOPs}
     int n_levels() const { return int(output.size()); }
 
   private:
@@ -141,6 +143,7 @@ class Model {
     std::vector<float*> logits;      // per level, fp32 planar
     std::vector<void*> dlogits;      // per level, fp16 [v][Cp]
     std::vector<int> level_dims;     // d,h,w per level
+    std::vector<int> head_step;      // per level: index of the head conv in `steps` (-1 = none)
     bool planned = false, planned_training = false;
     bool packs_dirty = true;
     float* d_in_f32 = nullptr;

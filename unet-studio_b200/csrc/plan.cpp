@@ -11,11 +11,21 @@ int choose_kc(int c0p, int c1p) {
     return 16;
 }
 
-void choose_ntile(int np, int& ntile, int& ntiles) {
-    int nt = np < 256 ? np : 256;
-    while (np % nt) nt -= 16;
-    ntile = nt;
-    ntiles = np / nt;
+// N tile: minimises (waves of 148 CTAs) x (time of one M=128,K=16 MMA), the MMA costing ~max(45, N/2) clk (tools/mma_bench.cu:
+// the A-operand read from shared memory makes every N <= 64 equally expensive).  The deep levels have only 2..75 M tiles, so a
+// full-width N tile would leave most of the 148 SMs idle; ties go to the wider tile (less re-reading of A through L2).
+void choose_ntile(int np, long long m_voxels, int& ntile, int& ntiles) {
+    const long long mt = (m_voxels + 119) / 120;
+    int best = 16;
+    long long best_cost = -1;
+    for (int nt = 16; nt <= (np < 256 ? np : 256); nt += 16) {
+        if (np % nt) continue;
+        const long long items = mt * (np / nt);
+        const long long cost = ((items + 147) / 148) * (nt / 2 > 45 ? nt / 2 : 45);
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = nt; }
+    }
+    ntile = best;
+    ntiles = np / best;
 }
 
 size_t pack_bytes(const PackDesc& d) {
@@ -34,7 +44,8 @@ void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vect
     const int c0p = pad16(g.cin[0]), c1p = g.cin[1] ? pad16(g.cin[1]) : 0;
     kc = force_kc ? force_kc : choose_kc(c0p, c1p);
     int ntile, ntiles;
-    choose_ntile(pad16(g.cout), ntile, ntiles);
+    choose_ntile(pad16(g.cout), (g.transposed ? 8LL : 1LL) * (g.transposed ? g.in_d : g.out_d) * (g.transposed ? g.in_h : g.out_h) *
+                                    (g.transposed ? g.in_w : g.out_w), ntile, ntiles);
     if (!g.transposed) {
         ConvProblem P;
         zero_problem(P);
@@ -101,7 +112,7 @@ void plan_dgrad(const LayerGeom& g, int src, std::vector<ConvProblem>& probs, st
     kc = force_kc ? force_kc : choose_kc(coutp, 0);
     const int n_real = g.cin[src];
     int ntile, ntiles;
-    choose_ntile(pad16(n_real), ntile, ntiles);
+    choose_ntile(pad16(n_real), 1LL * g.in_d * g.in_h * g.in_w, ntile, ntiles);   // dx lattice (all parity problems together)
     const int n_off = src ? g.cin[0] : 0;
     auto base = [&](ConvProblem& P, PackDesc& K) {
         zero_problem(P);

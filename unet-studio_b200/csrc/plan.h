@@ -38,7 +38,7 @@ struct LayerGeom {
 };
 
 int choose_kc(int c0p, int c1p);
-void choose_ntile(int np, int& ntile, int& ntiles);
+void choose_ntile(int np, long long m_voxels, int& ntile, int& ntiles);
 
 // Forward: fills `probs` (operand/destination pointers left null) and `packs` (one per problem, w/out null).
 void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vector<PackDesc>& packs, int& kc, int force_kc = 0);

@@ -110,7 +110,11 @@ int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch&
 
 bool conv_halo_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
 int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
-int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);  // halo or gather kernel
+int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);  // halo, TMA or gather kernel
+int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);  // profile family conv_launch will use: 0 igemm, 2 halo, 4 tma
+bool conv_tma_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
+int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
+unsigned int read_device_error_tma();
 bool conv_halo_wants_kc16(int ks, int stride, int transposed, int k_channels_padded, int n_channels_padded, long long voxels);
 unsigned int read_device_error_halo();
 
