@@ -1,0 +1,482 @@
+// x-banded halo convolution (3x3x3, stride 1) on tcgen05 / TMEM for the full-resolution 16/32-channel layers that carry most
+// of the U-Net's FLOPs (levels 0-1), forward and data gradient.
+//
+// Why: a tcgen05.mma with M = 128, K = 16 costs ~45 clk for every N <= 64 (tools/mma_bench.cu) because the 4 KB A operand
+// read from shared memory, not the tensor pipe, is the limit.  With "voxels on M, Cout on N" a 16-channel layer uses N = 16:
+// a quarter of what each A read could feed.  Here one M row is a GROUP of G consecutive output voxels along x and N = G*Cout
+// (64): D[group][xo*Cout + co].  A tap (dz,dy) needs the G+2 input voxels xi = 0..G+1 of the group; input xi contributes to
+// output xo through kernel column kx = xi - xo, so per (dz,dy,xi) ONE MMA multiplies the xi-th input voxel of every group
+// (K = Cin) with the weight blocks [W(kx=2) | W(kx=1) | W(kx=0)] placed at the matching output columns.  Only the useful
+// blocks are issued (N = Cout, 2Cout, 3Cout sub-ranges of the accumulator), so there is no zero-padding work on the tensor
+// pipe and the weights are stored once ([9 (dz,dy)][K chunk][kx reversed][Cout] + one zero block for the first MMA).
+// MMAs per G outputs per (dz,dy): G+2 instead of 3G  ->  G = 4: 54 instead of 108 per 128 rows of 4 voxels = 4x fewer A reads
+// per voxel than conv_halo.cu.
+//
+// Shared-memory layout of one input z-plane of a tile ("slot"):   xs[cg][r][row p][8 ch]
+//   cg = channel group of 8, r = hx mod G ("phase"), p = hy*HQ + hx div G.  For a fixed (cg, r) the rows are 16 B apart, so any
+//   run of 128 consecutive p is a canonical SWIZZLE_NONE K-major operand (SBO = 128 B, LBO = distance between cg planes) and
+//   every (dy, xi) is just a different start address:  p0 + dy*HQ + xi div G  in phase plane xi mod G.
+// The CTA marches along z through a 4-slot ring of planes (3 in use, 1 loading): every input plane is fetched once per
+// (x,y) tile column, there is no halo re-read along z at all.
+//
+// CTA = 416 threads: warps 0-3 epilogue, warps 4-11 producers (16-byte cp.async, zero fill = padding), warp 12 MMA issuer.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "plan.h"
+#include "u3d.h"
+
+namespace u3d {
+namespace {
+
+constexpr int kBThreads = 32 * 13;
+constexpr int kBProducers = 256;
+constexpr int kSlots = 4;
+
+struct BParams {
+    ConvProblem P;
+    int G, CO, KS;         // outputs per group, padded Cout, K chunks of 16
+    int TX, TY, HX, HY, HQ, ROWS;
+    int tiles_x, tiles_y, zchunks, zlen, total_items;
+    int ncg;               // channel groups of 8 (both sources)
+    int NB;                // columns of one weight block: 4*CO
+    uint32_t slot_bytes, w_bytes, off_w, off_stats, off_bars;
+    float* stats;
+    int epi;
+};
+
+template <int HALF, int BIT>
+__device__ __forceinline__ void halve_step_b(float (&a)[16], float (&q)[16], int lane) {
+    const bool hi = (lane & BIT) != 0;
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+        const float sa = hi ? a[j] : a[j + HALF];
+        const float ka = hi ? a[j + HALF] : a[j];
+        a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, BIT);
+        const float sq = hi ? q[j] : q[j + HALF];
+        const float kq = hi ? q[j + HALF] : q[j];
+        q[j] = kq + __shfl_xor_sync(0xffffffffu, sq, BIT);
+    }
+}
+
+template <int G, int CO, int KS>
+__global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_constant__ BParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int N = G * CO;            // accumulator columns (64)
+    constexpr int XI = G + 2;
+    constexpr int NB = 4 * CO;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sW = sbase + p.off_w;
+    float* sstats = reinterpret_cast<float*>(smem + p.off_stats);
+    const uint32_t bars = sbase + p.off_bars;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kSlots + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * kSlots + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * kSlots + 2 + a); };
+    const uint32_t wfull_bar = bars + 8u * (2 * kSlots + 4);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kSlots + 5));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSlots; ++s) {
+            mbar_init(full_bar(s), kBProducers);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        mbar_init(wfull_bar, kBProducers);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 8 * CO + CO; i += kBThreads) sstats[i] = 0.f;
+    if (warp == 12) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), 2 * N < 32 ? 32 : 2 * N);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const ConvProblem& P = p.P;
+    const int D = P.in_d, H = P.in_h, W = P.in_w;
+
+    if (warp >= 4 && warp < 12) {
+        // ===================================== producers =====================================
+        const int t = threadIdx.x - 128;
+        {   // resident weights
+            const uint8_t* wsrc = static_cast<const uint8_t*>(P.wpack);
+            for (uint32_t o = t * 16u; o < p.w_bytes; o += kBProducers * 16u) cp_async16(sW + o, wsrc + o, 16u);
+            cp_async_mbar_arrive(wfull_bar);
+        }
+        const int ncg0 = P.c0p / 8, ncg = p.ncg;
+        const uint8_t* const s0 = static_cast<const uint8_t*>(P.src0);
+        const uint8_t* const s1 = static_cast<const uint8_t*>(P.src1);
+        const uint32_t pitch0 = uint32_t(P.c0p) * 2u, pitch1 = uint32_t(P.c1p) * 2u;
+        const int HX = p.HX, HY = p.HY, HQ = p.HQ, ROWS = p.ROWS;
+        const int per_plane = HY * HX * ncg;
+        uint32_t cnt = 0;   // planes loaded by this CTA so far (ring position)
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int rem = item;
+            const int zc = rem % p.zchunks; rem /= p.zchunks;
+            const int tx = rem % p.tiles_x;
+            const int ty = rem / p.tiles_x;
+            const int x0 = tx * p.TX - 1, y0 = ty * p.TY - 1;
+            const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
+            for (int gz = z0 - 1; gz <= z1; ++gz, ++cnt) {
+                const int slot = cnt % kSlots;
+                mbar_wait(empty_bar(slot), ((cnt / kSlots) & 1) ^ 1, 0x2100u | slot);
+                const uint32_t blk = sbase + slot * p.slot_bytes;
+                const bool zok = (unsigned)gz < (unsigned)D;
+                // consecutive lanes: the 16-byte chunks of one voxel, then the next voxel along x (coalesced)
+#pragma unroll 2
+                for (int idx = t; idx < per_plane; idx += kBProducers) {
+                    const int cg = idx % ncg;
+                    const int pos = idx / ncg;
+                    const int hx = pos % HX, hy = pos / HX;
+                    const int gx = x0 + hx, gy = y0 + hy;
+                    const bool ok = zok && (unsigned)gx < (unsigned)W && (unsigned)gy < (unsigned)H;
+                    const size_t vox = (size_t(gz) * H + gy) * W + gx;
+                    const uint8_t* src;
+                    if (cg < ncg0) src = ok ? s0 + vox * pitch0 + cg * 16 : s0;
+                    else src = ok ? s1 + vox * pitch1 + (cg - ncg0) * 16 : s1;
+                    const int r = hx % G, hq = hx / G;
+                    cp_async16(blk + uint32_t((cg * G + r) * ROWS + hy * HQ + hq) * 16u, src, ok ? 16u : 0u);
+                }
+                cp_async_mbar_arrive(full_bar(slot));
+            }
+        }
+        cp_async_wait<0>();
+    } else if (warp == 12) {
+        // ===================================== MMA issuer ====================================
+        if (lane == 0) {
+            const int HQ = p.HQ, ROWS = p.ROWS;
+            const uint32_t lbo_a = uint32_t(G * ROWS) * 16u;             // next channel group of 8
+            const uint64_t a_ks_u = uint64_t((2u * lbo_a) >> 4);         // next K chunk of 16 channels
+            const uint32_t lbo_b = uint32_t(NB) * 16u;
+            const uint64_t b_ks_u = uint64_t((2u * lbo_b) >> 4);
+            const uint64_t b_desc0 = umma_smem_desc(sW, lbo_b, 128u);
+            // per-xi constants: A offset (phase plane + group shift), B column offset, D column offset, N
+            uint32_t a_xi[XI], b_xi[XI], d_xi[XI], i_xi[XI];
+#pragma unroll
+            for (int xi = 0; xi < XI; ++xi) {
+                const int xo_lo = xi - 2 < 0 ? 0 : xi - 2, xo_hi = xi < G - 1 ? xi : G - 1;   // outputs fed by this input column
+                const int nblk = xo_hi - xo_lo + 1;
+                const int kx_hi = xi - xo_lo;                                                  // kernel column of the first block
+                a_xi[xi] = uint32_t((xi % G) * ROWS + xi / G);                                 // 16-byte units
+                b_xi[xi] = uint32_t((2 - kx_hi) * CO);                                         // blocks are stored kx = 2,1,0,zero
+                d_xi[xi] = uint32_t(xo_lo * CO);
+                i_xi[xi] = umma_idesc(128, nblk * CO, 0, 0, 0, 0);
+            }
+            const uint32_t idesc_full = umma_idesc(128, N, 0, 0, 0, 0);
+            constexpr int XI0 = G - 2 >= 0 ? (G == 2 ? 1 : 2) : 0;   // the first MMA of a tile must write all N columns:
+                                                                      // G = 4: xi = 2 with the zero block, G = 2: xi = 1
+            mbar_wait(wfull_bar, 0, 0x2200u);
+            fence_proxy_async();
+            uint32_t cnt = 0, acc_cnt = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int zc = item % p.zchunks;
+                const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
+                const int nz = z1 - z0;
+                // planes cnt, cnt+1 (relative z0-1, z0) must be resident before output plane 0; plane j+2 before output j
+                mbar_wait(full_bar(cnt % kSlots), (cnt / kSlots) & 1, 0x2300u);
+                mbar_wait(full_bar((cnt + 1) % kSlots), ((cnt + 1) / kSlots) & 1, 0x2301u);
+#pragma unroll 1
+                for (int j = 0; j < nz; ++j, ++acc_cnt) {
+                    const uint32_t c2 = cnt + j + 2;
+                    mbar_wait(full_bar(c2 % kSlots), (c2 / kSlots) & 1, 0x2302u);
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const int acc = acc_cnt & 1;
+                    mbar_wait(tempty_bar(acc), ((acc_cnt >> 1) & 1) ^ 1, 0x2400u | acc);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + uint32_t(acc * N);
+                    // row p0 = HQ (hy = 1, hq = 0) of each of the three planes
+                    uint64_t a_pl[3];
+#pragma unroll
+                    for (int dz = 0; dz < 3; ++dz)
+                        a_pl[dz] = umma_smem_desc(sbase + ((cnt + j + dz) % kSlots) * p.slot_bytes + uint32_t(HQ) * 16u, lbo_a, 128u);
+                    // first MMA: full width, overwrite
+                    {
+                        const uint64_t ad = a_pl[0] - uint64_t(HQ) + a_xi[XI0];
+                        const uint64_t bd = b_desc0 + (G == 4 ? 0u : uint32_t(CO));
+                        umma_f16_first(d_tmem, ad, bd, G == 4 ? idesc_full : i_xi[XI0]);
+                    }
+#pragma unroll
+                    for (int dz = 0; dz < 3; ++dz) {
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint64_t a_row = a_pl[dz] + uint64_t((long long)(dy - 1) * HQ);
+                            const uint64_t b_tap = b_desc0 + uint64_t((dz * 3 + dy) * KS) * b_ks_u;
+#pragma unroll
+                            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                                for (int xi = 0; xi < XI; ++xi) {
+                                    if (dz == 0 && dy == 0 && ks == 0 && xi == XI0) continue;   // issued above
+                                    umma_f16_acc(d_tmem + d_xi[xi], a_row + uint64_t(ks) * a_ks_u + a_xi[xi],
+                                                 b_tap + uint64_t(ks) * b_ks_u + b_xi[xi], i_xi[xi]);
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(tfull_bar(acc));
+                    umma_commit(empty_bar((cnt + j) % kSlots));     // plane z-1 is no longer needed
+                }
+                umma_commit(empty_bar((cnt + nz) % kSlots));
+                umma_commit(empty_bar((cnt + nz + 1) % kSlots));
+                cnt += uint32_t(nz + 2);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================== epilogue ======================================
+        const int r = threadIdx.x;
+        const int HQ = p.HQ;
+        uint32_t acc_cnt = 0;
+        float ssum[CO], ssq[CO];
+#pragma unroll
+        for (int j = 0; j < CO; ++j) ssum[j] = ssq[j] = 0.f;
+        float* sbias = sstats + 8 * CO;
+        for (int j = r; j < CO; j += 128) sbias[j] = (P.bias != nullptr && j < P.n_real) ? __ldg(P.bias + j) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool want_stats = p.stats != nullptr;
+        const bool accum = p.epi == EPI_ACCUM16;
+        const int hy = 1 + r / HQ, hq = r % HQ;
+        const bool row_in_tile = r < p.TY * HQ && hq < p.TX / G;
+        uint8_t* const dst = static_cast<uint8_t*>(P.dst) + P.dst_coff * 2;
+        const uint32_t dst_pitch = uint32_t(P.dst_cp) * 2u;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int rem = item;
+            const int zc = rem % p.zchunks; rem /= p.zchunks;
+            const int tx = rem % p.tiles_x;
+            const int ty = rem / p.tiles_x;
+            const int gx0 = tx * p.TX + hq * G, gy = ty * p.TY + hy - 1;
+            const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
+            const bool rv_xy = row_in_tile && gy < H && gx0 < W;
+#pragma unroll 1
+            for (int gz = z0; gz < z1; ++gz, ++acc_cnt) {
+                const size_t vox0 = (size_t(gz) * H + gy) * W + gx0;
+                const int acc = acc_cnt & 1;
+                mbar_wait(tfull_bar(acc), (acc_cnt >> 1) & 1, 0x2500u | acc);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(acc * N);
+#pragma unroll
+                for (int xo = 0; xo < G; ++xo) {
+                    const bool rv = rv_xy && gx0 + xo < W;
+#pragma unroll
+                    for (int c0 = 0; c0 < CO; c0 += 16) {
+                        float v[16];
+                        tmem_ld16(t_row + uint32_t(xo * CO + c0), v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += sbias[c0 + j];
+                        uint4* out = reinterpret_cast<uint4*>(dst + (vox0 + xo) * dst_pitch + c0 * 2);
+                        if (accum && rv) {
+                            const uint4 o0 = out[0], o1 = out[1];
+                            const uint32_t ow_[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 f = unpack2<false>(ow_[j]);
+                                v[2 * j] += f.x;
+                                v[2 * j + 1] += f.y;
+                            }
+                        }
+                        if (rv) {
+                            uint4 q0v, q1v;
+                            q0v.x = pack2<false>(v[0], v[1]); q0v.y = pack2<false>(v[2], v[3]);
+                            q0v.z = pack2<false>(v[4], v[5]); q0v.w = pack2<false>(v[6], v[7]);
+                            q1v.x = pack2<false>(v[8], v[9]); q1v.y = pack2<false>(v[10], v[11]);
+                            q1v.z = pack2<false>(v[12], v[13]); q1v.w = pack2<false>(v[14], v[15]);
+                            out[0] = q0v;
+                            out[1] = q1v;
+                            if (want_stats) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    ssum[c0 + j] += v[j];
+                                    ssq[c0 + j] = fmaf(v[j], v[j], ssq[c0 + j]);
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));
+            }
+        }
+        if (want_stats) {
+#pragma unroll
+            for (int c0 = 0; c0 < CO; c0 += 16) {
+                float a[16], qq[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { a[j] = ssum[c0 + j]; qq[j] = ssq[c0 + j]; }
+                halve_step_b<8, 16>(a, qq, lane);
+                halve_step_b<4, 8>(a, qq, lane);
+                halve_step_b<2, 4>(a, qq, lane);
+                halve_step_b<1, 2>(a, qq, lane);
+                a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+                qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
+                if ((lane & 1) == 0) {
+                    const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    float* ws = sstats + warp * 2 * CO;
+                    ws[col] = a[0];
+                    ws[CO + col] = qq[0];
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = r; i < 2 * CO; i += 128)
+                p.stats[size_t(blockIdx.x) * 2 * CO + i] = ((sstats[i] + sstats[2 * CO + i]) + sstats[4 * CO + i]) + sstats[6 * CO + i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem_base, 2 * N < 32 ? 32 : 2 * N);
+}
+
+// ---- weight pack: reference fp32 tensor -> [9 (dz,dy)][KS][2 k-groups][NB = 4*CO columns][8] fp16, columns = kernel column
+// kx = 2,1,0 then a zero block; the (dz,dy,dx) offsets come from the problem's own tap list (forward: k-1, dgrad: 1-k) ----
+__global__ void pack_weights_band_kernel(const __grid_constant__ PackDesc d) {
+    const int KS = d.nch[0] + d.nch[1];
+    const int NB = 4 * d.band_co;
+    const long long total = 9LL * KS * 2 * NB * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int k8 = int(r % 8); r /= 8;
+        const int col = int(r % NB); r /= NB;
+        const int kg = int(r % 2); r /= 2;
+        const int ks = int(r % KS); r /= KS;
+        const int t9 = int(r);
+        const int blk = col / d.band_co, nn = col % d.band_co;
+        float v = 0.f;
+        if (blk < 3) {
+            const int oz = t9 / 3 - 1, oy = t9 % 3 - 1, ox = (2 - blk) - 1;   // input offset of this block relative to the output voxel
+            int tap = -1;
+            for (int t = 0; t < 27; ++t)
+                if (d.band_taps[t].dz == oz && d.band_taps[t].dy == oy && d.band_taps[t].dx == ox) tap = t;
+            const int s = ks < d.nch[0] ? 0 : 1;
+            const int kk = (ks - (s ? d.nch[0] : 0)) * 16 + kg * 8 + k8;
+            if (tap >= 0 && kk < d.k_real[s] && nn < d.n_real) {
+                const int kidx = d.k_off[s] + kk, nidx = d.n_off + nn;
+                const long long a = d.n_is_A ? nidx : kidx, b = d.n_is_A ? kidx : nidx;
+                v = d.w[(a * d.dimB + b) * d.ktaps + d.tap_ref[tap]];
+            }
+        }
+        static_cast<__half*>(d.out)[i] = __float2half_rn(v);
+    }
+}
+
+}  // namespace
+
+unsigned int read_device_error_band() {
+    unsigned int v = 0;
+    cudaMemcpyFromSymbol(&v, g_dev_error, sizeof(v));
+    return v;
+}
+
+size_t pack_bytes_band(const PackDesc& d) { return size_t(9) * (d.nch[0] + d.nch[1]) * 2 * (4 * d.band_co) * 8 * 2; }
+
+int pack_weights_band_launch(const PackDesc& d, cudaStream_t stream) {
+    const long long total = (long long)pack_bytes_band(d) / 2;
+    const int grid = int(std::min<long long>((total + 255) / 256, 148 * 4));
+    pack_weights_band_kernel<<<grid, 256, 0, stream>>>(d);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// planner hook: k3 s1 layer with 16|32 padded input channels (both sources together) and 16|32 padded output channels
+bool conv_band_wants(int k_channels_padded, int n_channels_padded, long long voxels) {
+    static const bool disabled = std::getenv("U3D_NO_BAND") != nullptr || std::getenv("U3D_NO_HALO") != nullptr;
+    return !disabled && (k_channels_padded == 16 || k_channels_padded == 32) && (n_channels_padded == 16 || n_channels_padded == 32) &&
+           voxels >= 32768;
+}
+
+bool conv_band_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg) {
+    if (probs.size() != 1 || !probs[0].banded) return false;
+    const ConvProblem& P = probs[0];
+    if (cfg.kc != 16 || cfg.epi == EPI_PLANAR32 || cfg.a_bf16 || cfg.b_bf16) return false;
+    if (P.ntaps != 27 || P.istride != 1 || P.ostep != 1 || P.ntiles != 1) return false;
+    if (P.od != P.in_d || P.oh != P.in_h || P.ow != P.in_w || P.coff0 || P.coff1) return false;
+    const int k = P.c0p + P.c1p;
+    if ((k != 16 && k != 32) || (P.ntile != 16 && P.ntile != 32) || (P.nch0 + P.nch1) * 16 != k) return false;
+    if (P.dst_cp % 8 || P.dst_coff % 8) return false;
+    return true;
+}
+
+template <int G, int CO, int KS>
+static int launch_band_t(const BParams& bp, int grid, size_t smem, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<G, CO, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    conv_band_kernel<G, CO, KS><<<grid, kBThreads, smem, stream>>>(bp);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream) {
+    BParams bp;
+    std::memset(&bp, 0, sizeof(bp));
+    bp.P = probs[0];
+    const ConvProblem& P = bp.P;
+    bp.CO = P.ntile;
+    bp.G = bp.CO == 16 ? 4 : 2;
+    bp.KS = (P.c0p + P.c1p) / 16;
+    bp.ncg = (P.c0p + P.c1p) / 8;
+    bp.NB = 4 * bp.CO;
+    // tile: TX x TY outputs per z-plane with TY*HQ <= 128 rows; pick the (TX, TY) with the fewest plane tiles
+    long long best = -1;
+    for (int TX = 4 * bp.G; TX <= 64; TX += 4 * bp.G) {
+        const int HQ = (TX + 2 + bp.G - 1) / bp.G;
+        const int ty_max = 128 / HQ;
+        if (ty_max < 1) continue;
+        const int tiles_y0 = (P.in_h + ty_max - 1) / ty_max;
+        const int TY = (P.in_h + tiles_y0 - 1) / tiles_y0;
+        const long long tiles = 1LL * ((P.in_w + TX - 1) / TX) * tiles_y0;
+        if (best < 0 || tiles < best) { best = tiles; bp.TX = TX; bp.TY = TY; }
+    }
+    bp.HX = bp.TX + 2; bp.HY = bp.TY + 2;
+    bp.HQ = (bp.HX + bp.G - 1) / bp.G;
+    bp.ROWS = (2 * bp.HQ + 129 + 7) / 8 * 8;
+    bp.tiles_x = (P.in_w + bp.TX - 1) / bp.TX;
+    bp.tiles_y = (P.in_h + bp.TY - 1) / bp.TY;
+    // z chunks: enough items for >= ~4 waves of the SMs, at least 8 planes per chunk (2 halo planes are re-read per chunk)
+    const int sms = device_sm_count();
+    const int cols = bp.tiles_x * bp.tiles_y;
+    int zchunks = std::max(1, std::min(P.in_d / 8, (4 * sms + cols - 1) / cols));
+    {   // prefer a chunk count whose item total fills whole waves
+        double best_eff = -1;
+        int best_zc = zchunks;
+        for (int zc = std::max(1, zchunks / 2); zc <= std::max(1, std::min(P.in_d / 4, zchunks * 2)); ++zc) {
+            const int zl = (P.in_d + zc - 1) / zc;
+            const int zc_eff = (P.in_d + zl - 1) / zl;
+            const long long items = 1LL * cols * zc_eff;
+            const long long waves = (items + sms - 1) / sms;
+            const double eff = double(items) / double(waves * sms) * double(zl) / double(zl + 2);
+            if (eff > best_eff) { best_eff = eff; best_zc = zc_eff; }
+        }
+        zchunks = best_zc;
+    }
+    bp.zlen = (P.in_d + zchunks - 1) / zchunks;
+    bp.zchunks = (P.in_d + bp.zlen - 1) / bp.zlen;
+    bp.total_items = cols * bp.zchunks;
+    bp.slot_bytes = uint32_t(bp.ncg * bp.G * bp.ROWS * 16);
+    bp.w_bytes = uint32_t(9 * bp.KS * 2 * bp.NB * 16);
+    bp.off_w = kSlots * bp.slot_bytes;
+    bp.off_stats = bp.off_w + bp.w_bytes;
+    bp.off_bars = uint32_t((bp.off_stats + 9 * bp.CO * 4 + 15) & ~15u);
+    const size_t smem = bp.off_bars + 8 * (2 * kSlots + 5) + 16;
+    if (smem > 227 * 1024) { set_error("conv_band_launch: tile does not fit in shared memory"); return 1; }
+    bp.epi = cfg.epi;
+    bp.stats = cfg.epi == EPI_STORE16 ? cfg.stats_partials : nullptr;
+    const int grid = std::max(1, std::min(bp.total_items, sms));
+    if (cfg.stats_grid_out) *cfg.stats_grid_out = grid;
+    if (bp.CO == 16 && bp.KS == 1) return launch_band_t<4, 16, 1>(bp, grid, smem, stream);
+    if (bp.CO == 16 && bp.KS == 2) return launch_band_t<4, 16, 2>(bp, grid, smem, stream);
+    if (bp.CO == 32 && bp.KS == 1) return launch_band_t<2, 32, 1>(bp, grid, smem, stream);
+    return launch_band_t<2, 32, 2>(bp, grid, smem, stream);
+}
+
+}  // namespace u3d

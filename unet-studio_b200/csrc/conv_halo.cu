@@ -332,7 +332,7 @@ unsigned int read_device_error_halo() {
 // 16-bit NDHWC epilogues.  The caller packs the weights with kc = 16 (chunk order = [tap][k16]).
 bool conv_halo_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg) {
     static const bool disabled = std::getenv("U3D_NO_HALO") != nullptr;
-    if (disabled || probs.empty() || probs.size() > kMaxHaloProb) return false;
+    if (disabled || probs.empty() || probs.size() > kMaxHaloProb || probs[0].banded) return false;
     if (cfg.kc != 16 || cfg.epi == EPI_PLANAR32) return false;
     for (const auto& P : probs) {
         if (P.ntaps != 27 || P.istride != 1 || P.ostep != 1 || P.ntiles != 1 || P.ntile > 32) return false;
@@ -403,12 +403,15 @@ int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
 
 // Single entry point used by the model and the op-level API: halo kernel when the problem set qualifies, gather kernel otherwise.
 int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream) {
+    if (conv_band_eligible(probs, cfg)) return conv_band_launch(probs, cfg, stream);
+    if (!probs.empty() && probs[0].banded) { set_error("conv_launch: banded weight pack but the problem is not eligible for conv_band"); return 1; }
     if (conv_halo_eligible(probs, cfg)) return conv_halo_launch(probs, cfg, stream);
     if (conv_tma_eligible(probs, cfg)) return conv_tma_launch(probs, cfg, stream);
     return conv_igemm_launch(probs, cfg, nullptr, stream);
 }
 
 int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg) {
+    if (conv_band_eligible(probs, cfg)) return 5;
     if (conv_halo_eligible(probs, cfg)) return 2;
     return conv_tma_eligible(probs, cfg) ? 4 : 0;
 }

@@ -426,6 +426,8 @@ unsigned int read_device_error() {
     v = read_device_error_halo();
     if (v) return v;
     v = read_device_error_tma();
+    if (v) return v;
+    v = read_device_error_band();
     return v ? v : read_device_error_rows();
 }
 

@@ -84,6 +84,7 @@ inline int grid_for(long long total, int block) {
 }  // namespace
 
 int pack_weights_launch(const PackDesc& d, cudaStream_t stream) {
+    if (d.banded) return pack_weights_band_launch(d, stream);
     const long long total = (long long)pack_bytes(d) / 2;
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(d);
     U3D_CUDA_CHECK(cudaGetLastError());

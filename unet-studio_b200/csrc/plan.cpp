@@ -29,6 +29,7 @@ void choose_ntile(int np, long long m_voxels, int& ntile, int& ntiles) {
 }
 
 size_t pack_bytes(const PackDesc& d) {
+    if (d.banded) return pack_bytes_band(d);
     return size_t(d.ntaps) * (d.nch[0] + d.nch[1]) * d.ntiles * d.ntile * d.kc * 2;
 }
 
@@ -74,6 +75,11 @@ void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vect
         K.k_off[0] = 0; K.k_real[0] = g.cin[0]; K.nch[0] = P.nch0;
         K.k_off[1] = g.cin[0]; K.k_real[1] = g.cin[1]; K.nch[1] = P.nch1;
         K.kc = kc; K.ntaps = P.ntaps;
+        if (force_kc == 16 && g.ks == 3 && g.stride == 1 && ntiles == 1 &&
+            conv_band_wants(c0p + c1p, pad16(g.cout), 1LL * g.out_d * g.out_h * g.out_w)) {
+            P.banded = 1; K.banded = 1; K.band_co = pad16(g.cout);
+            std::memcpy(K.band_taps, P.taps, sizeof(K.band_taps));
+        }
         probs.push_back(P);
         packs.push_back(K);
     } else {
@@ -143,6 +149,10 @@ void plan_dgrad(const LayerGeom& g, int src, std::vector<ConvProblem>& probs, st
         P.od = g.in_d; P.oh = g.in_h; P.ow = g.in_w;
         P.ostep = 1;
         K.dimA = g.cout; K.dimB = g.cin[0] + g.cin[1]; K.ktaps = P.ntaps; K.n_is_A = 0; K.ntaps = P.ntaps;
+        if (force_kc == 16 && g.ks == 3 && ntiles == 1 && conv_band_wants(coutp, pad16(n_real), 1LL * g.in_d * g.in_h * g.in_w)) {
+            P.banded = 1; K.banded = 1; K.band_co = pad16(n_real);
+            std::memcpy(K.band_taps, P.taps, sizeof(K.band_taps));
+        }
         probs.push_back(P);
         packs.push_back(K);
     } else if (!g.transposed) {

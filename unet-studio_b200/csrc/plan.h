@@ -20,7 +20,12 @@ struct PackDesc {
     int tap_ref[27];
     void* out;
     int out_bf16;
+    int banded;              // 1: x-banded layout of conv_band.cu ([9 (dz,dy)][K chunk][kx 2,1,0,zero][band_co])
+    int band_co;
+    ConvTap band_taps[27];   // the problem's tap offsets (which reference tap each (dz,dy,dx) offset reads)
 };
+size_t pack_bytes_band(const PackDesc& d);
+int pack_weights_band_launch(const PackDesc& d, cudaStream_t stream);
 size_t pack_bytes(const PackDesc& d);
 int pack_weights_launch(const PackDesc& d, cudaStream_t stream);
 

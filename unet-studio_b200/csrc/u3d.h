@@ -59,6 +59,7 @@ struct ConvProblem {
     int mtiles;            // ceil(M/128)              (filled by the launcher)
     int tap_delta[27];     // (dz*in_h + dy)*in_w + dx  (filled by the launcher)
     int item_base;         // first work item           (filled by the launcher)
+    int banded;            // planner: weights packed for the x-banded halo kernel (conv_band.cu)
 };
 
 struct ConvLaunch {
@@ -111,7 +112,11 @@ int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch&
 bool conv_halo_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
 int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
 int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);  // halo, TMA or gather kernel
-int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);  // profile family conv_launch will use: 0 igemm, 2 halo, 4 tma
+int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);  // profile family conv_launch will use: 0 igemm, 2 halo, 4 tma, 5 band
+bool conv_band_wants(int k_channels_padded, int n_channels_padded, long long voxels);
+bool conv_band_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
+int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
+unsigned int read_device_error_band();
 bool conv_tma_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
 int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
 unsigned int read_device_error_tma();
