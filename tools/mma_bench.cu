@@ -220,10 +220,58 @@ __global__ void __launch_bounds__(128, 1) bench_mn(int n, int iters, long long* 
     if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
+// MN-major operands with 128-byte aligned chunk strides (wgrad_band layout): A chunks sbo_a apart, B chunks sbo_b apart, LBO = 128
+__global__ void __launch_bounds__(128, 1) bench_mn2(int n, int iters, long long* out, int sbo_a, int sbo_b, int nacc, int lbo) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tptr;
+    const uint32_t sb = smem_u32(smem);
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tptr), 512); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tptr;
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        const uint32_t idesc = umma_idesc(128, n, 0, 0, 1, 1);
+        const uint64_t a_base = umma_smem_desc(sb, lbo, sbo_a);
+        const uint64_t b_base = umma_smem_desc(sb + 100 * 1024, lbo, sbo_b);
+        long long t0 = clock64();
+        for (int i = 0; i < iters / 6; ++i) {
+            const uint64_t a_row = a_base + uint64_t(i & 7) * uint64_t(2 * 128 >> 4);
+            const uint64_t b_row = b_base + uint64_t(i & 3) * uint64_t(6 * 128 >> 4);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const uint64_t ad = a_row + uint64_t((k / 3) * (2 * lbo >> 4));
+                const uint64_t bd = b_row + uint64_t((k / 3) * (2 * lbo >> 4));
+                if (i == 0) umma_f16_first(tm + (k % nacc) * n, ad, bd, idesc); else umma_f16_acc(tm + (k % nacc) * n, ad, bd, idesc);
+            }
+        }
+        long long t1 = clock64();
+        umma_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0, 0xF00);
+        long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    tc_fence_before(); __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
 int main() {
     long long* d; cudaMalloc(&d, 16);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 4096;
+    cudaFuncSetAttribute(bench_mn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int n : {16, 48, 64, 96, 128, 192})
+        for (int sa : {128, 512})
+            for (int sbo_b : {128, 512}) {
+                const int lbo = (sa == 128 || sbo_b == 128) ? 4096 : 128;
+                const int nacc = 3 * n <= 512 ? 3 : 1;
+                bench_mn2<<<1, 128, 200 * 1024>>>(n, 6 * 400, d, sa == 128 ? 128 : (lbo == 4096 ? 256 : sa), sbo_b == 128 ? 128 : (lbo == 4096 ? 256 : sbo_b), nacc, lbo);
+                cudaError_t e = cudaDeviceSynchronize();
+                long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+                printf("mn2 N %3d sbo_a %4d sbo_b %4d : issue %.1f cyc/mma, complete %.1f (%s)\n", n, sa, sbo_b, double(h[0]) / (6 * 400), double(h[1]) / (6 * 400), cudaGetErrorString(e));
+            }
     for (int mode = 0; mode < 0; ++mode)
         for (int n : {16, 32, 64, 128, 256})
             for (int nacc : {1, 2}) {
@@ -235,7 +283,7 @@ int main() {
                        double(h[1]) / iters, cudaGetErrorString(e));
             }
     cudaFuncSetAttribute(bench_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    for (int n : {16, 32, 64}) {
+    for (int n : {16, 64}) {
         bench_lean<<<1, 128, 200 * 1024>>>(n, 27 * 150, d, 35200);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);

@@ -428,6 +428,8 @@ unsigned int read_device_error() {
     v = read_device_error_tma();
     if (v) return v;
     v = read_device_error_band();
+    if (v) return v;
+    v = read_device_error_wband();
     return v ? v : read_device_error_rows();
 }
 

@@ -1,0 +1,306 @@
+// N-stacked weight gradient for the 3x3x3 stride-1 convolutions of the large-volume levels (16 / 32 channels).
+//
+//   dW[co][ci][dz,dy,dx] = sum_v x[v + (dz,dy,dx)][ci] * dy[v][co]
+//
+// Both operands come straight from the NDHWC tensors, i.e. MN-major (channels contiguous, the reduction index = voxels along
+// x strided).  Measured (tools/mma_bench.cu): an MN-major tcgen05.mma M = 128, K = 16 costs ~122 clk whatever N is (16..192), so
+// the kernel is organised to make N as wide as TMEM allows:
+//   M = (a: 16/ncg consecutive x-rows hy0+a) x Cin            (one descriptor: the row/channel-group runs are 512 B apart)
+//   N = (b: R consecutive dy-rows ly0+b) x (3 copies of the row shifted by dx = -1,0,+1) x Cout      (R*3*Cout <= 144 columns)
+//   K = 16 of the 32 INPUT x positions of the tile (the dy copies carry the +-1 halo, x does not)
+//   D[(a,ci)][(b,dx,co)] += sum_x' x[z+dz][hy0+a][x'][ci] * dy[z][ly0+b][x'-dx][co]      -> tap (dz, dy = a-b-1, dx) if |dy| <= 1
+// One accumulator per dz (3 x N columns of TMEM) lives for the CTA's whole life; per R rows x 32 voxels the CTA issues
+// 3 (dz) x 2 (K steps) MMAs instead of the 18 of conv_wgrad_rows.cu.  The CTA marches along z through a ring of x planes
+// (4 slots: z-1, z, z+1 in use, one loading) and dy planes (2 slots), so every plane is fetched once per (x,y) tile column.
+// One epilogue at the end adds the useful (a,b) blocks into the reference-layout gradient with fp32 atomics.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "u3d.h"
+
+namespace u3d {
+namespace {
+
+constexpr int kWThreads = 32 * 13;   // warps 0-3 epilogue, 4-11 producers, 12 MMA issuer
+constexpr int kWProducers = 256;
+constexpr int kXSlots = 4, kYSlots = 2;
+
+struct WBParams {
+    WgradProblem P;
+    int TY, HYA;               // rows per tile, allocated x rows per plane (TY + 2 halo + junk rows the M = 128 descriptor runs into)
+    int tiles_x, tiles_y, zchunks, zlen, total_items;
+    uint32_t x_slot_bytes, y_slot_bytes, off_y, off_bars;
+};
+
+template <int NCG, int CO>
+__global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __grid_constant__ WBParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int NCGY = CO / 8;
+    constexpr int AROWS = 16 / NCG;                         // x rows covered by one M = 128 operand
+    constexpr int R = (CO == 16 ? 3 : 1) < AROWS - 2 ? (CO == 16 ? 3 : 1) : AROWS - 2;   // dy rows per MMA
+    constexpr int N = R * 3 * CO;
+    constexpr int TMEM_COLS = 3 * N <= 256 ? 256 : 512;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + p.off_bars;
+    auto xfull = [&](int s) { return bars + 8u * s; };
+    auto xempty = [&](int s) { return bars + 8u * (kXSlots + s); };
+    auto yfull = [&](int s) { return bars + 8u * (2 * kXSlots + s); };
+    auto yempty = [&](int s) { return bars + 8u * (2 * kXSlots + kYSlots + s); };
+    const uint32_t done_bar = bars + 8u * (2 * kXSlots + 2 * kYSlots);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kXSlots + 2 * kYSlots + 1));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kXSlots; ++s) { mbar_init(xfull(s), kWProducers); mbar_init(xempty(s), 1); }
+        for (int s = 0; s < kYSlots; ++s) { mbar_init(yfull(s), kWProducers); mbar_init(yempty(s), 1); }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 12) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const WgradProblem& P = p.P;
+    const int D = P.t_d, H = P.t_h, W = P.t_w;
+    const bool has_work = int(blockIdx.x) < p.total_items;
+
+    if (warp >= 4 && warp < 12) {
+        // ===================================== producers =====================================
+        const int t = threadIdx.x - 128;
+        const uint8_t* const xsrc = static_cast<const uint8_t*>(P.T) + P.t_coff * 2;
+        const uint8_t* const ysrc = static_cast<const uint8_t*>(P.U) + P.u_coff * 2;
+        const uint32_t xpitch = uint32_t(P.t_cp) * 2u, ypitch = uint32_t(P.u_cp) * 2u;
+        const int TY = p.TY;
+        const int xtotal = (TY + 2) * 32 * NCG;
+        const int ytotal = TY * 3 * 32 * NCGY;
+        uint32_t xcnt = 0, ycnt = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int rem = item;
+            const int zc = rem % p.zchunks; rem /= p.zchunks;
+            const int tx = rem % p.tiles_x;
+            const int ty = rem / p.tiles_x;
+            const int x0 = tx * 32, y0 = ty * TY;
+            const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
+            for (int gz = z0 - 1; gz <= z1; ++gz) {
+                {   // x plane gz (rows y0-1 .. y0+TY), no halo along x
+                    const int slot = xcnt % kXSlots;
+                    mbar_wait(xempty(slot), ((xcnt / kXSlots) & 1) ^ 1, 0x3100u | slot);
+                    const uint32_t blk = sbase + slot * p.x_slot_bytes;
+                    const bool zok = (unsigned)gz < (unsigned)D;
+#pragma unroll 2
+                    for (int idx = t; idx < xtotal; idx += kWProducers) {
+                        const int cg = idx % NCG;
+                        const int q = idx / NCG;
+                        const int lx = q % 32, hy = q / 32;
+                        const int gx = x0 + lx, gy = y0 + hy - 1;
+                        const bool ok = zok && gx < W && (unsigned)gy < (unsigned)H;
+                        const uint8_t* src = ok ? xsrc + ((size_t(gz) * H + gy) * W + gx) * xpitch + cg * 16 : xsrc;
+                        cp_async16(blk + uint32_t((hy * NCG + cg) * 32 + lx) * 16u, src, ok ? 16u : 0u);
+                    }
+                    cp_async_mbar_arrive(xfull(slot));
+                    ++xcnt;
+                }
+                if (gz >= z0 && gz < z1) {   // dy plane gz: per row three copies shifted by dx = -1, 0, +1 (real neighbours, zero outside)
+                    const int slot = ycnt % kYSlots;
+                    mbar_wait(yempty(slot), ((ycnt / kYSlots) & 1) ^ 1, 0x3200u | slot);
+                    const uint32_t blk = sbase + p.off_y + slot * p.y_slot_bytes;
+#pragma unroll 2
+                    for (int idx = t; idx < ytotal; idx += kWProducers) {
+                        const int cg = idx % NCGY;
+                        int q = idx / NCGY;
+                        const int lx = q % 32; q /= 32;
+                        const int dxc = q % 3;
+                        const int ly = q / 3;
+                        const int gx = x0 + lx - (dxc - 1), gy = y0 + ly;   // copy dxc holds dy[x' - dx]
+                        const bool ok = (unsigned)gx < (unsigned)W && gy < H;
+                        const uint8_t* src = ok ? ysrc + ((size_t(gz) * H + gy) * W + gx) * ypitch + cg * 16 : ysrc;
+                        cp_async16(blk + uint32_t(((ly * 3 + dxc) * NCGY + cg) * 32 + lx) * 16u, src, ok ? 16u : 0u);
+                    }
+                    cp_async_mbar_arrive(yfull(slot));
+                    ++ycnt;
+                }
+            }
+        }
+        cp_async_wait<0>();
+    } else if (warp == 12) {
+        // ===================================== MMA issuer ====================================
+        if (lane == 0 && has_work) {
+            const uint32_t idesc = umma_idesc(128, N, 0, 0, 1, 1);    // both operands MN-major
+            const uint64_t a_rows_u = uint64_t((R * NCG * 512u) >> 4);       // R x rows further
+            const uint64_t b_rows_u = uint64_t((R * 3 * NCGY * 512u) >> 4);  // R dy rows further
+            uint32_t xcnt = 0, ycnt = 0;
+            uint32_t first_mask = 7u;   // accumulators not yet written
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int zc = item % p.zchunks;
+                const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
+                const int nz = z1 - z0;
+                mbar_wait(xfull(xcnt % kXSlots), (xcnt / kXSlots) & 1, 0x3300u);
+                mbar_wait(xfull((xcnt + 1) % kXSlots), ((xcnt + 1) / kXSlots) & 1, 0x3301u);
+#pragma unroll 1
+                for (int j = 0; j < nz; ++j, ++ycnt) {
+                    const uint32_t c2 = xcnt + j + 2;
+                    mbar_wait(xfull(c2 % kXSlots), (c2 / kXSlots) & 1, 0x3302u);
+                    mbar_wait(yfull(ycnt % kYSlots), (ycnt / kYSlots) & 1, 0x3303u);
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint64_t b_pl = umma_smem_desc(sbase + p.off_y + (ycnt % kYSlots) * p.y_slot_bytes, 128u, 512u);
+#pragma unroll
+                    for (int dz = 0; dz < 3; ++dz) {
+                        const uint64_t a_pl = umma_smem_desc(sbase + ((xcnt + j + dz) % kXSlots) * p.x_slot_bytes, 128u, 512u);
+                        const uint32_t d_tmem = tmem_base + uint32_t(dz * N);
+                        uint32_t accumulate = (first_mask >> dz) & 1u ? 0u : 1u;
+#pragma unroll 1
+                        for (int rg = 0; rg < p.TY / R; ++rg) {
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                umma_f16(d_tmem, a_pl + uint64_t(rg) * a_rows_u + uint64_t(ks * 16), b_pl + uint64_t(rg) * b_rows_u + uint64_t(ks * 16),
+                                         idesc, accumulate);
+                                accumulate = 1u;
+                            }
+                        }
+                    }
+                    first_mask = 0u;
+                    umma_commit(yempty(ycnt % kYSlots));
+                    umma_commit(xempty((xcnt + j) % kXSlots));
+                }
+                umma_commit(xempty((xcnt + nz) % kXSlots));
+                umma_commit(xempty((xcnt + nz + 1) % kXSlots));
+                xcnt += uint32_t(nz + 2);
+            }
+            umma_commit(done_bar);
+        }
+        __syncwarp();
+    } else if (has_work) {
+        // ===================================== epilogue (once) ================================
+        const int r = threadIdx.x;
+        mbar_wait(done_bar, 0, 0x3400u);
+        tc_fence_after();
+        const int a = r / (NCG * 8);
+        const int ci = r % (NCG * 8);
+        const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
+        const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
+        const bool ci_ok = ci < P.t_creal;
+#pragma unroll 1
+        for (int dz = 0; dz < 3; ++dz) {
+#pragma unroll 1
+            for (int b = 0; b < R; ++b) {
+                const int dyi = a - b;   // = dy + 1
+                const bool ok = ci_ok && dyi >= 0 && dyi <= 2;
+#pragma unroll 1
+                for (int dxc = 0; dxc < 3; ++dxc) {
+                    const int tap = (dz * 3 + dyi) * 3 + dxc;
+                    float* dwrow = P.dw + size_t(P.w_moff + ci) * P.w_ktaps + tap;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < CO; c0 += 16) {
+                        float v[16];
+                        tmem_ld16(t_row + uint32_t(dz * N + (b * 3 + dxc) * CO + c0), v);
+                        if (ok) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < P.u_creal) atomicAdd(dwrow + size_t(P.w_noff + c0 + j) * nstride, v[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int NCG, int CO>
+int launch_wband_t(const WBParams& wp, int grid, size_t smem, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_band_kernel<NCG, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    conv_wgrad_band_kernel<NCG, CO><<<grid, kWThreads, smem, stream>>>(wp);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+unsigned int read_device_error_wband() {
+    unsigned int v = 0;
+    cudaMemcpyFromSymbol(&v, g_dev_error, sizeof(v));
+    return v;
+}
+
+bool conv_wgrad_band_eligible(const WgradProblem& P) {
+    static const bool disabled = std::getenv("U3D_NO_WBAND") != nullptr || std::getenv("U3D_NO_HALO") != nullptr;
+    if (disabled) return false;
+    if (P.ntaps != 27 || P.tstride != 1 || P.w_ktaps != 27) return false;
+    if (P.t_c != 16 && P.t_c != 32) return false;
+    if (P.u_c != 16 && P.u_c != 32) return false;
+    if (P.t_d != P.ld || P.t_h != P.lh || P.t_w != P.lw) return false;
+    if (1LL * P.ld * P.lh * P.lw < 32768) return false;
+    for (int t = 0; t < 27; ++t)   // forward tap order (kz,ky,kx) with offsets k-1 and identity tap_ref
+        if (P.taps[t].dz != t / 9 - 1 || P.taps[t].dy != (t / 3) % 3 - 1 || P.taps[t].dx != t % 3 - 1 || P.tap_ref[t] != t) return false;
+    return true;
+}
+
+int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream) {
+    WBParams wp;
+    std::memset(&wp, 0, sizeof(wp));
+    wp.P = P;
+    const int ncg = P.t_c / 8, ncgy = P.u_c / 8;
+    const int arows = 16 / ncg;
+    const int R = std::min(P.u_c == 16 ? 3 : 1, arows - 2);
+    // rows per tile: multiple of R, as many as fit next to the rings
+    int TY = 0;
+    for (int ty = R; ty <= 24; ty += R) {
+        const int hya = std::max(ty + 2, ty - R + arows);
+        const size_t need = size_t(kXSlots) * hya * ncg * 512 + size_t(kYSlots) * ty * 3 * ncgy * 512 + 1024;
+        if (need <= 200 * 1024 && ty <= std::max(R, P.lh)) TY = ty;
+    }
+    if (TY == 0) { set_error("conv_wgrad_band_launch: tile does not fit in shared memory"); return 1; }
+    {   // do not pay for rows past the volume: even out the tiles
+        const int tiles = (P.lh + TY - 1) / TY;
+        int even = (P.lh + tiles - 1) / tiles;
+        even = (even + R - 1) / R * R;
+        TY = std::min(TY, even);
+    }
+    wp.TY = TY;
+    wp.HYA = std::max(TY + 2, TY - R + arows);
+    wp.tiles_x = (P.lw + 31) / 32;
+    wp.tiles_y = (P.lh + TY - 1) / TY;
+    const int sms = device_sm_count();
+    const int cols = wp.tiles_x * wp.tiles_y;
+    int best_zc = 1;
+    double best_eff = -1;
+    for (int zc = 1; zc <= std::max(1, P.ld / 4); ++zc) {
+        const int zl = (P.ld + zc - 1) / zc;
+        const int zc_eff = (P.ld + zl - 1) / zl;
+        const long long items = 1LL * cols * zc_eff;
+        const long long waves = (items + sms - 1) / sms;
+        const double eff = double(items) / double(waves * sms) * double(zl) / double(zl + 2);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_zc = zc_eff; }
+    }
+    wp.zlen = (P.ld + best_zc - 1) / best_zc;
+    wp.zchunks = (P.ld + wp.zlen - 1) / wp.zlen;
+    wp.total_items = cols * wp.zchunks;
+    wp.x_slot_bytes = uint32_t(wp.HYA * ncg * 512);
+    wp.y_slot_bytes = uint32_t(TY * 3 * ncgy * 512);
+    wp.off_y = kXSlots * wp.x_slot_bytes;
+    wp.off_bars = wp.off_y + kYSlots * wp.y_slot_bytes;
+    const size_t smem = wp.off_bars + 8 * (2 * kXSlots + 2 * kYSlots + 1) + 16;
+    if (smem > 227 * 1024) { set_error("conv_wgrad_band_launch: tile does not fit in shared memory"); return 1; }
+    const int grid = std::max(1, std::min(wp.total_items, sms));
+    if (ncg == 2 && P.u_c == 16) return launch_wband_t<2, 16>(wp, grid, smem, stream);
+    if (ncg == 2) return launch_wband_t<2, 32>(wp, grid, smem, stream);
+    if (P.u_c == 16) return launch_wband_t<4, 16>(wp, grid, smem, stream);
+    return launch_wband_t<4, 32>(wp, grid, smem, stream);
+}
+
+}  // namespace u3d

@@ -274,7 +274,10 @@ int conv_wgrad_dispatch(const std::vector<WgradProblem>& probs, const WgradLaunc
     std::vector<WgradProblem> rest;
     int n = 0;
     for (const auto& P : probs) {
-        if (conv_wgrad_rows_eligible(P)) {
+        if (conv_wgrad_band_eligible(P)) {
+            if (conv_wgrad_band_launch(P, stream)) return 1;
+            ++n;
+        } else if (conv_wgrad_rows_eligible(P)) {
             if (conv_wgrad_rows_launch(P, stream)) return 1;
             ++n;
         } else

@@ -763,7 +763,7 @@ int Model::run_backward() {
             }
             WgradLaunch wc{};
             bool all_rows = !s.wg.empty();
-            for (const auto& wp : s.wg) all_rows = all_rows && conv_wgrad_rows_eligible(wp);
+            for (const auto& wp : s.wg) all_rows = all_rows && (conv_wgrad_band_eligible(wp) || conv_wgrad_rows_eligible(wp));
             prof_begin(all_rows ? 3 : 1, s.flops);
             int nl = 0;
             M_CHECK(conv_wgrad_dispatch(s.wg, wc, stream, &nl));

@@ -123,6 +123,9 @@ unsigned int read_device_error_tma();
 bool conv_halo_wants_kc16(int ks, int stride, int transposed, int k_channels_padded, int n_channels_padded, long long voxels);
 unsigned int read_device_error_halo();
 
+bool conv_wgrad_band_eligible(const WgradProblem& P);
+int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream);
+unsigned int read_device_error_wband();
 bool conv_wgrad_rows_eligible(const WgradProblem& P);
 int conv_wgrad_rows_launch(const WgradProblem& P, cudaStream_t stream);
 // row-stacked halo kernel per eligible problem, generic kernel for the rest; *launches = kernels launched
