@@ -19,7 +19,7 @@
 // The CTA marches along z through a 4-slot ring of planes (3 in use, 1 loading): every input plane is fetched once per
 // (x,y) tile column, there is no halo re-read along z at all.
 //
-// CTA = 416 threads: warps 0-3 epilogue, warps 4-11 producers (16-byte cp.async, zero fill = padding), warp 12 MMA issuer.
+// CTA = 448 threads: warps 0-3 epilogue, warps 4-11 producers (16-byte cp.async, zero fill = padding), warps 12-13 MMA issuers.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -32,9 +32,9 @@
 namespace u3d {
 namespace {
 
-constexpr int kBThreads = 32 * 13;
+constexpr int kBThreads = 32 * 14;
 constexpr int kBProducers = 256;
-constexpr int kSlots = 4;
+constexpr int kMaxSlots = 8;   // ring of input z-planes: 3 in use + (nslots - 3) in flight
 
 struct BParams {
     ConvProblem P;
@@ -43,6 +43,7 @@ struct BParams {
     int tiles_x, tiles_y, zchunks, zlen, total_items;
     int ncg;               // channel groups of 8 (both sources)
     int NB;                // columns of one weight block: 4*CO
+    int nslots;
     uint32_t slot_bytes, w_bytes, off_w, off_stats, off_bars;
     float* stats;
     int epi;
@@ -74,17 +75,18 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
     const uint32_t sW = sbase + p.off_w;
     float* sstats = reinterpret_cast<float*>(smem + p.off_stats);
     const uint32_t bars = sbase + p.off_bars;
-    auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (kSlots + s); };
-    auto tfull_bar = [&](int a) { return bars + 8u * (2 * kSlots + a); };
-    auto tempty_bar = [&](int a) { return bars + 8u * (2 * kSlots + 2 + a); };
-    const uint32_t wfull_bar = bars + 8u * (2 * kSlots + 4);
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kSlots + 5));
+    const uint32_t kSlots = uint32_t(p.nslots);
+    auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bars + 8u * (kMaxSlots + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxSlots + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * kMaxSlots + 2 + a); };
+    const uint32_t wfull_bar = bars + 8u * (2 * kMaxSlots + 4);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kMaxSlots + 5));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSlots; ++s) {
+        for (uint32_t s = 0; s < kSlots; ++s) {
             mbar_init(full_bar(s), kBProducers);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), 2);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -119,6 +121,8 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
         const uint32_t pitch0 = uint32_t(P.c0p) * 2u, pitch1 = uint32_t(P.c1p) * 2u;
         const int HX = p.HX, HY = p.HY, HQ = p.HQ, ROWS = p.ROWS;
         const int per_plane = HY * HX * ncg;
+        const uint32_t inv_hx = (1u << 20) / uint32_t(HX) + 1u;     // pos / HX == (pos * inv_hx) >> 20 for pos < HX*HY (no integer division in the loop)
+        const int cg_shift = ncg == 2 ? 1 : 2;
         uint32_t cnt = 0;   // planes loaded by this CTA so far (ring position)
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             int rem = item;
@@ -128,31 +132,40 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
             const int x0 = tx * p.TX - 1, y0 = ty * p.TY - 1;
             const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
             for (int gz = z0 - 1; gz <= z1; ++gz, ++cnt) {
-                const int slot = cnt % kSlots;
+                const uint32_t slot = cnt % kSlots;
                 mbar_wait(empty_bar(slot), ((cnt / kSlots) & 1) ^ 1, 0x2100u | slot);
                 const uint32_t blk = sbase + slot * p.slot_bytes;
                 const bool zok = (unsigned)gz < (unsigned)D;
+                // plane origin (gz, y0, x0); only offsets of in-range voxels are ever added to it
+                const long long vox0 = ((long long)(zok ? gz : 0) * H + y0) * W + x0;
+                const uint8_t* const p0 = s0 + vox0 * (long long)pitch0;
+                const uint8_t* const p1 = s1 + vox0 * (long long)pitch1;
                 // consecutive lanes: the 16-byte chunks of one voxel, then the next voxel along x (coalesced)
 #pragma unroll 2
                 for (int idx = t; idx < per_plane; idx += kBProducers) {
-                    const int cg = idx % ncg;
-                    const int pos = idx / ncg;
-                    const int hx = pos % HX, hy = pos / HX;
-                    const int gx = x0 + hx, gy = y0 + hy;
-                    const bool ok = zok && (unsigned)gx < (unsigned)W && (unsigned)gy < (unsigned)H;
-                    const size_t vox = (size_t(gz) * H + gy) * W + gx;
+                    const int cg = idx & (ncg - 1);
+                    const uint32_t pos = uint32_t(idx) >> cg_shift;
+                    const int hy = int((pos * inv_hx) >> 20);
+                    const int hx = int(pos) - hy * HX;
+                    const bool ok = zok && (unsigned)(x0 + hx) < (unsigned)W && (unsigned)(y0 + hy) < (unsigned)H;
+                    const int off = hy * W + hx;
                     const uint8_t* src;
-                    if (cg < ncg0) src = ok ? s0 + vox * pitch0 + cg * 16 : s0;
-                    else src = ok ? s1 + vox * pitch1 + (cg - ncg0) * 16 : s1;
-                    const int r = hx % G, hq = hx / G;
+                    if (cg < ncg0) src = ok ? p0 + (long long)off * pitch0 + cg * 16 : s0;
+                    else src = ok ? p1 + (long long)off * pitch1 + (cg - ncg0) * 16 : s1;
+                    const int r = hx & (G - 1), hq = hx / G;
                     cp_async16(blk + uint32_t((cg * G + r) * ROWS + hy * HQ + hq) * 16u, src, ok ? 16u : 0u);
                 }
                 cp_async_mbar_arrive(full_bar(slot));
             }
         }
         cp_async_wait<0>();
-    } else if (warp == 12) {
-        // ===================================== MMA issuer ====================================
+    } else if (warp >= 12) {
+        // ===================================== MMA issuers ===================================
+        // Two issuing threads: issuer wi owns TMEM accumulator wi and every output plane whose running index has parity wi.  A single
+        // thread sustains one MMA per ~87 clk in this loop (ncu: it never waits, it is issue-bound), the hardware accepts one per ~40.
+        // Plane release protocol (empty barrier count 2 = one arrival per issuer): an issuer arrives on plane q after ITS last
+        // output that reads q (outputs q-2, q-1, q of its parity); planes it never reads are released as soon as they are resident.
+        const uint32_t wi = uint32_t(warp - 12);
         if (lane == 0) {
             const int HQ = p.HQ, ROWS = p.ROWS;
             const uint32_t lbo_a = uint32_t(G * ROWS) * 16u;             // next channel group of 8
@@ -185,9 +198,16 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                 // planes cnt, cnt+1 (relative z0-1, z0) must be resident before output plane 0; plane j+2 before output j
                 mbar_wait(full_bar(cnt % kSlots), (cnt / kSlots) & 1, 0x2300u);
                 mbar_wait(full_bar((cnt + 1) % kSlots), ((cnt + 1) / kSlots) & 1, 0x2301u);
+                if ((acc_cnt & 1u) != wi) {          // output 0 belongs to the other issuer: this one never reads plane 0 (nor 1 if nz == 1)
+                    mbar_arrive(empty_bar(cnt % kSlots));
+                    if (nz == 1) mbar_arrive(empty_bar((cnt + 1) % kSlots));
+                }
+                const uint32_t last_owner = (acc_cnt + uint32_t(nz - 1)) & 1u;
 #pragma unroll 1
                 for (int j = 0; j < nz; ++j, ++acc_cnt) {
-                    const uint32_t c2 = cnt + j + 2;
+                    if ((acc_cnt & 1u) != wi) continue;
+                    const uint32_t c1 = cnt + j + 1, c2 = cnt + j + 2;
+                    mbar_wait(full_bar(c1 % kSlots), (c1 / kSlots) & 1, 0x2303u);
                     mbar_wait(full_bar(c2 % kSlots), (c2 / kSlots) & 1, 0x2302u);
                     fence_proxy_async();
                     tc_fence_after();
@@ -224,10 +244,15 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                         }
                     }
                     umma_commit(tfull_bar(acc));
-                    umma_commit(empty_bar((cnt + j) % kSlots));     // plane z-1 is no longer needed
+                    umma_commit(empty_bar((cnt + j) % kSlots));
+                    umma_commit(empty_bar(c1 % kSlots));
+                    if (j >= nz - 2) umma_commit(empty_bar(c2 % kSlots));   // this issuer has no later output reading plane j+2
                 }
-                umma_commit(empty_bar((cnt + nz) % kSlots));
-                umma_commit(empty_bar((cnt + nz + 1) % kSlots));
+                if (last_owner != wi) {              // plane nz+1 is read by output nz-1 only
+                    const uint32_t c = cnt + uint32_t(nz + 1);
+                    mbar_wait(full_bar(c % kSlots), (c / kSlots) & 1, 0x2304u);
+                    mbar_arrive(empty_bar(c % kSlots));
+                }
                 cnt += uint32_t(nz + 2);
             }
         }
@@ -439,7 +464,7 @@ int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
     }
     bp.HX = bp.TX + 2; bp.HY = bp.TY + 2;
     bp.HQ = (bp.HX + bp.G - 1) / bp.G;
-    bp.ROWS = (2 * bp.HQ + 129 + 7) / 8 * 8;
+    bp.ROWS = (2 * bp.HQ + 129) | 1;   // odd: the 16-byte chunks of the ncg*G phase planes fall into different banks (conflict-free cp.async writes)
     bp.tiles_x = (P.in_w + bp.TX - 1) / bp.TX;
     bp.tiles_y = (P.in_h + bp.TY - 1) / bp.TY;
     // z chunks: enough items for >= ~4 waves of the SMs, at least 8 planes per chunk (2 halo planes are re-read per chunk)
@@ -464,10 +489,12 @@ int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
     bp.total_items = cols * bp.zchunks;
     bp.slot_bytes = uint32_t(bp.ncg * bp.G * bp.ROWS * 16);
     bp.w_bytes = uint32_t(9 * bp.KS * 2 * bp.NB * 16);
-    bp.off_w = kSlots * bp.slot_bytes;
+    bp.nslots = int(std::min<size_t>(kMaxSlots, (size_t(222) * 1024 - bp.w_bytes - 9 * bp.CO * 4) / bp.slot_bytes));
+    if (bp.nslots < 4) { set_error("conv_band_launch: plane ring does not fit in shared memory"); return 1; }
+    bp.off_w = bp.nslots * bp.slot_bytes;
     bp.off_stats = bp.off_w + bp.w_bytes;
     bp.off_bars = uint32_t((bp.off_stats + 9 * bp.CO * 4 + 15) & ~15u);
-    const size_t smem = bp.off_bars + 8 * (2 * kSlots + 5) + 16;
+    const size_t smem = bp.off_bars + 8 * (2 * kMaxSlots + 5) + 16;
     if (smem > 227 * 1024) { set_error("conv_band_launch: tile does not fit in shared memory"); return 1; }
     bp.epi = cfg.epi;
     bp.stats = cfg.epi == EPI_STORE16 ? cfg.stats_partials : nullptr;

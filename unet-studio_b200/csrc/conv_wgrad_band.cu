@@ -24,9 +24,11 @@
 namespace u3d {
 namespace {
 
-constexpr int kWThreads = 32 * 13;   // warps 0-3 epilogue, 4-11 producers, 12 MMA issuer
+constexpr int kWThreads = 32 * 15;   // warps 0-3 epilogue, 4-11 producers, 12-14 MMA issuers (one per dz)
 constexpr int kWProducers = 256;
 constexpr int kXSlots = 4, kYSlots = 2;
+constexpr int kRun = 33;             // a run of 32 voxels (512 B) + 16 B pad: the channel-group runs a warp writes fall into different banks
+constexpr uint32_t kRunB = kRun * 16u;
 
 struct WBParams {
     WgradProblem P;
@@ -55,9 +57,9 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kXSlots + 2 * kYSlots + 1));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kXSlots; ++s) { mbar_init(xfull(s), kWProducers); mbar_init(xempty(s), 1); }
-        for (int s = 0; s < kYSlots; ++s) { mbar_init(yfull(s), kWProducers); mbar_init(yempty(s), 1); }
-        mbar_init(done_bar, 1);
+        for (int s = 0; s < kXSlots; ++s) { mbar_init(xfull(s), kWProducers); mbar_init(xempty(s), 3); }
+        for (int s = 0; s < kYSlots; ++s) { mbar_init(yfull(s), kWProducers); mbar_init(yempty(s), 3); }
+        mbar_init(done_bar, 3);
         fence_barrier_init();
     }
     if (warp == 12) {
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
         const uint32_t xpitch = uint32_t(P.t_cp) * 2u, ypitch = uint32_t(P.u_cp) * 2u;
         const int TY = p.TY;
         const int xtotal = (TY + 2) * 32 * NCG;
-        const int ytotal = TY * 3 * 32 * NCGY;
+        const int ytotal = TY * 32 * NCGY;
         uint32_t xcnt = 0, ycnt = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             int rem = item;
@@ -95,15 +97,15 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
                     mbar_wait(xempty(slot), ((xcnt / kXSlots) & 1) ^ 1, 0x3100u | slot);
                     const uint32_t blk = sbase + slot * p.x_slot_bytes;
                     const bool zok = (unsigned)gz < (unsigned)D;
+                    const uint8_t* const xpl = xsrc + (((long long)(zok ? gz : 0) * H + (y0 - 1)) * W + x0) * (long long)xpitch;
 #pragma unroll 2
                     for (int idx = t; idx < xtotal; idx += kWProducers) {
                         const int cg = idx % NCG;
                         const int q = idx / NCG;
                         const int lx = q % 32, hy = q / 32;
-                        const int gx = x0 + lx, gy = y0 + hy - 1;
-                        const bool ok = zok && gx < W && (unsigned)gy < (unsigned)H;
-                        const uint8_t* src = ok ? xsrc + ((size_t(gz) * H + gy) * W + gx) * xpitch + cg * 16 : xsrc;
-                        cp_async16(blk + uint32_t((hy * NCG + cg) * 32 + lx) * 16u, src, ok ? 16u : 0u);
+                        const bool ok = zok && x0 + lx < W && (unsigned)(y0 + hy - 1) < (unsigned)H;
+                        const uint8_t* src = ok ? xpl + (long long)(hy * W + lx) * xpitch + cg * 16 : xsrc;
+                        cp_async16(blk + uint32_t((hy * NCG + cg) * kRun + lx) * 16u, src, ok ? 16u : 0u);
                     }
                     cp_async_mbar_arrive(xfull(slot));
                     ++xcnt;
@@ -112,17 +114,21 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
                     const int slot = ycnt % kYSlots;
                     mbar_wait(yempty(slot), ((ycnt / kYSlots) & 1) ^ 1, 0x3200u | slot);
                     const uint32_t blk = sbase + p.off_y + slot * p.y_slot_bytes;
+                    const uint8_t* const ypl = ysrc + (((long long)gz * H + y0) * W + x0) * (long long)ypitch;
 #pragma unroll 2
                     for (int idx = t; idx < ytotal; idx += kWProducers) {
                         const int cg = idx % NCGY;
-                        int q = idx / NCGY;
-                        const int lx = q % 32; q /= 32;
-                        const int dxc = q % 3;
-                        const int ly = q / 3;
-                        const int gx = x0 + lx - (dxc - 1), gy = y0 + ly;   // copy dxc holds dy[x' - dx]
-                        const bool ok = (unsigned)gx < (unsigned)W && gy < H;
-                        const uint8_t* src = ok ? ysrc + ((size_t(gz) * H + gy) * W + gx) * ypitch + cg * 16 : ysrc;
-                        cp_async16(blk + uint32_t(((ly * 3 + dxc) * NCGY + cg) * 32 + lx) * 16u, src, ok ? 16u : 0u);
+                        const int q = idx / NCGY;
+                        const int lx = q % 32, ly = q / 32;
+                        const bool yok = y0 + ly < H;
+                        const uint8_t* const s = ypl + (long long)(ly * W + lx) * ypitch + cg * 16;
+                        const uint32_t d0 = blk + uint32_t((ly * 3 * NCGY + cg) * kRun + lx) * 16u;
+#pragma unroll
+                        for (int dxc = 0; dxc < 3; ++dxc) {   // copy dxc holds dy[x' - dx], dx = dxc - 1
+                            const int gx = x0 + lx - (dxc - 1);
+                            const bool ok = yok && (unsigned)gx < (unsigned)W;
+                            cp_async16(d0 + uint32_t(dxc * NCGY * kRun) * 16u, ok ? s - (long long)(dxc - 1) * ypitch : ysrc, ok ? 16u : 0u);
+                        }
                     }
                     cp_async_mbar_arrive(yfull(slot));
                     ++ycnt;
@@ -130,49 +136,51 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
             }
         }
         cp_async_wait<0>();
-    } else if (warp == 12) {
-        // ===================================== MMA issuer ====================================
+    } else if (warp >= 12) {
+        // ===================================== MMA issuers ===================================
+        // one issuing thread per dz (own accumulator): a single thread's issue loop, not the tensor pipe, limits the MMA rate
+        const int dz = warp - 12;
         if (lane == 0 && has_work) {
             const uint32_t idesc = umma_idesc(128, N, 0, 0, 1, 1);    // both operands MN-major
-            const uint64_t a_rows_u = uint64_t((R * NCG * 512u) >> 4);       // R x rows further
-            const uint64_t b_rows_u = uint64_t((R * 3 * NCGY * 512u) >> 4);  // R dy rows further
+            const uint64_t a_rows_u = uint64_t((R * NCG * kRunB) >> 4);       // R x rows further
+            const uint64_t b_rows_u = uint64_t((R * 3 * NCGY * kRunB) >> 4);  // R dy rows further
+            const uint32_t d_tmem = tmem_base + uint32_t(dz * N);
+            const int nrg = p.TY / R;
             uint32_t xcnt = 0, ycnt = 0;
-            uint32_t first_mask = 7u;   // accumulators not yet written
+            bool first = true;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 const int zc = item % p.zchunks;
                 const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
                 const int nz = z1 - z0;
-                mbar_wait(xfull(xcnt % kXSlots), (xcnt / kXSlots) & 1, 0x3300u);
-                mbar_wait(xfull((xcnt + 1) % kXSlots), ((xcnt + 1) / kXSlots) & 1, 0x3301u);
+                // x planes this issuer never reads (relative q < dz and q > nz-1+dz): release them once they are resident
+                for (int q = 0; q < dz; ++q) {
+                    const uint32_t c = xcnt + q;
+                    mbar_wait(xfull(c % kXSlots), (c / kXSlots) & 1, 0x3300u);
+                    mbar_arrive(xempty(c % kXSlots));
+                }
 #pragma unroll 1
                 for (int j = 0; j < nz; ++j, ++ycnt) {
-                    const uint32_t c2 = xcnt + j + 2;
-                    mbar_wait(xfull(c2 % kXSlots), (c2 / kXSlots) & 1, 0x3302u);
+                    const uint32_t cq = xcnt + j + dz;     // x plane z + dz - 1
+                    mbar_wait(xfull(cq % kXSlots), (cq / kXSlots) & 1, 0x3302u);
                     mbar_wait(yfull(ycnt % kYSlots), (ycnt / kYSlots) & 1, 0x3303u);
                     fence_proxy_async();
                     tc_fence_after();
-                    const uint64_t b_pl = umma_smem_desc(sbase + p.off_y + (ycnt % kYSlots) * p.y_slot_bytes, 128u, 512u);
-#pragma unroll
-                    for (int dz = 0; dz < 3; ++dz) {
-                        const uint64_t a_pl = umma_smem_desc(sbase + ((xcnt + j + dz) % kXSlots) * p.x_slot_bytes, 128u, 512u);
-                        const uint32_t d_tmem = tmem_base + uint32_t(dz * N);
-                        uint32_t accumulate = (first_mask >> dz) & 1u ? 0u : 1u;
+                    uint64_t ad = umma_smem_desc(sbase + (cq % kXSlots) * p.x_slot_bytes, 128u, kRunB);
+                    uint64_t bd = umma_smem_desc(sbase + p.off_y + (ycnt % kYSlots) * p.y_slot_bytes, 128u, kRunB);
 #pragma unroll 1
-                        for (int rg = 0; rg < p.TY / R; ++rg) {
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                umma_f16(d_tmem, a_pl + uint64_t(rg) * a_rows_u + uint64_t(ks * 16), b_pl + uint64_t(rg) * b_rows_u + uint64_t(ks * 16),
-                                         idesc, accumulate);
-                                accumulate = 1u;
-                            }
-                        }
+                    for (int rg = 0; rg < nrg; ++rg, ad += a_rows_u, bd += b_rows_u) {
+                        if (first) { umma_f16_first(d_tmem, ad, bd, idesc); first = false; }
+                        else umma_f16_acc(d_tmem, ad, bd, idesc);
+                        umma_f16_acc(d_tmem, ad + 16u, bd + 16u, idesc);
                     }
-                    first_mask = 0u;
                     umma_commit(yempty(ycnt % kYSlots));
-                    umma_commit(xempty((xcnt + j) % kXSlots));
+                    umma_commit(xempty(cq % kXSlots));
                 }
-                umma_commit(xempty((xcnt + nz) % kXSlots));
-                umma_commit(xempty((xcnt + nz + 1) % kXSlots));
+                for (int q = nz + dz; q <= nz + 1; ++q) {
+                    const uint32_t c = xcnt + q;
+                    mbar_wait(xfull(c % kXSlots), (c / kXSlots) & 1, 0x3304u);
+                    mbar_arrive(xempty(c % kXSlots));
+                }
                 xcnt += uint32_t(nz + 2);
             }
             umma_commit(done_bar);
@@ -261,7 +269,7 @@ int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream) {
     int TY = 0;
     for (int ty = R; ty <= 24; ty += R) {
         const int hya = std::max(ty + 2, ty - R + arows);
-        const size_t need = size_t(kXSlots) * hya * ncg * 512 + size_t(kYSlots) * ty * 3 * ncgy * 512 + 1024;
+        const size_t need = size_t(kXSlots) * hya * ncg * kRunB + size_t(kYSlots) * ty * 3 * ncgy * kRunB + 1024;
         if (need <= 200 * 1024 && ty <= std::max(R, P.lh)) TY = ty;
     }
     if (TY == 0) { set_error("conv_wgrad_band_launch: tile does not fit in shared memory"); return 1; }
@@ -290,8 +298,8 @@ int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream) {
     wp.zlen = (P.ld + best_zc - 1) / best_zc;
     wp.zchunks = (P.ld + wp.zlen - 1) / wp.zlen;
     wp.total_items = cols * wp.zchunks;
-    wp.x_slot_bytes = uint32_t(wp.HYA * ncg * 512);
-    wp.y_slot_bytes = uint32_t(TY * 3 * ncgy * 512);
+    wp.x_slot_bytes = uint32_t(wp.HYA * ncg * kRunB + 127) & ~127u;
+    wp.y_slot_bytes = uint32_t(TY * 3 * ncgy * kRunB + 127) & ~127u;
     wp.off_y = kXSlots * wp.x_slot_bytes;
     wp.off_bars = wp.off_y + kYSlots * wp.y_slot_bytes;
     const size_t smem = wp.off_bars + 8 * (2 * kXSlots + 2 * kYSlots + 1) + 16;
