@@ -36,6 +36,11 @@ CASES = [
     ("halo_cat16_16_to32", 0, 3, 1, 12, 9, 24, (33, 35, 30)),
     ("halo_cat32_32_k64", 0, 3, 1, 32, 32, 32, (40, 28, 30)),
     ("halo_64_16_k64", 0, 3, 1, 64, 0, 16, (34, 33, 31)),
+    # x-banded kernel (conv_band.cu) and N-stacked wgrad (conv_wgrad_band.cu): ragged tiles in x, y and z chunks
+    ("band_16_16_ragged", 0, 3, 1, 16, 0, 16, (37, 29, 33)),
+    ("band_32_32_ragged", 0, 3, 1, 32, 0, 32, (41, 30, 27)),
+    ("band_cat16_16_flat", 0, 3, 1, 16, 16, 16, (70, 60, 9)),
+    ("band_5_20", 0, 3, 1, 5, 0, 20, (66, 34, 21)),
 ]
 
 

@@ -257,10 +257,68 @@ __global__ void __launch_bounds__(128, 1) bench_mn2(int n, int iters, long long*
     if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
+// conv_band issue pattern: 6 MMAs per (dz,dy) with N = 16,32,48,48,32,16 at D column offsets 0,0,0,16,32,48 (mode 0), or the
+// same A/B/D addresses with one uniform N (mode 1: N = 64 at offset 0; mode 2: N = 48 at offsets 0/16)
+__global__ void __launch_bounds__(128, 1) bench_mixed(int iters, long long* out, int mode) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tptr;
+    const uint32_t sb = smem_u32(smem);
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tptr), 512); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tptr;
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        uint32_t idesc[6], doff[6], boff[6], aoff[6];
+        const int nn[6] = {16, 32, 48, 48, 32, 16};
+        const int dd[6] = {0, 0, 0, 16, 32, 48};
+        const int bb[6] = {32, 16, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            idesc[k] = umma_idesc(128, mode == 0 ? nn[k] : (mode == 1 ? 64 : 48), 0, 0, 0, 0);
+            doff[k] = mode == 0 ? dd[k] : (mode == 1 ? 0 : (k & 1) * 16);
+            boff[k] = mode == 0 ? bb[k] : 0;
+            aoff[k] = (k % 4) * 152 + k / 4;
+        }
+        const uint64_t a_base = umma_smem_desc(sb + 4096, 9728u, 128u);
+        const uint64_t b_base = umma_smem_desc(sb + 128 * 1024, 1024u, 128u);
+        long long t0 = clock64();
+        for (int i = 0; i < iters / 54; ++i) {
+            const uint32_t d = tm + (i & 1) * 64;
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9) {
+                const uint64_t ar = a_base + uint64_t((t9 % 3) * 9 + (t9 / 3) * 1216);
+                const uint64_t br = b_base + uint64_t(t9 * 128);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    if (t9 == 0 && k == 0) umma_f16_first(d + doff[k], ar + aoff[k], br + boff[k], idesc[k]);
+                    else umma_f16_acc(d + doff[k], ar + aoff[k], br + boff[k], idesc[k]);
+                }
+            }
+        }
+        long long t1 = clock64();
+        umma_commit(smem_u32(&bar));
+        mbar_wait(smem_u32(&bar), 0, 0xF00);
+        long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    tc_fence_before(); __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
 int main() {
     long long* d; cudaMalloc(&d, 16);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 4096;
+    cudaFuncSetAttribute(bench_mixed, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int mode : {0, 1, 2}) {
+        bench_mixed<<<1, 128, 200 * 1024>>>(54 * 100, d, mode);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("mixed mode %d : issue %.1f cyc/mma, complete %.1f (%s)\n", mode, double(h[0]) / 5400, double(h[1]) / 5400, cudaGetErrorString(e));
+    }
     cudaFuncSetAttribute(bench_mn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int n : {16, 48, 64, 96, 128, 192})
         for (int sa : {128, 512})

@@ -78,17 +78,19 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
     const uint32_t kSlots = uint32_t(p.nslots);
     auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
     auto empty_bar = [&](uint32_t s) { return bars + 8u * (kMaxSlots + s); };
-    auto tfull_bar = [&](int a) { return bars + 8u * (2 * kMaxSlots + a); };
-    auto tempty_bar = [&](int a) { return bars + 8u * (2 * kMaxSlots + 2 + a); };
-    const uint32_t wfull_bar = bars + 8u * (2 * kMaxSlots + 4);
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kMaxSlots + 5));
+    // 4 TMEM accumulators: issuer wi alternates between accumulators wi and wi+2, so it can issue its next plane while the epilogue
+    // still drains its previous one
+    auto tfull_bar = [&](uint32_t a) { return bars + 8u * (2 * kMaxSlots + a); };
+    auto tempty_bar = [&](uint32_t a) { return bars + 8u * (2 * kMaxSlots + 4 + a); };
+    const uint32_t wfull_bar = bars + 8u * (2 * kMaxSlots + 8);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kMaxSlots + 9));
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < kSlots; ++s) {
             mbar_init(full_bar(s), kBProducers);
             mbar_init(empty_bar(s), 2);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (uint32_t a = 0; a < 4; ++a) {
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 128);
         }
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
     }
     for (int i = threadIdx.x; i < 8 * CO + CO; i += kBThreads) sstats[i] = 0.f;
     if (warp == 12) {
-        tmem_alloc(smem_u32(tmem_ptr_smem), 2 * N < 32 ? 32 : 2 * N);
+        tmem_alloc(smem_u32(tmem_ptr_smem), 4 * N);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -211,10 +213,10 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                     mbar_wait(full_bar(c2 % kSlots), (c2 / kSlots) & 1, 0x2302u);
                     fence_proxy_async();
                     tc_fence_after();
-                    const int acc = acc_cnt & 1;
-                    mbar_wait(tempty_bar(acc), ((acc_cnt >> 1) & 1) ^ 1, 0x2400u | acc);
+                    const uint32_t acc = acc_cnt & 3u;
+                    mbar_wait(tempty_bar(acc), ((acc_cnt >> 2) & 1) ^ 1, 0x2400u | acc);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + uint32_t(acc * N);
+                    const uint32_t d_tmem = tmem_base + acc * uint32_t(N);
                     // row p0 = HQ (hy = 1, hq = 0) of each of the three planes
                     uint64_t a_pl[3];
 #pragma unroll
@@ -285,10 +287,10 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
 #pragma unroll 1
             for (int gz = z0; gz < z1; ++gz, ++acc_cnt) {
                 const size_t vox0 = (size_t(gz) * H + gy) * W + gx0;
-                const int acc = acc_cnt & 1;
-                mbar_wait(tfull_bar(acc), (acc_cnt >> 1) & 1, 0x2500u | acc);
+                const uint32_t acc = acc_cnt & 3u;
+                mbar_wait(tfull_bar(acc), (acc_cnt >> 2) & 1, 0x2500u | acc);
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(acc * N);
+                const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16) + acc * uint32_t(N);
 #pragma unroll
                 for (int xo = 0; xo < G; ++xo) {
                     const bool rv = rv_xy && gx0 + xo < W;
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem_base, 2 * N < 32 ? 32 : 2 * N);
+    if (warp == 12) tmem_dealloc(tmem_base, 4 * N);
 }
 
 // ---- weight pack: reference fp32 tensor -> [9 (dz,dy)][KS][2 k-groups][NB = 4*CO columns][8] fp16, columns = kernel column
@@ -494,7 +496,7 @@ int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
     bp.off_w = bp.nslots * bp.slot_bytes;
     bp.off_stats = bp.off_w + bp.w_bytes;
     bp.off_bars = uint32_t((bp.off_stats + 9 * bp.CO * 4 + 15) & ~15u);
-    const size_t smem = bp.off_bars + 8 * (2 * kMaxSlots + 5) + 16;
+    const size_t smem = bp.off_bars + 8 * (2 * kMaxSlots + 9) + 16;
     if (smem > 227 * 1024) { set_error("conv_band_launch: tile does not fit in shared memory"); return 1; }
     bp.epi = cfg.epi;
     bp.stats = cfg.epi == EPI_STORE16 ? cfg.stats_partials : nullptr;

@@ -26,7 +26,7 @@ namespace {
 
 constexpr int kWThreads = 32 * 15;   // warps 0-3 epilogue, 4-11 producers, 12-14 MMA issuers (one per dz)
 constexpr int kWProducers = 256;
-constexpr int kXSlots = 4, kYSlots = 2;
+constexpr int kXSlots = 4, kYSlots = 3;   // dy ring of 3: with 2 the producers block on it and the x planes behind it arrive late (ncu)
 constexpr int kRun = 33;             // a run of 32 voxels (512 B) + 16 B pad: the channel-group runs a warp writes fall into different banks
 constexpr uint32_t kRunB = kRun * 16u;
 
