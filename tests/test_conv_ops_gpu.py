@@ -27,6 +27,8 @@ CASES = [
     ("ct_256_256", 1, 2, 2, 256, 0, 256, (5, 6, 5)),
     ("k3s1_odd_24_40", 0, 3, 1, 24, 0, 40, (13, 7, 9)),
     ("k3s2_odd", 0, 3, 2, 16, 0, 16, (14, 10, 6)),
+    ("k3s2_odd_dims", 0, 3, 2, 16, 0, 24, (15, 9, 7)),
+    ("ct_64_32_odd", 1, 2, 2, 64, 0, 32, (7, 5, 3)),
     ("k3s1_320", 0, 3, 1, 32, 0, 320, (8, 8, 4)),
     # >= 32768 voxels, K,N <= 32: these go through the halo-block kernel (conv_halo.cu), incl. ragged tile edges
     ("halo_16_16", 0, 3, 1, 16, 0, 16, (40, 36, 28)),

@@ -454,6 +454,10 @@ int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& c
             set_error("conv_igemm_launch: bad problem shape");
             return 1;
         }
+        if (P.shuffle_cp) {
+            set_error("conv_igemm_launch: parity-stacked problems need the TMA kernel");
+            return 1;
+        }
         const long long M = 1LL * P.od * P.oh * P.ow;
         P.mtiles = int((M + 127) / 128);
         for (int t = 0; t < P.ntaps; ++t) P.tap_delta[t] = (P.taps[t].dz * P.in_h + P.taps[t].dy) * P.in_w + P.taps[t].dx;

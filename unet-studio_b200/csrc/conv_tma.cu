@@ -250,11 +250,23 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
             for (int c0 = 0; c0 < P.ntile; c0 += 16) {
                 float v[16];
                 tmem_ld16(t_row + c0, v);
-                const int n0 = w.nt * P.ntile + c0;
+                int n0 = w.nt * P.ntile + c0;
+                int nreal = P.n_real;
+                bool rvc = rv;
+                size_t voxc = vox;
+                if (P.shuffle_cp) {
+                    // parity-stacked columns: block (pz,py,px) of lattice voxel o is destination voxel 2*o + (pz,py,px)
+                    const int par = n0 / P.shuffle_cp;
+                    n0 -= par * P.shuffle_cp;
+                    nreal = P.shuffle_nreal;
+                    const int zz = 2 * oz + (par >> 2), yy = 2 * oy + ((par >> 1) & 1), xx = 2 * ox + (par & 1);
+                    rvc = rv && zz < P.OD && yy < P.OH && xx < P.OW;
+                    voxc = (size_t(zz) * P.OH + yy) * P.OW + xx;
+                }
                 if (P.bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (n0 + j < P.n_real) v[j] += __ldg(P.bias + n0 + j);
+                        if (n0 + j < nreal) v[j] += __ldg(P.bias + n0 + j);
                 }
                 if constexpr (EPI == EPI_PLANAR32) {
                     if (rv) {
@@ -264,9 +276,9 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                             if (n0 + j < P.n_real) out[size_t(n0 + j) * M + m] = v[j];
                     }
                 } else {
-                    uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.dst) + (vox * P.dst_cp + P.dst_coff + n0) * 2);
+                    uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.dst) + (voxc * P.dst_cp + P.dst_coff + n0) * 2);
                     if constexpr (EPI == EPI_ACCUM16) {
-                        if (rv) {
+                        if (rvc) {
                             const uint4 o0 = out[0], o1 = out[1];
                             const uint32_t ow_[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
@@ -277,7 +289,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                             }
                         }
                     }
-                    if (rv) {
+                    if (rvc) {
                         uint4 q0, q1;
                         q0.x = pack2<false>(v[0], v[1]); q0.y = pack2<false>(v[2], v[3]);
                         q0.z = pack2<false>(v[4], v[5]); q0.w = pack2<false>(v[6], v[7]);
@@ -387,6 +399,11 @@ unsigned int read_device_error_tma() {
     return v;
 }
 
+bool conv_tma_available() {
+    static const bool disabled = std::getenv("U3D_NO_TMA") != nullptr;
+    return !disabled && encode_fn() != nullptr;
+}
+
 bool conv_tma_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg) {
     static const bool disabled = std::getenv("U3D_NO_TMA") != nullptr;
     static const int min_kc = std::getenv("U3D_TMA_MIN_KC") ? std::atoi(std::getenv("U3D_TMA_MIN_KC")) : 16;
@@ -395,6 +412,7 @@ bool conv_tma_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& 
     if (cfg.kc < min_kc || cfg.a_bf16 || cfg.b_bf16) return false;
     for (const auto& P : probs) {
         if (P.istride != 1 && P.istride != 2) return false;
+        if (P.shuffle_cp && cfg.epi == EPI_PLANAR32) return false;
         if (P.ntile % 16 || P.ntile < 16 || P.ntile > 256 || P.ntaps < 1 || P.ntaps > 27 || P.nch0 + P.nch1 < 1) return false;
         // tensor-map constraints: 16-byte aligned base and strides
         if ((reinterpret_cast<uintptr_t>(P.src0) & 15) || (P.c0p * 2) % 16) return false;

@@ -61,12 +61,17 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackDesc d) {
         const int tap = int(r);
         const int s = ch < d.nch[0] ? 0 : 1;
         const int kk = (ch - (s ? d.nch[0] : 0)) * d.kc + kg * 8 + k8;
-        const int nn = nt * d.ntile + n;
+        int nn = nt * d.ntile + n;
+        int ref = d.tap_ref[tap];
+        if (d.stack_cp) {   // parity-stacked columns: the reference tap depends on the column block
+            ref = d.stack_ref[tap][nn / d.stack_cp];
+            nn = nn % d.stack_cp;
+        }
         float v = 0.f;
-        if (kk < d.k_real[s] && nn < d.n_real) {
+        if (ref >= 0 && kk < d.k_real[s] && nn < d.n_real) {
             const int kidx = d.k_off[s] + kk, nidx = d.n_off + nn;
             const long long a = d.n_is_A ? nidx : kidx, b = d.n_is_A ? kidx : nidx;
-            v = d.w[(a * d.dimB + b) * d.ktaps + d.tap_ref[tap]];
+            v = d.w[(a * d.dimB + b) * d.ktaps + ref];
         }
         if (d.out_bf16)
             static_cast<__nv_bfloat16*>(d.out)[i] = __float2bfloat16_rn(v);

@@ -82,6 +82,35 @@ void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vect
         }
         probs.push_back(P);
         packs.push_back(K);
+    } else if (conv_tma_available()) {
+        // conv_transpose k2 s2 as ONE problem: a 1x1 conv with N = 8 parity blocks of Cout, scattered by the epilogue (no overlap
+        // between the 8 taps, so nothing is summed across blocks)
+        const int cp = pad16(g.cout);
+        choose_ntile(8 * cp, 1LL * g.in_d * g.in_h * g.in_w, ntile, ntiles);
+        ConvProblem P;
+        zero_problem(P);
+        PackDesc K;
+        init_pack(K);
+        P.c0p = c0p; P.c1p = 0;
+        P.nch0 = c0p / kc; P.nch1 = 0;
+        P.in_d = g.in_d; P.in_h = g.in_h; P.in_w = g.in_w;
+        P.istride = 1;
+        P.ntaps = 1;
+        P.taps[0] = ConvTap{0, 0, 0, 0};
+        P.od = g.in_d; P.oh = g.in_h; P.ow = g.in_w;
+        P.OD = g.out_d; P.OH = g.out_h; P.OW = g.out_w;
+        P.ostep = 2;
+        P.dst_cp = cp;
+        P.ntile = ntile; P.ntiles = ntiles; P.n_real = 8 * cp;
+        P.shuffle_cp = cp; P.shuffle_nreal = g.cout;
+        K.dimA = g.cin[0]; K.dimB = g.cout; K.ktaps = 8;
+        K.n_is_A = 0; K.n_off = 0; K.n_real = g.cout; K.ntile = ntile; K.ntiles = ntiles;
+        K.k_off[0] = 0; K.k_real[0] = g.cin[0]; K.nch[0] = P.nch0;
+        K.kc = kc; K.ntaps = 1;
+        K.stack_cp = cp;
+        for (int par = 0; par < 8; ++par) K.stack_ref[0][par] = (signed char)par;
+        probs.push_back(P);
+        packs.push_back(K);
     } else {
         for (int a = 0; a < 2; ++a)
             for (int b = 0; b < 2; ++b)
@@ -153,6 +182,36 @@ void plan_dgrad(const LayerGeom& g, int src, std::vector<ConvProblem>& probs, st
             P.banded = 1; K.banded = 1; K.band_co = pad16(n_real);
             std::memcpy(K.band_taps, P.taps, sizeof(K.band_taps));
         }
+        probs.push_back(P);
+        packs.push_back(K);
+    } else if (!g.transposed && conv_tma_available()) {
+        // stride 2, k3, pad 1 as ONE problem: lattice voxel j gathers dy[j + off], off in {0,1}^3 (8 taps), and produces the 8 input
+        // voxels 2j + p, p in {0,1}^3, as 8 parity blocks of N.  Per dimension (off, p) -> kernel index k:  (0,0) -> 1, (0,1) -> 2,
+        // (1,1) -> 0, (1,0) -> none  (y[o] = sum_k W[k] x[2o + k - 1]); absent combinations are zero blocks of the weight pack.
+        const int cp = pad16(n_real);
+        const int ld = (g.in_d + 1) / 2, lh = (g.in_h + 1) / 2, lw = (g.in_w + 1) / 2;
+        choose_ntile(8 * cp, 1LL * ld * lh * lw, ntile, ntiles);
+        ConvProblem P;
+        PackDesc K;
+        base(P, K);
+        P.ntile = ntile; P.ntiles = ntiles; P.n_real = 8 * cp;
+        K.ntile = ntile; K.ntiles = ntiles;
+        P.istride = 1;
+        P.od = ld; P.oh = lh; P.ow = lw;
+        P.ostep = 2;
+        P.ntaps = 8;
+        P.shuffle_cp = cp; P.shuffle_nreal = n_real;
+        K.stack_cp = cp;
+        const int kof[2][2] = {{1, 2}, {-1, 0}};   // [off][p]
+        for (int t = 0; t < 8; ++t) {
+            const int oz = t >> 2, oy = (t >> 1) & 1, ox = t & 1;
+            P.taps[t] = ConvTap{int8_t(oz), int8_t(oy), int8_t(ox), 0};
+            for (int par = 0; par < 8; ++par) {
+                const int kz = kof[oz][par >> 2], ky = kof[oy][(par >> 1) & 1], kx = kof[ox][par & 1];
+                K.stack_ref[t][par] = (kz < 0 || ky < 0 || kx < 0) ? (signed char)-1 : (signed char)((kz * 3 + ky) * 3 + kx);
+            }
+        }
+        K.dimA = g.cout; K.dimB = g.cin[0] + g.cin[1]; K.ktaps = 27; K.n_is_A = 0; K.ntaps = 8;
         probs.push_back(P);
         packs.push_back(K);
     } else if (!g.transposed) {

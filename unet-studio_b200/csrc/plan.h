@@ -20,6 +20,8 @@ struct PackDesc {
     int tap_ref[27];
     void* out;
     int out_bf16;
+    int stack_cp;            // > 0: N = 8 parity blocks of stack_cp columns; block `par` of GEMM tap t reads reference tap stack_ref[t][par] (-1 = zero)
+    signed char stack_ref[8][8];
     int banded;              // 1: x-banded layout of conv_band.cu ([9 (dz,dy)][K chunk][kx 2,1,0,zero][band_co])
     int band_co;
     ConvTap band_taps[27];   // the problem's tap offsets (which reference tap each (dz,dy,dx) offset reads)

@@ -60,6 +60,9 @@ struct ConvProblem {
     int tap_delta[27];     // (dz*in_h + dy)*in_w + dx  (filled by the launcher)
     int item_base;         // first work item           (filled by the launcher)
     int banded;            // planner: weights packed for the x-banded halo kernel (conv_band.cu)
+    int shuffle_cp;        // > 0: the N columns are 8 output-parity blocks of shuffle_cp channels; block (pz,py,px) of lattice voxel o goes
+                           // to destination voxel 2*o + (pz,py,px) (conv_transpose k2 s2 forward, data gradient of conv k3 s2): conv_tma.cu only
+    int shuffle_nreal;     // real channels per parity block
 };
 
 struct ConvLaunch {
@@ -117,6 +120,7 @@ bool conv_band_wants(int k_channels_padded, int n_channels_padded, long long vox
 bool conv_band_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
 int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
 unsigned int read_device_error_band();
+bool conv_tma_available();   // the driver exposes cuTensorMapEncodeTiled and the kernel is not disabled
 bool conv_tma_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
 int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
 unsigned int read_device_error_tma();
