@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
         }
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < 8 * p.ntot_max; i += kTThreads) sstats[i] = 0.f;
+    for (int i = threadIdx.x; i < 9 * p.ntot_max; i += kTThreads) sstats[i] = 0.f;   // [4 warps][2][ntot] statistics + [ntot] bias
     if (warp == 5) {
         tmem_alloc(smem_u32(tmem_ptr_smem), p.tmem_cols);
         tmem_relinquish();
@@ -225,11 +225,28 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
         __syncwarp();
     } else {
         // ===================================== epilogue ======================================
+        // Instruction-lean on purpose (ncu: with per-element predicated bias loads and 64-bit index math per 16-column chunk the
+        // epilogue, not the copy engine or the tensor pipe, paced the cheap layers at ~13k clk per item): bias staged in shared
+        // memory per problem, per-item invariants in registers, parity/column position advanced incrementally.
         const int r = threadIdx.x;  // 0..127 == TMEM lane == row of the box
         uint32_t acc_cnt = 0;
+        float* sbias = sstats + 8 * p.ntot_max;   // [ntot_max], indexed by the (stacked) column
+        int bias_prob = -1;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++acc_cnt) {
             const TItem w = decode_titem(p, item);
             const ConvProblem& P = p.probs[w.pi];
+            const int cp = P.shuffle_cp, ntile = P.ntile;
+            if (w.pi != bias_prob) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int ntot = ntile * P.ntiles;
+                const int nreal = cp ? P.shuffle_nreal : P.n_real;
+                for (int j = r; j < ntot; j += 128) {
+                    const int jl = cp ? j % cp : j;
+                    sbias[j] = (P.bias != nullptr && jl < nreal) ? __ldg(P.bias + jl) : 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                bias_prob = w.pi;
+            }
             const TBox bx = p.box[w.pi];
             const int txi = w.mt % bx.tiles_x;
             const int rest = w.mt / bx.tiles_x;
@@ -237,46 +254,51 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
             const int lx = r % bx.bx, lrest = r / bx.bx;
             const int ox = txi * bx.bx + lx, oy = tyi * bx.by + lrest % bx.by, oz = tzi * bx.bz + lrest / bx.by;
             const bool rv = r < bx.rows && ox < P.ow && oy < P.oh && oz < P.od;
+            const int OH = P.OH, OW = P.OW, OD = P.OD;
             const long long M = 1LL * P.od * P.oh * P.ow;
             const long long m = (1LL * oz * P.oh + oy) * P.ow + ox;
             size_t vox = 0;
             if (rv && EPI != EPI_PLANAR32)
-                vox = (size_t(oz * P.ostep + P.ooff_z) * P.OH + (oy * P.ostep + P.ooff_y)) * P.OW + (ox * P.ostep + P.ooff_x);
+                vox = (size_t(oz * P.ostep + P.ooff_z) * OH + (oy * P.ostep + P.ooff_y)) * OW + (ox * P.ostep + P.ooff_x);
+            uint8_t* const dst_base = static_cast<uint8_t*>(P.dst) + P.dst_coff * 2;
+            const uint32_t dst_pitch = uint32_t(P.dst_cp) * 2u;
+            const int n_real = P.n_real;
+            int ncol = w.nt * ntile;                 // (stacked) column of the current chunk
+            int par = 0, nloc = ncol;                // parity block and column inside it
+            if (cp) { par = ncol / cp; nloc = ncol - par * cp; }
             const int acc = acc_cnt & 1;
             mbar_wait(tfull_bar(acc), (acc_cnt >> 1) & 1, 0x1400u | acc);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(acc * p.ntile_max);
 #pragma unroll 1
-            for (int c0 = 0; c0 < P.ntile; c0 += 16) {
+            for (int c0 = 0; c0 < ntile; c0 += 16, ncol += 16) {
                 float v[16];
                 tmem_ld16(t_row + c0, v);
-                int n0 = w.nt * P.ntile + c0;
-                int nreal = P.n_real;
+                {
+                    const float4* sb4 = reinterpret_cast<const float4*>(sbias + ncol);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bq = sb4[j];
+                        v[4 * j] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
+                    }
+                }
                 bool rvc = rv;
                 size_t voxc = vox;
-                if (P.shuffle_cp) {
+                if (cp) {
                     // parity-stacked columns: block (pz,py,px) of lattice voxel o is destination voxel 2*o + (pz,py,px)
-                    const int par = n0 / P.shuffle_cp;
-                    n0 -= par * P.shuffle_cp;
-                    nreal = P.shuffle_nreal;
                     const int zz = 2 * oz + (par >> 2), yy = 2 * oy + ((par >> 1) & 1), xx = 2 * ox + (par & 1);
-                    rvc = rv && zz < P.OD && yy < P.OH && xx < P.OW;
-                    voxc = (size_t(zz) * P.OH + yy) * P.OW + xx;
-                }
-                if (P.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + j < nreal) v[j] += __ldg(P.bias + n0 + j);
+                    rvc = rv && zz < OD && yy < OH && xx < OW;
+                    voxc = (size_t(zz) * OH + yy) * OW + xx;
                 }
                 if constexpr (EPI == EPI_PLANAR32) {
                     if (rv) {
                         float* out = static_cast<float*>(P.dst);
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (n0 + j < P.n_real) out[size_t(n0 + j) * M + m] = v[j];
+                            if (ncol + j < n_real) out[size_t(ncol + j) * M + m] = v[j];
                     }
                 } else {
-                    uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.dst) + (voxc * P.dst_cp + P.dst_coff + n0) * 2);
+                    uint4* out = reinterpret_cast<uint4*>(dst_base + voxc * dst_pitch + nloc * 2);
                     if constexpr (EPI == EPI_ACCUM16) {
                         if (rvc) {
                             const uint4 o0 = out[0], o1 = out[1];
@@ -312,13 +334,15 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                         a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
                         q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
                         if ((lane & 1) == 0) {
-                            const int col = n0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                            const int col = ncol + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
                             float* ws = sstats + warp * 2 * p.ntot_max;   // one row per warp, one lane per column: fixed order
                             ws[col] += a[0];
                             ws[p.ntot_max + col] += q[0];
                         }
                     }
                 }
+                nloc += 16;
+                if (cp && nloc == cp) { nloc = 0; ++par; }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
@@ -466,14 +490,14 @@ int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg
     const int spg = 64 / kc;
     tp.a_stage_bytes = uint32_t(128 * kc * 2 * spg);                 // 16 KB
     tp.b_stage_bytes = uint32_t(ntile_max * kc * 2 * spg);
-    const size_t fixed = size_t(8) * ntot_max * 4 + 8 * (2 * 16 + 4) + 16 + 2048;
+    const size_t fixed = size_t(9) * ntot_max * 4 + 8 * (2 * 16 + 4) + 16 + 2048;
     int stages = int((220 * 1024 - fixed) / (tp.a_stage_bytes + tp.b_stage_bytes));
     stages = std::min(stages, 12);
     if (stages < 2) { set_error("conv_tma_launch: tile too large for the smem ring"); return 1; }
     tp.stages = stages;
     tp.off_b = uint32_t(stages) * tp.a_stage_bytes;
     tp.off_stats = tp.off_b + uint32_t(stages) * tp.b_stage_bytes;
-    tp.off_bars = uint32_t((tp.off_stats + 8 * ntot_max * 4 + 15) & ~15u);
+    tp.off_bars = uint32_t((tp.off_stats + 9 * ntot_max * 4 + 15) & ~15u);
     const size_t smem = tp.off_bars + 8 * (2 * stages + 4) + 16;
     tp.stats = (cfg.epi == EPI_STORE16 && probs.size() == 1) ? cfg.stats_partials : nullptr;
     const int grid = std::max(1, std::min(items, device_sm_count()));
