@@ -120,24 +120,45 @@ __global__ void channel_reduce_kernel(const ReduceArgs a) {
         }
     }
     if (vsub < k) {
-        for (long long v = (long long)blockIdx.x * k + vsub; v < a.V; v += (long long)gridDim.x * k) {
-            float x[8];
+        const long long vstride = (long long)gridDim.x * k;
+        for (long long v = (long long)blockIdx.x * k + vsub; v < a.V; v += 2 * vstride) {
+            const long long v2 = v + vstride;
+            const bool has2 = v2 < a.V;
+            float x[8], x2[8];
             load8(a.x + v * nch + ch, x);
+            if (has2) load8(a.x + v2 * nch + ch, x2);
             if (MODE == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     s0[j] += x[j];
                     s1[j] += x[j] * x[j];
                 }
+                if (has2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        s0[j] += x2[j];
+                        s1[j] += x2[j] * x2[j];
+                    }
+                }
             } else {
-                float d[8];
+                float d[8], d2[8];
                 load8(a.dy + v * nch + ch, d);
+                if (has2) load8(a.dy + v2 * nch + ch, d2);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float z = sc[j] * x[j] + sh[j];
                     const float dz = d[j] * act_grad(z, a.act);
                     s0[j] += dz;
                     s1[j] += dz * (x[j] - mu[j]) * rs[j];
+                }
+                if (has2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float z = sc[j] * x2[j] + sh[j];
+                        const float dz = d2[j] * act_grad(z, a.act);
+                        s0[j] += dz;
+                        s1[j] += dz * (x2[j] - mu[j]) * rs[j];
+                    }
                 }
             }
         }
@@ -192,16 +213,34 @@ __global__ void norm_act_fwd_kernel(const ApplyArgs a) {
     __syncthreads();
     const int nch = a.Cp / 8;
     const long long total = a.V * nch;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = int(i % nch);
-        float x[8];
+    // two 16-byte chunks per thread and iteration (independent loads in flight); the channel group of a chunk is tracked with
+    // 32-bit adds instead of a 64-bit modulo per element
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int smod = int(stride % nch);
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int ch = int(i % nch);
+    for (; i < total; i += 2 * stride) {
+        const long long i2 = i + stride;
+        int ch2 = ch + smod; if (ch2 >= nch) ch2 -= nch;
+        const bool has2 = i2 < total;
+        float x[8], y[8];
         load8(a.x + i, x);
+        if (has2) load8(a.x + i2, y);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = ch * 8 + j;
             x[j] = c < a.C ? act_fwd(sc[c] * x[j] + sh[c], a.act) : 0.f;
         }
         store8(a.y + i, x);
+        if (has2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = ch2 * 8 + j;
+                y[j] = c < a.C ? act_fwd(sc[c] * y[j] + sh[c], a.act) : 0.f;
+            }
+            store8(a.y + i2, y);
+        }
+        ch = ch2 + smod; if (ch >= nch) ch -= nch;
     }
 }
 
@@ -245,14 +284,14 @@ __global__ void norm_act_bwd_apply_kernel(const BwdApplyArgs a) {
     __syncthreads();
     const int nch = a.Cp / 8;
     const long long total = a.V * nch;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = int(i % nch);
-        float x[8], d[8];
-        load8(a.x + i, x);
-        load8(a.dy + i, d);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int smod = int(stride % nch);
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int ch = int(i % nch);
+    auto one = [&](int chq, float (&x)[8], float (&d)[8]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = ch * 8 + j;
+            const int c = chq * 8 + j;
             if (c < a.C) {
                 const float z = sc[c] * x[j] + sh[c];
                 const float dz = d[j] * act_grad(z, a.act);
@@ -261,32 +300,50 @@ __global__ void norm_act_bwd_apply_kernel(const BwdApplyArgs a) {
             } else
                 d[j] = 0.f;
         }
+    };
+    for (; i < total; i += 2 * stride) {
+        const long long i2 = i + stride;
+        int ch2 = ch + smod; if (ch2 >= nch) ch2 -= nch;
+        const bool has2 = i2 < total;
+        float x[8], d[8], x2[8], d2[8];
+        load8(a.x + i, x);
+        load8(a.dy + i, d);
+        if (has2) { load8(a.x + i2, x2); load8(a.dy + i2, d2); }
+        one(ch, x, d);
         store8(a.dx + i, d);
+        if (has2) {
+            one(ch2, x2, d2);
+            store8(a.dx + i2, d2);
+        }
+        ch = ch2 + smod; if (ch >= nch) ch -= nch;
     }
 }
 
-// sums partial rows into totals [2][Cp]; optionally accumulates into the gamma/beta gradients.  One warp per channel.
-__global__ void finalize_bwd_sums_kernel(const float* __restrict__ partials, int rows, int Cp, int C, float* __restrict__ sums,
-                                         float* dgamma, float* dbeta) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c >= Cp) return;
-    double a = 0, q = 0;
-    for (int r = lane; r < rows; r += 32) {
-        a += partials[size_t(r) * 2 * Cp + c];
-        q += partials[size_t(r) * 2 * Cp + Cp + c];
+// sums partial rows into totals [2][Cp]; optionally accumulates into the gamma/beta gradients.  ONE block: thread (g, col) walks the
+// rows g, g+G, ... of column col (coalesced 2*Cp-float rows, independent loads in flight), then a fixed-order tree over the G row
+// groups in shared memory (deterministic).  The previous warp-per-channel version spent ~15 us per call on dependent strided loads.
+__global__ void __launch_bounds__(1024) finalize_bwd_sums_kernel(const float* __restrict__ partials, int rows, int Cp, int C,
+                                                                 float* __restrict__ sums, float* dgamma, float* dbeta) {
+    __shared__ double red[1024];
+    const int ncol = 2 * Cp;                     // <= 512
+    const int G = 1024 / ncol;                   // row groups (>= 2)
+    const int col = threadIdx.x % ncol, g = threadIdx.x / ncol;
+    double a = 0;
+    if (g < G) {
+#pragma unroll 4
+        for (int r = g; r < rows; r += G) a += double(partials[size_t(r) * ncol + col]);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (lane != 0) return;
-    sums[c] = float(a);
-    sums[Cp + c] = float(q);
-    if (c < C) {
-        if (dbeta) dbeta[c] += float(a);
-        if (dgamma) dgamma[c] += float(q);
+    red[threadIdx.x] = (g < G) ? a : 0.0;
+    __syncthreads();
+    if (g == 0) {
+        double t = 0;
+        for (int k = 0; k < G; ++k) t += red[k * ncol + col];
+        sums[col] = float(t);
+        const int c = col < Cp ? col : col - Cp;
+        if (c < C) {
+            if (col < Cp) { if (dbeta) dbeta[c] += float(t); }
+            else if (dgamma) dgamma[c] += float(t);
+        }
     }
 }
 
@@ -473,7 +530,8 @@ int norm_act_bwd_launch(const void* x, const void* dy, void* dx, long long V, in
         r.has_norm = 1; r.act = act; r.mean = mean; r.rstd = rstd; r.gamma = gamma; r.beta = beta; r.partials = partials;
         int rows = 0;
         if (reduce_launch(1, r, &rows, s)) return 1;
-        finalize_bwd_sums_kernel<<<(Cp * 32 + 127) / 128, 128, 0, s>>>(partials, rows, Cp, C, sums, dgamma, dbeta);
+        if (2 * Cp > 1024) { set_error("norm_act_bwd_launch: more than 512 padded channels"); return 1; }
+        finalize_bwd_sums_kernel<<<1, 1024, 0, s>>>(partials, rows, Cp, C, sums, dgamma, dbeta);
         U3D_CUDA_CHECK(cudaGetLastError());
     }
     BwdApplyArgs a{};
