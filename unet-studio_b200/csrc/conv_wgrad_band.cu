@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
                         for (int dxc = 0; dxc < 3; ++dxc) {   // copy dxc holds dy[x' - dx], dx = dxc - 1
                             const int gx = x0 + lx - (dxc - 1);
                             const bool ok = yok && (unsigned)gx < (unsigned)W;
-                            cp_async16(d0 + uint32_t(dxc * NCGY * kRun) * 16u, ok ? s - (long long)(dxc - 1) * ypitch : ysrc, ok ? 16u : 0u);
+                            cp_async16_ca(d0 + uint32_t(dxc * NCGY * kRun) * 16u, ok ? s - (long long)(dxc - 1) * ypitch : ysrc, ok ? 16u : 0u);
                         }
                     }
                     cp_async_mbar_arrive(yfull(slot));
