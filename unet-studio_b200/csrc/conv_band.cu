@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                     if (cg < ncg0) src = ok ? p0 + (long long)off * pitch0 + cg * 16 : s0;
                     else src = ok ? p1 + (long long)off * pitch1 + (cg - ncg0) * 16 : s1;
                     const int r = hx & (G - 1), hq = hx / G;
-                    cp_async16(blk + uint32_t((cg * G + r) * ROWS + hy * HQ + hq) * 16u, src, ok ? 16u : 0u);
+                    cp_async16_ca(blk + uint32_t((cg * G + r) * ROWS + hy * HQ + hq) * 16u, src, ok ? 16u : 0u);
                 }
                 cp_async_mbar_arrive(full_bar(slot));
             }

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
                         const int lx = q % 32, hy = q / 32;
                         const bool ok = zok && x0 + lx < W && (unsigned)(y0 + hy - 1) < (unsigned)H;
                         const uint8_t* src = ok ? xpl + (long long)(hy * W + lx) * xpitch + cg * 16 : xsrc;
-                        cp_async16(blk + uint32_t((hy * NCG + cg) * kRun + lx) * 16u, src, ok ? 16u : 0u);
+                        cp_async16_ca(blk + uint32_t((hy * NCG + cg) * kRun + lx) * 16u, src, ok ? 16u : 0u);
                     }
                     cp_async_mbar_arrive(xfull(slot));
                     ++xcnt;
