@@ -219,6 +219,32 @@ __global__ void norm_act_fwd_kernel(const ApplyArgs a) {
     const int smod = int(stride % nch);
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int ch = int(i % nch);
+    if (smod == 0) {
+        float csc[8], csh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            csc[j] = c < a.C ? sc[c] : 0.f;
+            csh[j] = c < a.C ? sh[c] : 0.f;
+        }
+        const int act = a.act;
+        for (; i < total; i += 2 * stride) {
+            const long long i2 = i + stride;
+            const bool has2 = i2 < total;
+            float x[8], y[8];
+            load8(a.x + i, x);
+            if (has2) load8(a.x + i2, y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = act_fwd(csc[j] * x[j] + csh[j], act);
+            store8(a.y + i, x);
+            if (has2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = act_fwd(csc[j] * y[j] + csh[j], act);
+                store8(a.y + i2, y);
+            }
+        }
+        return;
+    }
     for (; i < total; i += 2 * stride) {
         const long long i2 = i + stride;
         int ch2 = ch + smod; if (ch2 >= nch) ch2 -= nch;
@@ -288,6 +314,47 @@ __global__ void norm_act_bwd_apply_kernel(const BwdApplyArgs a) {
     const int smod = int(stride % nch);
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int ch = int(i % nch);
+    if (smod == 0) {
+        // the grid stride is a multiple of the channel groups: every chunk of this thread has the same 8 channels -> coefficients
+        // live in registers (the shared-memory version issued 96 LDS per iteration and was LSU-bound, not HBM-bound)
+        float csc[8], csh[8], cmu[8], crs[8], cm1[8], cm2[8];
+        bool creal[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            csc[j] = sc[c]; csh[j] = sh[c]; cmu[j] = mu[c]; crs[j] = rs[c]; cm1[j] = m1[c]; cm2[j] = m2[c];
+            creal[j] = c < a.C;
+        }
+        const bool hn = a.has_norm != 0;
+        const int act = a.act;
+        for (; i < total; i += 2 * stride) {
+            const long long i2 = i + stride;
+            const bool has2 = i2 < total;
+            float x[8], d[8], x2[8], d2[8];
+            load8(a.x + i, x);
+            load8(a.dy + i, d);
+            if (has2) { load8(a.x + i2, x2); load8(a.dy + i2, d2); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float z = csc[j] * x[j] + csh[j];
+                const float dz = d[j] * act_grad(z, act);
+                const float xh = (x[j] - cmu[j]) * crs[j];
+                d[j] = creal[j] ? (hn ? csc[j] * (dz - cm1[j] - xh * cm2[j]) : dz) : 0.f;
+            }
+            store8(a.dx + i, d);
+            if (has2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float z = csc[j] * x2[j] + csh[j];
+                    const float dz = d2[j] * act_grad(z, act);
+                    const float xh = (x2[j] - cmu[j]) * crs[j];
+                    d2[j] = creal[j] ? (hn ? csc[j] * (dz - cm1[j] - xh * cm2[j]) : dz) : 0.f;
+                }
+                store8(a.dx + i2, d2);
+            }
+        }
+        return;
+    }
     auto one = [&](int chq, float (&x)[8], float (&d)[8]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {

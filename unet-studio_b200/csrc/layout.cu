@@ -49,14 +49,16 @@ __global__ void unpack_act_kernel(const uint4* __restrict__ in, float* __restric
 }
 
 __global__ void pack_weights_kernel(const __grid_constant__ PackDesc d) {
-    const int nch = d.nch[0] + d.nch[1];
-    const long long total = (long long)d.ntaps * nch * d.ntiles * d.ntile * d.kc;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long r = i;
-        const int k8 = int(r % 8); r /= 8;
-        const int n = int(r % d.ntile); r /= d.ntile;
-        const int kg = int(r % (d.kc / 8)); r /= (d.kc / 8);
-        const int nt = int(r % d.ntiles); r /= d.ntiles;
+    // 32-bit index arithmetic (a pack has < 2^31 elements): the six div/mod per element dominated this kernel in 64 bit
+    const uint32_t nch = uint32_t(d.nch[0] + d.nch[1]);
+    const uint32_t ntile = uint32_t(d.ntile), ntiles = uint32_t(d.ntiles), kg_n = uint32_t(d.kc / 8);
+    const uint32_t total = uint32_t(d.ntaps) * nch * ntiles * ntile * uint32_t(d.kc);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t r = i;
+        const int k8 = int(r & 7u); r >>= 3;
+        const int n = int(r % ntile); r /= ntile;
+        const int kg = int(r % kg_n); r /= kg_n;
+        const int nt = int(r % ntiles); r /= ntiles;
         const int ch = int(r % nch); r /= nch;
         const int tap = int(r);
         const int s = ch < d.nch[0] ? 0 : 1;
