@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                     const bool ok = vv && ((cok >> i) & 1u) && (unsigned)(bz + cdz[i]) < (unsigned)t_d &&
                                     (unsigned)(by + cdy[i]) < (unsigned)t_h && (unsigned)(bx + cdx[i]) < (unsigned)t_w;
                     const uint8_t* src = ok ? tbase + (vbase + cdelta[i]) * t_pitch + ccoff[i] : tbase;
-                    cp_async16(a_dst + i * (2u * kKB * 16u), src, ok ? 16u : 0u);
+                    cp_async16_ca(a_dst + i * (2u * kKB * 16u), src, ok ? 16u : 0u);
                 }
                 // ---- B: untapped tensor
                 const uint32_t b_dst = sB + stage * b_stage_bytes + v * 16u;
