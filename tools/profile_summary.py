@@ -1,5 +1,5 @@
-"""Turns an `ncu --metrics gpu__time_duration.sum --csv` launch list into a per-kernel summary (markdown) of the LAST
-step in the capture (everything after the last pack_act_kernel launch = start of a forward)."""
+"""Turns an `ncu --metrics gpu__time_duration.sum --csv` launch list into a per-kernel summary (markdown) of one complete
+step in the capture (from one pack_act_kernel launch = start of a forward to the next)."""
 import collections
 import csv
 import sys
@@ -9,7 +9,8 @@ def main(path, title):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
     idx = [i for i, r in enumerate(rows) if "pack_act" in r["Kernel Name"]]
-    seg = rows[idx[-1]:] if idx else rows
+    # a complete step = from one pack_act (start of a forward) to the next; fall back to the tail of the capture
+    seg = rows[idx[0]:idx[1]] if len(idx) >= 2 else (rows[idx[-1]:] if idx else rows)
     seg = [r for r in seg if "at::" not in r["Kernel Name"]]
     agg = collections.OrderedDict()
     for r in seg:
