@@ -121,7 +121,7 @@ extern "C" int u3d_op_conv_forward(int transposed, int ks, int stride, int cin0,
     int grid = 0;
     cfg.stats_grid_out = &grid;
     const int ntot = probs[0].ntile * probs[0].ntiles;
-    if (stats_sum_sumsq && probs.size() == 1 && !planar_fp32) {
+    if (stats_sum_sumsq && (probs.size() == 1 || probs[0].band_pass) && !planar_fp32) {
         if (dstats.alloc(size_t(device_sm_count()) * 2 * ntot * 4)) { set_error("cudaMalloc failed"); return 1; }
         cfg.stats_partials = static_cast<float*>(dstats.p);
     }

@@ -420,8 +420,14 @@ bool conv_band_wants(int k_channels_padded, int n_channels_padded, long long vox
 }
 
 bool conv_band_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg) {
-    if (probs.size() != 1 || !probs[0].banded) return false;
-    const ConvProblem& P = probs[0];
+    if (probs.empty() || !probs[0].banded) return false;
+    if (probs.size() == 2) {   // two-pass split of a 32 + 32 channel concat layer
+        if (probs[0].band_pass != 1 || probs[1].band_pass != 2 || cfg.epi != EPI_STORE16) return false;
+        if (probs[0].c0p != 32 || probs[0].c1p != 32) return false;
+    } else if (probs.size() != 1 || probs[0].band_pass != 0)
+        return false;
+    ConvProblem P = probs[0];
+    if (P.band_pass) { P.c1p = 0; P.nch1 = 0; }
     if (cfg.kc != 16 || cfg.epi == EPI_PLANAR32 || cfg.a_bf16 || cfg.b_bf16) return false;
     if (P.ntaps != 27 || P.istride != 1 || P.ostep != 1 || P.ntiles != 1) return false;
     if (P.od != P.in_d || P.oh != P.in_h || P.ow != P.in_w || P.coff0 || P.coff1) return false;
@@ -443,10 +449,26 @@ static int launch_band_t(const BParams& bp, int grid, size_t smem, cudaStream_t 
     return 0;
 }
 
+static int conv_band_launch_one(const ConvProblem& P, const ConvLaunch& cfg, bool stats, cudaStream_t stream);
+
 int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream) {
+    if (probs.size() == 2) {
+        ConvProblem A = probs[0], B = probs[1];
+        A.c1p = 0; A.nch1 = 0; A.src1 = nullptr;
+        B.src0 = B.src1; B.c0p = B.c1p; B.nch0 = B.nch1; B.c1p = 0; B.nch1 = 0; B.src1 = nullptr; B.bias = nullptr;
+        ConvLaunch c1 = cfg, c2 = cfg;
+        c1.epi = EPI_STORE16; c1.stats_partials = nullptr; c1.stats_grid_out = nullptr;
+        c2.epi = EPI_ACCUM16;
+        if (conv_band_launch_one(A, c1, false, stream)) return 1;
+        return conv_band_launch_one(B, c2, cfg.stats_partials != nullptr, stream);
+    }
+    return conv_band_launch_one(probs[0], cfg, cfg.epi == EPI_STORE16 && cfg.stats_partials != nullptr, stream);
+}
+
+static int conv_band_launch_one(const ConvProblem& Pin, const ConvLaunch& cfg, bool stats, cudaStream_t stream) {
     BParams bp;
     std::memset(&bp, 0, sizeof(bp));
-    bp.P = probs[0];
+    bp.P = Pin;
     const ConvProblem& P = bp.P;
     bp.CO = P.ntile;
     bp.G = bp.CO == 16 ? 4 : 2;
@@ -499,7 +521,7 @@ int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
     const size_t smem = bp.off_bars + 8 * (2 * kMaxSlots + 9) + 16;
     if (smem > 227 * 1024) { set_error("conv_band_launch: tile does not fit in shared memory"); return 1; }
     bp.epi = cfg.epi;
-    bp.stats = cfg.epi == EPI_STORE16 ? cfg.stats_partials : nullptr;
+    bp.stats = stats ? cfg.stats_partials : nullptr;
     const int grid = std::max(1, std::min(bp.total_items, sms));
     if (cfg.stats_grid_out) *cfg.stats_grid_out = grid;
     if (bp.CO == 16 && bp.KS == 1) return launch_band_t<4, 16, 1>(bp, grid, smem, stream);

@@ -57,7 +57,7 @@ __device__ __forceinline__ void eval_voxel(const LossLevel& L, long long vox, in
         for (int c = 0; c < MAXC; ++c)
             if (c < Cc) l[c] = L.logits[c * nv + vox];
     }
-    const long long li = ((long long)(z << L.shift) * L.H0 + (y << L.shift)) * L.W0 + (x << L.shift);
+    const long long li = L.shift == 0 ? vox : ((long long)(z << L.shift) * L.H0 + (y << L.shift)) * L.W0 + (x << L.shift);
     const long long traw = (long long)L.label[li];
     const bool valid = traw < L.C;
     long long t = traw;
@@ -96,9 +96,14 @@ __global__ void loss_reduce_kernel(const LossLevel L) {
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) a_i[c] = a_k[c] = 0.f;
     for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < nv; vox += (long long)gridDim.x * blockDim.x) {
-        const int x = int(vox % L.w);
-        const long long q = vox / L.w;
-        const int y = int(q % L.h), z = int(q / L.h);
+        int x = 0, y = 0, z = 0;
+        if (L.shift != 0) {   // level 0 reads label[vox] directly; deeper levels need (x,y,z) (32-bit: a level has < 2^31 voxels)
+            const unsigned uv = unsigned(vox);
+            x = int(uv % unsigned(L.w));
+            const unsigned q = uv / unsigned(L.w);
+            y = int(q % unsigned(L.h));
+            z = int(q / unsigned(L.h));
+        }
         Voxel<MAXC> o;
         eval_voxel<MAXC>(L, vox, x, y, z, o);
         a_n += o.v;
@@ -222,9 +227,14 @@ __global__ void loss_grad_kernel(const LossLevel L) {
     const float invZ = 1.f / float(Cc - 1 > 1 ? Cc - 1 : 1);
     __half* out = static_cast<__half*>(L.dlogits);
     for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < nv; vox += (long long)gridDim.x * blockDim.x) {
-        const int x = int(vox % L.w);
-        const long long q = vox / L.w;
-        const int y = int(q % L.h), z = int(q / L.h);
+        int x = 0, y = 0, z = 0;
+        if (L.shift != 0) {   // level 0 reads label[vox] directly; deeper levels need (x,y,z) (32-bit: a level has < 2^31 voxels)
+            const unsigned uv = unsigned(vox);
+            x = int(uv % unsigned(L.w));
+            const unsigned q = uv / unsigned(L.w);
+            y = int(q % unsigned(L.h));
+            z = int(q / unsigned(L.h));
+        }
         Voxel<MAXC> o;
         eval_voxel<MAXC>(L, vox, x, y, z, o);
         float dlo[MAXC];
@@ -318,9 +328,14 @@ __global__ void __launch_bounds__(128) loss_grad_head_kernel(const LossLevel L, 
         for (int k = 0; k < XCP; ++k) aw[c][k] = 0.f;
     }
     for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < nv; vox += (long long)gridDim.x * blockDim.x) {
-        const int x = int(vox % L.w);
-        const long long q = vox / L.w;
-        const int y = int(q % L.h), z = int(q / L.h);
+        int x = 0, y = 0, z = 0;
+        if (L.shift != 0) {   // level 0 reads label[vox] directly; deeper levels need (x,y,z) (32-bit: a level has < 2^31 voxels)
+            const unsigned uv = unsigned(vox);
+            x = int(uv % unsigned(L.w));
+            const unsigned q = uv / unsigned(L.w);
+            y = int(q % unsigned(L.h));
+            z = int(q / unsigned(L.h));
+        }
         Voxel<CT> o;
         eval_voxel<CT>(L, vox, x, y, z, o);
         float dlo[CT];

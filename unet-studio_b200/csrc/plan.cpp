@@ -79,6 +79,21 @@ void plan_forward(const LayerGeom& g, std::vector<ConvProblem>& probs, std::vect
             conv_band_wants(c0p + c1p, pad16(g.cout), 1LL * g.out_d * g.out_h * g.out_w)) {
             P.banded = 1; K.banded = 1; K.band_co = pad16(g.cout);
             std::memcpy(K.band_taps, P.taps, sizeof(K.band_taps));
+        } else if (force_kc == 16 && g.ks == 3 && g.stride == 1 && ntiles == 1 && c0p == 32 && c1p == 32 &&
+                   conv_band_wants(32, pad16(g.cout), 1LL * g.out_d * g.out_h * g.out_w)) {
+            // concat of 32 + 32 channels: two banded launches, one per source (see ConvProblem::band_pass)
+            P.banded = 1; K.banded = 1; K.band_co = pad16(g.cout);
+            std::memcpy(K.band_taps, P.taps, sizeof(K.band_taps));
+            ConvProblem P2 = P;
+            PackDesc K2 = K;
+            P.band_pass = 1; P2.band_pass = 2;
+            K.nch[1] = 0; K.k_real[1] = 0;
+            K2.k_off[0] = g.cin[0]; K2.k_real[0] = g.cin[1]; K2.nch[0] = P.nch1; K2.nch[1] = 0; K2.k_real[1] = 0;
+            probs.push_back(P);
+            packs.push_back(K);
+            probs.push_back(P2);
+            packs.push_back(K2);
+            return;
         }
         probs.push_back(P);
         packs.push_back(K);

@@ -60,6 +60,8 @@ struct ConvProblem {
     int tap_delta[27];     // (dz*in_h + dy)*in_w + dx  (filled by the launcher)
     int item_base;         // first work item           (filled by the launcher)
     int banded;            // planner: weights packed for the x-banded halo kernel (conv_band.cu)
+    int band_pass;         // 0 = whole layer; 1 / 2 = a 32+32-channel concat layer split in two launches: source 0 (store), then source 1
+                           // (read-add-store + statistics) -- the resident weights of K = 64 do not fit next to the plane ring
     int shuffle_cp;        // > 0: the N columns are 8 output-parity blocks of shuffle_cp channels; block (pz,py,px) of lattice voxel o goes
                            // to destination voxel 2*o + (pz,py,px) (conv_transpose k2 s2 forward, data gradient of conv k3 s2): conv_tma.cu only
     int shuffle_nreal;     // real channels per parity block
