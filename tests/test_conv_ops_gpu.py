@@ -43,6 +43,10 @@ CASES = [
     ("band_32_32_ragged", 0, 3, 1, 32, 0, 32, (41, 30, 27)),
     ("band_cat16_16_flat", 0, 3, 1, 16, 16, 16, (70, 60, 9)),
     ("band_5_20", 0, 3, 1, 5, 0, 20, (66, 34, 21)),
+    # wide layers through the N-stacked wgrad kernel as channel-group pairs (one (gi, go) block of dW per CTA)
+    ("wband_64_64", 0, 3, 1, 64, 0, 64, (40, 24, 12)),
+    ("wband_cat64_64_64", 0, 3, 1, 64, 64, 64, (32, 24, 12)),
+    ("wband_48_72", 0, 3, 1, 48, 0, 72, (36, 30, 16)),
 ]
 
 

@@ -34,6 +34,7 @@ struct WBParams {
     WgradProblem P;
     int TY, HYA;               // rows per tile, allocated x rows per plane (TY + 2 halo + junk rows the M = 128 descriptor runs into)
     int tiles_x, tiles_y, zchunks, zlen, total_items;
+    int ngo, npairs, cpp;      // channel-group pairs (gi, go) of a wide layer: CTA b owns pair b % npairs and every cpp-th tile of it
     uint32_t x_slot_bytes, y_slot_bytes, off_y, off_bars;
 };
 
@@ -72,19 +73,22 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
     const uint32_t tmem_base = *tmem_ptr_smem;
     const WgradProblem& P = p.P;
     const int D = P.t_d, H = P.t_h, W = P.t_w;
-    const bool has_work = int(blockIdx.x) < p.total_items;
+    // wide layers (Cin, Cout > 32) are cut into channel-group pairs: each CTA accumulates ONE (gi, go) block of the gradient
+    const int pair = int(blockIdx.x) % p.npairs, rank = int(blockIdx.x) / p.npairs;
+    const int gi = pair / p.ngo, go = pair % p.ngo;
+    const bool has_work = rank < p.total_items;
 
     if (warp >= 4 && warp < 12) {
         // ===================================== producers =====================================
         const int t = threadIdx.x - 128;
-        const uint8_t* const xsrc = static_cast<const uint8_t*>(P.T) + P.t_coff * 2;
-        const uint8_t* const ysrc = static_cast<const uint8_t*>(P.U) + P.u_coff * 2;
+        const uint8_t* const xsrc = static_cast<const uint8_t*>(P.T) + (P.t_coff + gi * NCG * 8) * 2;
+        const uint8_t* const ysrc = static_cast<const uint8_t*>(P.U) + (P.u_coff + go * CO) * 2;
         const uint32_t xpitch = uint32_t(P.t_cp) * 2u, ypitch = uint32_t(P.u_cp) * 2u;
         const int TY = p.TY;
         const int xtotal = (TY + 2) * 32 * NCG;
         const int ytotal = TY * 32 * NCGY;
         uint32_t xcnt = 0, ycnt = 0;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        for (int item = rank; item < p.total_items; item += p.cpp) {
             int rem = item;
             const int zc = rem % p.zchunks; rem /= p.zchunks;
             const int tx = rem % p.tiles_x;
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
             const int nrg = p.TY / R;
             uint32_t xcnt = 0, ycnt = 0;
             bool first = true;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            for (int item = rank; item < p.total_items; item += p.cpp) {
                 const int zc = item % p.zchunks;
                 const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
                 const int nz = z1 - z0;
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
         mbar_wait(done_bar, 0, 0x3400u);
         tc_fence_after();
         const int a = r / (NCG * 8);
-        const int ci = r % (NCG * 8);
+        const int ci = gi * NCG * 8 + r % (NCG * 8);
         const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
         const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
         const bool ci_ok = ci < P.t_creal;
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
                         if (ok) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (c0 + j < P.u_creal) atomicAdd(dwrow + size_t(P.w_noff + c0 + j) * nstride, v[j]);
+                                if (go * CO + c0 + j < P.u_creal) atomicAdd(dwrow + size_t(P.w_noff + go * CO + c0 + j) * nstride, v[j]);
                         }
                     }
                 }
@@ -249,10 +253,11 @@ bool conv_wgrad_band_eligible(const WgradProblem& P) {
     static const bool disabled = std::getenv("U3D_NO_WBAND") != nullptr || std::getenv("U3D_NO_HALO") != nullptr;
     if (disabled) return false;
     if (P.ntaps != 27 || P.tstride != 1 || P.w_ktaps != 27) return false;
-    if (P.t_c != 16 && P.t_c != 32) return false;
-    if (P.u_c != 16 && P.u_c != 32) return false;
+    if (P.t_c % 16 || P.u_c % 16 || P.t_c < 16 || P.u_c < 16) return false;
     if (P.t_d != P.ld || P.t_h != P.lh || P.t_w != P.lw) return false;
-    if (1LL * P.ld * P.lh * P.lw < 32768) return false;
+    // small-channel layers need a big volume to fill the machine; wide layers bring (Cin/32)*(Cout/32) independent pairs
+    const long long pairs = (P.t_c > 32 || P.u_c > 32) ? 1LL * (P.t_c / 16) * (P.u_c / 16) / 4 : 1;
+    if (1LL * P.ld * P.lh * P.lw * pairs < 32768 || 1LL * P.ld * P.lh * P.lw < 4096 || pairs > 64) return false;
     for (int t = 0; t < 27; ++t)   // forward tap order (kz,ky,kx) with offsets k-1 and identity tap_ref
         if (P.taps[t].dz != t / 9 - 1 || P.taps[t].dy != (t / 3) % 3 - 1 || P.taps[t].dx != t % 3 - 1 || P.tap_ref[t] != t) return false;
     return true;
@@ -262,9 +267,12 @@ int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream) {
     WBParams wp;
     std::memset(&wp, 0, sizeof(wp));
     wp.P = P;
-    const int ncg = P.t_c / 8, ncgy = P.u_c / 8;
+    // channel groups per CTA: 32 x 32 when both sides allow it, else 16 x 16 (also the native shapes of the 16/32-channel layers)
+    const int tcg = (P.t_c % 32 == 0) ? 32 : 16, ucg = (P.u_c % 32 == 0) ? 32 : 16;
+    const int ncg = tcg / 8, ncgy = ucg / 8;
     const int arows = 16 / ncg;
-    const int R = std::min(P.u_c == 16 ? 3 : 1, arows - 2);
+    const int R = std::min(ucg == 16 ? 3 : 1, arows - 2);
+    const int ngi = P.t_c / tcg, ngo = P.u_c / ucg;
     // rows per tile: multiple of R, as many as fit next to the rings
     int TY = 0;
     for (int ty = R; ty <= 24; ty += R) {
@@ -283,7 +291,10 @@ int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream) {
     wp.HYA = std::max(TY + 2, TY - R + arows);
     wp.tiles_x = (P.lw + 31) / 32;
     wp.tiles_y = (P.lh + TY - 1) / TY;
-    const int sms = device_sm_count();
+    const int sms0 = device_sm_count();
+    wp.ngo = ngo;
+    wp.npairs = ngi * ngo;
+    const int sms = std::max(1, sms0 / wp.npairs);    // CTAs per pair
     const int cols = wp.tiles_x * wp.tiles_y;
     int best_zc = 1;
     double best_eff = -1;
@@ -304,10 +315,11 @@ int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream) {
     wp.off_bars = wp.off_y + kYSlots * wp.y_slot_bytes;
     const size_t smem = wp.off_bars + 8 * (2 * kXSlots + 2 * kYSlots + 1) + 16;
     if (smem > 227 * 1024) { set_error("conv_wgrad_band_launch: tile does not fit in shared memory"); return 1; }
-    const int grid = std::max(1, std::min(wp.total_items, sms));
-    if (ncg == 2 && P.u_c == 16) return launch_wband_t<2, 16>(wp, grid, smem, stream);
+    wp.cpp = std::max(1, std::min(wp.total_items, sms));
+    const int grid = wp.cpp * wp.npairs;
+    if (ncg == 2 && ucg == 16) return launch_wband_t<2, 16>(wp, grid, smem, stream);
     if (ncg == 2) return launch_wband_t<2, 32>(wp, grid, smem, stream);
-    if (P.u_c == 16) return launch_wband_t<4, 16>(wp, grid, smem, stream);
+    if (ucg == 16) return launch_wband_t<4, 16>(wp, grid, smem, stream);
     return launch_wband_t<4, 32>(wp, grid, smem, stream);
 }
 
