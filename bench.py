@@ -179,7 +179,6 @@ def main():
     l_host = torch.from_numpy(lab).pin_memory()
     x_dev, l_dev = x_host.cuda(), l_host.cuda()
     x_aug, l_aug = torch.empty_like(x_dev), torch.empty_like(l_dev)
-    xa_host, la_host = torch.empty_like(x_host).pin_memory(), torch.empty_like(l_host).pin_memory()
     total_steps = 1000
     step_no = [0]
 
@@ -197,13 +196,13 @@ def main():
         return loss
 
     def one_step_host():
+        # end to end through the C-ABI with HOST buffers: the raw sample is uploaded from pinned memory (train.cpp:615-626), augmented
+        # (train.cpp:459-473) and trained on in one call, the losses come back to the host, then the update
         s = step_no[0]
-        xin, lin = x_host.numpy(), l_host.numpy()
-        if augment:   # drop-in order of train.cpp:459-473 + 615-626: augment host buffers in place, then step on host buffers
-            xa_host.copy_(x_host); la_host.copy_(l_host)
-            pkg.vpa_augment_on(net, xa_host.data_ptr(), la_host.data_ptr(), W, H, D, IN_C, seed=s * world + rank, where=0)
-            xin, lin = xa_host.numpy(), la_host.numpy()
-        loss = net.train_microbatch(xin, lin)
+        if augment:
+            loss = pkg.train_microbatch_augmented(net, x_host.numpy(), l_host.numpy(), seed=s * world + rank)
+        else:
+            loss = net.train_microbatch(x_host.numpy(), l_host.numpy())
         net.step(world, pkg.poly_lr(lr0, s, total_steps), comm)
         step_no[0] += 1
         return loss
@@ -307,8 +306,9 @@ def main():
                    "l2": "no explicit flush: each step streams > 3 GB of activations, far above the 126 MB L2",
                    "arithmetic": "fp16 operands, fp32 accumulate (tcgen05), fp32 stats/loss/optimizer, loss scale %g" % train_loss_scale},
         "loss": [float(v) for v in loss],
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (2 if augment else 1) * (IN_C + 1) * vox * 4,
-                "d2h_bytes_per_step": ((IN_C + 1) * vox * 4 if augment else 0) + 15 * 4 + 16},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (IN_C + 1) * vox * 4,
+                "d2h_bytes_per_step": 15 * 4 + 16,
+                "api": "unet3d_train_microbatch_augmented (host image + label in, losses out) + unet3d_step"},
         "gpu_launches": int(launches),
         "inference": {"workload": f"cfg1: UNet3d({IN_C},1,default) forward()[0] of one {W}x{H}x{D} window per GPU (windows sharded, no collective)",
                       "value": world * n_inf * (W * H * D) / 1e6 / (inf_ms / 1e3), "unit": "Mvoxel/s",

@@ -131,6 +131,13 @@ int vpa_augment(const char* const* keys, const float* vals, int n_opts, float* i
 int unet3d_vpa_augment(unet3d_t* h, const char* const* keys, const float* vals, int n_opts, float* image, float* label, int is_label,
                        int w, int hgt, int d, int channels, uint64_t seed, int where);
 
+/* train.cpp:459-473 + 615-706 in one call: upload the RAW sample once (host pointers, label = float-stored integers), run
+ * visual_perception_augmentation on it in HBM (is_label = 1) and feed the result straight into the micro-batch.  Saves the
+ * device->host->device round trip of the augmented sample that the two separate where = 0 calls make. */
+int unet3d_train_microbatch_augmented(unet3d_t* h, const char* const* keys, const float* vals, int n_opts, const float* image_host,
+                                      const float* label_host, uint64_t seed, int collapse_before, int use_ce, int use_dice, int use_mse,
+                                      float loss_out3[3]);
+
 /* NCCL plumbing for the data-parallel step (bootstrap the 128-byte id through any host channel) */
 int unet3d_nccl_unique_id(void* id128);
 int unet3d_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);

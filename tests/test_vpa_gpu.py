@@ -83,3 +83,29 @@ def test_full_size_properties():
         assert set(np.unique(out_l)).issubset(set(np.unique(lab)))
         again_i, again_l = m.vpa_augment(img, lab, None, True, seed)
         assert np.array_equal(again_i, out_i) and np.array_equal(again_l, out_l)   # same seed -> same sample
+
+
+def test_fused_augment_microbatch_equals_the_two_calls():
+    """unet3d_train_microbatch_augmented (one upload, augmentation and micro-batch in HBM) must give the losses of
+    vpa_augment (host, in place) followed by train_microbatch on the augmented host buffers."""
+    m = load()
+    W, H, D = 64, 48, 32
+    feature = ("conv16,ks3,stride1+norm,leaky_relu\nconv32,ks3,stride2+norm,leaky_relu+conv_trans16,ks2,stride2\n"
+               "conv16,ks3,stride1+norm,leaky_relu+conv2,ks1,stride1")
+    img, lab = phantom(W, H, D, 1, 3)
+    lab = np.minimum(lab, 1.0)
+    nets = []
+    for _ in range(2):
+        net = m.UNet3d(1, 2, feature, gpu=0)
+        net.init_params(11)
+        net.set_dim(W, H, D)
+        net.train(True)
+        nets.append(net)
+    fused = m.train_microbatch_augmented(nets[0], img[None], lab[None], seed=5)
+    ai, al = m.vpa_augment(img.copy(), lab.copy(), None, True, 5)
+    two, _ = nets[1].train_microbatch(ai[None], al[None], all_levels=True)
+    assert np.isfinite(fused).all()
+    np.testing.assert_allclose(fused, two, rtol=2e-4, atol=2e-5)
+    g0 = nets[0].get_grad(0)
+    g1 = nets[1].get_grad(0)
+    assert np.linalg.norm(g0 - g1) <= 1e-3 * max(np.linalg.norm(g1), 1e-20)

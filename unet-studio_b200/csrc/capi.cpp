@@ -326,6 +326,36 @@ int unet3d_vpa_augment(unet3d_t* h, const char* const* keys, const float* vals, 
     GUARD_END
 }
 
+int unet3d_train_microbatch_augmented(unet3d_t* h, const char* const* keys, const float* vals, int n_opts, const float* image_host,
+                                      const float* label_host, uint64_t seed, int collapse_before, int use_ce, int use_dice, int use_mse,
+                                      float loss_out3[3]) {
+    GUARD_BEGIN NEED(h)
+    Model* m = h->m;
+    cudaSetDevice(m->device);
+    float* din = nullptr;
+    float* dlab = nullptr;
+    if (m->staging(&din, &dlab)) return 1;
+    const int w = m->dim[0], hgt = m->dim[1], d = m->dim[2], channels = m->in_count;
+    const size_t V = size_t(w) * hgt * d;
+    const size_t need = u3d::vpa_workspace_bytes(w, hgt, d, channels) + (size_t(channels) + 1) * V * 4;
+    if (m->vpa_ws_bytes < need) {
+        cudaStreamSynchronize(m->stream);
+        if (m->vpa_ws) cudaFree(m->vpa_ws);
+        m->vpa_ws_bytes = 0;
+        if (cudaMalloc(&m->vpa_ws, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+        m->vpa_ws_bytes = need;
+    }
+    // one upload of the raw sample; augmentation and the micro-batch run stream-ordered on it without leaving HBM
+    if (cudaMemcpyAsync(din, image_host, size_t(channels) * V * 4, cudaMemcpyHostToDevice, m->stream) != cudaSuccess ||
+        cudaMemcpyAsync(dlab, label_host, V * 4, cudaMemcpyHostToDevice, m->stream) != cudaSuccess) {
+        set_error("unet3d_train_microbatch_augmented: upload failed");
+        return 1;
+    }
+    if (vpa_impl(keys, vals, n_opts, din, dlab, 1, w, hgt, d, channels, seed, 1, m->vpa_ws, m->stream, &m->launches)) return 1;
+    return m->train_microbatch(din, dlab, collapse_before, use_ce, use_dice, use_mse, loss_out3, nullptr, 1);
+    GUARD_END
+}
+
 int unet3d_nccl_unique_id(void* id128) {
     GUARD_BEGIN return u3d::nccl_unique_id(id128);
     GUARD_END

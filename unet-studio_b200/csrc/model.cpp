@@ -874,6 +874,13 @@ int Model::train_microbatch(const float* in, const float* label, int collapse_be
     return 0;
 }
 
+int Model::staging(float** in_dev, float** label_dev) {
+    M_CHECK(ensure_plan());
+    *in_dev = d_in_f32;
+    *label_dev = d_label;
+    return 0;
+}
+
 // validation forward + level-0 losses (train.cpp:826-851)
 int Model::validate(const float* in, const float* label, int collapse_before, float* loss_out3, int where) {
     M_CHECK(ensure_plan());

@@ -119,6 +119,8 @@ class Model {
     int train_microbatch(const float* in, const float* label, int collapse_before, int use_ce, int use_dice, int use_mse,
                          float* loss_out3, float* all_levels, int where);
     int validate(const float* in, const float* label, int collapse_before, float* loss_out3, int where);
+    // device staging buffers of the network input ([in][D][H][W] fp32) and label ([D][H][W] fp32) of the current plan
+    int staging(float** in_dev, float** label_dev);
     int step(int batch_size, double lr, void* nccl_comm);
     int copy_from(const Model& src);
     int sync();

@@ -42,6 +42,19 @@ def vpa_augment(image, label, options=None, is_label=True, seed=0, gpu=0):
     return image, label
 
 
+def train_microbatch_augmented(net, image, label, options=None, seed=0, collapse_before=0, use_ce=True, use_dice=True, use_mse=True):
+    """Raw host sample -> one upload -> augmentation in HBM -> micro-batch (unet3d_train_microbatch_augmented).  Returns (ce, dice, mse)."""
+    from . import check
+    karr, varr, n = _opts(options)
+    image = np.ascontiguousarray(image, np.float32)
+    label = np.ascontiguousarray(label, np.float32)
+    out = np.zeros(3, np.float32)
+    check(net._lib.unet3d_train_microbatch_augmented(net._h, karr, varr, n, image.ctypes.data_as(_F), label.ctypes.data_as(_F),
+                                                     ctypes.c_uint64(seed), int(collapse_before), int(use_ce), int(use_dice), int(use_mse),
+                                                     out.ctypes.data_as(_F)))
+    return out
+
+
 def vpa_augment_on(net, image_ptr, label_ptr, w, h, d, channels, options=None, is_label=True, seed=0, where=1):
     """In place on raw pointers (device when where=1), stream-ordered on `net`'s stream."""
     from . import check
