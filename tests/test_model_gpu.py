@@ -238,3 +238,41 @@ def test_gradients_match_fp16_emulating_oracle_tightly(name):
     print(name, "vs fp16-emulating oracle: global grad rel err", np.sqrt(num / den), "worst weight tensor", worst)
     assert np.sqrt(num / den) < 1.2e-2, np.sqrt(num / den)
     assert worst < 5e-2, worst
+
+
+def test_default_net_training_microbatch_matches_oracle_at_band_kernel_sizes():
+    """Default net (1 in / 2 out) at 128x96x64: large enough that the x-banded conv, the N-stacked weight gradient (levels 0-1
+    natively, level 2 as channel-group pairs), the parity-stacked transpose / stride-2 data gradients, the TMA kernel and the
+    fused output heads are all on the path.  Losses of all five levels and the parameter gradients against the fp32 CPU
+    oracle on the same weights and sample (tolerances as in the golden-fixture training test: layers next to the loss
+    tight, the whole gradient incl. the early layers that amplify the fp16 storage error ~50x looser)."""
+    m = load()
+    W, H, D = 128, 96, 64
+    feature = O.default_feature(2)
+    onet = O.parse_feature(1, 2, feature)
+    P = [p.clone().requires_grad_(True) for p in O.init_params(onet, 9)]
+    img, lab = synth_volume(W, H, D, seed=4)
+    net = m.UNet3d(1, 2, feature)
+    net.load_parameters([p.detach().numpy() for p in P])
+    net.set_dim(W, H, D)
+    net.train(True)
+    net.create_optimizer(1e-3)
+    l0, lv = net.train_microbatch(img, lab, all_levels=True)
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    total, per_level, _ = O.micro_batch_loss(onet, P, torch.from_numpy(img), torch.from_numpy(lab).long())
+    total.backward()
+    ref = torch.stack(per_level).detach().numpy()
+    np.testing.assert_allclose(lv, ref, rtol=0, atol=2e-3)
+    num = den = 0.0
+    n = net.param_count()
+    for i in range(n):
+        g = net.get_grad(i)
+        gr = P[i].grad.numpy() if P[i].grad is not None else np.zeros_like(g)
+        num += float(((g - gr).astype(np.float64) ** 2).sum()); den += float((gr.astype(np.float64) ** 2).sum())
+        name_i = net.param_name(i)
+        if name_i.startswith(("output", "decode0")) and np.linalg.norm(gr) > 1e-4:
+            assert rel(g, gr) < 1e-2, (name_i, rel(g, gr))
+    print("128x96x64 default net: global gradient rel err vs fp32 oracle", np.sqrt(num / den))
+    assert np.sqrt(num / den) < 5e-2, np.sqrt(num / den)
+    net.step(1, 1e-3)
+    assert not net.last_step_skipped()
