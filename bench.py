@@ -91,6 +91,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_name(augment=True):
+    return (f"cfg2: UNet3d({IN_C},{OUT_C},default_feature) single-template training step, human T1 skull-strip "
+            f"{W}x{H}x{D}, batch 1 per GPU, {'with' if augment else 'WITHOUT'} visual_perception_augmentation, "
+            f"ce+dice+mse deep supervision, clip 12, Nesterov SGD")
+
+
 def cpu_reference_step(steps, warmup, threads=None):
     """Times the reference (oracle/_ref) training step on the host on the bounded sample grid; returns dict."""
     if not os.path.exists(REF_BIN):
@@ -119,7 +125,9 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg2: UNet3d({IN_C},{OUT_C},default) train step, {W}x{H}x{D}, batch 1, reference libtorch CPU path"},
+            "config": {"workload": workload_name(True), "grid": [W, H, D], "in_count": IN_C, "out_count": OUT_C,
+                       "arm": "reference unet.cpp + libtorch CPU (oracle/_ref/unet_ref) on the host cores; augmentation (TIPL) not compilable here, "
+                              "so the CPU step excludes it -- it is in the GPU arm's timed region"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -298,9 +306,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"cfg2: UNet3d({IN_C},{OUT_C},default_feature) single-template training step, human T1 skull-strip "
-                               f"{W}x{H}x{D}, batch 1 per GPU, {'with' if augment else 'WITHOUT'} visual_perception_augmentation, "
-                               f"ce+dice+mse deep supervision, clip 12, Nesterov SGD",
+        "config": {"workload": workload_name(augment),
                    "grid": [W, H, D], "in_count": IN_C, "out_count": OUT_C, "micro_batches_per_gpu_per_step": 1,
                    "global_batch": world, "parallelism": f"dp{world}", "augmentation": bool(augment),
                    "l2": "no explicit flush: each step streams > 3 GB of activations, far above the 126 MB L2",
