@@ -218,8 +218,6 @@ def main():
     # ---------------- device-resident timing ----------------
     for _ in range(max(args.warmup, 3)):
         one_step_device()
-    net.profile(True)
-    net.profile_read(reset=True)
     clocks = ClockSampler(local_rank)
     launches0 = net.launch_count()
     barrier()
@@ -232,6 +230,12 @@ def main():
     barrier()
     clk = clocks.stop()
     launches = net.launch_count() - launches0
+    # ---------------- per-family attribution: the same steps again with a CUDA-event pair around every tensor-kernel launch.  The
+    # library serialises the weight-gradient side stream while profiling, so these per-kernel times are not the concurrent ones ----
+    net.profile(True)
+    net.profile_read(reset=True)
+    for _ in range(args.steps):
+        one_step_device()
     prof = net.profile_read(reset=True)
     net.profile(False)
     # ---------------- end-to-end timing through the C-ABI with host buffers ----------------

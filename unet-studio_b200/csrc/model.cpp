@@ -195,6 +195,10 @@ Model::Model(int in_c, int out_c, const std::string& feature, bool host_only_)
     if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess)
         throw std::runtime_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(cudaGetLastError()) +
                                  " (libunet3d_b200 needs a CUDA device; there is no CPU fallback)");
+    if (cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+        throw std::runtime_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(cudaGetLastError()));
     const size_t fb = size_t(flat_n) * sizeof(float);
     if (cudaMalloc(&d_params, fb) != cudaSuccess || cudaMalloc(&d_grads, fb) != cudaSuccess || cudaMalloc(&d_mom, fb) != cudaSuccess)
         throw std::runtime_error("cudaMalloc of the parameter buffers failed");
@@ -233,6 +237,9 @@ Model::~Model() {
     if (host_only) return;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     free_plan();
     cudaFree(d_params); cudaFree(d_grads); cudaFree(d_mom);
     if (vpa_ws) cudaFree(vpa_ws);
@@ -342,7 +349,7 @@ int Model::set_mode(int train) {
     return 0;
 }
 
-void Model::prof_begin(int kind, double flops) {
+void Model::prof_begin(int kind, double flops, cudaStream_t on) {
     if (!prof_on) return;
     if (prof_used + 2 > prof_ev.size()) {
         cudaEvent_t a, b;
@@ -355,11 +362,11 @@ void Model::prof_begin(int kind, double flops) {
     }
     prof_kind[prof_used / 2] = kind;
     prof_flops[prof_used / 2] = flops;
-    cudaEventRecord(prof_ev[prof_used], stream);
+    cudaEventRecord(prof_ev[prof_used], on ? on : stream);
 }
-void Model::prof_end() {
+void Model::prof_end(cudaStream_t on) {
     if (!prof_on) return;
-    cudaEventRecord(prof_ev[prof_used + 1], stream);
+    cudaEventRecord(prof_ev[prof_used + 1], on ? on : stream);
     prof_used += 2;
 }
 int Model::prof_read(double out[18], int reset) {
@@ -744,6 +751,8 @@ int Model::forward(const float* in, float* const* out_levels, int n_levels_wante
 // backward (autograd of the step body, train.cpp:706)
 // ------------------------------------------------------------------------------------------------
 int Model::run_backward() {
+    static const bool no_side = std::getenv("U3D_ONE_STREAM") != nullptr;
+    const bool two_streams = !no_side && !prof_on && stream2 != nullptr;   // the per-family event profile needs serial kernels
     std::fill(grad_written.begin(), grad_written.end(), 0);
     // fused heads: the loss-gradient kernel (launched before this function) already stored dL/dx of the head input
     for (const Step& s : steps)
@@ -761,13 +770,20 @@ int Model::run_backward() {
                 M_CHECK(colsum_accumulate_launch(dy, Vout, s.g.cout, pad16(s.g.cout), d_partials, grad_ptr(s.p_b), stream));
                 launches += 2;
             }
+            // weight gradient on the side stream: it only reads x and dy (both final here) and adds into this layer's slice of the
+            // flat gradient, so it can overlap the data gradient below (the small deep-level launches fill the SMs the other leaves idle)
             WgradLaunch wc{};
             bool all_rows = !s.wg.empty();
             for (const auto& wp : s.wg) all_rows = all_rows && (conv_wgrad_band_eligible(wp) || conv_wgrad_rows_eligible(wp));
-            prof_begin(all_rows ? 3 : 1, s.flops);
+            cudaStream_t ws = two_streams ? stream2 : stream;
+            if (two_streams) {
+                M_CUDA(cudaEventRecord(ev_fork, stream));
+                M_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0));
+            }
+            prof_begin(all_rows ? 3 : 1, s.flops, ws);
             int nl = 0;
-            M_CHECK(conv_wgrad_dispatch(s.wg, wc, stream, &nl));
-            prof_end();
+            M_CHECK(conv_wgrad_dispatch(s.wg, wc, ws, &nl));
+            prof_end(ws);
             launches += nl;
             const int ins[2] = {s.in0, s.in1};
             for (int src = 0; src < 2; ++src) {
@@ -807,6 +823,10 @@ int Model::run_backward() {
             }
             grad_written[s.in0] = 1;
         }
+    }
+    if (two_streams) {   // the update (and the next forward) must see every weight gradient
+        M_CUDA(cudaEventRecord(ev_join, stream2));
+        M_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
     }
     return 0;
 }

@@ -91,6 +91,8 @@ class Model {
 
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // weight gradients of a layer run here, concurrently with its data gradient on `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float* d_params = nullptr;
     float* d_grads = nullptr;
     float* d_mom = nullptr;
@@ -134,8 +136,8 @@ class Model {
     std::vector<int> prof_kind;
     std::vector<double> prof_flops;
     size_t prof_used = 0;
-    void prof_begin(int kind, double flops);
-    void prof_end();
+    void prof_begin(int kind, double flops, cudaStream_t on = nullptr);
+    void prof_end(cudaStream_t on = nullptr);
     int prof_read(double out[18], int reset);  // per kind: {ms, launches, algorithmic FLOPs}
     int n_levels() const { return int(output.size()); }
 
