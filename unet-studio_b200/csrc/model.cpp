@@ -197,7 +197,8 @@ Model::Model(int in_c, int out_c, const std::string& feature, bool host_only_)
                                  " (libunet3d_b200 needs a CUDA device; there is no CPU fallback)");
     if (cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_pack, cudaEventDisableTiming) != cudaSuccess)
         throw std::runtime_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(cudaGetLastError()));
     const size_t fb = size_t(flat_n) * sizeof(float);
     if (cudaMalloc(&d_params, fb) != cudaSuccess || cudaMalloc(&d_grads, fb) != cudaSuccess || cudaMalloc(&d_mom, fb) != cudaSuccess)
@@ -237,14 +238,16 @@ Model::~Model() {
     if (host_only) return;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    if (stream2) { cudaStreamSynchronize(stream2); cudaStreamDestroy(stream2); }
+    if (stream2) cudaStreamSynchronize(stream2);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_pack) cudaEventDestroy(ev_pack);
     free_plan();
     cudaFree(d_params); cudaFree(d_grads); cudaFree(d_mom);
     if (vpa_ws) cudaFree(vpa_ws);
     for (auto b : d_buffers) cudaFree(b);
     cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_losses);
+    if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -255,6 +258,8 @@ int Model::alloc(void** p, size_t bytes) {
 }
 
 void Model::free_plan() {
+    if (stream2) cudaStreamSynchronize(stream2);   // an asynchronous re-pack may still be writing the blobs freed below
+    pack_pending = false;
     for (void* p : owned) cudaFree(p);
     owned.clear();
     tens.clear();
@@ -646,14 +651,23 @@ int Model::ensure_plan() {
     return 0;
 }
 
-int Model::repack() {
-    if (!packs_dirty) return 0;
+int Model::repack_on(cudaStream_t on) {
     for (auto& s : steps) {
         if (s.kind != Step::CONV) continue;
-        for (auto& k : s.fpacks) { M_CHECK(pack_weights_launch(k, stream)); ++launches; }
+        for (auto& k : s.fpacks) { M_CHECK(pack_weights_launch(k, on)); ++launches; }
         for (int src = 0; src < 2; ++src)
-            for (auto& k : s.dg[src].packs) { M_CHECK(pack_weights_launch(k, stream)); ++launches; }
+            for (auto& k : s.dg[src].packs) { M_CHECK(pack_weights_launch(k, on)); ++launches; }
     }
+    return 0;
+}
+
+int Model::repack() {
+    if (pack_pending) {   // the re-pack that Model::step started on the side stream (it overlaps the next sample's augmentation)
+        M_CUDA(cudaStreamWaitEvent(stream, ev_pack, 0));
+        pack_pending = false;
+    }
+    if (!packs_dirty) return 0;
+    M_CHECK(repack_on(stream));
     packs_dirty = false;
     return 0;
 }

@@ -92,7 +92,8 @@ class Model {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // weight gradients of a layer run here, concurrently with its data gradient on `stream`
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr;
+    bool pack_pending = false;       // a weight re-pack launched on stream2 after the last update has not been joined yet
     float* d_params = nullptr;
     float* d_grads = nullptr;
     float* d_mom = nullptr;
@@ -140,6 +141,7 @@ class Model {
     void prof_end(cudaStream_t on = nullptr);
     int prof_read(double out[18], int reset);  // per kind: {ms, launches, algorithmic FLOPs}
     int n_levels() const { return int(output.size()); }
+    bool planned_for_pack() const { return planned && !packs_dirty; }   // blobs exist and hold the pre-update weights
 
   private:
     std::vector<Ten> tens;
@@ -170,6 +172,7 @@ class Model {
     int build_steps();
     int alloc(void** p, size_t bytes);
     int repack();
+    int repack_on(cudaStream_t s);
     int run_forward(int levels_wanted);
     int run_backward();
     int upload_input(const float* in, int where);

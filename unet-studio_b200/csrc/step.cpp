@@ -6,6 +6,7 @@
 #include <nccl.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 
@@ -27,6 +28,17 @@ int Model::step(int batch_size, double lr, void* nccl_comm) {
                         d_status, stream))
         return 1;
     launches += 2;
+    // re-pack the fp16 weight blobs right away on the side stream: ordered after the update, overlapping whatever the main stream does
+    // next (read-back below, the next sample's upload and augmentation); the next forward joins it (Model::repack)
+    static const bool no_side = std::getenv("U3D_ONE_STREAM") != nullptr;
+    bool async_pack = false;
+    if (planned_for_pack() && stream2 != nullptr && !no_side) {
+        if (cudaEventRecord(ev_fork, stream) != cudaSuccess || cudaStreamWaitEvent(stream2, ev_fork, 0) != cudaSuccess) { set_error("step: event"); return 1; }
+        if (repack_on(stream2)) return 1;
+        if (cudaEventRecord(ev_pack, stream2) != cudaSuccess) { set_error("step: event"); return 1; }
+        pack_pending = true;
+        async_pack = true;
+    }
     SgdStatus st{};
     cudaError_t e = cudaMemcpyAsync(&st, d_status, sizeof(st), cudaMemcpyDeviceToHost, stream);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return 1; }
@@ -40,7 +52,7 @@ int Model::step(int batch_size, double lr, void* nccl_comm) {
     } else {
         mom_initialized = true;
         if (++good_steps >= 500 && loss_scale < loss_scale_max) { loss_scale *= 2.0f; good_steps = 0; }
-        packs_dirty = true;
+        packs_dirty = !async_pack;
     }
     return 0;
 }
