@@ -186,29 +186,39 @@ def main():
     x_host = torch.from_numpy(img).pin_memory()
     l_host = torch.from_numpy(lab).pin_memory()
     x_dev, l_dev = x_host.cuda(), l_host.cuda()
-    x_aug, l_aug = torch.empty_like(x_dev), torch.empty_like(l_dev)
     total_steps = 1000
     step_no = [0]
+    pending = [False]   # a prefetched sample is waiting in the handle
+
+    def seed_of(s):
+        return s * world + rank
 
     def one_step_device():
+        # the sample is resident in HBM; its augmentation for step s+1 runs on the handle's prefetch stream while step s computes
+        # (the reference augments in worker threads beside the trainer, train.cpp:446-485)
         s = step_no[0]
-        xin, lin = x_dev, l_dev
-        if augment:   # augmentation output feeds the step without leaving HBM
-            x_aug.copy_(x_dev); l_aug.copy_(l_dev)
-            torch.cuda.current_stream().synchronize()
-            pkg.vpa_augment_on(net, x_aug.data_ptr(), l_aug.data_ptr(), W, H, D, IN_C, seed=s * world + rank, where=1)
-            xin, lin = x_aug, l_aug
-        loss = net.device_train_microbatch(xin.data_ptr(), lin.data_ptr())
+        if augment:
+            if not pending[0]:
+                pkg.prefetch_augmented(net, x_dev.data_ptr(), l_dev.data_ptr(), seed=seed_of(s), where=1)
+            pkg.prefetch_augmented(net, x_dev.data_ptr(), l_dev.data_ptr(), seed=seed_of(s + 1), where=1)
+            pending[0] = True
+            loss = pkg.train_microbatch_prefetched(net)
+        else:
+            loss = net.device_train_microbatch(x_dev.data_ptr(), l_dev.data_ptr())
         net.step(world, pkg.poly_lr(lr0, s, total_steps), comm)
         step_no[0] += 1
         return loss
 
     def one_step_host():
-        # end to end through the C-ABI with HOST buffers: the raw sample is uploaded from pinned memory (train.cpp:615-626), augmented
-        # (train.cpp:459-473) and trained on in one call, the losses come back to the host, then the update
+        # end to end through the C-ABI with HOST buffers: the raw sample of step s+1 is uploaded from pinned memory and augmented on the
+        # prefetch stream (train.cpp:446-485, 615-626) while step s trains; the losses come back to the host, then the update
         s = step_no[0]
         if augment:
-            loss = pkg.train_microbatch_augmented(net, x_host.numpy(), l_host.numpy(), seed=s * world + rank)
+            if not pending[0]:
+                pkg.prefetch_augmented(net, x_host.numpy(), l_host.numpy(), seed=seed_of(s), where=0)
+            pkg.prefetch_augmented(net, x_host.numpy(), l_host.numpy(), seed=seed_of(s + 1), where=0)
+            pending[0] = True
+            loss = pkg.train_microbatch_prefetched(net)
         else:
             loss = net.train_microbatch(x_host.numpy(), l_host.numpy())
         net.step(world, pkg.poly_lr(lr0, s, total_steps), comm)
@@ -318,7 +328,7 @@ def main():
         "loss": [float(v) for v in loss],
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (IN_C + 1) * vox * 4,
                 "d2h_bytes_per_step": 15 * 4 + 16,
-                "api": "unet3d_train_microbatch_augmented (host image + label in, losses out) + unet3d_step"},
+                "api": "unet3d_prefetch_augmented(next host sample) + unet3d_train_microbatch_prefetched (losses out) + unet3d_step"},
         "gpu_launches": int(launches),
         "inference": {"workload": f"cfg1: UNet3d({IN_C},1,default) forward()[0] of one {W}x{H}x{D} window per GPU (windows sharded, no collective)",
                       "value": world * n_inf * (W * H * D) / 1e6 / (inf_ms / 1e3), "unit": "Mvoxel/s",

@@ -138,6 +138,15 @@ int unet3d_train_microbatch_augmented(unet3d_t* h, const char* const* keys, cons
                                       const float* label_host, uint64_t seed, int collapse_before, int use_ce, int use_dice, int use_mse,
                                       float loss_out3[3]);
 
+/* The reference augments samples in worker threads beside the trainer (train.cpp:446-485, slots in_data[i] / data_ready[i]).
+ * unet3d_prefetch_augmented starts upload (where = 0: host pointers, which must stay valid until the matching
+ * unet3d_train_microbatch_prefetched returns; where = 1: device pointers) + augmentation of the NEXT sample on a side stream and
+ * returns immediately; unet3d_train_microbatch_prefetched makes the micro-batch wait for it and consumes it.  Call order per
+ * step: prefetch(i+1), train_prefetched(i), step (after an initial prefetch(0)).  Two staging slots, consumed first-in first-out. */
+int unet3d_prefetch_augmented(unet3d_t* h, const char* const* keys, const float* vals, int n_opts, const float* image, const float* label,
+                              uint64_t seed, int where);
+int unet3d_train_microbatch_prefetched(unet3d_t* h, int collapse_before, int use_ce, int use_dice, int use_mse, float loss_out3[3]);
+
 /* NCCL plumbing for the data-parallel step (bootstrap the 128-byte id through any host channel) */
 int unet3d_nccl_unique_id(void* id128);
 int unet3d_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);

@@ -109,3 +109,38 @@ def test_fused_augment_microbatch_equals_the_two_calls():
     g0 = nets[0].get_grad(0)
     g1 = nets[1].get_grad(0)
     assert np.linalg.norm(g0 - g1) <= 1e-3 * max(np.linalg.norm(g1), 1e-20)
+
+
+def test_prefetched_samples_equal_the_fused_call_and_come_out_in_order():
+    """unet3d_prefetch_augmented / unet3d_train_microbatch_prefetched (upload + augmentation of the next sample on a side stream,
+    two staging slots, first-in first-out) must give the losses of the synchronous fused call for the same samples and seeds."""
+    m = load()
+    W, H, D = 64, 48, 32
+    feature = ("conv16,ks3,stride1+norm,leaky_relu\nconv32,ks3,stride2+norm,leaky_relu+conv_trans16,ks2,stride2\n"
+               "conv16,ks3,stride1+norm,leaky_relu+conv2,ks1,stride1")
+    samples = []
+    for k in range(3):
+        img, lab = phantom(W, H, D, 1, 10 + k)
+        samples.append((np.ascontiguousarray(img[None]), np.ascontiguousarray(np.minimum(lab, 1.0)[None])))
+    nets = []
+    for _ in range(2):
+        net = m.UNet3d(1, 2, feature, gpu=0)
+        net.init_params(12)
+        net.set_dim(W, H, D)
+        net.train(True)
+        net.create_optimizer(1e-2)
+        nets.append(net)
+    ref = []
+    for k, (img, lab) in enumerate(samples):
+        ref.append(m.train_microbatch_augmented(nets[0], img, lab, seed=20 + k))
+        nets[0].step(1, 1e-2)
+    got = []
+    m.prefetch_augmented(nets[1], samples[0][0], samples[0][1], seed=20)
+    for k in range(3):
+        if k + 1 < 3:
+            m.prefetch_augmented(nets[1], samples[k + 1][0], samples[k + 1][1], seed=20 + k + 1)
+        got.append(m.train_microbatch_prefetched(nets[1]))
+        nets[1].step(1, 1e-2)
+    np.testing.assert_allclose(np.array(got), np.array(ref), rtol=5e-4, atol=5e-5)
+    with pytest.raises(m.U3DError, match="no prefetched sample"):
+        m.train_microbatch_prefetched(nets[1])

@@ -356,6 +356,50 @@ int unet3d_train_microbatch_augmented(unet3d_t* h, const char* const* keys, cons
     GUARD_END
 }
 
+int unet3d_prefetch_augmented(unet3d_t* h, const char* const* keys, const float* vals, int n_opts, const float* image, const float* label,
+                              uint64_t seed, int where) {
+    GUARD_BEGIN NEED(h)
+    Model* m = h->m;
+    cudaSetDevice(m->device);
+    float* din = nullptr;
+    float* dlab = nullptr;
+    int slot = 0;
+    if (m->prefetch_slot(&din, &dlab, &slot)) return 1;
+    const int w = m->dim[0], hgt = m->dim[1], d = m->dim[2], channels = m->in_count;
+    const size_t V = size_t(w) * hgt * d;
+    const size_t need = u3d::vpa_workspace_bytes(w, hgt, d, channels) + (size_t(channels) + 1) * V * 4;
+    if (m->vpa_ws_bytes < need) {
+        cudaStreamSynchronize(m->stream);
+        cudaStreamSynchronize(m->stream3);
+        if (m->vpa_ws) cudaFree(m->vpa_ws);
+        m->vpa_ws_bytes = 0;
+        if (cudaMalloc(&m->vpa_ws, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+        m->vpa_ws_bytes = need;
+    }
+    const cudaMemcpyKind kind = where == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (cudaMemcpyAsync(din, image, size_t(channels) * V * 4, kind, m->stream3) != cudaSuccess ||
+        cudaMemcpyAsync(dlab, label, V * 4, kind, m->stream3) != cudaSuccess) {
+        set_error("unet3d_prefetch_augmented: copy failed");
+        return 1;
+    }
+    if (vpa_impl(keys, vals, n_opts, din, dlab, 1, w, hgt, d, channels, seed, 1, m->vpa_ws, m->stream3, &m->launches)) return 1;
+    if (cudaEventRecord(m->ev_sample[slot], m->stream3) != cudaSuccess) { set_error("unet3d_prefetch_augmented: event"); return 1; }
+    m->pf_mark(slot);
+    return 0;
+    GUARD_END
+}
+
+int unet3d_train_microbatch_prefetched(unet3d_t* h, int collapse_before, int use_ce, int use_dice, int use_mse, float loss_out3[3]) {
+    GUARD_BEGIN NEED(h)
+    Model* m = h->m;
+    cudaSetDevice(m->device);
+    float* din = nullptr;
+    float* dlab = nullptr;
+    if (m->consume_prefetched(&din, &dlab)) return 1;
+    return m->train_microbatch(din, dlab, collapse_before, use_ce, use_dice, use_mse, loss_out3, nullptr, 1);
+    GUARD_END
+}
+
 int unet3d_nccl_unique_id(void* id128) {
     GUARD_BEGIN return u3d::nccl_unique_id(id128);
     GUARD_END

@@ -247,6 +247,8 @@ Model::~Model() {
     if (vpa_ws) cudaFree(vpa_ws);
     for (auto b : d_buffers) cudaFree(b);
     cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_losses);
+    if (stream3) { cudaStreamSynchronize(stream3); cudaStreamDestroy(stream3); }
+    for (int i = 0; i < 2; ++i) { if (ev_sample[i]) cudaEventDestroy(ev_sample[i]); if (pf_in[i]) cudaFree(pf_in[i]); }
     if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -905,6 +907,44 @@ int Model::train_microbatch(const float* in, const float* label, int collapse_be
     M_CHECK(sync());
     if (loss_out3) std::memcpy(loss_out3, h.data(), 12);
     if (all_levels) std::memcpy(all_levels, h.data(), h.size() * 4);
+    return 0;
+}
+
+int Model::prefetch_slot(float** in_dev, float** label_dev, int* slot) {
+    cudaSetDevice(device);
+    const size_t V = size_t(dim[0]) * dim[1] * dim[2];
+    const size_t need = (size_t(in_count) + 1) * V * 4;
+    if (!stream3) {
+        M_CUDA(cudaStreamCreateWithFlags(&stream3, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) M_CUDA(cudaEventCreateWithFlags(&ev_sample[i], cudaEventDisableTiming));
+    }
+    if (pf_bytes < need) {
+        M_CUDA(cudaStreamSynchronize(stream3));
+        M_CUDA(cudaStreamSynchronize(stream));
+        for (int i = 0; i < 2; ++i) {
+            if (pf_in[i]) cudaFree(pf_in[i]);
+            pf_in[i] = nullptr;
+            M_CUDA(cudaMalloc(reinterpret_cast<void**>(&pf_in[i]), need));
+            pf_label[i] = pf_in[i] + size_t(in_count) * V;
+        }
+        pf_bytes = need;
+        pf_pending[0] = pf_pending[1] = false;
+        pf_next = pf_head = 0;
+    }
+    if (pf_pending[pf_next]) { set_error("prefetch: both staging slots hold samples that have not been consumed"); return 1; }
+    *slot = pf_next;
+    *in_dev = pf_in[pf_next];
+    *label_dev = pf_label[pf_next];
+    return 0;
+}
+
+int Model::consume_prefetched(float** in_dev, float** label_dev) {
+    if (!pf_pending[pf_head]) { set_error("no prefetched sample (call unet3d_prefetch_augmented first)"); return 1; }
+    M_CUDA(cudaStreamWaitEvent(stream, ev_sample[pf_head], 0));
+    *in_dev = pf_in[pf_head];
+    *label_dev = pf_label[pf_head];
+    pf_pending[pf_head] = false;
+    pf_head ^= 1;
     return 0;
 }
 

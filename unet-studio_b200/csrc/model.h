@@ -93,6 +93,19 @@ class Model {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // weight gradients of a layer run here, concurrently with its data gradient on `stream`
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr;
+    // sample prefetch (train.cpp:446-485: augmentation workers run beside the trainer): upload + augmentation of the NEXT sample on a
+    // third stream into one of two staging slots while the current micro-batch computes
+    cudaStream_t stream3 = nullptr;
+    cudaEvent_t ev_sample[2] = {nullptr, nullptr};
+    float* pf_in[2] = {nullptr, nullptr};
+    float* pf_label[2] = {nullptr, nullptr};
+    size_t pf_bytes = 0;
+    int pf_next = 0;                 // slot the next prefetch writes
+    int pf_head = 0;                 // oldest pending slot
+    bool pf_pending[2] = {false, false};   // slot holds a prefetched sample that has not been consumed
+    void pf_mark(int slot) { pf_pending[slot] = true; pf_next = slot ^ 1; }
+    int prefetch_slot(float** in_dev, float** label_dev, int* slot);   // allocates / returns the staging slot to fill on stream3
+    int consume_prefetched(float** in_dev, float** label_dev);          // main stream waits for the slot; returns its buffers
     bool pack_pending = false;       // a weight re-pack launched on stream2 after the last update has not been joined yet
     float* d_params = nullptr;
     float* d_grads = nullptr;

@@ -55,6 +55,26 @@ def train_microbatch_augmented(net, image, label, options=None, seed=0, collapse
     return out
 
 
+def prefetch_augmented(net, image, label, options=None, seed=0, where=0):
+    """Starts upload + augmentation of the next sample on the handle's side stream (unet3d_prefetch_augmented).  image / label:
+    host numpy arrays (where=0; keep them alive and unchanged until train_microbatch_prefetched returns) or raw device pointers."""
+    from . import check
+    karr, varr, n = _opts(options)
+    if where == 0:
+        ip, lp = image.ctypes.data_as(_F), label.ctypes.data_as(_F)
+    else:
+        ip, lp = ctypes.cast(image, _F), ctypes.cast(label, _F)
+    check(net._lib.unet3d_prefetch_augmented(net._h, karr, varr, n, ip, lp, ctypes.c_uint64(seed), int(where)))
+
+
+def train_microbatch_prefetched(net, collapse_before=0, use_ce=True, use_dice=True, use_mse=True):
+    from . import check
+    out = np.zeros(3, np.float32)
+    check(net._lib.unet3d_train_microbatch_prefetched(net._h, int(collapse_before), int(use_ce), int(use_dice), int(use_mse),
+                                                      out.ctypes.data_as(_F)))
+    return out
+
+
 def vpa_augment_on(net, image_ptr, label_ptr, w, h, d, channels, options=None, is_label=True, seed=0, where=1):
     """In place on raw pointers (device when where=1), stream-ordered on `net`'s stream."""
     from . import check
