@@ -28,7 +28,10 @@ constexpr int kTMaxProb = 8;
 struct TBox {
     int bx, by, bz;        // box of output voxels per M tile
     int tiles_x, tiles_y;  // tiles along x, y (z follows from mtiles)
-    int rows;              // bx*by*bz
+    int rows;              // rows the copy engine writes: pitch*by*bz
+    int pitch;             // row pitch along x: bx, or bx + 2 in x-halo mode
+    int xhalo;             // 1: k3 s1 problem, ONE box with a one-voxel x halo per (dz,dy); the three dx taps are start-row shifts of it
+    int min_dx;            // smallest dx of a tap triple (x origin of the halo box)
 };
 
 struct TParams {
@@ -155,6 +158,27 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                 const CUtensorMap* m1 = &maps.m[2 * w.pi + 1];
                 const int coff0 = P.coff0, coff1 = P.coff1, ntiles = P.ntiles;
                 int tap = 0, ch = 0;
+                if (KC == 64 && bx.xhalo) {
+                    // x-halo mode: per (dz,dy) pair and K chunk one box of (bx+2) x by x bz voxels + the weight slices of its 3 dx taps
+#pragma unroll 1
+                    for (int tp3 = 0; tp3 < ntaps; tp3 += 3) {
+                        const ConvTap tp = P.taps[tp3];
+#pragma unroll 1
+                        for (int c = 0; c < nch; ++c) {
+                            mbar_wait(empty_bar(stage), phase ^ 1, 0x1100u | stage);
+                            mbar_arrive_expect_tx(full_bar(stage), a_bytes + 3u * b_bytes);
+                            const bool first = c < nch0;
+                            const int c0 = first ? coff0 + c * KC : coff1 + (c - nch0) * KC;
+                            tma_load_4d(sA + stage * p.a_stage_bytes, first ? m0 : m1, full_bar(stage), c0, ix0 + bx.min_dx, iy0 + tp.dy, iz0 + tp.dz);
+                            const uint32_t bdst = sB + stage * p.b_stage_bytes;
+#pragma unroll
+                            for (int j = 0; j < 3; ++j)
+                                bulk_g2s(bdst + j * b_bytes, wbase + ((size_t(tp3 + j) * nch + c) * ntiles + w.nt) * b_bytes, b_bytes, full_bar(stage));
+                            if (++stage == S) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll 1
                 for (int g = 0; g < nsteps; g += SPG) {
                     const int cnt = min(SPG, nsteps - g);
@@ -200,6 +224,38 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                 const uint64_t b_k_u = uint64_t((2u * b_lbo) >> 4);
                 const uint64_t b_desc0 = umma_smem_desc(sB, b_lbo, 128u);
                 bool first = true;
+                if (KC == 64 && p.box[w.pi].xhalo) {
+                    const int nch = P.nch0 + P.nch1, min_dx = p.box[w.pi].min_dx;
+#pragma unroll 1
+                    for (int tp3 = 0; tp3 < P.ntaps; tp3 += 3) {
+                        uint32_t sh[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) sh[j] = uint32_t(P.taps[tp3 + j].dx - min_dx);   // start row of this dx tap inside the halo box
+#pragma unroll 1
+                        for (int c = 0; c < nch; ++c) {
+                            mbar_wait(full_bar(stage), phase, 0x1300u | stage);
+                            tc_fence_after();
+                            const uint64_t ad0 = a_desc0 + uint64_t(stage) * a_stage_u;
+                            const uint64_t bd0 = b_desc0 + uint64_t(stage) * b_stage_u;
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                // start row sh (128 B each) inside the 1024-byte swizzle atom: descriptor address + 8*sh.  The swizzle is applied
+                                // on absolute shared-memory address bits, so base_offset stays 0 (measured: setting it to sh gives wrong results)
+                                const uint64_t ad = ad0 + uint64_t(8u * sh[j]);
+                                const uint64_t bd = bd0 + uint64_t(j) * b_sub_u;
+#pragma unroll
+                                for (int k = 0; k < KC / 16; ++k) {
+                                    if (first) { umma_f16_first(d_tmem, ad + uint64_t(2 * k), bd + uint64_t(k) * b_k_u, idesc); first = false; }
+                                    else umma_f16_acc(d_tmem, ad + uint64_t(2 * k), bd + uint64_t(k) * b_k_u, idesc);
+                                }
+                            }
+                            umma_commit(empty_bar(stage));
+                            if (++stage == S) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    umma_commit(tfull_bar(acc));
+                    continue;
+                }
 #pragma unroll 1
                 for (int g = 0; g < nsteps; g += SPG) {
                     const int cnt = min(SPG, nsteps - g);
@@ -251,9 +307,9 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
             const int txi = w.mt % bx.tiles_x;
             const int rest = w.mt / bx.tiles_x;
             const int tyi = rest % bx.tiles_y, tzi = rest / bx.tiles_y;
-            const int lx = r % bx.bx, lrest = r / bx.bx;
+            const int lx = r % bx.pitch, lrest = r / bx.pitch;
             const int ox = txi * bx.bx + lx, oy = tyi * bx.by + lrest % bx.by, oz = tzi * bx.bz + lrest / bx.by;
-            const bool rv = r < bx.rows && ox < P.ow && oy < P.oh && oz < P.od;
+            const bool rv = r < bx.rows && lx < bx.bx && ox < P.ow && oy < P.oh && oz < P.od;
             const int OH = P.OH, OW = P.OW, OD = P.OD;
             const long long M = 1LL * P.od * P.oh * P.ow;
             const long long m = (1LL * oz * P.oh + oy) * P.ow + ox;
@@ -377,13 +433,16 @@ EncodeTiledFn encode_fn() {
 }
 
 // fewest boxes of <= 128 voxels that cover the lattice; ties -> longest run along x
-void choose_box(int ow, int oh, int od, int istride, TBox& b) {
+void choose_box(int ow, int oh, int od, int istride, int halo, TBox& b) {
+    // halo = 2: the box carries a one-voxel x halo on both sides and the M = 128 operand may start up to 2 rows into it
+    const int cap = halo ? 126 : 128;
     long long best = -1;
-    for (int bx = 1; bx <= std::min(ow, 128); ++bx) {
+    b.bx = 0;
+    for (int bx = 1; bx <= std::min(ow, cap - halo); ++bx) {
         if (bx * istride > 256) break;
-        for (int by = 1; by <= std::min(oh, 128 / bx); ++by) {
+        for (int by = 1; by <= std::min(oh, cap / (bx + halo)); ++by) {
             if (by * istride > 256) break;
-            const int bz = std::min({od, 128 / (bx * by), 256 / istride});
+            const int bz = std::min({od, cap / ((bx + halo) * by), 256 / istride});
             const long long tiles = 1LL * ((ow + bx - 1) / bx) * ((oh + by - 1) / by) * ((od + bz - 1) / bz);
             if (best < 0 || tiles < best || (tiles == best && bx > b.bx)) {
                 best = tiles;
@@ -393,7 +452,26 @@ void choose_box(int ow, int oh, int od, int istride, TBox& b) {
     }
     b.tiles_x = (ow + b.bx - 1) / b.bx;
     b.tiles_y = (oh + b.by - 1) / b.by;
-    b.rows = b.bx * b.by * b.bz;
+    b.pitch = b.bx + halo;
+    b.rows = b.pitch * b.by * b.bz;
+    b.xhalo = halo ? 1 : 0;
+}
+
+// k3 s1 problem whose 27 taps come as 9 triples sharing (dz,dy) with dx covering {-1,0,1}: eligible for the x-halo box
+bool xhalo_ok(const ConvProblem& P, int kc, int* min_dx) {
+    static const bool disabled = std::getenv("U3D_NO_XHALO") != nullptr;
+    if (disabled || kc != 64 || P.ntaps != 27 || P.istride != 1 || P.shuffle_cp) return false;
+    for (int t = 0; t < 27; t += 3) {
+        int seen = 0;
+        for (int j = 0; j < 3; ++j) {
+            const ConvTap& a = P.taps[t + j];
+            if (a.dz != P.taps[t].dz || a.dy != P.taps[t].dy || a.dx < -1 || a.dx > 1) return false;
+            seen |= 1 << (a.dx + 1);
+        }
+        if (seen != 7) return false;
+    }
+    *min_dx = -1;
+    return true;
 }
 
 template <int EPI, int KC>
@@ -454,11 +532,16 @@ int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg
     const int kc = cfg.kc;
     const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     int items = 0, ntile_max = 16, ntot_max = 16;
+    bool any_xhalo = false;
     for (int i = 0; i < tp.nprob; ++i) {
         ConvProblem& P = tp.probs[i];
         P = probs[i];
         TBox& b = tp.box[i];
-        choose_box(P.ow, P.oh, P.od, P.istride, b);
+        int min_dx = 0;
+        const bool xh = P.ntile <= 128 && xhalo_ok(P, kc, &min_dx);   // 3 weight slices per stage: wider N tiles leave < 3 stages
+        choose_box(P.ow, P.oh, P.od, P.istride, xh ? 2 : 0, b);
+        b.min_dx = min_dx;
+        any_xhalo = any_xhalo || xh;
         P.mtiles = b.tiles_x * b.tiles_y * ((P.od + b.bz - 1) / b.bz);
         P.item_base = items;
         items += P.mtiles * P.ntiles;
@@ -470,7 +553,7 @@ int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg
             if (s && P.nch1 == 0) continue;
             const cuuint64_t gdim[4] = {cuuint64_t(cp), cuuint64_t(P.in_w), cuuint64_t(P.in_h), cuuint64_t(P.in_d)};
             const cuuint64_t gstr[3] = {cuuint64_t(cp) * 2, cuuint64_t(cp) * 2 * P.in_w, cuuint64_t(cp) * 2 * P.in_w * P.in_h};
-            const cuuint32_t box[4] = {cuuint32_t(kc), cuuint32_t(b.bx * P.istride), cuuint32_t(b.by * P.istride), cuuint32_t(b.bz * P.istride)};
+            const cuuint32_t box[4] = {cuuint32_t(kc), cuuint32_t(b.pitch * P.istride), cuuint32_t(b.by * P.istride), cuuint32_t(b.bz * P.istride)};
             const cuuint32_t estr[4] = {1, cuuint32_t(P.istride), cuuint32_t(P.istride), cuuint32_t(P.istride)};
             const CUresult r = encode_fn()(&maps.m[2 * i + s], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -490,6 +573,10 @@ int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg
     const int spg = 64 / kc;
     tp.a_stage_bytes = uint32_t(128 * kc * 2 * spg);                 // 16 KB
     tp.b_stage_bytes = uint32_t(ntile_max * kc * 2 * spg);
+    if (any_xhalo) {   // 130 rows (the operand may start 2 rows in), swizzle atoms stay 1024-byte aligned; 3 weight slices per stage
+        tp.a_stage_bytes = 17 * 1024;
+        tp.b_stage_bytes *= 3;
+    }
     const size_t fixed = size_t(9) * ntot_max * 4 + 8 * (2 * 16 + 4) + 16 + 2048;
     int stages = int((220 * 1024 - fixed) / (tp.a_stage_bytes + tp.b_stage_bytes));
     stages = std::min(stages, 12);
