@@ -340,6 +340,9 @@ int Model::set_dim(int w, int h, int d) {
     if (w != dim[0] || h != dim[1] || d != dim[2]) {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
+        if (stream3) cudaStreamSynchronize(stream3);
+        pf_pending[0] = pf_pending[1] = false;   // prefetched samples of the old grid are dropped
+        pf_next = pf_head = 0;
         free_plan();
     }
     dim[0] = w; dim[1] = h; dim[2] = d;
