@@ -41,10 +41,13 @@ struct LossLevel {
     int shift;             // level index k: label voxel = (z<<k, y<<k, x<<k)  (nearest interpolate, train.cpp:645-662)
     float w_ce, w_dice, w_mse;  // level weight (1/2^k)/sum x cost flags (train.cpp:686-699)
     float loss_scale;
-    double* acc;           // device scratch: 3 + 2*32 doubles, zeroed by the launcher
+    double* acc;           // device scratch: 3 + 2*32 doubles (totals, written by the finalize kernel)
+    float* part;           // device scratch: [loss_part_rows()][3 + 2*32] per-block partial sums (fixed-order reduction => deterministic losses)
     float* out3;           // device: ce, dice, mse of this level
 };
 int loss_level_launch(const LossLevel& L, cudaStream_t s);
+int loss_part_rows();     // rows of LossLevel::part
+int loss_part_cols();
 
 // 1x1 output head (Conv3d k1 of the `output` token, unet.cpp:186-187) on CUDA cores for head inputs of <= 32 channels:
 // these levels are bandwidth-bound (2*C*xc FLOP per 32..64 bytes), so the tensor path only adds launches and round trips.

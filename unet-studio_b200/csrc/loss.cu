@@ -123,35 +123,60 @@ __global__ void loss_reduce_kernel(const LossLevel L) {
             }
         a_mse += (pp - 2.f * pt + 1.f) * o.v;
     }
-    __shared__ float red[kAccN];
-    for (int i = threadIdx.x; i < kAccN; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
+    // per-warp rows in shared memory, fixed-order sum over the warps, one partial row per block: no atomics, deterministic
+    __shared__ float red[8][kAccN];
     a_ce = warp_sum(a_ce); a_n = warp_sum(a_n); a_mse = warp_sum(a_mse);
 #pragma unroll
     for (int c = 1; c < MAXC; ++c)
         if (c < Cc) { a_i[c] = warp_sum(a_i[c]); a_k[c] = warp_sum(a_k[c]); }
+    const int wid = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&red[0], a_ce); atomicAdd(&red[1], a_n); atomicAdd(&red[2], a_mse);
+        red[wid][0] = a_ce; red[wid][1] = a_n; red[wid][2] = a_mse;
+        red[wid][3] = 0.f; red[wid][4] = 0.f;
 #pragma unroll
         for (int c = 1; c < MAXC; ++c)
-            if (c < Cc) { atomicAdd(&red[3 + 2 * c], a_i[c]); atomicAdd(&red[4 + 2 * c], a_k[c]); }
+            if (c < Cc) { red[wid][3 + 2 * c] = a_i[c]; red[wid][4 + 2 * c] = a_k[c]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 + 2 * Cc + 2; i += blockDim.x)
-        if (i < kAccN && red[i] != 0.f) atomicAdd(&L.acc[i], double(red[i]));
+    const int nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 3 + 2 * Cc; i += blockDim.x) {
+        float t = 0.f;
+        for (int w = 0; w < nw; ++w) t += red[w][i];
+        L.part[size_t(blockIdx.x) * kAccN + i] = t;
+    }
 }
 
-__global__ void loss_finalize_kernel(const LossLevel L) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void loss_finalize_kernel(const LossLevel L, int rows) {
     const int Cc = L.collapse_before ? L.C - L.collapse_before + 1 : L.C;
-    const double n = L.acc[1] > 1.0 ? L.acc[1] : 1.0;
+    // fixed-order double sum over the per-block partial rows: thread (g, i) walks rows g, g+G, ... of accumulator i (coalesced rows,
+    // independent loads), then thread i adds the G group sums in order
+    __shared__ double tot[kAccN];
+    __shared__ double grp[10][96];
+    const int i = threadIdx.x % 96, g = threadIdx.x / 96;
+    const int nacc = 3 + 2 * Cc;
+    double t = 0;
+    if (g < 10 && i < nacc) {
+#pragma unroll 8
+        for (int r = g; r < rows; r += 10) t += double(L.part[size_t(r) * kAccN + i]);
+    }
+    if (g < 10) grp[g][i] = t;
+    __syncthreads();
+    if (g == 0 && i < nacc) {
+        double a = 0;
+        for (int k = 0; k < 10; ++k) a += grp[k][i];
+        tot[i] = a;
+        L.acc[i] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double n = tot[1] > 1.0 ? tot[1] : 1.0;
     double dice_sum = 0;
     const double eps = double(1e-5f);
-    for (int c = 1; c < Cc; ++c) dice_sum += (2.0 * L.acc[3 + 2 * c] + eps) / (L.acc[4 + 2 * c] + eps);
+    for (int c = 1; c < Cc; ++c) dice_sum += (2.0 * tot[3 + 2 * c] + eps) / (tot[4 + 2 * c] + eps);
     const double Z = double(Cc - 1 > 1 ? Cc - 1 : 1);
-    L.out3[0] = float(L.acc[0] / n);
+    L.out3[0] = float(tot[0] / n);
     L.out3[1] = float(1.0 - dice_sum / Z);
-    L.out3[2] = float(L.acc[2] / n);
+    L.out3[2] = float(tot[2] / n);
 }
 
 // dL/dlogit (x loss_scale) for the ORIGINAL output channels j < L.C of one voxel (un-collapsed), from the softmax `o`
@@ -401,6 +426,9 @@ __global__ void __launch_bounds__(128) loss_grad_head_kernel(const LossLevel L, 
 
 }  // namespace
 
+int loss_part_rows() { return 148 * 8; }
+int loss_part_cols() { return kAccN; }
+
 bool head_fwd_supported(int C, int xcp) { return C >= 1 && C <= kMaxC && (xcp == 16 || xcp == 32); }
 bool head_bwd_supported(int C, int xcp) {
     if (xcp != 16 && xcp != 32) return false;
@@ -429,13 +457,13 @@ int loss_level_launch(const LossLevel& L, const HeadFuse* Hd, cudaStream_t s) {
         set_error("invalid collapse_before");  // train.cpp:507-508
         return 1;
     }
-    U3D_CUDA_CHECK(cudaMemsetAsync(L.acc, 0, sizeof(double) * kAccN, s));
+    if (L.part == nullptr) { set_error("loss_level_launch: partial-sum scratch missing"); return 1; }
     const long long nv = (long long)L.d * L.h * L.w;
     long long g = (nv + 255) / 256;
     const int grid = int(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
     if (L.C <= 8) loss_reduce_kernel<8><<<grid, 256, 0, s>>>(L);
     else loss_reduce_kernel<kMaxC><<<grid, 256, 0, s>>>(L);
-    loss_finalize_kernel<<<1, 32, 0, s>>>(L);
+    loss_finalize_kernel<<<1, 960, 0, s>>>(L, grid);
     if (Hd != nullptr) {
         if (!head_bwd_supported(L.C, Hd->xcp)) { set_error("loss_level_launch: unsupported fused head shape"); return 1; }
         long long gh = (nv + 127) / 128;

@@ -231,6 +231,7 @@ Model::Model(int in_c, int out_c, const std::string& feature, bool host_only_)
     cudaMemcpy(d_chunks, chunks.data(), chunks.size() * sizeof(SgdChunk), cudaMemcpyHostToDevice);
     cudaMalloc(&d_status, sizeof(SgdStatus));
     cudaMalloc(&d_loss_acc, sizeof(double) * 8 * 80);
+    cudaMalloc(&d_loss_part, sizeof(float) * 8 * size_t(loss_part_rows()) * loss_part_cols());
     cudaMalloc(&d_losses, sizeof(float) * 8 * 3 * 2);
 }
 
@@ -246,7 +247,7 @@ Model::~Model() {
     cudaFree(d_params); cudaFree(d_grads); cudaFree(d_mom);
     if (vpa_ws) cudaFree(vpa_ws);
     for (auto b : d_buffers) cudaFree(b);
-    cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_losses);
+    cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_loss_part); cudaFree(d_losses);
     if (stream3) { cudaStreamSynchronize(stream3); cudaStreamDestroy(stream3); }
     for (int i = 0; i < 2; ++i) { if (ev_sample[i]) cudaEventDestroy(ev_sample[i]); if (pf_in[i]) cudaFree(pf_in[i]); }
     if (stream2) cudaStreamDestroy(stream2);
@@ -890,6 +891,7 @@ int Model::train_microbatch(const float* in, const float* label, int collapse_be
         Q.w_mse = use_mse ? nw : 0.f;
         Q.loss_scale = loss_scale;
         Q.acc = d_loss_acc + 80 * k;
+        Q.part = d_loss_part + size_t(k) * loss_part_rows() * loss_part_cols();
         Q.out3 = d_losses + 3 * k;
         HeadFuse Hd{};
         const Step* hs = head_step[k] >= 0 ? &steps[head_step[k]] : nullptr;
@@ -975,7 +977,7 @@ int Model::validate(const float* in, const float* label, int collapse_before, fl
     Q.C = out_count; Q.Cp = pad16(out_count); Q.collapse_before = collapse_before;
     Q.d = level_dims[0]; Q.h = level_dims[1]; Q.w = level_dims[2];
     Q.H0 = dim[1]; Q.W0 = dim[0]; Q.shift = 0;
-    Q.acc = d_loss_acc; Q.out3 = d_losses;
+    Q.acc = d_loss_acc; Q.part = d_loss_part; Q.out3 = d_losses;
     M_CHECK(loss_level_launch(Q, stream));
     launches += 3;
     M_CUDA(cudaMemcpyAsync(loss_out3, d_losses, 12, cudaMemcpyDeviceToHost, stream));

@@ -172,6 +172,7 @@ class Model {
     void* d_scratch = nullptr;       // gradient staging for multi-consumer tensors
     size_t scratch_bytes = 0;
     double* d_loss_acc = nullptr;
+    float* d_loss_part = nullptr;    // per level: [loss_part_rows()][loss_part_cols()] partial sums
     float* d_losses = nullptr;
     SgdChunk* d_chunks = nullptr;
     int n_chunks = 0;
