@@ -184,14 +184,14 @@ def test_param_roundtrip_momentum_copy_from_and_windows():
     W, H, D = 16, 16, 32
     a.set_dim(W, H, D)
     a.prepare_for_inference()
-    wins = [np.random.default_rng(i).random((1, 2, D, H, W), dtype=np.float32) for i in range(3)]
+    wins = [np.random.default_rng(i).random((1, 2, D, H, W), dtype=np.float32) for i in range(5)]
     singles = [a.forward(w, n_levels=1)[0] for w in wins]
     import ctypes
     F = ctypes.POINTER(ctypes.c_float)
     outs = [np.empty_like(s) for s in singles]
-    inp = (F * 3)(*[w.ctypes.data_as(F) for w in wins])
-    outp = (F * 3)(*[o.ctypes.data_as(F) for o in outs])
-    m.check(m.lib().unet3d_evaluate_windows(a._h, inp, outp, 3, 0))
+    inp = (F * 5)(*[w.ctypes.data_as(F) for w in wins])
+    outp = (F * 5)(*[o.ctypes.data_as(F) for o in outs])
+    m.check(m.lib().unet3d_evaluate_windows(a._h, inp, outp, 5, 0))   # pipelined: two staging slots each way are reused
     for s, o in zip(singles, outs):
         assert np.array_equal(s, o)
 

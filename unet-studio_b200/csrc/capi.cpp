@@ -181,11 +181,7 @@ int unet3d_forward(unet3d_t* h, const float* in, float* const* out_levels, int n
 
 int unet3d_evaluate_windows(unet3d_t* h, const float* const* in_windows, float* const* out_windows, int n_windows, int where) {
     GUARD_BEGIN NEED(h)
-    for (int i = 0; i < n_windows; ++i) {
-        float* outs[1] = {out_windows[i]};
-        if (h->m->forward(in_windows[i], outs, 1, where)) return 1;
-    }
-    return 0;
+    return h->m->evaluate_windows(in_windows, out_windows, n_windows, where);
     GUARD_END
 }
 

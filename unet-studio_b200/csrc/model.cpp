@@ -250,6 +250,7 @@ Model::~Model() {
     cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_loss_part); cudaFree(d_losses);
     if (stream3) { cudaStreamSynchronize(stream3); cudaStreamDestroy(stream3); }
     for (int i = 0; i < 2; ++i) { if (ev_sample[i]) cudaEventDestroy(ev_sample[i]); if (pf_in[i]) cudaFree(pf_in[i]); }
+    for (int i = 0; i < 2; ++i) { if (ew_in[i]) cudaFree(ew_in[i]); if (ew_out[i]) cudaFree(ew_out[i]); }
     if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -765,6 +766,73 @@ int Model::forward(const float* in, float* const* out_levels, int n_levels_wante
     }
     if (where == 0) return sync();
     return 0;
+}
+
+int Model::evaluate_windows(const float* const* in_windows, float* const* out_windows, int n_windows, int where) {
+    if (n_windows <= 0) return 0;
+    if (where != 0 || n_windows == 1) {
+        for (int i = 0; i < n_windows; ++i) {
+            float* outs[1] = {out_windows[i]};
+            M_CHECK(forward(in_windows[i], outs, 1, where));
+        }
+        return 0;
+    }
+    M_CHECK(ensure_plan());
+    M_CHECK(repack());
+    if (!logits[0]) { set_error("undefined output at level 0"); return 1; }
+    const long long V0 = tens[0].V();
+    const size_t in_bytes = size_t(in_count) * V0 * 4, out_bytes = size_t(out_count) * V0 * 4;
+    if (ew_in_bytes < in_bytes || ew_out_bytes < out_bytes) {
+        M_CUDA(cudaStreamSynchronize(stream));
+        for (int i = 0; i < 2; ++i) {
+            if (ew_in[i]) cudaFree(ew_in[i]);
+            if (ew_out[i]) cudaFree(ew_out[i]);
+            ew_in[i] = ew_out[i] = nullptr;
+            M_CUDA(cudaMalloc(reinterpret_cast<void**>(&ew_in[i]), in_bytes));
+            M_CUDA(cudaMalloc(reinterpret_cast<void**>(&ew_out[i]), out_bytes));
+        }
+        ew_in_bytes = in_bytes;
+        ew_out_bytes = out_bytes;
+    }
+    if (!stream3) M_CUDA(cudaStreamCreateWithFlags(&stream3, cudaStreamNonBlocking));
+    cudaStream_t up = stream3, down = stream2;
+    cudaEvent_t ev_up[2], ev_packed[2], ev_out[2], ev_down[2];
+    for (int i = 0; i < 2; ++i) {
+        M_CUDA(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
+        M_CUDA(cudaEventCreateWithFlags(&ev_packed[i], cudaEventDisableTiming));
+        M_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        M_CUDA(cudaEventCreateWithFlags(&ev_down[i], cudaEventDisableTiming));
+    }
+    int rc = 0;
+    auto upload = [&](int i) {
+        const int s = i & 1;
+        if (i >= 2) cudaStreamWaitEvent(up, ev_packed[s], 0);   // the slot's previous window has been packed into the NDHWC input
+        cudaMemcpyAsync(ew_in[s], in_windows[i], in_bytes, cudaMemcpyHostToDevice, up);
+        cudaEventRecord(ev_up[s], up);
+    };
+    upload(0);
+    for (int i = 0; i < n_windows && !rc; ++i) {
+        const int s = i & 1;
+        if (i + 1 < n_windows) upload(i + 1);
+        cudaStreamWaitEvent(stream, ev_up[s], 0);
+        rc = pack_act_launch(ew_in[s], tens[0].p, in_count, tens[0].Cp, V0, false, stream);
+        ++launches;
+        cudaEventRecord(ev_packed[s], stream);
+        if (!rc) rc = run_forward(1);
+        if (rc) break;
+        if (i >= 2) cudaStreamWaitEvent(stream, ev_down[s], 0);  // the slot's previous window has left for the host
+        cudaMemcpyAsync(ew_out[s], logits[0], out_bytes, cudaMemcpyDeviceToDevice, stream);
+        cudaEventRecord(ev_out[s], stream);
+        cudaStreamWaitEvent(down, ev_out[s], 0);
+        cudaMemcpyAsync(out_windows[i], ew_out[s], out_bytes, cudaMemcpyDeviceToHost, down);
+        cudaEventRecord(ev_down[s], down);
+    }
+    cudaStreamSynchronize(up);
+    cudaStreamSynchronize(down);
+    if (!rc) rc = sync();
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_packed[i]); cudaEventDestroy(ev_out[i]); cudaEventDestroy(ev_down[i]); }
+    if (!rc && cudaGetLastError() != cudaSuccess) { set_error("evaluate_windows: copy failed"); rc = 1; }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -135,6 +135,12 @@ class Model {
     int train_microbatch(const float* in, const float* label, int collapse_before, int use_ce, int use_dice, int use_mse,
                          float* loss_out3, float* all_levels, int where);
     int validate(const float* in, const float* label, int collapse_before, float* loss_out3, int where);
+    // evaluate.cpp:223-230 over a list of windows; host pointers: upload of window i+1 and download of window i-1 overlap the
+    // forward of window i (two staging slots each way, copy streams = the side streams that are idle during inference)
+    int evaluate_windows(const float* const* in_windows, float* const* out_windows, int n_windows, int where);
+    float* ew_in[2] = {nullptr, nullptr};
+    float* ew_out[2] = {nullptr, nullptr};
+    size_t ew_in_bytes = 0, ew_out_bytes = 0;
     // device staging buffers of the network input ([in][D][H][W] fp32) and label ([D][H][W] fp32) of the current plan
     int staging(float** in_dev, float** label_dev);
     int step(int batch_size, double lr, void* nccl_comm);

@@ -142,6 +142,21 @@ class UNet3d:
         check(self._lib.unet3d_forward(self._h, _fp(x), ptrs, n, 0))
         return outs
 
+    def evaluate_windows(self, windows, outs=None):
+        """forward()[0] of a list of windows [1,in,D,H,W] (evaluate.cpp:223-230); uploads / downloads overlap the compute."""
+        from . import check
+        windows = [np.ascontiguousarray(w, np.float32) for w in windows]
+        d, h, w = windows[0].shape[2:]
+        if (w, h, d) != self.dim:
+            self.set_dim(w, h, d)
+        if outs is None:
+            outs = [np.empty(self._level_shape(0), np.float32) for _ in windows]
+        n = len(windows)
+        inp = (_F * n)(*[_fp(a) for a in windows])
+        outp = (_F * n)(*[_fp(o) for o in outs])
+        check(self._lib.unet3d_evaluate_windows(self._h, inp, outp, n, 0))
+        return outs
+
     def create_optimizer(self, lr):
         from . import check
         check(self._lib.unet3d_create_optimizer(self._h, ctypes.c_float(lr)))
