@@ -93,7 +93,8 @@ extern "C" int u3d_op_conv_forward(int transposed, int ks, int stride, int cin0,
     std::vector<ConvProblem> probs;
     std::vector<PackDesc> packs;
     int kc = 0;
-    plan_forward(g, probs, packs, kc, (!planar_fp32 && conv_halo_wants_kc16(ks, stride, transposed, pad16(cin0) + (cin1 ? pad16(cin1) : 0), pad16(cout), Vout)) ? 16 : 0);
+    plan_forward(g, probs, packs, kc, (!planar_fp32 && (conv_halo_wants_kc16(ks, stride, transposed, pad16(cin0) + (cin1 ? pad16(cin1) : 0), pad16(cout), Vout) ||
+                                                        conv_s2_wants_kc16(ks, stride, transposed, pad16(cin0), cin1 ? 2 : 1, pad16(cout), Vout))) ? 16 : 0);
     DevBuf dx0, dx1, dw, db, dy, dstats, dyf;
     OP_CHECK(upload_act(dx0, x0, cin0, Vin, false, s));
     if (cin1) OP_CHECK(upload_act(dx1, x1, cin1, Vin, false, s));

@@ -405,6 +405,7 @@ int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
 int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream) {
     if (conv_band_eligible(probs, cfg)) return conv_band_launch(probs, cfg, stream);
     if (!probs.empty() && probs[0].banded) { set_error("conv_launch: banded weight pack but the problem is not eligible for conv_band"); return 1; }
+    if (conv_s2_eligible(probs, cfg)) return conv_s2_launch(probs, cfg, stream);
     if (conv_halo_eligible(probs, cfg)) return conv_halo_launch(probs, cfg, stream);
     if (conv_tma_eligible(probs, cfg)) return conv_tma_launch(probs, cfg, stream);
     return conv_igemm_launch(probs, cfg, nullptr, stream);
@@ -412,7 +413,7 @@ int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cu
 
 int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg) {
     if (conv_band_eligible(probs, cfg)) return 5;
-    if (conv_halo_eligible(probs, cfg)) return 2;
+    if (conv_s2_eligible(probs, cfg) || conv_halo_eligible(probs, cfg)) return 2;
     return conv_tma_eligible(probs, cfg) ? 4 : 0;
 }
 

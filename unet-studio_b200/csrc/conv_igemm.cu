@@ -430,6 +430,8 @@ unsigned int read_device_error() {
     v = read_device_error_band();
     if (v) return v;
     v = read_device_error_wband();
+    if (v) return v;
+    v = read_device_error_s2();
     return v ? v : read_device_error_rows();
 }
 

@@ -586,7 +586,9 @@ int Model::ensure_plan() {
                 const long long vox = 1LL * s.g.out_d * s.g.out_h * s.g.out_w;
                 const bool halo = s.head_level < 0 && conv_halo_wants_kc16(s.g.ks, s.g.stride, s.g.transposed,
                                                                            pad16(s.g.cin[0]) + (s.g.cin[1] ? pad16(s.g.cin[1]) : 0), pad16(s.g.cout), vox);
-                plan_forward(s.g, s.fprobs, s.fpacks, s.fkc, halo ? 16 : 0);
+                const bool s2 = s.head_level < 0 && conv_s2_wants_kc16(s.g.ks, s.g.stride, s.g.transposed, pad16(s.g.cin[0]), s.g.cin[1] ? 2 : 1,
+                                                                       pad16(s.g.cout), vox);
+                plan_forward(s.g, s.fprobs, s.fpacks, s.fkc, (halo || s2) ? 16 : 0);
             }
             s.flops = 2.0 * double(s.g.cin[0] + s.g.cin[1]) * s.g.cout * (s.g.transposed ? 1.0 : double(s.g.ks * s.g.ks * s.g.ks)) *
                       double(s.g.out_d) * s.g.out_h * s.g.out_w;

@@ -119,6 +119,10 @@ int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
 int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);  // halo, TMA or gather kernel
 int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);  // profile family conv_launch will use: 0 igemm, 2 halo, 4 tma, 5 band
 bool conv_band_wants(int k_channels_padded, int n_channels_padded, long long voxels);
+bool conv_s2_wants_kc16(int ks, int stride, int transposed, int cin_padded, int n_sources, int cout_padded, long long out_voxels);
+bool conv_s2_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
+int conv_s2_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
+unsigned int read_device_error_s2();
 bool conv_band_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
 int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
 unsigned int read_device_error_band();
