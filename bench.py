@@ -181,6 +181,8 @@ def main():
     net.train(True)
     lr0 = 1e-3
     net.create_optimizer(lr0)
+    if comm is not None and not os.environ.get("U3D_NO_AR_OVERLAP"):
+        net.attach_comm(comm, 1)     # one micro-batch per rank and step: overlap the gradient all-reduce with the backward pass
     img, lab = synth_sample(rank)                      # each rank trains on its own sample (data parallel)
     augment = not args.no_augment
     x_host = torch.from_numpy(img).pin_memory()

@@ -151,6 +151,12 @@ int unet3d_train_microbatch_prefetched(unet3d_t* h, int collapse_before, int use
 int unet3d_nccl_unique_id(void* id128);
 int unet3d_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);
 int unet3d_nccl_comm_destroy(void* comm);
+/* Optional: tell the handle its communicator and how many micro-batches THIS rank runs per step.  The backward pass of the last
+ * micro-batch then all-reduces the gradient bucket of everything behind the first encoder levels (94 % of the parameters of the
+ * default net) on its own stream as soon as that bucket is complete, overlapping the rest of the backward pass; unet3d_step (same
+ * comm) reduces only the remaining prefix.  Results are identical to the un-attached path up to the order of fp32 additions inside
+ * NCCL.  comm = NULL detaches. */
+int unet3d_attach_comm(unet3d_t* h, void* comm, int microbatches_per_step);
 
 /* ---- operator level (one reference layer, host buffers) — used by the per-layer parity tests ---------
  * Conv3d k1s1|k3s1|k3s2 pad (k-1)/2 (unet.cpp:59-72) or ConvTranspose3d k2s2 (unet.cpp:46-57), input given

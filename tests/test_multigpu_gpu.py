@@ -33,6 +33,7 @@ def _worker(rank, world, port, outdir):
     net = m.UNet3d(1, 2, FEATURE, gpu=rank)
     net.init_params(7)
     net.set_dim(W, H, D); net.train(True); net.create_optimizer(0.01)
+    net.attach_comm(comm, 1)      # the tail gradient bucket is all-reduced during the backward pass
     for step in range(2):
         for b in m.dist.shard_microbatches(world, world, rank):
             x, t = _data(m.dist.sample_seed(step, world, b))

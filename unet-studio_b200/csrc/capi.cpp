@@ -406,4 +406,9 @@ int unet3d_nccl_comm_init(void** comm, int nranks, int rank, const void* id128) 
 }
 int unet3d_nccl_comm_destroy(void* comm) { return u3d::nccl_comm_destroy(comm); }
 
+int unet3d_attach_comm(unet3d_t* h, void* comm, int microbatches_per_step) {
+    GUARD_BEGIN NEED(h) return h->m->attach_comm(comm, microbatches_per_step);
+    GUARD_END
+}
+
 }  // extern "C"

@@ -1,5 +1,7 @@
 #include "model.h"
 
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -243,6 +245,9 @@ Model::~Model() {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (ev_pack) cudaEventDestroy(ev_pack);
+    if (stream4) { cudaStreamSynchronize(stream4); cudaStreamDestroy(stream4); }
+    if (ev_ar_ready) cudaEventDestroy(ev_ar_ready);
+    if (ev_ar_done) cudaEventDestroy(ev_ar_done);
     free_plan();
     cudaFree(d_params); cudaFree(d_grads); cudaFree(d_mom);
     if (vpa_ws) cudaFree(vpa_ws);
@@ -649,6 +654,15 @@ int Model::ensure_plan() {
         }
     }
     grad_written.assign(tens.size(), 0);
+    // data-parallel overlap split: the first conv (forward order) that has >= 5 % of the parameters in front of it.  In the default net
+    // that is encode4's first conv: levels 0-3 hold 6 % of the parameters but the last ~20 % of the backward time.
+    dp_split_step = -1;
+    dp_split = 0;
+    for (size_t si = 0; si < steps.size(); ++si) {
+        if (steps[si].kind != Step::CONV || steps[si].head_level >= 0) continue;
+        const long long off = params[steps[si].p_w].offset;
+        if (off * 20 >= flat_n && off < flat_n) { dp_split_step = int(si); dp_split = off; break; }
+    }
     if (loss_scale == 0.f) {
         int e = int(std::floor(std::log2(double(std::max<long long>(V0, 1))))) - 2;
         e = std::max(4, std::min(e, 24));
@@ -843,6 +857,12 @@ int Model::evaluate_windows(const float* const* in_windows, float* const* out_wi
 int Model::run_backward() {
     static const bool no_side = std::getenv("U3D_ONE_STREAM") != nullptr;
     const bool two_streams = !no_side && !prof_on && stream2 != nullptr;   // the per-family event profile needs serial kernels
+    ++dp_seen;
+    if (dp_comm != nullptr && dp_seen > dp_microbatches) {
+        set_error("more micro-batches in this step than declared in unet3d_attach_comm (the tail gradient bucket is already reduced)");
+        return 1;
+    }
+    const bool dp_overlap_now = dp_comm != nullptr && stream4 != nullptr && dp_split_step >= 0 && dp_seen == dp_microbatches && !no_side;
     std::fill(grad_written.begin(), grad_written.end(), 0);
     // fused heads: the loss-gradient kernel (launched before this function) already stored dL/dx of the head input
     for (const Step& s : steps)
@@ -886,6 +906,21 @@ int Model::run_backward() {
                 prof_end();
                 ++launches;
                 grad_written[ins[src]] = 1;
+            }
+            if (dp_overlap_now && si == dp_split_step) {
+                // every contribution to the tail bucket has been issued: weight gradients on stream2, bias / norm / head gradients on
+                // the main stream.  Reduce it on stream4 while the (parameter-poor, time-rich) first encoder levels run their backward.
+                M_CUDA(cudaEventRecord(ev_ar_ready, stream));
+                M_CUDA(cudaStreamWaitEvent(stream4, ev_ar_ready, 0));
+                if (two_streams) {
+                    M_CUDA(cudaEventRecord(ev_join, stream2));
+                    M_CUDA(cudaStreamWaitEvent(stream4, ev_join, 0));
+                }
+                const ncclResult_t nr = ncclAllReduce(d_grads + dp_split, d_grads + dp_split, size_t(flat_n - dp_split), ncclFloat, ncclSum,
+                                                      static_cast<ncclComm_t>(dp_comm), stream4);
+                if (nr != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(nr)); return 1; }
+                M_CUDA(cudaEventRecord(ev_ar_done, stream4));
+                dp_tail_reduced = true;
             }
         } else {
             if (!grad_written[s.out]) continue;

@@ -95,6 +95,18 @@ class Model {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr;
     // sample prefetch (train.cpp:446-485: augmentation workers run beside the trainer): upload + augmentation of the NEXT sample on a
     // third stream into one of two staging slots while the current micro-batch computes
+    // data-parallel overlap: with an attached communicator the gradient bucket of everything behind the first (cheap-in-parameters,
+    // expensive-in-time) encoder levels is all-reduced on a fourth stream as soon as its last contribution has been issued in the
+    // backward pass of the step's LAST micro-batch; Model::step then only reduces the small prefix
+    void* dp_comm = nullptr;
+    int dp_microbatches = 1;         // micro-batches this rank runs per step
+    int dp_seen = 0;                 // micro-batches since the last step
+    bool dp_tail_reduced = false;    // the tail bucket [dp_split, flat_n) of this step is already in flight / reduced
+    long long dp_split = 0;          // first element of the tail bucket
+    int dp_split_step = -1;          // conv step (forward order) whose backward completes the tail bucket
+    cudaStream_t stream4 = nullptr;
+    cudaEvent_t ev_ar_ready = nullptr, ev_ar_done = nullptr;
+    int attach_comm(void* comm, int microbatches_per_step);
     cudaStream_t stream3 = nullptr;
     cudaEvent_t ev_sample[2] = {nullptr, nullptr};
     float* pf_in[2] = {nullptr, nullptr};

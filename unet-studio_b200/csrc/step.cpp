@@ -14,15 +14,40 @@
 
 namespace u3d {
 
+int Model::attach_comm(void* comm, int microbatches_per_step) {
+    if (microbatches_per_step < 1) { set_error("attach_comm: micro-batches per step must be >= 1"); return 1; }
+    cudaSetDevice(device);
+    if (comm != nullptr && stream4 == nullptr) {
+        if (cudaStreamCreateWithFlags(&stream4, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_ar_ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_ar_done, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("attach_comm: stream/event creation failed");
+            return 1;
+        }
+    }
+    dp_comm = comm;
+    dp_microbatches = microbatches_per_step;
+    dp_seen = 0;
+    dp_tail_reduced = false;
+    return 0;
+}
+
 int Model::step(int batch_size, double lr, void* nccl_comm) {
     if (!optimizer_created) { set_error("create_optimizer has not been called"); return 1; }
     if (batch_size < 1) { set_error("batch_size must be >= 1"); return 1; }
     cudaSetDevice(device);
     if (loss_scale == 0.f) { set_error("step called before any micro-batch"); return 1; }
     if (nccl_comm != nullptr) {
-        ncclResult_t r = ncclAllReduce(d_grads, d_grads, size_t(flat_n), ncclFloat, ncclSum, static_cast<ncclComm_t>(nccl_comm), stream);
-        if (r != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(r)); return 1; }
+        // the tail bucket may already have been reduced on stream4 during the backward pass (Model::run_backward)
+        const size_t count = dp_tail_reduced ? size_t(dp_split) : size_t(flat_n);
+        if (count) {
+            ncclResult_t r = ncclAllReduce(d_grads, d_grads, count, ncclFloat, ncclSum, static_cast<ncclComm_t>(nccl_comm), stream);
+            if (r != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(r)); return 1; }
+        }
+        if (dp_tail_reduced && cudaStreamWaitEvent(stream, ev_ar_done, 0) != cudaSuccess) { set_error("step: event"); return 1; }
     }
+    dp_tail_reduced = false;
+    dp_seen = 0;
     const float inv = 1.0f / (loss_scale * float(batch_size));
     if (sgd_step_launch(d_params, d_grads, d_mom, flat_n, d_chunks, n_chunks, inv, float(lr), 0.99f, 12.0f, mom_initialized ? 0 : 1,
                         d_status, stream))

@@ -182,6 +182,10 @@ class UNet3d:
         check(self._lib.unet3d_validate(self._h, _fp(x), _fp(label), int(collapse_before), _fp(out), 0))
         return out
 
+    def attach_comm(self, nccl_comm, microbatches_per_step=1):
+        from . import check
+        check(self._lib.unet3d_attach_comm(self._h, nccl_comm, int(microbatches_per_step)))
+
     def step(self, batch_size, lr, nccl_comm=None):
         from . import check
         check(self._lib.unet3d_step(self._h, int(batch_size), ctypes.c_double(lr), nccl_comm))
