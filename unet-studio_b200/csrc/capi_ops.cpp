@@ -121,6 +121,8 @@ extern "C" int u3d_op_conv_forward(int transposed, int ks, int stride, int cin0,
     cfg.epi = planar_fp32 ? EPI_PLANAR32 : EPI_STORE16;
     int grid = 0;
     cfg.stats_grid_out = &grid;
+    DevBuf dsplit;   // scratch for the deterministic split-K of the small deep-level shapes
+    if (Vout <= 16384 && !dsplit.alloc(size_t(48) << 20)) { cfg.splitk_scratch = static_cast<float*>(dsplit.p); cfg.splitk_scratch_bytes = size_t(48) << 20; }
     const int ntot = probs[0].ntile * probs[0].ntiles;
     if (stats_sum_sumsq && (probs.size() == 1 || probs[0].band_pass) && !planar_fp32) {
         if (dstats.alloc(size_t(device_sm_count()) * 2 * ntot * 4)) { set_error("cudaMalloc failed"); return 1; }
@@ -192,6 +194,8 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
         ConvLaunch cfg{};
         cfg.kc = kc;
         cfg.epi = acc ? EPI_ACCUM16 : EPI_STORE16;
+        DevBuf dsplit;
+        if (Vin <= 16384 && !dsplit.alloc(size_t(48) << 20)) { cfg.splitk_scratch = static_cast<float*>(dsplit.p); cfg.splitk_scratch_bytes = size_t(48) << 20; }
         OP_CHECK(conv_launch(probs, cfg, s));
         OP_CHECK(finish(s));
         OP_CHECK(download_act(dgx[src].p, gx[src], cin[src], Vin, false, s));

@@ -43,6 +43,8 @@ struct TParams {
     int ntile_max, ntot_max, tmem_cols;
     uint32_t a_stage_bytes, b_stage_bytes, off_b, off_stats, off_bars;
     float* stats;
+    int ksplit;            // > 1: deterministic split-K -- work item (mt, nt, ks) reduces a contiguous range of the K units and writes its fp32
+    float* split_scratch;  // accumulator to split_scratch[ks][lattice voxel][ntot]; conv_splitk_finalize_kernel sums the slices in order
 };
 
 struct alignas(64) TMaps {
@@ -50,7 +52,7 @@ struct alignas(64) TMaps {
 };
 
 struct TItem {
-    int pi, mt, nt;
+    int pi, mt, nt, ks;
 };
 
 __device__ __forceinline__ TItem decode_titem(const TParams& p, int item) {
@@ -58,9 +60,11 @@ __device__ __forceinline__ TItem decode_titem(const TParams& p, int item) {
 #pragma unroll 1
     for (int i = 1; i < p.nprob; ++i)
         if (item >= p.probs[i].item_base) pi = i;
-    const int local = item - p.probs[pi].item_base;
+    int local = item - p.probs[pi].item_base;
+    const int ks = local % p.ksplit;
+    local /= p.ksplit;
     const int ntiles = p.probs[pi].ntiles;
-    return TItem{pi, local / ntiles, local % ntiles};
+    return TItem{pi, local / ntiles, local % ntiles, ks};
 }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -160,11 +164,13 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                 int tap = 0, ch = 0;
                 if (KC == 64 && bx.xhalo) {
                     // x-halo mode: per (dz,dy) pair and K chunk one box of (bx+2) x by x bz voxels + the weight slices of its 3 dx taps
+                    const int U = (ntaps / 3) * nch;
+                    const int u0 = w.ks * U / p.ksplit, u1 = (w.ks + 1) * U / p.ksplit;
 #pragma unroll 1
-                    for (int tp3 = 0; tp3 < ntaps; tp3 += 3) {
+                    for (int u = u0; u < u1; ++u) {
+                        const int tp3 = (u / nch) * 3, c = u % nch;
                         const ConvTap tp = P.taps[tp3];
-#pragma unroll 1
-                        for (int c = 0; c < nch; ++c) {
+                        {
                             mbar_wait(empty_bar(stage), phase ^ 1, 0x1100u | stage);
                             mbar_arrive_expect_tx(full_bar(stage), a_bytes + 3u * b_bytes);
                             const bool first = c < nch0;
@@ -179,9 +185,12 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                     }
                     continue;
                 }
+                const int g0 = p.ksplit > 1 ? w.ks * nsteps / p.ksplit : 0;
+                const int g1 = p.ksplit > 1 ? (w.ks + 1) * nsteps / p.ksplit : nsteps;
+                tap = g0 / nch; ch = g0 % nch;
 #pragma unroll 1
-                for (int g = 0; g < nsteps; g += SPG) {
-                    const int cnt = min(SPG, nsteps - g);
+                for (int g = g0; g < g1; g += SPG) {
+                    const int cnt = min(SPG, g1 - g);
                     mbar_wait(empty_bar(stage), phase ^ 1, 0x1100u | stage);
                     mbar_arrive_expect_tx(full_bar(stage), (a_bytes + b_bytes) * cnt);
                     const uint32_t adst = sA + stage * p.a_stage_bytes;
@@ -226,13 +235,15 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                 bool first = true;
                 if (KC == 64 && p.box[w.pi].xhalo) {
                     const int nch = P.nch0 + P.nch1, min_dx = p.box[w.pi].min_dx;
+                    const int U = (P.ntaps / 3) * nch;
+                    const int u0 = w.ks * U / p.ksplit, u1 = (w.ks + 1) * U / p.ksplit;
 #pragma unroll 1
-                    for (int tp3 = 0; tp3 < P.ntaps; tp3 += 3) {
+                    for (int u = u0; u < u1; ++u) {
+                        const int tp3 = (u / nch) * 3;
                         uint32_t sh[3];
 #pragma unroll
                         for (int j = 0; j < 3; ++j) sh[j] = uint32_t(P.taps[tp3 + j].dx - min_dx);   // start row of this dx tap inside the halo box
-#pragma unroll 1
-                        for (int c = 0; c < nch; ++c) {
+                        {
                             mbar_wait(full_bar(stage), phase, 0x1300u | stage);
                             tc_fence_after();
                             const uint64_t ad0 = a_desc0 + uint64_t(stage) * a_stage_u;
@@ -256,9 +267,11 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                     umma_commit(tfull_bar(acc));
                     continue;
                 }
+                const int g0 = p.ksplit > 1 ? w.ks * nsteps / p.ksplit : 0;
+                const int g1 = p.ksplit > 1 ? (w.ks + 1) * nsteps / p.ksplit : nsteps;
 #pragma unroll 1
-                for (int g = 0; g < nsteps; g += SPG) {
-                    const int cnt = min(SPG, nsteps - g);
+                for (int g = g0; g < g1; g += SPG) {
+                    const int cnt = min(SPG, g1 - g);
                     mbar_wait(full_bar(stage), phase, 0x1300u | stage);
                     tc_fence_after();
                     uint64_t ad = a_desc0 + uint64_t(stage) * a_stage_u;
@@ -330,6 +343,15 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
             for (int c0 = 0; c0 < ntile; c0 += 16, ncol += 16) {
                 float v[16];
                 tmem_ld16(t_row + c0, v);
+                if (p.ksplit > 1) {
+                    // split-K: raw fp32 partial sums of this K range; bias / statistics / 16-bit store happen in the finalize kernel
+                    if (rv) {
+                        float4* o4 = reinterpret_cast<float4*>(p.split_scratch + (size_t(w.ks) * size_t(M) + size_t(m)) * size_t(ntile * P.ntiles) + ncol);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    continue;
+                }
                 {
                     const float4* sb4 = reinterpret_cast<const float4*>(sbias + ncol);
 #pragma unroll
@@ -403,7 +425,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
         }
-        if (p.stats != nullptr) {
+        if (p.stats != nullptr && p.ksplit == 1) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = r; i < 2 * p.ntot_max; i += 128)
                 p.stats[size_t(blockIdx.x) * 2 * p.ntot_max + i] =
@@ -413,6 +435,74 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// Split-K finalize: out[m][n] = sum_ks scratch[ks][m][n] (fixed order => deterministic) + bias, optional read-add, 16-bit NDHWC store,
+// per-block partial rows of (sum, sum of squares) for the norm that follows.  Thread = (voxel, 8-channel chunk).
+__global__ void conv_splitk_finalize_kernel(const float* __restrict__ scratch, int ksplit, long long M, int ntot, const float* __restrict__ bias,
+                                            int n_real, uint8_t* __restrict__ dst, int dst_cp, int dst_coff, int accumulate,
+                                            float* __restrict__ stats) {
+    extern __shared__ float sm[];
+    const int nch = ntot / 8;
+    const int k = blockDim.x / nch;
+    const int t = threadIdx.x;
+    const int ch = t % nch, vsub = t / nch;
+    float s0[8], s1[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s0[j] = s1[j] = 0.f;
+        b[j] = (bias != nullptr && ch * 8 + j < n_real) ? bias[ch * 8 + j] : 0.f;
+    }
+    if (vsub < k) {
+        for (long long m = (long long)blockIdx.x * k + vsub; m < M; m += (long long)gridDim.x * k) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            for (int ks = 0; ks < ksplit; ++ks) {
+                const float4* q = reinterpret_cast<const float4*>(scratch + (size_t(ks) * size_t(M) + size_t(m)) * size_t(ntot) + ch * 8);
+                const float4 a0 = q[0], a1 = q[1];
+                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+                v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += b[j];
+            uint4* out = reinterpret_cast<uint4*>(dst + (size_t(m) * dst_cp + dst_coff + ch * 8) * 2);
+            if (accumulate) {
+                const uint4 o = *out;
+                const uint32_t ow_[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack2<false>(ow_[j]);
+                    v[2 * j] += f.x;
+                    v[2 * j + 1] += f.y;
+                }
+            }
+            uint4 qv;
+            qv.x = pack2<false>(v[0], v[1]); qv.y = pack2<false>(v[2], v[3]);
+            qv.z = pack2<false>(v[4], v[5]); qv.w = pack2<false>(v[6], v[7]);
+            *out = qv;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s0[j] += v[j];
+                s1[j] = fmaf(v[j], v[j], s1[j]);
+            }
+        }
+    }
+    if (stats == nullptr) return;
+    float* row = sm + size_t(vsub) * ntot * 2;
+    if (vsub < k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            row[ch * 8 + j] = s0[j];
+            row[ntot + ch * 8 + j] = s1[j];
+        }
+    }
+    __syncthreads();
+    for (int i = t; i < 2 * ntot; i += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < k; ++r) acc += sm[size_t(r) * ntot * 2 + i];
+        stats[size_t(blockIdx.x) * 2 * ntot + i] = acc;
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -544,7 +634,7 @@ int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg
         any_xhalo = any_xhalo || xh;
         P.mtiles = b.tiles_x * b.tiles_y * ((P.od + b.bz - 1) / b.bz);
         P.item_base = items;
-        items += P.mtiles * P.ntiles;
+        items += P.mtiles * P.ntiles;   // (x ksplit below: split-K only with a single problem)
         ntile_max = std::max(ntile_max, P.ntile);
         ntot_max = std::max(ntot_max, P.ntile * P.ntiles);
         for (int s = 0; s < 2; ++s) {
@@ -561,6 +651,28 @@ int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg
             if (r != CUDA_SUCCESS) {
                 set_error("conv_tma_launch: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
                 return 1;
+            }
+        }
+    }
+    // deterministic split-K for the deep levels: a handful of boxes x N tiles cannot fill 148 SMs, and each item walks hundreds of K
+    // units serially.  Split the K units over up to 16 items that write separate fp32 slices; a finalize kernel sums them in order.
+    tp.ksplit = 1;
+    tp.split_scratch = nullptr;
+    {
+        const ConvProblem& P0 = tp.probs[0];
+        static const bool no_split = std::getenv("U3D_NO_SPLITK") != nullptr;
+        const int nch = P0.nch0 + P0.nch1;
+        const int units = tp.box[0].xhalo ? (P0.ntaps / 3) * nch : P0.ntaps * nch;
+        const long long M = 1LL * P0.od * P0.oh * P0.ow;
+        if (!no_split && tp.nprob == 1 && kc == 64 && !P0.shuffle_cp && P0.ostep == 1 && cfg.epi != EPI_PLANAR32 && items * 2 <= device_sm_count() &&
+            units >= 8 && cfg.splitk_scratch != nullptr && P0.od == P0.OD && P0.oh == P0.OH && P0.ow == P0.OW) {
+            int ks = std::min({units / 4, device_sm_count() / items, 16});
+            const size_t per_slice = size_t(M) * size_t(ntot_max) * 4;
+            while (ks > 1 && per_slice * ks > cfg.splitk_scratch_bytes) --ks;
+            if (ks > 1) {
+                tp.ksplit = ks;
+                tp.split_scratch = cfg.splitk_scratch;
+                items *= ks;
             }
         }
     }
@@ -589,6 +701,22 @@ int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg
     tp.stats = (cfg.epi == EPI_STORE16 && probs.size() == 1) ? cfg.stats_partials : nullptr;
     const int grid = std::max(1, std::min(items, device_sm_count()));
     if (cfg.stats_grid_out) *cfg.stats_grid_out = grid;
+    if (tp.ksplit > 1) {
+        if (launch_tma_kc<EPI_STORE16>(tp, maps, kc, grid, smem, stream)) return 1;
+        const ConvProblem& P0 = tp.probs[0];
+        const long long M = 1LL * P0.od * P0.oh * P0.ow;
+        const int nch8 = ntot_max / 8;
+        const int k = nch8 >= 256 ? 1 : 256 / nch8;
+        const int block = nch8 * k;
+        const int fgrid = int(std::max<long long>(1, std::min<long long>((M + k - 1) / k, device_sm_count())));
+        float* st = tp.stats;
+        conv_splitk_finalize_kernel<<<fgrid, block, st ? size_t(k) * ntot_max * 2 * sizeof(float) : 0, stream>>>(
+            tp.split_scratch, tp.ksplit, M, ntot_max, P0.bias, P0.n_real, static_cast<uint8_t*>(P0.dst), P0.dst_cp, P0.dst_coff,
+            cfg.epi == EPI_ACCUM16 ? 1 : 0, st);
+        U3D_CUDA_CHECK(cudaGetLastError());
+        if (cfg.stats_grid_out) *cfg.stats_grid_out = fgrid;
+        return 0;
+    }
     if (cfg.epi == EPI_PLANAR32) return launch_tma_kc<EPI_PLANAR32>(tp, maps, kc, grid, smem, stream);
     if (cfg.epi == EPI_STORE16) return launch_tma_kc<EPI_STORE16>(tp, maps, kc, grid, smem, stream);
     return launch_tma_kc<EPI_ACCUM16>(tp, maps, kc, grid, smem, stream);

@@ -278,6 +278,8 @@ void Model::free_plan() {
     level_dims.clear();
     d_in_f32 = d_label = d_partials = d_sums = nullptr;
     d_scratch = nullptr;
+    d_splitk = nullptr;
+    splitk_bytes = 0;
     planned = false;
 }
 
@@ -564,6 +566,8 @@ int Model::ensure_plan() {
         M_CHECK(alloc(&d_scratch, max_bytes));
         scratch_bytes = max_bytes;
     }
+    splitk_bytes = size_t(96) << 20;   // 16 slices x (< 74 boxes x 120 voxels) x 256 channels x 4 B fits with room to spare
+    M_CHECK(alloc(reinterpret_cast<void**>(&d_splitk), splitk_bytes));
     const int L = int(output.size());
     logits.assign(L, nullptr);
     dlogits.assign(L, nullptr);
@@ -714,6 +718,7 @@ int Model::run_forward(int levels_wanted) {
             int rows = 0;
             cfg.stats_grid_out = &rows;
             if (s.stats) cfg.stats_partials = d_partials;
+            cfg.splitk_scratch = d_splitk; cfg.splitk_scratch_bytes = splitk_bytes;
             prof_begin(conv_kernel_kind(s.fprobs, cfg), s.flops);
             M_CHECK(conv_launch(s.fprobs, cfg, stream));
             prof_end();
@@ -901,6 +906,7 @@ int Model::run_backward() {
                 ConvLaunch cfg{};
                 cfg.kc = s.dg[src].kc;
                 cfg.epi = grad_written[ins[src]] ? EPI_ACCUM16 : EPI_STORE16;
+                cfg.splitk_scratch = d_splitk; cfg.splitk_scratch_bytes = splitk_bytes;
                 prof_begin(conv_kernel_kind(s.dg[src].probs, cfg), s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
                 M_CHECK(conv_launch(s.dg[src].probs, cfg, stream));
                 prof_end();

@@ -188,6 +188,8 @@ class Model {
     float* d_partials = nullptr;
     float* d_sums = nullptr;
     void* d_scratch = nullptr;       // gradient staging for multi-consumer tensors
+    float* d_splitk = nullptr;       // fp32 slices of the deterministic split-K convs of the deep levels (conv_tma.cu)
+    size_t splitk_bytes = 0;
     size_t scratch_bytes = 0;
     double* d_loss_acc = nullptr;
     float* d_loss_part = nullptr;    // per level: [loss_part_rows()][loss_part_cols()] partial sums

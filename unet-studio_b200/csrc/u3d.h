@@ -74,6 +74,8 @@ struct ConvLaunch {
     EpiMode epi;
     float* stats_partials; // [grid][2][ntile*ntiles] or nullptr (single-problem launches only)
     int* stats_grid_out;   // host pointer: receives the grid size used (number of partial rows)
+    float* splitk_scratch; // optional fp32 scratch for the deterministic split-K of conv_tma (deep levels); nullptr = no split-K
+    size_t splitk_scratch_bytes;
 };
 
 int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, ConvProblem* dev_scratch,
