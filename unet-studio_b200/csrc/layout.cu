@@ -11,22 +11,26 @@ namespace {
 
 template <bool BF16>
 __global__ void pack_act_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, int Cp, long long V) {
-    const long long total = V * (Cp / 8);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long vox = i % V;
-        const int chunk = int(i / V);
-        float f[8];
+    // thread = voxel: reads its C planar fp32 values (coalesced per channel plane), writes the whole padded NDHWC row (Cp * 2 bytes,
+    // contiguous across the threads of a warp); no 64-bit div/mod per element, zero chunks cost only the store
+    const int nch = Cp / 8;
+    for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < V; vox += (long long)gridDim.x * blockDim.x) {
+        for (int chunk = 0; chunk < nch; ++chunk) {
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (chunk * 8 < C) {
+                float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = chunk * 8 + j;
-            f[j] = c < C ? in[(long long)c * V + vox] : 0.f;
+                for (int j = 0; j < 8; ++j) {
+                    const int c = chunk * 8 + j;
+                    f[j] = c < C ? in[(long long)c * V + vox] : 0.f;
+                }
+                q.x = pack2<BF16>(f[0], f[1]);
+                q.y = pack2<BF16>(f[2], f[3]);
+                q.z = pack2<BF16>(f[4], f[5]);
+                q.w = pack2<BF16>(f[6], f[7]);
+            }
+            out[vox * nch + chunk] = q;
         }
-        uint4 q;
-        q.x = pack2<BF16>(f[0], f[1]);
-        q.y = pack2<BF16>(f[2], f[3]);
-        q.z = pack2<BF16>(f[4], f[5]);
-        q.w = pack2<BF16>(f[6], f[7]);
-        out[vox * (Cp / 8) + chunk] = q;
     }
 }
 
@@ -99,11 +103,10 @@ int pack_weights_launch(const PackDesc& d, cudaStream_t stream) {
 }
 
 int pack_act_launch(const float* in, void* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream) {
-    const long long total = V * (Cp / 8);
     if (bf16)
-        pack_act_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(in, static_cast<uint4*>(out), C, Cp, V);
+        pack_act_kernel<true><<<grid_for(V, 256), 256, 0, stream>>>(in, static_cast<uint4*>(out), C, Cp, V);
     else
-        pack_act_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(in, static_cast<uint4*>(out), C, Cp, V);
+        pack_act_kernel<false><<<grid_for(V, 256), 256, 0, stream>>>(in, static_cast<uint4*>(out), C, Cp, V);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
