@@ -52,6 +52,8 @@ CASES = [
     ("s2_16_64", 0, 3, 2, 16, 0, 64, (66, 62, 34)),
     ("s2_32_64_tma", 0, 3, 2, 32, 0, 64, (66, 62, 34)),
     ("s2_9_24_odd", 0, 3, 2, 9, 0, 24, (75, 53, 35)),
+    ("s2_big_16_32", 0, 3, 2, 16, 0, 32, (72, 60, 40)),
+    ("s2_big_12_20_odd", 0, 3, 2, 12, 0, 20, (75, 61, 37)),
 ]
 
 
