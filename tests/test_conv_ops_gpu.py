@@ -47,6 +47,7 @@ CASES = [
     ("wband_64_64", 0, 3, 1, 64, 0, 64, (40, 24, 12)),
     ("wband_cat64_64_64", 0, 3, 1, 64, 64, 64, (32, 24, 12)),
     ("wband_48_72", 0, 3, 1, 48, 0, 72, (36, 30, 16)),
+    ("wband_256_256_level4", 0, 3, 1, 256, 0, 256, (10, 12, 10)),
     # halo-resident stride-2 forward (conv_s2.cu): >= 16384 output voxels, ragged tiles and odd input sizes
     ("s2_16_32", 0, 3, 2, 16, 0, 32, (64, 48, 44)),
     ("s2_16_64", 0, 3, 2, 16, 0, 64, (66, 62, 34)),

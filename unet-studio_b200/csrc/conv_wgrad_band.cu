@@ -257,7 +257,7 @@ bool conv_wgrad_band_eligible(const WgradProblem& P) {
     if (P.t_d != P.ld || P.t_h != P.lh || P.t_w != P.lw) return false;
     // small-channel layers need a big volume to fill the machine; wide layers bring (Cin/32)*(Cout/32) independent pairs
     const long long pairs = (P.t_c > 32 || P.u_c > 32) ? 1LL * (P.t_c / 16) * (P.u_c / 16) / 4 : 1;
-    if (1LL * P.ld * P.lh * P.lw * pairs < 32768 || 1LL * P.ld * P.lh * P.lw < 4096 || pairs > 64) return false;
+    if (1LL * P.ld * P.lh * P.lw * pairs < 32768 || 1LL * P.ld * P.lh * P.lw < 1024 || pairs > 64) return false;
     for (int t = 0; t < 27; ++t)   // forward tap order (kz,ky,kx) with offsets k-1 and identity tap_ref
         if (P.taps[t].dz != t / 9 - 1 || P.taps[t].dy != (t / 3) % 3 - 1 || P.taps[t].dx != t % 3 - 1 || P.tap_ref[t] != t) return false;
     return true;
