@@ -24,13 +24,14 @@ namespace {
 
 constexpr int kSThreads = 32 * 13;
 constexpr int kSProducers = 256;
-constexpr int kSSlots = 5;
+constexpr int kSMaxSlots = 8;   // ring of input planes: 3 in use per output plane, the rest in flight (the kernel is DRAM-latency bound)
 
 struct SParams {
     ConvProblem P;
     int OTX, OTY, HQ, ROWS, HX, HY;   // output tile, smem row pitch, rows per parity plane, input halo extent per plane
     int tiles_x, tiles_y, zchunks, zlen, total_items;
     int ncg, n;                        // input channel groups of 8, padded Cout
+    int nslots;
     uint32_t slot_bytes, w_bytes, off_w, off_stats, off_bars;
     float* stats;
 };
@@ -59,12 +60,13 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_s2_kernel(const __grid_cons
     const uint32_t sW = sbase + p.off_w;
     float* sstats = reinterpret_cast<float*>(smem + p.off_stats);
     const uint32_t bars = sbase + p.off_bars;
+    const uint32_t kSSlots = uint32_t(p.nslots);
     auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
-    auto empty_bar = [&](uint32_t s) { return bars + 8u * (kSSlots + s); };
-    auto tfull_bar = [&](uint32_t a) { return bars + 8u * (2 * kSSlots + a); };
-    auto tempty_bar = [&](uint32_t a) { return bars + 8u * (2 * kSSlots + 2 + a); };
-    const uint32_t wfull_bar = bars + 8u * (2 * kSSlots + 4);
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kSSlots + 5));
+    auto empty_bar = [&](uint32_t s) { return bars + 8u * (kSMaxSlots + s); };
+    auto tfull_bar = [&](uint32_t a) { return bars + 8u * (2 * kSMaxSlots + a); };
+    auto tempty_bar = [&](uint32_t a) { return bars + 8u * (2 * kSMaxSlots + 2 + a); };
+    const uint32_t wfull_bar = bars + 8u * (2 * kSMaxSlots + 4);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kSMaxSlots + 5));
     constexpr uint32_t TCOLS = 2 * N < 32 ? 32 : 2 * N;
 
     if (threadIdx.x == 0) {
@@ -362,10 +364,12 @@ int conv_s2_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg,
     sp.slot_bytes = uint32_t(sp.ncg * 4 * sp.ROWS * 16);
     const int KS = P.c0p / 16;
     sp.w_bytes = uint32_t(27 * KS * sp.n * 32);
-    sp.off_w = kSSlots * sp.slot_bytes;
+    sp.nslots = int(std::min<size_t>(kSMaxSlots, (size_t(222) * 1024 - sp.w_bytes - 9 * sp.n * 4) / sp.slot_bytes));
+    if (sp.nslots < 4) { set_error("conv_s2_launch: plane ring does not fit in shared memory"); return 1; }
+    sp.off_w = uint32_t(sp.nslots) * sp.slot_bytes;
     sp.off_stats = sp.off_w + sp.w_bytes;
     sp.off_bars = uint32_t((sp.off_stats + 9 * sp.n * 4 + 15) & ~15u);
-    const size_t smem = sp.off_bars + 8 * (2 * kSSlots + 5) + 16;
+    const size_t smem = sp.off_bars + 8 * (2 * kSMaxSlots + 5) + 16;
     if (smem > 227 * 1024) { set_error("conv_s2_launch: tile does not fit in shared memory"); return 1; }
     sp.stats = cfg.stats_partials;
     const int grid = std::max(1, std::min(sp.total_items, sms));
