@@ -91,9 +91,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_name(augment=True):
+def workload_name(augment=True, simulate=False):
     return (f"cfg2: UNet3d({IN_C},{OUT_C},default_feature) single-template training step, human T1 skull-strip "
-            f"{W}x{H}x{D}, batch 1 per GPU, {'with' if augment else 'WITHOUT'} visual_perception_augmentation, "
+            f"{W}x{H}x{D}, batch 1 per GPU, {'with' if augment else 'WITHOUT'} "
+            f"{'simulate_modality + ' if augment and simulate else ''}visual_perception_augmentation, "
             f"ce+dice+mse deep supervision, clip 12, Nesterov SGD")
 
 
@@ -125,9 +126,9 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(True), "grid": [W, H, D], "in_count": IN_C, "out_count": OUT_C,
-                       "arm": "reference unet.cpp + libtorch CPU (oracle/_ref/unet_ref) on the host cores; augmentation (TIPL) not compilable here, "
-                              "so the CPU step excludes it -- it is in the GPU arm's timed region"},
+            "config": {"workload": workload_name(True, True), "grid": [W, H, D], "in_count": IN_C, "out_count": OUT_C,
+                       "arm": "reference unet.cpp + libtorch CPU (oracle/_ref/unet_ref) on the host cores; simulate_modality and the augmentation "
+                              "(TIPL) are not compilable here, so the CPU step excludes them -- they are in the GPU arm's timed region"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -142,6 +143,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-augment", action="store_true")
+    ap.add_argument("--no-simulate", action="store_true", help="skip simulate_modality (train.cpp:459) in front of the augmentation")
     ap.add_argument("--no-inference", action="store_true", help="skip the cfg1 inference leg (profiling runs under ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -185,6 +187,9 @@ def main():
         net.attach_comm(comm, 1)     # one micro-batch per rank and step: overlap the gradient all-reduce with the backward pass
     img, lab = synth_sample(rank)                      # each rank trains on its own sample (data parallel)
     augment = not args.no_augment
+    simulate = augment and not args.no_simulate
+    if simulate:
+        pkg.set_simulate_modality(net, 1)   # the template sample goes through the labelled overload first (train.cpp:459-460)
     x_host = torch.from_numpy(img).pin_memory()
     l_host = torch.from_numpy(lab).pin_memory()
     x_dev, l_dev = x_host.cuda(), l_host.cuda()
@@ -325,9 +330,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": workload_name(augment),
+        "config": {"workload": workload_name(augment, simulate),
                    "grid": [W, H, D], "in_count": IN_C, "out_count": OUT_C, "micro_batches_per_gpu_per_step": 1,
-                   "global_batch": world, "parallelism": f"dp{world}", "augmentation": bool(augment),
+                   "global_batch": world, "parallelism": f"dp{world}", "augmentation": bool(augment), "simulate_modality": bool(simulate),
                    "l2": "no explicit flush: each step streams > 3 GB of activations, far above the 126 MB L2",
                    "arithmetic": "fp16 operands, fp32 accumulate (tcgen05), fp32 stats/loss/optimizer, loss scale %g" % train_loss_scale},
         "loss": [float(v) for v in loss],

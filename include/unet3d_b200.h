@@ -147,6 +147,19 @@ int unet3d_prefetch_augmented(unet3d_t* h, const char* const* keys, const float*
                               uint64_t seed, int where);
 int unet3d_train_microbatch_prefetched(unet3d_t* h, int collapse_before, int use_ce, int use_dice, int use_mse, float loss_out3[3]);
 
+/* simulate_modality (train.cpp:43-117 labelled-template overload, :119-180 image-only overload; call site train.cpp:459-462):
+ * synthesises a random contrast in place on `t1w` ({D,H,W} fp32 in [0,1]).  label = NULL selects the image-only overload;
+ * otherwise label holds float-stored integers 0..max_label (the caller passes model->out_count, train.cpp:459).  seed is the
+ * sample seed (rand_int = mt19937(seed), rand_float = mt19937(seed+1)).  where = 0 host pointers, 1 device pointers.
+ * simulate_modality is standalone (own stream on `gpu`, returns when done); unet3d_simulate_modality runs stream-ordered on the
+ * handle's stream.  unet3d_set_simulate_modality makes unet3d_train_microbatch_augmented / unet3d_prefetch_augmented run it on the
+ * uploaded sample before the augmentation, like the reference's augmentation thread: mode 0 off (default), 1 labelled template
+ * (train_image_is_template), 2 image only. */
+int simulate_modality(float* t1w, const float* label, unsigned max_label, unsigned seed, int w, int h, int d, int where, int gpu);
+int unet3d_simulate_modality(unet3d_t* h, float* t1w, const float* label, unsigned max_label, unsigned seed, int w, int hgt, int d,
+                             int where);
+int unet3d_set_simulate_modality(unet3d_t* h, int mode);
+
 /* NCCL plumbing for the data-parallel step (bootstrap the 128-byte id through any host channel) */
 int unet3d_nccl_unique_id(void* id128);
 int unet3d_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);

@@ -7,6 +7,8 @@
 #include "../../include/unet3d_b200.h"
 #include "model.h"
 #include "vpa.h"
+#include "simulate.h"
+#include <algorithm>
 #include <mutex>
 #include <map>
 
@@ -258,6 +260,59 @@ std::mutex g_vpa_mu;
 std::map<int, VpaWs> g_vpa_ws;
 }  // namespace
 
+// workspace shared by the two sample-preparation stages (they run one after the other on one stream): scratch first, then a
+// staging area for host-buffer calls
+static size_t sample_ws_need(int w, int h, int d, int channels) {
+    const size_t stage = (size_t(channels) + 1) * size_t(w) * h * d * 4;
+    return std::max(u3d::vpa_workspace_bytes(w, h, d, channels), u3d::simulate_workspace_bytes(w, h, d)) + stage;
+}
+
+static int ensure_model_ws(Model* m, size_t need) {
+    if (m->vpa_ws_bytes >= need) return 0;
+    cudaStreamSynchronize(m->stream);
+    if (m->stream3) cudaStreamSynchronize(m->stream3);
+    if (m->vpa_ws) cudaFree(m->vpa_ws);
+    m->vpa_ws = nullptr;
+    m->vpa_ws_bytes = 0;
+    if (cudaMalloc(&m->vpa_ws, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+    m->vpa_ws_bytes = need;
+    return 0;
+}
+
+// simulate_modality (train.cpp:43-180): label == nullptr selects the image-only overload
+static int sim_impl(float* t1w, const float* label, unsigned max_label, unsigned seed, int w, int h, int d, int where, void* ws,
+                    cudaStream_t stream, long long* launches) {
+    u3d::SimPlan plan;
+    if (u3d::simulate_make_plan(label != nullptr, max_label, seed, w, h, d, plan)) return 1;
+    const size_t V = size_t(w) * h * d;
+    float* dimg = t1w;
+    const float* dlab = label;
+    if (where == 0) {
+        float* stage = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + u3d::simulate_workspace_bytes(w, h, d));
+        dimg = stage;
+        cudaMemcpyAsync(dimg, t1w, V * 4, cudaMemcpyHostToDevice, stream);
+        if (label) {
+            cudaMemcpyAsync(stage + V, label, V * 4, cudaMemcpyHostToDevice, stream);
+            dlab = stage + V;
+        }
+    }
+    int rc = u3d::simulate_run(plan, dimg, dlab, ws, stream, launches);
+    if (where == 0) {
+        if (!rc) cudaMemcpyAsync(t1w, dimg, V * 4, cudaMemcpyDeviceToHost, stream);
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (!rc && e != cudaSuccess) { set_error(std::string("simulate_modality: ") + cudaGetErrorString(e)); rc = 1; }
+    }
+    return rc;
+}
+
+// the fused / prefetched sample calls run simulate_modality first when the handle asks for it (train.cpp:459-462)
+static int sim_stage(Model* m, float* din, const float* dlab, uint64_t seed, cudaStream_t stream) {
+    if (!m->sim_mode) return 0;
+    if (m->in_count != 1) { set_error("simulate_modality needs a single-channel image"); return 1; }
+    return sim_impl(din, m->sim_mode == 1 ? dlab : nullptr, unsigned(m->out_count), unsigned(seed), m->dim[0], m->dim[1], m->dim[2], 1,
+                    m->vpa_ws, stream, &m->launches);
+}
+
 static int vpa_impl(const char* const* keys, const float* vals, int n_opts, float* image, float* label, int is_label, int w, int h,
                     int d, int channels, uint64_t seed, int where, void* ws, cudaStream_t stream, long long* launches) {
     u3d::VpaPlan plan;
@@ -291,7 +346,7 @@ int vpa_augment(const char* const* keys, const float* vals, int n_opts, float* i
     if (cudaSetDevice(gpu) != cudaSuccess) { set_error("no CUDA device: vpa_augment has no CPU fallback"); return 1; }
     std::lock_guard<std::mutex> lock(g_vpa_mu);
     VpaWs& W = g_vpa_ws[gpu];
-    const size_t need = u3d::vpa_workspace_bytes(w, h, d, channels) + (size_t(channels) + 1) * size_t(w) * h * d * 4;
+    const size_t need = sample_ws_need(w, h, d, channels);
     if (!W.s && cudaStreamCreateWithFlags(&W.s, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return 1; }
     if (W.bytes < need) {
         if (W.p) cudaFree(W.p);
@@ -310,14 +365,7 @@ int unet3d_vpa_augment(unet3d_t* h, const char* const* keys, const float* vals, 
     GUARD_BEGIN NEED(h)
     Model* m = h->m;
     cudaSetDevice(m->device);
-    const size_t need = u3d::vpa_workspace_bytes(w, hgt, d, channels) + (size_t(channels) + 1) * size_t(w) * hgt * d * 4;
-    if (m->vpa_ws_bytes < need) {
-        cudaStreamSynchronize(m->stream);
-        if (m->vpa_ws) cudaFree(m->vpa_ws);
-        m->vpa_ws_bytes = 0;
-        if (cudaMalloc(&m->vpa_ws, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
-        m->vpa_ws_bytes = need;
-    }
+    if (ensure_model_ws(m, sample_ws_need(w, hgt, d, channels))) return 1;
     return vpa_impl(keys, vals, n_opts, image, label, is_label, w, hgt, d, channels, seed, where, m->vpa_ws, m->stream, &m->launches);
     GUARD_END
 }
@@ -333,20 +381,14 @@ int unet3d_train_microbatch_augmented(unet3d_t* h, const char* const* keys, cons
     if (m->staging(&din, &dlab)) return 1;
     const int w = m->dim[0], hgt = m->dim[1], d = m->dim[2], channels = m->in_count;
     const size_t V = size_t(w) * hgt * d;
-    const size_t need = u3d::vpa_workspace_bytes(w, hgt, d, channels) + (size_t(channels) + 1) * V * 4;
-    if (m->vpa_ws_bytes < need) {
-        cudaStreamSynchronize(m->stream);
-        if (m->vpa_ws) cudaFree(m->vpa_ws);
-        m->vpa_ws_bytes = 0;
-        if (cudaMalloc(&m->vpa_ws, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
-        m->vpa_ws_bytes = need;
-    }
+    if (ensure_model_ws(m, sample_ws_need(w, hgt, d, channels))) return 1;
     // one upload of the raw sample; augmentation and the micro-batch run stream-ordered on it without leaving HBM
     if (cudaMemcpyAsync(din, image_host, size_t(channels) * V * 4, cudaMemcpyHostToDevice, m->stream) != cudaSuccess ||
         cudaMemcpyAsync(dlab, label_host, V * 4, cudaMemcpyHostToDevice, m->stream) != cudaSuccess) {
         set_error("unet3d_train_microbatch_augmented: upload failed");
         return 1;
     }
+    if (sim_stage(m, din, dlab, seed, m->stream)) return 1;
     if (vpa_impl(keys, vals, n_opts, din, dlab, 1, w, hgt, d, channels, seed, 1, m->vpa_ws, m->stream, &m->launches)) return 1;
     return m->train_microbatch(din, dlab, collapse_before, use_ce, use_dice, use_mse, loss_out3, nullptr, 1);
     GUARD_END
@@ -363,21 +405,14 @@ int unet3d_prefetch_augmented(unet3d_t* h, const char* const* keys, const float*
     if (m->prefetch_slot(&din, &dlab, &slot)) return 1;
     const int w = m->dim[0], hgt = m->dim[1], d = m->dim[2], channels = m->in_count;
     const size_t V = size_t(w) * hgt * d;
-    const size_t need = u3d::vpa_workspace_bytes(w, hgt, d, channels) + (size_t(channels) + 1) * V * 4;
-    if (m->vpa_ws_bytes < need) {
-        cudaStreamSynchronize(m->stream);
-        cudaStreamSynchronize(m->stream3);
-        if (m->vpa_ws) cudaFree(m->vpa_ws);
-        m->vpa_ws_bytes = 0;
-        if (cudaMalloc(&m->vpa_ws, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
-        m->vpa_ws_bytes = need;
-    }
+    if (ensure_model_ws(m, sample_ws_need(w, hgt, d, channels))) return 1;
     const cudaMemcpyKind kind = where == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     if (cudaMemcpyAsync(din, image, size_t(channels) * V * 4, kind, m->stream3) != cudaSuccess ||
         cudaMemcpyAsync(dlab, label, V * 4, kind, m->stream3) != cudaSuccess) {
         set_error("unet3d_prefetch_augmented: copy failed");
         return 1;
     }
+    if (sim_stage(m, din, dlab, seed, m->stream3)) return 1;
     if (vpa_impl(keys, vals, n_opts, din, dlab, 1, w, hgt, d, channels, seed, 1, m->vpa_ws, m->stream3, &m->launches)) return 1;
     if (cudaEventRecord(m->ev_sample[slot], m->stream3) != cudaSuccess) { set_error("unet3d_prefetch_augmented: event"); return 1; }
     m->pf_mark(slot);
@@ -393,6 +428,45 @@ int unet3d_train_microbatch_prefetched(unet3d_t* h, int collapse_before, int use
     float* dlab = nullptr;
     if (m->consume_prefetched(&din, &dlab)) return 1;
     return m->train_microbatch(din, dlab, collapse_before, use_ce, use_dice, use_mse, loss_out3, nullptr, 1);
+    GUARD_END
+}
+
+int simulate_modality(float* t1w, const float* label, unsigned max_label, unsigned seed, int w, int h, int d, int where, int gpu) {
+    GUARD_BEGIN
+    if (cudaSetDevice(gpu) != cudaSuccess) { set_error("no CUDA device: simulate_modality has no CPU fallback"); return 1; }
+    if (!t1w) { set_error("simulate_modality: null image"); return 1; }
+    std::lock_guard<std::mutex> lock(g_vpa_mu);
+    VpaWs& W = g_vpa_ws[gpu];
+    const size_t need = sample_ws_need(w, h, d, 1);
+    if (!W.s && cudaStreamCreateWithFlags(&W.s, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return 1; }
+    if (W.bytes < need) {
+        if (W.p) cudaFree(W.p);
+        W.bytes = 0;
+        if (cudaMalloc(&W.p, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+        W.bytes = need;
+    }
+    int rc = sim_impl(t1w, label, max_label, seed, w, h, d, where, W.p, W.s, nullptr);
+    if (!rc && where != 0 && cudaStreamSynchronize(W.s) != cudaSuccess) { set_error("simulate_modality: kernel failed"); rc = 1; }
+    return rc;
+    GUARD_END
+}
+
+int unet3d_simulate_modality(unet3d_t* h, float* t1w, const float* label, unsigned max_label, unsigned seed, int w, int hgt, int d,
+                             int where) {
+    GUARD_BEGIN NEED(h)
+    Model* m = h->m;
+    cudaSetDevice(m->device);
+    if (!t1w) { set_error("simulate_modality: null image"); return 1; }
+    if (ensure_model_ws(m, sample_ws_need(w, hgt, d, 1))) return 1;
+    return sim_impl(t1w, label, max_label, seed, w, hgt, d, where, m->vpa_ws, m->stream, &m->launches);
+    GUARD_END
+}
+
+int unet3d_set_simulate_modality(unet3d_t* h, int mode) {
+    GUARD_BEGIN NEED(h)
+    if (mode < 0 || mode > 2) { set_error("unet3d_set_simulate_modality: mode must be 0 (off), 1 (labelled template) or 2 (image only)"); return 1; }
+    h->m->sim_mode = mode;
+    return 0;
     GUARD_END
 }
 

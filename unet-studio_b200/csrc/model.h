@@ -135,6 +135,7 @@ class Model {
     long long launches = 0;          // kernels launched by this handle (bench "gpu_launches")
     void* vpa_ws = nullptr;          // augmentation workspace (unet3d_vpa_augment)
     size_t vpa_ws_bytes = 0;
+    int sim_mode = 0;                // simulate_modality before augmentation in the fused / prefetched sample calls: 0 off, 1 labelled, 2 image only
 
     int init_params(uint64_t seed);
     int get_flat(const float* base, int i, float* host, float scale);

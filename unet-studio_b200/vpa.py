@@ -81,3 +81,32 @@ def vpa_augment_on(net, image_ptr, label_ptr, w, h, d, channels, options=None, i
     karr, varr, n = _opts(options)
     check(net._lib.unet3d_vpa_augment(net._h, karr, varr, n, ctypes.cast(image_ptr, _F), ctypes.cast(label_ptr, _F), int(is_label),
                                       int(w), int(h), int(d), int(channels), ctypes.c_uint64(seed), int(where)))
+
+
+def simulate_modality(t1w, label=None, max_label=0, seed=0, gpu=0):
+    """simulate_modality (train.cpp:43-180) on host arrays: t1w [D,H,W] fp32 in [0,1]; label [D,H,W] fp32 integers 0..max_label or
+    None for the image-only overload.  Returns the simulated copy (the reference works in place)."""
+    from . import lib, check
+    t1w = np.array(t1w, np.float32, copy=True, order="C")
+    d, h, w = t1w.shape
+    lp = None
+    if label is not None:
+        label = np.ascontiguousarray(label, np.float32)
+        lp = label.ctypes.data_as(_F)
+    check(lib().simulate_modality(t1w.ctypes.data_as(_F), lp, ctypes.c_uint(max_label), ctypes.c_uint(seed & 0xFFFFFFFF), w, h, d, 0, int(gpu)))
+    return t1w
+
+
+def simulate_modality_on(net, t1w_ptr, label_ptr, w, h, d, max_label=0, seed=0, where=1):
+    """In place on raw pointers (device when where=1), stream-ordered on `net`'s stream; label_ptr None / 0 = image-only overload."""
+    from . import check
+    lp = ctypes.cast(label_ptr, _F) if label_ptr else None
+    check(net._lib.unet3d_simulate_modality(net._h, ctypes.cast(t1w_ptr, _F), lp, ctypes.c_uint(max_label), ctypes.c_uint(seed & 0xFFFFFFFF),
+                                            int(w), int(h), int(d), int(where)))
+
+
+def set_simulate_modality(net, mode):
+    """0 off, 1 labelled template overload, 2 image-only overload: run by train_microbatch_augmented / prefetch_augmented on the
+    uploaded sample before the augmentation (train.cpp:459-462)."""
+    from . import check
+    check(net._lib.unet3d_set_simulate_modality(net._h, int(mode)))
