@@ -33,6 +33,15 @@ def test_image_only_overload_matches_oracle(seed):
     assert np.abs(out - ref).max() <= ATOL, np.abs(out - ref).max()
 
 
+@pytest.mark.parametrize("labelled", [True, False])
+def test_width_not_a_multiple_of_four_takes_the_scalar_star(labelled):
+    m = load()
+    img, lab = phantom(30, 20, 12, 1, 6)
+    ref = SO.simulate_modality(img[0], lab if labelled else None, 3, 17)
+    out = m.simulate_modality(img[0], lab if labelled else None, 3, 17)
+    assert np.abs(out - ref).max() <= ATOL, np.abs(out - ref).max()
+
+
 def test_uniform_image_is_left_unscaled():
     """max == min over the selected voxels: the reference skips the rescale (train.cpp:111)."""
     m = load()

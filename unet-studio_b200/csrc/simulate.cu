@@ -81,6 +81,55 @@ __global__ void __launch_bounds__(256) k_sim_star(const float* __restrict__ src,
     }
 }
 
+// Same star, four consecutive voxels per thread with 16-byte loads (W and n multiples of 4): 6 vector + 2 scalar loads per 4 voxels
+// instead of 28 scalar ones.  Same additions in the same order.
+template <bool LUT>
+__global__ void __launch_bounds__(256) k_sim_star4(const float* __restrict__ src, float* __restrict__ dst, long long n4, int W, long long WH,
+                                                   const __grid_constant__ SimLut lut, int n_lut) {
+    __shared__ float slut[LUT ? kSimMaxLut : 1];
+    if (LUT) {
+        for (int k = threadIdx.x; k < n_lut; k += blockDim.x) slut[k] = lut.v[k];
+        __syncthreads();
+    }
+    auto conv = [&](float v) -> float {
+        if (!LUT) return v;
+        int k = int(v);
+        k = k < 0 ? 0 : (k >= n_lut ? n_lut - 1 : k);
+        return slut[k];
+    };
+    auto conv4 = [&](float4 v) { return make_float4(conv(v.x), conv(v.y), conv(v.z), conv(v.w)); };
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    const long long n = n4 * 4, W4 = W / 4, WH4 = WH / 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4; q += stride) {
+        const long long i = q * 4;
+        const float4 c = conv4(__ldg(s4 + q));
+        const bool hl = i >= 1, hr = i + 4 < n, hu = q >= W4, hd = q + W4 < n4, hf = q >= WH4, hb = q + WH4 < n4;
+        const float l = hl ? conv(__ldg(src + i - 1)) : 0.f, r = hr ? conv(__ldg(src + i + 4)) : 0.f;
+        float4 u, d, f, b;
+        if (hu) u = conv4(__ldg(s4 + q - W4));
+        if (hd) d = conv4(__ldg(s4 + q + W4));
+        if (hf) f = conv4(__ldg(s4 + q - WH4));
+        if (hb) b = conv4(__ldg(s4 + q + WH4));
+        const float cc[4] = {c.x, c.y, c.z, c.w};
+        const float lf[4] = {l, c.x, c.y, c.z}, rt[4] = {c.y, c.z, c.w, r};
+        const float uu[4] = {u.x, u.y, u.z, u.w}, dd[4] = {d.x, d.y, d.z, d.w}, ff[4] = {f.x, f.y, f.z, f.w}, bb[4] = {b.x, b.y, b.z, b.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = __fmul_rn(cc[j], 2.0f);
+            if (j > 0 || hl) a = __fadd_rn(a, lf[j]);
+            if (j < 3 || hr) a = __fadd_rn(a, rt[j]);
+            if (hu) a = __fadd_rn(a, uu[j]);
+            if (hd) a = __fadd_rn(a, dd[j]);
+            if (hf) a = __fadd_rn(a, ff[j]);
+            if (hb) a = __fadd_rn(a, bb[j]);
+            o[j] = __fmul_rn(a, 0.125f);
+        }
+        reinterpret_cast<float4*>(dst)[q] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 struct SimTerms {
     uint8_t code[kSimTerms];   // a | b << 2 | c << 4 | d << 6
     float w[kSimTerms];
@@ -234,11 +283,22 @@ int simulate_run(const SimPlan& plan, float* t1w, const float* label, void* work
     const int grid = int(std::min<long long>((n + 255) / 256, 148LL * 8));
     SimLut lut;
     std::memcpy(lut.v, plan.lut, sizeof(lut.v));
-    if (plan.labelled)
-        k_sim_star<true><<<grid, 256, 0, s>>>(label, ta, n, plan.W, 1LL * plan.W * plan.H, lut, plan.n_lut);
-    else
-        k_sim_star<false><<<grid, 256, 0, s>>>(t1w, ta, n, plan.W, 1LL * plan.W * plan.H, lut, 0);
-    k_sim_star<false><<<grid, 256, 0, s>>>(ta, tb, n, plan.W, 1LL * plan.W * plan.H, lut, 0);
+    const long long WH = 1LL * plan.W * plan.H;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(t1w) | reinterpret_cast<uintptr_t>(label)) & 15u) == 0;
+    if (plan.W % 4 == 0 && aligned) {   // n is then a multiple of 4 as well and every row start is 16-byte aligned
+        const int g4 = int(std::min<long long>((n / 4 + 255) / 256, 148LL * 8));
+        if (plan.labelled)
+            k_sim_star4<true><<<g4, 256, 0, s>>>(label, ta, n / 4, plan.W, WH, lut, plan.n_lut);
+        else
+            k_sim_star4<false><<<g4, 256, 0, s>>>(t1w, ta, n / 4, plan.W, WH, lut, 0);
+        k_sim_star4<false><<<g4, 256, 0, s>>>(ta, tb, n / 4, plan.W, WH, lut, 0);
+    } else {
+        if (plan.labelled)
+            k_sim_star<true><<<grid, 256, 0, s>>>(label, ta, n, plan.W, WH, lut, plan.n_lut);
+        else
+            k_sim_star<false><<<grid, 256, 0, s>>>(t1w, ta, n, plan.W, WH, lut, 0);
+        k_sim_star<false><<<grid, 256, 0, s>>>(ta, tb, n, plan.W, WH, lut, 0);
+    }
     SimTerms T;
     for (int t = 0; t < kSimTerms; ++t) T.code[t] = uint8_t(plan.a[t] | plan.b[t] << 2 | plan.c[t] << 4 | plan.d[t] << 6);
     std::memcpy(T.w, plan.w, sizeof(T.w));
