@@ -61,25 +61,35 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.rows, self.proc, self.windows = gpu, [], None, []
 
     def start(self):
+        """Started BEFORE the warm-up (nvidia-smi needs ~100 ms to deliver its first row); rows are time-stamped on arrival and
+        only those inside a timed window (begin() .. end()) are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
+            self.rows.append((time.perf_counter(), [t.strip() for t in line.split(",")]))
+
+    def begin(self):
+        self._t0 = time.perf_counter()
+
+    def end(self):
+        self.windows.append((self._t0, time.perf_counter()))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for t, r in self.rows:
+            if not any(b <= t <= e + 0.005 for b, e in self.windows):
+                continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -88,7 +98,8 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "rows_total": len(self.rows),
+                "windows": "device-timed steps + end-to-end steps + inference windows"}
 
 
 def workload_name(augment=True, simulate=False):
@@ -138,7 +149,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -233,19 +244,20 @@ def main():
         return loss
 
     # ---------------- device-resident timing ----------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         one_step_device()
-    clocks = ClockSampler(local_rank)
     launches0 = net.launch_count()
     barrier()
-    clocks.start()
+    clocks.begin()
     net.timer_start()
     loss = None
     for _ in range(args.steps):
         loss = one_step_device()
     ms = net.timer_stop()
     barrier()
-    clk = clocks.stop()
+    clocks.end()
     launches = net.launch_count() - launches0
     # ---------------- per-family attribution: the same steps again with a CUDA-event pair around every tensor-kernel launch.  The
     # library serialises the weight-gradient side stream while profiling, so these per-kernel times are not the concurrent ones ----
@@ -259,11 +271,13 @@ def main():
     for _ in range(2):
         one_step_host()
     barrier()
+    clocks.begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         one_step_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks.end()
     barrier()
     if world > 1:
         import torch.distributed as dist
@@ -289,10 +303,12 @@ def main():
         inf.sync()
         n_inf = max(args.steps, 5)
         barrier()
+        clocks.begin()
         inf.timer_start()
         for _ in range(n_inf):
             inf.device_forward(x_dev.data_ptr(), [y_dev.data_ptr()])
         inf_ms = inf.timer_stop()
+        clocks.end()
         barrier()
         y_host2 = torch.empty(1, 1, D, H, W).pin_memory()
         outs = [(y_host if i % 2 == 0 else y_host2).numpy() for i in range(n_inf)]
@@ -302,6 +318,7 @@ def main():
         inf.evaluate_windows([x_host.numpy()] * n_inf, outs)
         inf_e2e_ms = (time.perf_counter() - t0) * 1000.0
         barrier()
+    clk = clocks.stop()
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([inf_ms, inf_e2e_ms], device="cuda", dtype=torch.float64)
