@@ -136,3 +136,18 @@ def test_conv_backward(case):
     gx0a, _, _ = m.conv_backward(x0.numpy(), w.numpy(), dy.numpy(), None if x1 is None else x1.numpy(),
                                  transposed=bool(tr), ks=ks, stride=st, gx0_init=init)
     assert rel(gx0a, gx_ref[:c0] + init) < 8e-4
+
+
+def test_opt_in_z_stacked_band_kernel_matches_too():
+    """conv_zband_kernel (U3D_ZBAND=1, read once per process): the 16 -> 16 channel cases, forward and data gradient, in a child
+    process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("U3D_ZBAND"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, U3D_ZBAND="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k", "k3s1_16_16 or k3s1_1_16 or halo_16_16 or halo_1_16 or band_16_16_ragged or band_5_20"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128, 1) bench_lean(int iters, int n, long long
     const uint32_t tm = tptr;
     if (threadIdx.x == 0) {
         const uint32_t idesc = umma_idesc(128, n, 0, 0, 0, 0);
-        const uint32_t bstep = uint32_t(n) * 32u, dstep = uint32_t(n < 64 ? n : 64);
+        const uint32_t bstep = n > 128 ? 0u : uint32_t(n) * 32u, dstep = uint32_t(n < 64 ? n : 64);   // N > 128: every MMA reads the same B tile
         uint64_t ad[kKS], bd[kKS * kAcc];
         uint32_t ta[2][kKS], dd[kAcc];
 #pragma unroll
@@ -249,7 +249,7 @@ int main() {
     size_t bad = 0;
     for (size_t i = 0; i < ref.size(); ++i) bad += ref[i] != got[i];
     printf("SS vs host max abs err %.3g ; TS vs SS mismatches %zu of %zu\n", herr, bad, ref.size());
-    const int ns[] = {16, 32, 48, 64, 96, 128};
+    const int ns[] = {16, 32, 48, 64, 96, 128, 192, 256};
     for (int n : ns)
         for (int mode = 0; mode < 3; ++mode) {
             const int iters = 400;

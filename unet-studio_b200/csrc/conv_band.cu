@@ -362,6 +362,296 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
     if (warp == 12) tmem_dealloc(tmem_base, 4 * N);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// z-stacked variant for 16 -> 16 channels (G = 4, one K chunk).  Measured (tools/mma_ts_bench.cu): a tcgen05.mma costs >= 45 clk per
+// SM whatever N <= 90 is, so the 54 narrow MMAs per plane tile of conv_band_kernel are dispatch-bound.  Here ONE MMA per
+// (input plane, dy, x column) writes the accumulators of all three output planes that input plane feeds: N = 3 x 64 columns
+// (output planes i-2, i-1, i <-> kz = 2, 1, 0) against a [dy][x column][2 k-groups][192][8] weight block expanded in shared memory
+// from the banded blob — 18 instructions of 96 clk per plane tile instead of 54 of 45+.  An input plane is consumed by one batch
+// of MMAs and released at once.  Eight accumulator slots of 64 columns (output q lives in slot q & 7; a batch that would run past
+// slot 7 is split in two); an instruction has one accumulate predicate for all its columns, so the epilogue hands every slot back
+// ZEROED (tcgen05.st) and every MMA accumulates.
+// Status (round 1): bit-compatible with conv_band_kernel on the 78 operator cases, but SLOWER in situ (206 vs 156 us per layer at
+// 160x192x160), so it is opt-in (U3D_ZBAND=1).  Timing experiments: no MMAs 129 us, no MMAs and no plane loads 94 us (epilogue alone),
+// MMAs + epilogue without plane loads 191 us: the wide back-to-back MMAs (tensor pipe ~100 % busy, 96 clk each alone) and the
+// epilogue's TMEM loads do not overlap — their times add — and a second epilogue warp group (one plane each) changes nothing.
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int kZAcc = 8;
+constexpr int kZThreads = 32 * 18;   // warps 0-3 + 14-17 epilogue, 4-11 producers, 12 MMA issuer (13 idle)
+constexpr uint32_t kZWBytes = 3 * 6 * 2 * 192 * 16;   // 110592
+
+__global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_constant__ BParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int G = 4, CO = 16, N = 64, XI = 6;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sW = sbase + p.off_w;
+    float* sstats = reinterpret_cast<float*>(smem + p.off_stats);
+    const uint32_t bars = sbase + p.off_bars;
+    const uint32_t kSlots = uint32_t(p.nslots);
+    auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bars + 8u * (kMaxSlots + s); };
+    auto tfull_bar = [&](uint32_t a) { return bars + 8u * (2 * kMaxSlots + a); };
+    auto tempty_bar = [&](uint32_t a) { return bars + 8u * (2 * kMaxSlots + kZAcc + a); };
+    const uint32_t wfull_bar = bars + 8u * (2 * kMaxSlots + 2 * kZAcc);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kMaxSlots + 2 * kZAcc + 1));
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < kSlots; ++s) {
+            mbar_init(full_bar(s), kBProducers);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t a = 0; a < kZAcc; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        mbar_init(wfull_bar, kBProducers);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 16 * CO; i += kZThreads) sstats[i] = 0.f;
+    for (int j = threadIdx.x; j < CO; j += kZThreads) sstats[16 * CO + j] = (p.P.bias != nullptr && j < p.P.n_real) ? __ldg(p.P.bias + j) : 0.f;
+    if (warp == 12) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (warp < 4) {   // all eight accumulator slots start zeroed
+        const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
+#pragma unroll 4
+        for (int c = 0; c < 512; c += 16) tmem_st16_zero(t_row + uint32_t(c));
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const ConvProblem& P = p.P;
+    const int D = P.in_d, H = P.in_h, W = P.in_w;
+
+    if (warp >= 4 && warp < 12) {
+        // ===================================== producers =====================================
+        const int t = threadIdx.x - 128;
+        {   // resident weights: expand the banded blob [9 (dz,dy)][2][kx = 2,1,0,zero][16][8] into [dy][xi][2][pl*64 + xo*16 + co][8]
+            const uint4* wsrc = static_cast<const uint4*>(P.wpack);
+            for (int n = t; n < 3 * XI * 2 * 192; n += kBProducers) {
+                const int row = n % 192, kc = (n / 192) & 1, dyxi = n / 384;
+                const int dy = dyxi / XI, xi = dyxi % XI;
+                const int pl = row >> 6, xo = (row >> 4) & 3, co = row & 15;
+                const int kx = xi - xo;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (kx >= 0 && kx <= 2) v = __ldg(wsrc + ((((2 - pl) * 3 + dy) * 2 + kc) * 64 + (2 - kx) * 16 + co));
+                *reinterpret_cast<uint4*>(smem + p.off_w + uint32_t(n) * 16u) = v;
+            }
+            fence_proxy_async();
+            mbar_arrive(wfull_bar);
+        }
+        const int ncg = p.ncg;
+        const uint8_t* const s0 = static_cast<const uint8_t*>(P.src0);
+        const uint32_t pitch0 = uint32_t(P.c0p) * 2u;
+        const int HX = p.HX, HY = p.HY, HQ = p.HQ, ROWS = p.ROWS;
+        const int per_plane = HY * HX * ncg;
+        const uint32_t inv_hx = (1u << 20) / uint32_t(HX) + 1u;
+        uint32_t cnt = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int rem = item;
+            const int zc = rem % p.zchunks; rem /= p.zchunks;
+            const int tx = rem % p.tiles_x;
+            const int ty = rem / p.tiles_x;
+            const int x0 = tx * p.TX - 1, y0 = ty * p.TY - 1;
+            const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
+            for (int gz = z0 - 1; gz <= z1; ++gz, ++cnt) {
+                const uint32_t slot = cnt % kSlots;
+                mbar_wait(empty_bar(slot), ((cnt / kSlots) & 1) ^ 1, 0x2100u | slot);
+                const uint32_t blk = sbase + slot * p.slot_bytes;
+                const bool zok = (unsigned)gz < (unsigned)D;
+                const long long vox0 = ((long long)(zok ? gz : 0) * H + y0) * W + x0;
+                const uint8_t* const p0 = s0 + vox0 * (long long)pitch0;
+#pragma unroll 2
+                for (int idx = t; idx < per_plane; idx += kBProducers) {
+                    const int cg = idx & 1;
+                    const uint32_t pos = uint32_t(idx) >> 1;
+                    const int hy = int((pos * inv_hx) >> 20);
+                    const int hx = int(pos) - hy * HX;
+                    const bool ok = zok && (unsigned)(x0 + hx) < (unsigned)W && (unsigned)(y0 + hy) < (unsigned)H;
+                    const uint8_t* src = ok ? p0 + (long long)(hy * W + hx) * pitch0 + cg * 16 : s0;
+                    const int r = hx & (G - 1), hq = hx / G;
+                    cp_async16_ca(blk + uint32_t((cg * G + r) * ROWS + hy * HQ + hq) * 16u, src, ok ? 16u : 0u);
+                }
+                cp_async_mbar_arrive(full_bar(slot));
+            }
+        }
+        cp_async_wait<0>();
+    } else if (warp == 12) {
+        // ===================================== MMA issuer ====================================
+        if (lane == 0) {
+            const int HQ = p.HQ, ROWS = p.ROWS;
+            const uint32_t lbo_a = uint32_t(G * ROWS) * 16u;
+            const uint64_t b_desc0 = umma_smem_desc(sW, 192u * 16u, 128u);
+            uint32_t a_xi[XI];
+#pragma unroll
+            for (int xi = 0; xi < XI; ++xi) a_xi[xi] = uint32_t((xi % G) * ROWS + xi / G);
+            const uint32_t idesc_n[4] = {0u, umma_idesc(128, 64, 0, 0, 0, 0), umma_idesc(128, 128, 0, 0, 0, 0), umma_idesc(128, 192, 0, 0, 0, 0)};
+            mbar_wait(wfull_bar, 0, 0x2200u);
+            fence_proxy_async();
+            uint32_t cnt = 0, q_base = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int zc = item % p.zchunks;
+                const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
+                const int nz = z1 - z0;
+#pragma unroll 1
+                for (int i = 0; i < nz + 2; ++i) {
+                    const uint32_t c = cnt + uint32_t(i);
+                    mbar_wait(full_bar(c % kSlots), (c / kSlots) & 1, 0x2300u);
+                    if (i < nz) {   // output plane i receives its first contribution from this input plane: its slot must be drained + zeroed
+                        const uint32_t q = q_base + uint32_t(i);
+                        mbar_wait(tempty_bar(q & 7u), ((q >> 3) & 1u) ^ 1u, 0x2400u | (q & 7u));
+                    }
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const int jlo = i - 2 < 0 ? 0 : i - 2, jhi = i < nz - 1 ? i : nz - 1;
+                    const int pl_lo = jlo - (i - 2), count = jhi - jlo + 1;
+                    const uint32_t sl0 = (q_base + uint32_t(jlo)) & 7u;
+                    const int n1 = count < int(8u - sl0) ? count : int(8u - sl0), n2 = count - n1;
+                    const uint32_t d1 = tmem_base + sl0 * uint32_t(N), d2 = tmem_base;
+                    const uint32_t id1 = idesc_n[n1], id2 = idesc_n[n2];
+                    const uint64_t a_pl = umma_smem_desc(sbase + (c % kSlots) * p.slot_bytes + uint32_t(HQ) * 16u, lbo_a, 128u);
+                    const uint64_t b_pl = b_desc0 + uint64_t(pl_lo * 64);        // 64 rows of 16 B per plane block (16-byte units)
+                    const uint64_t b_pl2 = b_pl + uint64_t(n1 * 64);
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint64_t a_row = a_pl + uint64_t((long long)(dy - 1) * HQ);
+#pragma unroll
+                        for (int xi = 0; xi < XI; ++xi) {
+                            const uint64_t boff = uint64_t((dy * XI + xi) * (2 * 192));
+                            umma_f16_acc(d1, a_row + a_xi[xi], b_pl + boff, id1);
+                            if (n2) umma_f16_acc(d2, a_row + a_xi[xi], b_pl2 + boff, id2);
+                        }
+                    }
+                    umma_commit(empty_bar(c % kSlots));                                   // the plane is consumed by this batch alone
+                    if (i >= 2) umma_commit(tfull_bar((q_base + uint32_t(i - 2)) & 7u));   // output i-2 has all 27 taps
+                }
+                cnt += uint32_t(nz + 2);
+                q_base += uint32_t(nz);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 4 || warp >= 14) {
+        // ===================================== epilogue ======================================
+        // two groups of four warps (0-3 and 14-17; a warp reaches the TMEM lanes of quarter warp % 4): group eg drains the output planes
+        // of parity eg, so the per-plane latency chain (barrier wait, 4 x TMEM load, stores) of one plane overlaps the next plane's
+        const uint32_t eg = warp < 4 ? 0u : 1u;
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const int HQ = p.HQ;
+        uint32_t acc_cnt = 0;
+        float ssum[CO], ssq[CO];
+#pragma unroll
+        for (int j = 0; j < CO; ++j) ssum[j] = ssq[j] = 0.f;
+        const float* sbias = sstats + 16 * CO;
+        const bool want_stats = p.stats != nullptr;
+        const bool accum = p.epi == EPI_ACCUM16;
+        const int hy = 1 + r / HQ, hq = r % HQ;
+        const bool row_in_tile = r < p.TY * HQ && hq < p.TX / G;
+        uint8_t* const dst = static_cast<uint8_t*>(P.dst) + P.dst_coff * 2;
+        const uint32_t dst_pitch = uint32_t(P.dst_cp) * 2u;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int rem = item;
+            const int zc = rem % p.zchunks; rem /= p.zchunks;
+            const int tx = rem % p.tiles_x;
+            const int ty = rem / p.tiles_x;
+            const int gx0 = tx * p.TX + hq * G, gy = ty * p.TY + hy - 1;
+            const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
+            const bool rv_xy = row_in_tile && gy < H && gx0 < W;
+#pragma unroll 1
+            for (int gz = z0; gz < z1; ++gz, ++acc_cnt) {
+                if ((acc_cnt & 1u) != eg) continue;
+                const size_t vox0 = (size_t(gz) * H + gy) * W + gx0;
+                const uint32_t acc = acc_cnt & 7u;
+                mbar_wait(tfull_bar(acc), (acc_cnt >> 3) & 1, 0x2500u | acc);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * uint32_t(N);
+#pragma unroll
+                for (int xo = 0; xo < G; ++xo) {
+                    const bool rv = rv_xy && gx0 + xo < W;
+                    float v[16];
+                    tmem_ld16(t_row + uint32_t(xo * CO), v);
+                    tmem_st16_zero(t_row + uint32_t(xo * CO));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += sbias[j];
+                    uint4* out = reinterpret_cast<uint4*>(dst + (vox0 + xo) * dst_pitch);
+                    if (accum && rv) {
+                        const uint4 o0 = out[0], o1 = out[1];
+                        const uint32_t ow_[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 f = unpack2<false>(ow_[j]);
+                            v[2 * j] += f.x;
+                            v[2 * j + 1] += f.y;
+                        }
+                    }
+                    if (rv) {
+                        uint4 q0v, q1v;
+                        q0v.x = pack2<false>(v[0], v[1]); q0v.y = pack2<false>(v[2], v[3]);
+                        q0v.z = pack2<false>(v[4], v[5]); q0v.w = pack2<false>(v[6], v[7]);
+                        q1v.x = pack2<false>(v[8], v[9]); q1v.y = pack2<false>(v[10], v[11]);
+                        q1v.z = pack2<false>(v[12], v[13]); q1v.w = pack2<false>(v[14], v[15]);
+                        out[0] = q0v;
+                        out[1] = q1v;
+                        if (want_stats) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                ssum[j] += v[j];
+                                ssq[j] = fmaf(v[j], v[j], ssq[j]);
+                            }
+                        }
+                    }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));
+            }
+        }
+        if (want_stats) {
+            float a[16], qq[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { a[j] = ssum[j]; qq[j] = ssq[j]; }
+            halve_step_b<8, 16>(a, qq, lane);
+            halve_step_b<4, 8>(a, qq, lane);
+            halve_step_b<2, 4>(a, qq, lane);
+            halve_step_b<1, 2>(a, qq, lane);
+            a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+            qq[0] += __shfl_xor_sync(0xffffffffu, qq[0], 1);
+            if ((lane & 1) == 0) {
+                const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                float* ws = sstats + (eg * 4 + quarter) * 2 * CO;
+                ws[col] = a[0];
+                ws[CO + col] = qq[0];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (eg == 0)
+                for (int i = r; i < 2 * CO; i += 128) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) t += sstats[w * 2 * CO + i];   // fixed order: deterministic
+                    p.stats[size_t(blockIdx.x) * 2 * CO + i] = t;
+                }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- weight pack: reference fp32 tensor -> [9 (dz,dy)][KS][2 k-groups][NB = 4*CO columns][8] fp16, columns = kernel column
 // kx = 2,1,0 then a zero block; the (dz,dy,dx) offsets come from the problem's own tap list (forward: k-1, dgrad: 1-k) ----
 __global__ void pack_weights_band_kernel(const __grid_constant__ PackDesc d) {
@@ -512,18 +802,32 @@ static int conv_band_launch_one(const ConvProblem& Pin, const ConvLaunch& cfg, b
     bp.zchunks = (P.in_d + bp.zlen - 1) / bp.zlen;
     bp.total_items = cols * bp.zchunks;
     bp.slot_bytes = uint32_t(bp.ncg * bp.G * bp.ROWS * 16);
-    bp.w_bytes = uint32_t(9 * bp.KS * 2 * bp.NB * 16);
-    bp.nslots = int(std::min<size_t>(kMaxSlots, (size_t(222) * 1024 - bp.w_bytes - 9 * bp.CO * 4) / bp.slot_bytes));
-    if (bp.nslots < 4) { set_error("conv_band_launch: plane ring does not fit in shared memory"); return 1; }
+    // experimental, opt-in (U3D_ZBAND=1): parity green, but 206 us vs 156 us per 16 -> 16 layer at 160x192x160 (see the kernel's header)
+    static const bool use_zband = std::getenv("U3D_ZBAND") != nullptr;
+    const bool zband = use_zband && bp.CO == 16 && bp.KS == 1 && P.c1p == 0;
+    bp.w_bytes = zband ? kZWBytes : uint32_t(9 * bp.KS * 2 * bp.NB * 16);
+    const uint32_t stats_bytes = uint32_t((zband ? 17 : 9) * bp.CO * 4);
+    bp.nslots = int(std::min<size_t>(kMaxSlots, (size_t(222) * 1024 - bp.w_bytes - stats_bytes) / bp.slot_bytes));
+    if (bp.nslots < (zband ? 3 : 4)) { set_error("conv_band_launch: plane ring does not fit in shared memory"); return 1; }
     bp.off_w = bp.nslots * bp.slot_bytes;
     bp.off_stats = bp.off_w + bp.w_bytes;
-    bp.off_bars = uint32_t((bp.off_stats + 9 * bp.CO * 4 + 15) & ~15u);
-    const size_t smem = bp.off_bars + 8 * (2 * kMaxSlots + 9) + 16;
+    bp.off_bars = uint32_t((bp.off_stats + stats_bytes + 15) & ~15u);
+    const size_t smem = bp.off_bars + 8 * (2 * kMaxSlots + 2 * kZAcc + 2) + 16;
     if (smem > 227 * 1024) { set_error("conv_band_launch: tile does not fit in shared memory"); return 1; }
     bp.epi = cfg.epi;
     bp.stats = stats ? cfg.stats_partials : nullptr;
     const int grid = std::max(1, std::min(bp.total_items, sms));
     if (cfg.stats_grid_out) *cfg.stats_grid_out = grid;
+    if (zband) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_zband_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = true;
+        }
+        conv_zband_kernel<<<grid, kZThreads, smem, stream>>>(bp);
+        U3D_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     if (bp.CO == 16 && bp.KS == 1) return launch_band_t<4, 16, 1>(bp, grid, smem, stream);
     if (bp.CO == 16 && bp.KS == 2) return launch_band_t<4, 16, 2>(bp, grid, smem, stream);
     if (bp.CO == 32 && bp.KS == 1) return launch_band_t<2, 32, 1>(bp, grid, smem, stream);
