@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int iters, int n, cons
 // Lean issue loop (what a production issuer looks like): every descriptor precomputed, constant accumulate predicate, the loop body is
 // nothing but the 18 (+6) tcgen05 instructions.  mode as above.
 template <int mode>
-__global__ void __launch_bounds__(128, 1) bench_lean(int iters, int n, long long* clk) {
+__global__ void __launch_bounds__(128, 1) bench_lean(int iters, int n, long long* clk, uint32_t a_lbo = 2048u, uint32_t a_step = 4096u, uint32_t a_off = 0u) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tptr;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128, 1) bench_lean(int iters, int n, long long
         uint32_t ta[2][kKS], dd[kAcc];
 #pragma unroll
         for (int ks = 0; ks < kKS; ++ks) {
-            ad[ks] = umma_smem_desc(a0 + ks * 4096u, 2048u, 128u);
+            ad[ks] = umma_smem_desc(a0 + a_off + ks * a_step, a_lbo, 128u);
             ta[0][ks] = tm + 256 + ks * 8;
             ta[1][ks] = tm + 256 + 48 + ks * 8;
 #pragma unroll
@@ -263,6 +263,17 @@ int main() {
             printf("N=%3d mode %d (%s): issue %.1f clk/MMA, complete %.1f clk/MMA\n", n, mode,
                    mode == 0 ? "A smem" : mode == 1 ? "A tmem + 6 cp per 18 MMAs" : "A tmem, no cp", double(c[0]) / (iters * 18),
                    double(c[1]) / (iters * 18));
+        }
+    // conv_band's A operand: 16-byte rows, K chunks 10432 B apart, start addresses at arbitrary 16-byte offsets
+    for (int n : {48, 64, 192})
+        for (int v = 0; v < 4; ++v) {
+            const uint32_t lbo = v == 0 ? 2048u : 10432u, step = v <= 1 ? 4096u : 144u, off = v == 3 ? 16u : 0u;
+            bench_lean<0><<<1, 128, smem>>>(400, n, dC, lbo, step, off);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("layout %d: %s\n", v, cudaGetErrorString(e)); return 1; }
+            long long c[2];
+            cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost);
+            printf("N=%3d A layout: LBO %5u, start step %4u B, offset %2u B: %.1f clk per MMA\n", n, lbo, step, off, double(c[1]) / (400 * 18));
         }
     cudaFuncSetAttribute(bench_multi<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     cudaFuncSetAttribute(bench_multi<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

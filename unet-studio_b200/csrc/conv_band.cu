@@ -167,8 +167,10 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
         // thread sustains one MMA per ~87 clk in this loop (ncu: it never waits, it is issue-bound), the hardware accepts one per ~40.
         // Plane release protocol (empty barrier count 2 = one arrival per issuer): an issuer arrives on plane q after ITS last
         // output that reads q (outputs q-2, q-1, q of its parity); planes it never reads are released as soon as they are resident.
+        // The WHOLE warp runs the loop: under `if (lane == 0)` the compiler cannot prove the descriptors uniform and feeds every
+        // tcgen05.mma through an R2UR / vote loop; with uniform control flow they stay in uniform registers and one elected lane issues.
         const uint32_t wi = uint32_t(warp - 12);
-        if (lane == 0) {
+        {
             const int HQ = p.HQ, ROWS = p.ROWS;
             const uint32_t lbo_a = uint32_t(G * ROWS) * 16u;             // next channel group of 8
             const uint64_t a_ks_u = uint64_t((2u * lbo_a) >> 4);         // next K chunk of 16 channels
@@ -200,10 +202,11 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                 // planes cnt, cnt+1 (relative z0-1, z0) must be resident before output plane 0; plane j+2 before output j
                 mbar_wait(full_bar(cnt % kSlots), (cnt / kSlots) & 1, 0x2300u);
                 mbar_wait(full_bar((cnt + 1) % kSlots), ((cnt + 1) / kSlots) & 1, 0x2301u);
-                if ((acc_cnt & 1u) != wi) {          // output 0 belongs to the other issuer: this one never reads plane 0 (nor 1 if nz == 1)
+                if ((acc_cnt & 1u) != wi && lane == 0) {   // output 0 belongs to the other issuer: this one never reads plane 0 (nor 1 if nz == 1)
                     mbar_arrive(empty_bar(cnt % kSlots));
                     if (nz == 1) mbar_arrive(empty_bar((cnt + 1) % kSlots));
                 }
+                __syncwarp();
                 const uint32_t last_owner = (acc_cnt + uint32_t(nz - 1)) & 1u;
 #pragma unroll 1
                 for (int j = 0; j < nz; ++j, ++acc_cnt) {
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
 #pragma unroll
                     for (int dz = 0; dz < 3; ++dz)
                         a_pl[dz] = umma_smem_desc(sbase + ((cnt + j + dz) % kSlots) * p.slot_bytes + uint32_t(HQ) * 16u, lbo_a, 128u);
+                    if (elect_one()) {
                     // first MMA: full width, overwrite
                     {
                         const uint64_t ad = a_pl[0] - uint64_t(HQ) + a_xi[XI0];
@@ -249,11 +253,14 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                     umma_commit(empty_bar((cnt + j) % kSlots));
                     umma_commit(empty_bar(c1 % kSlots));
                     if (j >= nz - 2) umma_commit(empty_bar(c2 % kSlots));   // this issuer has no later output reading plane j+2
+                    }
+                    __syncwarp();
                 }
                 if (last_owner != wi) {              // plane nz+1 is read by output nz-1 only
                     const uint32_t c = cnt + uint32_t(nz + 1);
                     mbar_wait(full_bar(c % kSlots), (c / kSlots) & 1, 0x2304u);
-                    mbar_arrive(empty_bar(c % kSlots));
+                    if (lane == 0) mbar_arrive(empty_bar(c % kSlots));
+                    __syncwarp();
                 }
                 cnt += uint32_t(nz + 2);
             }
@@ -407,10 +414,10 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < kSlots; ++s) {
             mbar_init(full_bar(s), kBProducers);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), 2);
         }
         for (uint32_t a = 0; a < kZAcc; ++a) {
-            mbar_init(tfull_bar(a), 1);
+            mbar_init(tfull_bar(a), 2);
             mbar_init(tempty_bar(a), 128);
         }
         mbar_init(wfull_bar, kBProducers);
@@ -477,7 +484,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
                 const long long vox0 = ((long long)(zok ? gz : 0) * H + y0) * W + x0;
                 const uint8_t* const p0 = s0 + vox0 * (long long)pitch0;
 #pragma unroll 2
-                for (int idx = t; idx < per_plane; idx += kBProducers) {
+                for (int idx = t; idx < ((p.NB & 8) ? 0 : per_plane); idx += kBProducers) {
                     const int cg = idx & 1;
                     const uint32_t pos = uint32_t(idx) >> 1;
                     const int hy = int((pos * inv_hx) >> 20);
@@ -491,9 +498,15 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
             }
         }
         cp_async_wait<0>();
-    } else if (warp == 12) {
-        // ===================================== MMA issuer ====================================
-        if (lane == 0) {
+    } else if (warp == 12 || warp == 13) {
+        // ===================================== MMA issuers ===================================
+        // two issuing threads share every batch (even / odd (dy, x column) pairs): one thread's descriptor arithmetic + issue costs
+        // ~190 clk per MMA in this loop, twice the 96 clk the instruction takes.  Both accumulate into the same columns (addition
+        // commutes; the tensor pipe executes the instructions one after the other) and both commit to every barrier (count 2).
+        // The WHOLE warp runs the loop (uniform control flow keeps the descriptor arithmetic in uniform registers; under `if (lane == 0)`
+        // every operand went through an R2UR chain, ~300 clk per MMA); one elected lane issues the tcgen05 instructions.
+        const int wi = warp - 12;
+        {
             const int HQ = p.HQ, ROWS = p.ROWS;
             const uint32_t lbo_a = uint32_t(G * ROWS) * 16u;
             const uint64_t b_desc0 = umma_smem_desc(sW, 192u * 16u, 128u);
@@ -527,11 +540,13 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
                     const uint64_t a_pl = umma_smem_desc(sbase + (c % kSlots) * p.slot_bytes + uint32_t(HQ) * 16u, lbo_a, 128u);
                     const uint64_t b_pl = b_desc0 + uint64_t(pl_lo * 64);        // 64 rows of 16 B per plane block (16-byte units)
                     const uint64_t b_pl2 = b_pl + uint64_t(n1 * 64);
+                    if (elect_one()) {
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         const uint64_t a_row = a_pl + uint64_t((long long)(dy - 1) * HQ);
 #pragma unroll
                         for (int xi = 0; xi < XI; ++xi) {
+                            if (((dy * XI + xi) & 1) != wi) continue;
                             const uint64_t boff = uint64_t((dy * XI + xi) * (2 * 192));
                             umma_f16_acc(d1, a_row + a_xi[xi], b_pl + boff, id1);
                             if (n2) umma_f16_acc(d2, a_row + a_xi[xi], b_pl2 + boff, id2);
@@ -539,6 +554,8 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
                     }
                     umma_commit(empty_bar(c % kSlots));                                   // the plane is consumed by this batch alone
                     if (i >= 2) umma_commit(tfull_bar((q_base + uint32_t(i - 2)) & 7u));   // output i-2 has all 27 taps
+                    }
+                    __syncwarp();
                 }
                 cnt += uint32_t(nz + 2);
                 q_base += uint32_t(nz);
@@ -584,8 +601,13 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
                 for (int xo = 0; xo < G; ++xo) {
                     const bool rv = rv_xy && gx0 + xo < W;
                     float v[16];
-                    tmem_ld16(t_row + uint32_t(xo * CO), v);
-                    tmem_st16_zero(t_row + uint32_t(xo * CO));
+                    if (p.NB & 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    } else {
+                        tmem_ld16(t_row + uint32_t(xo * CO), v);
+                        tmem_st16_zero(t_row + uint32_t(xo * CO));
+                    }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += sbias[j];
                     uint4* out = reinterpret_cast<uint4*>(dst + (vox0 + xo) * dst_pitch);
@@ -599,7 +621,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
                             v[2 * j + 1] += f.y;
                         }
                     }
-                    if (rv) {
+                    if (rv && !(p.NB & 2)) {
                         uint4 q0v, q1v;
                         q0v.x = pack2<false>(v[0], v[1]); q0v.y = pack2<false>(v[2], v[3]);
                         q0v.z = pack2<false>(v[4], v[5]); q0v.w = pack2<false>(v[6], v[7]);
@@ -819,6 +841,8 @@ static int conv_band_launch_one(const ConvProblem& Pin, const ConvLaunch& cfg, b
     const int grid = std::max(1, std::min(bp.total_items, sms));
     if (cfg.stats_grid_out) *cfg.stats_grid_out = grid;
     if (zband) {
+        static const int zdbg = std::getenv("U3D_ZDBG") ? atoi(std::getenv("U3D_ZDBG")) : 0;
+        bp.NB = zdbg;
         static bool attr_set = false;
         if (!attr_set) {
             U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_zband_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
