@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 5) {
         // ===================================== MMA issuer ====================================
-        if (lane == 0) {
+        // The whole warp runs the loop (uniform control flow: descriptors stay in uniform registers instead of an R2UR / vote loop per
+        // tcgen05.mma); one elected lane issues.
+        {
             int stage = 0, phase = 0;
             uint32_t acc_cnt = 0;
             const int total_items = p.total_items, nstride = gridDim.x, ntile_max = p.ntile_max;
@@ -248,6 +250,9 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                             tc_fence_after();
                             const uint64_t ad0 = a_desc0 + uint64_t(stage) * a_stage_u;
                             const uint64_t bd0 = b_desc0 + uint64_t(stage) * b_stage_u;
+                            const bool f = first;
+                            first = false;
+                            if (elect_one()) {
 #pragma unroll
                             for (int j = 0; j < 3; ++j) {
                                 // start row sh (128 B each) inside the 1024-byte swizzle atom: descriptor address + 8*sh.  The swizzle is applied
@@ -256,15 +261,18 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                                 const uint64_t bd = bd0 + uint64_t(j) * b_sub_u;
 #pragma unroll
                                 for (int k = 0; k < KC / 16; ++k) {
-                                    if (first) { umma_f16_first(d_tmem, ad + uint64_t(2 * k), bd + uint64_t(k) * b_k_u, idesc); first = false; }
+                                    if (f && j == 0 && k == 0) umma_f16_first(d_tmem, ad + uint64_t(2 * k), bd + uint64_t(k) * b_k_u, idesc);
                                     else umma_f16_acc(d_tmem, ad + uint64_t(2 * k), bd + uint64_t(k) * b_k_u, idesc);
                                 }
                             }
                             umma_commit(empty_bar(stage));
+                            }
+                            __syncwarp();
                             if (++stage == S) { stage = 0; phase ^= 1; }
                         }
                     }
-                    umma_commit(tfull_bar(acc));
+                    if (elect_one()) umma_commit(tfull_bar(acc));
+                    __syncwarp();
                     continue;
                 }
                 const int g0 = p.ksplit > 1 ? w.ks * nsteps / p.ksplit : 0;
@@ -276,19 +284,25 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_tma_kernel(const __grid_con
                     tc_fence_after();
                     uint64_t ad = a_desc0 + uint64_t(stage) * a_stage_u;
                     uint64_t bd = b_desc0 + uint64_t(stage) * b_stage_u;
+                    const bool f = first;
+                    first = false;
+                    if (elect_one()) {
 #pragma unroll 1
                     for (int j = 0; j < cnt; ++j, ad += a_sub_u, bd += b_sub_u) {
 #pragma unroll
                         for (int k = 0; k < KC / 16; ++k) {
                             // inside a swizzle row the next K = 16 slice is 32 bytes further (descriptor address + 2)
-                            if (first) { umma_f16_first(d_tmem, ad + uint64_t(2 * k), bd + uint64_t(k) * b_k_u, idesc); first = false; }
+                            if (f && j == 0 && k == 0) umma_f16_first(d_tmem, ad + uint64_t(2 * k), bd + uint64_t(k) * b_k_u, idesc);
                             else umma_f16_acc(d_tmem, ad + uint64_t(2 * k), bd + uint64_t(k) * b_k_u, idesc);
                         }
                     }
                     umma_commit(empty_bar(stage));
+                    }
+                    __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(acc));
+                if (elect_one()) umma_commit(tfull_bar(acc));
+                __syncwarp();
             }
         }
         __syncwarp();
