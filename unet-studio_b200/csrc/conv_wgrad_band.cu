@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
     } else if (warp >= 12) {
         // ===================================== MMA issuers ===================================
         // one issuing thread per dz (own accumulator): a single thread's issue loop, not the tensor pipe, limits the MMA rate
+        // The whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers); one elected lane issues.
         const int dz = warp - 12;
-        if (lane == 0 && has_work) {
+        if (has_work) {
             const uint32_t idesc = umma_idesc(128, N, 0, 0, 1, 1);    // both operands MN-major
             const uint64_t a_rows_u = uint64_t((R * NCG * kRunB) >> 4);       // R x rows further
             const uint64_t b_rows_u = uint64_t((R * 3 * NCGY * kRunB) >> 4);  // R dy rows further
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
                 for (int q = 0; q < dz; ++q) {
                     const uint32_t c = xcnt + q;
                     mbar_wait(xfull(c % kXSlots), (c / kXSlots) & 1, 0x3300u);
-                    mbar_arrive(xempty(c % kXSlots));
+                    if (lane == 0) mbar_arrive(xempty(c % kXSlots));
+                    __syncwarp();
                 }
 #pragma unroll 1
                 for (int j = 0; j < nz; ++j, ++ycnt) {
@@ -171,23 +173,29 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
                     tc_fence_after();
                     uint64_t ad = umma_smem_desc(sbase + (cq % kXSlots) * p.x_slot_bytes, 128u, kRunB);
                     uint64_t bd = umma_smem_desc(sbase + p.off_y + (ycnt % kYSlots) * p.y_slot_bytes, 128u, kRunB);
+                    const bool f = first;
+                    first = false;
+                    if (elect_one()) {
 #pragma unroll 1
-                    for (int rg = 0; rg < nrg; ++rg, ad += a_rows_u, bd += b_rows_u) {
-                        if (first) { umma_f16_first(d_tmem, ad, bd, idesc); first = false; }
-                        else umma_f16_acc(d_tmem, ad, bd, idesc);
-                        umma_f16_acc(d_tmem, ad + 16u, bd + 16u, idesc);
+                        for (int rg = 0; rg < nrg; ++rg, ad += a_rows_u, bd += b_rows_u) {
+                            if (f && rg == 0) umma_f16_first(d_tmem, ad, bd, idesc);
+                            else umma_f16_acc(d_tmem, ad, bd, idesc);
+                            umma_f16_acc(d_tmem, ad + 16u, bd + 16u, idesc);
+                        }
+                        umma_commit(yempty(ycnt % kYSlots));
+                        umma_commit(xempty(cq % kXSlots));
                     }
-                    umma_commit(yempty(ycnt % kYSlots));
-                    umma_commit(xempty(cq % kXSlots));
+                    __syncwarp();
                 }
                 for (int q = nz + dz; q <= nz + 1; ++q) {
                     const uint32_t c = xcnt + q;
                     mbar_wait(xfull(c % kXSlots), (c / kXSlots) & 1, 0x3304u);
-                    mbar_arrive(xempty(c % kXSlots));
+                    if (lane == 0) mbar_arrive(xempty(c % kXSlots));
+                    __syncwarp();
                 }
                 xcnt += uint32_t(nz + 2);
             }
-            umma_commit(done_bar);
+            if (elect_one()) umma_commit(done_bar);
         }
         __syncwarp();
     } else if (has_work) {
