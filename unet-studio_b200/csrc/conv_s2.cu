@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_s2_kernel(const __grid_cons
         cp_async_wait<0>();
     } else if (warp == 12) {
         // ===================================== MMA issuer ====================================
-        if (lane == 0) {
+        // the whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers); one elected lane issues
+        {
             const int HQ = p.HQ, ROWS = p.ROWS;
             const uint32_t idesc = umma_idesc(128, N, 0, 0, 0, 0);
             const uint32_t lbo_a = uint32_t(4 * ROWS) * 16u;                 // next channel group of 8
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_s2_kernel(const __grid_cons
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * uint32_t(N);
                     uint64_t bd = b_base;
+                    if (elect_one()) {
 #pragma unroll
                     for (int kz = 0; kz < 3; ++kz) {
                         const uint64_t a_pl = umma_smem_desc(sbase + ((c0 + kz) % kSSlots) * p.slot_bytes, lbo_a, 128u);
@@ -185,8 +187,11 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_s2_kernel(const __grid_cons
                     umma_commit(tfull_bar(acc));
                     umma_commit(empty_bar(c0 % kSSlots));          // planes 2j and 2j+1 are not needed by the next output plane
                     umma_commit(empty_bar((c0 + 1) % kSSlots));
+                    }
+                    __syncwarp();
                 }
-                umma_commit(empty_bar((cnt + 2 * nz) % kSSlots));  // the last plane of the chunk
+                if (elect_one()) umma_commit(empty_bar((cnt + 2 * nz) % kSSlots));  // the last plane of the chunk
+                __syncwarp();
                 cnt += uint32_t(2 * nz + 1);
             }
         }

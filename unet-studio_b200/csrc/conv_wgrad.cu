@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
         cp_async_wait<0>();
     } else if (warp == 8) {
         // ===================================== MMA issuer ====================================
-        if (lane == 0) {
-            // lean issue loop (see conv_halo.cu / tools/mma_bench.cu)
+        {
+            // lean issue loop (see conv_halo.cu / tools/mma_bench.cu).  The whole warp runs it (uniform control flow keeps the descriptors in
+            // uniform registers); one elected lane issues.
             int stage = 0, phase = 0;
             uint32_t acc_cnt = 0;
             const int total_items = p.total_items, nstride = gridDim.x, ntile_max = p.ntile_max;
@@ -210,15 +211,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
                     tc_fence_after();
                     const uint64_t ad = a_desc0 + uint64_t(stage) * a_stage_u;
                     const uint64_t bd = b_desc0 + uint64_t(stage) * b_stage_u;
+                    const bool f = first;
+                    first = false;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < kKB / 16; ++j) {
-                        if (first) { umma_f16_first(d_tmem, ad + uint64_t(j) * 16u, bd + uint64_t(j) * 16u, idesc); first = false; }
-                        else umma_f16_acc(d_tmem, ad + uint64_t(j) * 16u, bd + uint64_t(j) * 16u, idesc);
+                        for (int j = 0; j < kKB / 16; ++j) {
+                            if (f && j == 0) umma_f16_first(d_tmem, ad + uint64_t(j) * 16u, bd + uint64_t(j) * 16u, idesc);
+                            else umma_f16_acc(d_tmem, ad + uint64_t(j) * 16u, bd + uint64_t(j) * 16u, idesc);
+                        }
+                        umma_commit(empty_bar(stage));
                     }
-                    umma_commit(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(acc));
+                if (elect_one()) umma_commit(tfull_bar(acc));
+                __syncwarp();
                 ++acc_cnt;
             }
         }
