@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int iters, int n, cons
 // Lean issue loop (what a production issuer looks like): every descriptor precomputed, constant accumulate predicate, the loop body is
 // nothing but the 18 (+6) tcgen05 instructions.  mode as above.
 template <int mode>
-__global__ void __launch_bounds__(128, 1) bench_lean(int iters, int n, long long* clk, uint32_t a_lbo = 2048u, uint32_t a_step = 4096u, uint32_t a_off = 0u) {
+__global__ void __launch_bounds__(128, 1) bench_lean(int iters, int n, long long* clk, uint32_t a_lbo = 2048u, uint32_t a_step = 4096u, uint32_t a_off = 0u, int same_acc = 0) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tptr;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128, 1) bench_lean(int iters, int n, long long
             for (int acc = 0; acc < kAcc; ++acc) bd[ks * kAcc + acc] = umma_smem_desc(b0 + (ks * kAcc + acc) * bstep, uint32_t(n) * 16u, 128u);
         }
 #pragma unroll
-        for (int acc = 0; acc < kAcc; ++acc) dd[acc] = tm + acc * dstep;
+        for (int acc = 0; acc < kAcc; ++acc) dd[acc] = tm + (same_acc ? 0u : acc * dstep);
         if (mode == 2)
             for (int h = 0; h < 2; ++h)
                 for (int ks = 0; ks < kKS; ++ks) tmem_cp_128x256b(ta[h][ks], ad[ks]);
@@ -264,6 +264,14 @@ int main() {
                    mode == 0 ? "A smem" : mode == 1 ? "A tmem + 6 cp per 18 MMAs" : "A tmem, no cp", double(c[0]) / (iters * 18),
                    double(c[1]) / (iters * 18));
         }
+    for (int n : {64, 128, 192, 256}) {
+        bench_lean<0><<<1, 128, smem>>>(400, n, dC, 2048u, 4096u, 0u, 1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("same acc: %s\n", cudaGetErrorString(e)); return 1; }
+        long long c[2];
+        cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost);
+        printf("N=%3d every MMA into the SAME accumulator columns: %.1f clk per MMA\n", n, double(c[1]) / (400 * 18));
+    }
     // conv_band's A operand: 16-byte rows, K chunks 10432 B apart, start addresses at arbitrary 16-byte offsets
     for (int n : {48, 64, 192})
         for (int v = 0; v < 4; ++v) {
