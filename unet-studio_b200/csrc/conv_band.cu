@@ -76,6 +76,11 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
     float* sstats = reinterpret_cast<float*>(smem + p.off_stats);
     const uint32_t bars = sbase + p.off_bars;
     const uint32_t kSlots = uint32_t(p.nslots);
+    // ring arithmetic without run-time division (a 32-bit divide is ~100 clk of dependent latency in front of every barrier wait and
+    // descriptor): exact for c * kSlots < 2^32
+    const uint32_t slot_magic = 0xFFFFFFFFu / kSlots + 1u;
+    auto qdiv = [&](uint32_t c) { return __umulhi(c, slot_magic); };
+    auto qmod = [&](uint32_t c) { return c - __umulhi(c, slot_magic) * kSlots; };
     auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
     auto empty_bar = [&](uint32_t s) { return bars + 8u * (kMaxSlots + s); };
     // 4 TMEM accumulators: issuer wi alternates between accumulators wi and wi+2, so it can issue its next plane while the epilogue
@@ -134,8 +139,8 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
             const int x0 = tx * p.TX - 1, y0 = ty * p.TY - 1;
             const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
             for (int gz = z0 - 1; gz <= z1; ++gz, ++cnt) {
-                const uint32_t slot = cnt % kSlots;
-                mbar_wait(empty_bar(slot), ((cnt / kSlots) & 1) ^ 1, 0x2100u | slot);
+                const uint32_t slot = qmod(cnt);
+                mbar_wait(empty_bar(slot), ((qdiv(cnt)) & 1) ^ 1, 0x2100u | slot);
                 const uint32_t blk = sbase + slot * p.slot_bytes;
                 const bool zok = (unsigned)gz < (unsigned)D;
                 // plane origin (gz, y0, x0); only offsets of in-range voxels are ever added to it
@@ -200,11 +205,11 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                 const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
                 const int nz = z1 - z0;
                 // planes cnt, cnt+1 (relative z0-1, z0) must be resident before output plane 0; plane j+2 before output j
-                mbar_wait(full_bar(cnt % kSlots), (cnt / kSlots) & 1, 0x2300u);
-                mbar_wait(full_bar((cnt + 1) % kSlots), ((cnt + 1) / kSlots) & 1, 0x2301u);
+                mbar_wait(full_bar(qmod(cnt)), (qdiv(cnt)) & 1, 0x2300u);
+                mbar_wait(full_bar(qmod(cnt + 1)), (qdiv(cnt + 1)) & 1, 0x2301u);
                 if ((acc_cnt & 1u) != wi && lane == 0) {   // output 0 belongs to the other issuer: this one never reads plane 0 (nor 1 if nz == 1)
-                    mbar_arrive(empty_bar(cnt % kSlots));
-                    if (nz == 1) mbar_arrive(empty_bar((cnt + 1) % kSlots));
+                    mbar_arrive(empty_bar(qmod(cnt)));
+                    if (nz == 1) mbar_arrive(empty_bar(qmod(cnt + 1)));
                 }
                 __syncwarp();
                 const uint32_t last_owner = (acc_cnt + uint32_t(nz - 1)) & 1u;
@@ -212,8 +217,8 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                 for (int j = 0; j < nz; ++j, ++acc_cnt) {
                     if ((acc_cnt & 1u) != wi) continue;
                     const uint32_t c1 = cnt + j + 1, c2 = cnt + j + 2;
-                    mbar_wait(full_bar(c1 % kSlots), (c1 / kSlots) & 1, 0x2303u);
-                    mbar_wait(full_bar(c2 % kSlots), (c2 / kSlots) & 1, 0x2302u);
+                    mbar_wait(full_bar(qmod(c1)), (qdiv(c1)) & 1, 0x2303u);
+                    mbar_wait(full_bar(qmod(c2)), (qdiv(c2)) & 1, 0x2302u);
                     fence_proxy_async();
                     tc_fence_after();
                     const uint32_t acc = acc_cnt & 3u;
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                     uint64_t a_pl[3];
 #pragma unroll
                     for (int dz = 0; dz < 3; ++dz)
-                        a_pl[dz] = umma_smem_desc(sbase + ((cnt + j + dz) % kSlots) * p.slot_bytes + uint32_t(HQ) * 16u, lbo_a, 128u);
+                        a_pl[dz] = umma_smem_desc(sbase + (qmod(cnt + j + dz)) * p.slot_bytes + uint32_t(HQ) * 16u, lbo_a, 128u);
                     if (elect_one()) {
                     // first MMA: full width, overwrite
                     {
@@ -250,16 +255,16 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                         }
                     }
                     umma_commit(tfull_bar(acc));
-                    umma_commit(empty_bar((cnt + j) % kSlots));
-                    umma_commit(empty_bar(c1 % kSlots));
-                    if (j >= nz - 2) umma_commit(empty_bar(c2 % kSlots));   // this issuer has no later output reading plane j+2
+                    umma_commit(empty_bar(qmod(cnt + j)));
+                    umma_commit(empty_bar(qmod(c1)));
+                    if (j >= nz - 2) umma_commit(empty_bar(qmod(c2)));   // this issuer has no later output reading plane j+2
                     }
                     __syncwarp();
                 }
                 if (last_owner != wi) {              // plane nz+1 is read by output nz-1 only
                     const uint32_t c = cnt + uint32_t(nz + 1);
-                    mbar_wait(full_bar(c % kSlots), (c / kSlots) & 1, 0x2304u);
-                    if (lane == 0) mbar_arrive(empty_bar(c % kSlots));
+                    mbar_wait(full_bar(qmod(c)), (qdiv(c)) & 1, 0x2304u);
+                    if (lane == 0) mbar_arrive(empty_bar(qmod(c)));
                     __syncwarp();
                 }
                 cnt += uint32_t(nz + 2);
@@ -404,6 +409,11 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
     float* sstats = reinterpret_cast<float*>(smem + p.off_stats);
     const uint32_t bars = sbase + p.off_bars;
     const uint32_t kSlots = uint32_t(p.nslots);
+    // ring arithmetic without run-time division (a 32-bit divide is ~100 clk of dependent latency in front of every barrier wait and
+    // descriptor): exact for c * kSlots < 2^32
+    const uint32_t slot_magic = 0xFFFFFFFFu / kSlots + 1u;
+    auto qdiv = [&](uint32_t c) { return __umulhi(c, slot_magic); };
+    auto qmod = [&](uint32_t c) { return c - __umulhi(c, slot_magic) * kSlots; };
     auto full_bar = [&](uint32_t s) { return bars + 8u * s; };
     auto empty_bar = [&](uint32_t s) { return bars + 8u * (kMaxSlots + s); };
     auto tfull_bar = [&](uint32_t a) { return bars + 8u * (2 * kMaxSlots + a); };
@@ -477,14 +487,14 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
             const int x0 = tx * p.TX - 1, y0 = ty * p.TY - 1;
             const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
             for (int gz = z0 - 1; gz <= z1; ++gz, ++cnt) {
-                const uint32_t slot = cnt % kSlots;
-                mbar_wait(empty_bar(slot), ((cnt / kSlots) & 1) ^ 1, 0x2100u | slot);
+                const uint32_t slot = qmod(cnt);
+                mbar_wait(empty_bar(slot), ((qdiv(cnt)) & 1) ^ 1, 0x2100u | slot);
                 const uint32_t blk = sbase + slot * p.slot_bytes;
                 const bool zok = (unsigned)gz < (unsigned)D;
                 const long long vox0 = ((long long)(zok ? gz : 0) * H + y0) * W + x0;
                 const uint8_t* const p0 = s0 + vox0 * (long long)pitch0;
 #pragma unroll 2
-                for (int idx = t; idx < ((p.NB & 8) ? 0 : per_plane); idx += kBProducers) {
+                for (int idx = t; idx < per_plane; idx += kBProducers) {
                     const int cg = idx & 1;
                     const uint32_t pos = uint32_t(idx) >> 1;
                     const int hy = int((pos * inv_hx) >> 20);
@@ -524,7 +534,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
 #pragma unroll 1
                 for (int i = 0; i < nz + 2; ++i) {
                     const uint32_t c = cnt + uint32_t(i);
-                    mbar_wait(full_bar(c % kSlots), (c / kSlots) & 1, 0x2300u);
+                    mbar_wait(full_bar(qmod(c)), (qdiv(c)) & 1, 0x2300u);
                     if (i < nz) {   // output plane i receives its first contribution from this input plane: its slot must be drained + zeroed
                         const uint32_t q = q_base + uint32_t(i);
                         mbar_wait(tempty_bar(q & 7u), ((q >> 3) & 1u) ^ 1u, 0x2400u | (q & 7u));
@@ -537,7 +547,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
                     const int n1 = count < int(8u - sl0) ? count : int(8u - sl0), n2 = count - n1;
                     const uint32_t d1 = tmem_base + sl0 * uint32_t(N), d2 = tmem_base;
                     const uint32_t id1 = idesc_n[n1], id2 = idesc_n[n2];
-                    const uint64_t a_pl = umma_smem_desc(sbase + (c % kSlots) * p.slot_bytes + uint32_t(HQ) * 16u, lbo_a, 128u);
+                    const uint64_t a_pl = umma_smem_desc(sbase + (qmod(c)) * p.slot_bytes + uint32_t(HQ) * 16u, lbo_a, 128u);
                     const uint64_t b_pl = b_desc0 + uint64_t(pl_lo * 64);        // 64 rows of 16 B per plane block (16-byte units)
                     const uint64_t b_pl2 = b_pl + uint64_t(n1 * 64);
                     if (elect_one()) {
@@ -552,7 +562,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
                             if (n2) umma_f16_acc(d2, a_row + a_xi[xi], b_pl2 + boff, id2);
                         }
                     }
-                    umma_commit(empty_bar(c % kSlots));                                   // the plane is consumed by this batch alone
+                    umma_commit(empty_bar(qmod(c)));                                   // the plane is consumed by this batch alone
                     if (i >= 2) umma_commit(tfull_bar((q_base + uint32_t(i - 2)) & 7u));   // output i-2 has all 27 taps
                     }
                     __syncwarp();
@@ -601,13 +611,8 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
                 for (int xo = 0; xo < G; ++xo) {
                     const bool rv = rv_xy && gx0 + xo < W;
                     float v[16];
-                    if (p.NB & 1) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                    } else {
-                        tmem_ld16(t_row + uint32_t(xo * CO), v);
-                        tmem_st16_zero(t_row + uint32_t(xo * CO));
-                    }
+                    tmem_ld16(t_row + uint32_t(xo * CO), v);
+                    tmem_st16_zero(t_row + uint32_t(xo * CO));
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += sbias[j];
                     uint4* out = reinterpret_cast<uint4*>(dst + (vox0 + xo) * dst_pitch);
@@ -621,7 +626,7 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
                             v[2 * j + 1] += f.y;
                         }
                     }
-                    if (rv && !(p.NB & 2)) {
+                    if (rv) {
                         uint4 q0v, q1v;
                         q0v.x = pack2<false>(v[0], v[1]); q0v.y = pack2<false>(v[2], v[3]);
                         q0v.z = pack2<false>(v[4], v[5]); q0v.w = pack2<false>(v[6], v[7]);
@@ -841,8 +846,6 @@ static int conv_band_launch_one(const ConvProblem& Pin, const ConvLaunch& cfg, b
     const int grid = std::max(1, std::min(bp.total_items, sms));
     if (cfg.stats_grid_out) *cfg.stats_grid_out = grid;
     if (zband) {
-        static const int zdbg = std::getenv("U3D_ZDBG") ? atoi(std::getenv("U3D_ZDBG")) : 0;
-        bp.NB = zdbg;
         static bool attr_set = false;
         if (!attr_set) {
             U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_zband_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
