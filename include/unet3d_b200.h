@@ -159,6 +159,10 @@ int simulate_modality(float* t1w, const float* label, unsigned max_label, unsign
 int unet3d_simulate_modality(unet3d_t* h, float* t1w, const float* label, unsigned max_label, unsigned seed, int w, int hgt, int d,
                              int where);
 int unet3d_set_simulate_modality(unet3d_t* h, int mode);
+/* host only (no GPU needed): the random scalars simulate_modality draws for (overload, max_label, seed) in the reference's draw
+ * order (train.cpp:56-58 tissue LUT, :65-78 the 20 terms, :80 gamma): lut_out[max_label + 1] (labelled overload only),
+ * terms_out[20][5] = a, b, c, d, w, gamma_out[1].  Any output pointer may be NULL. */
+int simulate_modality_plan(int labelled, unsigned max_label, unsigned seed, float* lut_out, float* terms_out, float* gamma_out);
 
 /* NCCL plumbing for the data-parallel step (bootstrap the 128-byte id through any host channel) */
 int unet3d_nccl_unique_id(void* id128);

@@ -77,6 +77,7 @@ def simulate_modality(t1w, label=None, max_label=0, seed=0, trace=None):
         lut = np.array([F(F(0.4) + F(rand_float() * F(0.2))) for _ in range(max_label + 1)], F)   # train.cpp:56-58
         tissue = lut[label.astype(np.int64)]                                                        # :59-60
     else:
+        lut = np.zeros(0, F)
         tissue = t1w.copy()                                                                         # :127
     tissue = gaussian(gaussian(tissue))                                                             # :62-63
     terms = draw_terms(rand_int, rand_float)
@@ -100,7 +101,7 @@ def simulate_modality(t1w, label=None, max_label=0, seed=0, trace=None):
     sel = keep & (label != 0) if label is not None else keep                                         # :104-108 / :169-170
     sel = sel & ~np.isnan(out)            # std::min/max keep the running value when the new one is NaN
     if trace is not None:
-        trace.update(tissue=tissue, s=np.where(keep, s, F(0.0)), gamma=gamma, terms=terms, pre=out.copy())
+        trace.update(tissue=tissue, s=np.where(keep, s, F(0.0)), gamma=gamma, terms=terms, lut=lut, pre=out.copy())
     if sel.any():
         mn, mx = F(out[sel].min()), F(out[sel].max())
         if mx > mn:                                                                                  # :111-116

@@ -58,3 +58,30 @@ def test_properties():
         out2 = SO.simulate_modality(img, None, 0, seed)
         assert out2.min() >= 0 and out2.max() == 1 and (out2[img <= 0.02] == 0).all()
     assert not np.array_equal(SO.simulate_modality(img, lab, 2, 0), SO.simulate_modality(img, lab, 2, 1))
+
+
+def test_host_plan_of_the_library_draws_what_the_oracle_draws():
+    """simulate_modality_plan (host only, no GPU): tissue LUT, the 20 terms and gamma for several seeds and both overloads."""
+    import ctypes
+    from tests._pkg import load
+    m = load()
+    L = m.lib()
+    img = np.full((2, 2, 2), 0.5, np.float32)
+    lab = np.ones((2, 2, 2), np.float32)
+    FP = ctypes.POINTER(ctypes.c_float)
+    for seed in (0, 1, 77, 4000000000, 0xFFFFFFFF):
+        for labelled, max_label in ((1, 3), (1, 40), (0, 0)):
+            tr = {}
+            SO.simulate_modality(img, lab if labelled else None, max_label, seed, trace=tr)
+            lut = np.zeros(max_label + 1, np.float32)
+            terms = np.zeros((20, 5), np.float32)
+            gamma = ctypes.c_float(0)
+            rc = L.simulate_modality_plan(labelled, ctypes.c_uint(max_label), ctypes.c_uint(seed), lut.ctypes.data_as(FP),
+                                          terms.ctypes.data_as(FP), ctypes.byref(gamma))
+            assert rc == 0
+            if labelled:
+                assert np.array_equal(lut, tr["lut"])
+            assert np.array_equal(terms, np.array([[a, b, c, d, w] for a, b, c, d, w in tr["terms"]], np.float32))
+            assert np.float32(gamma.value) == tr["gamma"]
+    with np.testing.assert_raises(m.U3DError):
+        m.check(L.simulate_modality_plan(1, ctypes.c_uint(100000), ctypes.c_uint(0), None, None, None))

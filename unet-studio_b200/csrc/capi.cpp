@@ -462,6 +462,25 @@ int unet3d_simulate_modality(unet3d_t* h, float* t1w, const float* label, unsign
     GUARD_END
 }
 
+int simulate_modality_plan(int labelled, unsigned max_label, unsigned seed, float* lut_out, float* terms_out, float* gamma_out) {
+    GUARD_BEGIN
+    u3d::SimPlan plan;
+    if (u3d::simulate_make_plan(labelled, max_label, seed, 1, 1, 1, plan)) return 1;
+    if (lut_out)
+        for (int i = 0; i < plan.n_lut; ++i) lut_out[i] = plan.lut[i];
+    if (terms_out)
+        for (int t = 0; t < u3d::kSimTerms; ++t) {
+            terms_out[5 * t + 0] = float(plan.a[t]);
+            terms_out[5 * t + 1] = float(plan.b[t]);
+            terms_out[5 * t + 2] = float(plan.c[t]);
+            terms_out[5 * t + 3] = float(plan.d[t]);
+            terms_out[5 * t + 4] = plan.w[t];
+        }
+    if (gamma_out) *gamma_out = plan.gamma;
+    return 0;
+    GUARD_END
+}
+
 int unet3d_set_simulate_modality(unet3d_t* h, int mode) {
     GUARD_BEGIN NEED(h)
     if (mode < 0 || mode > 2) { set_error("unet3d_set_simulate_modality: mode must be 0 (off), 1 (labelled template) or 2 (image only)"); return 1; }
