@@ -131,6 +131,12 @@ int vpa_augment(const char* const* keys, const float* vals, int n_opts, float* i
 int unet3d_vpa_augment(unet3d_t* h, const char* const* keys, const float* vals, int n_opts, float* image, float* label, int is_label,
                        int w, int hgt, int d, int channels, uint64_t seed, int where);
 
+/* host only (no GPU needed): the scalars the augmentation draws for (options, shape, seed) in the reference's draw order
+ * (visual_perception_augmentation.cpp:180-320): the output->source affine M12 (3x4, row major), the perspective coefficients,
+ * and the local distortion foci (x, y, z, radius, magnitude; up to 12).  Any output pointer may be NULL. */
+int vpa_plan_describe(const char* const* keys, const float* vals, int n_opts, int is_label, int w, int h, int d, int channels,
+                      uint64_t seed, float M12[12], float persp3[3], int* nfoci, float* foci5);
+
 /* train.cpp:459-473 + 615-706 in one call: upload the RAW sample once (host pointers, label = float-stored integers), run
  * visual_perception_augmentation on it in HBM (is_label = 1) and feed the result straight into the micro-batch.  Saves the
  * device->host->device round trip of the augmented sample that the two separate where = 0 calls make. */

@@ -462,6 +462,28 @@ int unet3d_simulate_modality(unet3d_t* h, float* t1w, const float* label, unsign
     GUARD_END
 }
 
+int vpa_plan_describe(const char* const* keys, const float* vals, int n_opts, int is_label, int w, int h, int d, int channels,
+                      uint64_t seed, float M12[12], float persp3[3], int* nfoci, float* foci5) {
+    GUARD_BEGIN
+    u3d::VpaPlan plan;
+    if (u3d::vpa_make_plan(keys, vals, n_opts, is_label, w, h, d, channels, seed, plan)) return 1;
+    if (M12)
+        for (int i = 0; i < 12; ++i) M12[i] = plan.M[i];
+    if (persp3)
+        for (int i = 0; i < 3; ++i) persp3[i] = plan.has_persp ? plan.persp[i] : 0.f;
+    if (nfoci) *nfoci = plan.nfoci;
+    if (foci5)
+        for (int f = 0; f < plan.nfoci; ++f) {
+            foci5[5 * f + 0] = float(plan.foci[f].loc[0]);
+            foci5[5 * f + 1] = float(plan.foci[f].loc[1]);
+            foci5[5 * f + 2] = float(plan.foci[f].loc[2]);
+            foci5[5 * f + 3] = plan.foci[f].radius;
+            foci5[5 * f + 4] = plan.foci[f].mag;
+        }
+    return 0;
+    GUARD_END
+}
+
 int simulate_modality_plan(int labelled, unsigned max_label, unsigned seed, float* lut_out, float* terms_out, float* gamma_out) {
     GUARD_BEGIN
     u3d::SimPlan plan;
