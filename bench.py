@@ -27,9 +27,11 @@ if ROOT not in sys.path:
 W, H, D = 160, 192, 160
 IN_C, OUT_C = 1, 2
 METRIC = "train_steps_per_s"
-UNIT = "steps/s"
+# one "step" = one batch-1 training step (one micro-batch: forward, 5-level loss, backward, + the update).  At N GPUs every rank runs
+# one of them per optimizer update (weak scaling), so value = N x optimizer updates/s; at N = 1 the two are the same thing.
+UNIT = "micro-batch steps/s"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "unet_ref")
-CPU_SAMPLE_DIM = (96, 96, 96)   # bounded CPU sample: ~10-30 s of host work per step
+CPU_BUDGET_S = 150.0            # wall-time bound of the --impl reference run (the reference's CPU path at the REAL grid)
 
 
 def peaks():
@@ -109,59 +111,232 @@ def workload_name(augment=True, simulate=False):
             f"ce+dice+mse deep supervision, clip 12, Nesterov SGD")
 
 
-def cpu_reference_step(steps, warmup, threads=None):
-    """Times the reference (oracle/_ref) training step on the host on the bounded sample grid; returns dict."""
+def run_ref_bin(mode, out_c, dims, steps, warmup, batch=1, device="cpu", threads=None, budget_s=None, timeout=1700):
+    """oracle/_ref/unet_ref time ... -> its JSON line (None when the binary is not there)."""
     if not os.path.exists(REF_BIN):
         return None
     threads = threads or os.cpu_count() or 1
-    w, h, d = CPU_SAMPLE_DIM
-    cmd = [REF_BIN, "time", "--mode", "step", "--in_c", str(IN_C), "--out_c", str(OUT_C), "--feature", "default", "--dim", str(w), str(h),
-           str(d), "--steps", str(steps), "--warmup", str(warmup), "--threads", str(threads), "--batch", "1"]
-    out = subprocess.check_output(cmd, text=True, timeout=1500)
-    r = json.loads(out.strip().splitlines()[-1])
-    scale = (W * H * D) / float(w * h * d)
-    ms_full = r["ms_per_step"] * scale
-    return {"value": 1000.0 / ms_full, "unit": UNIT, "cores": int(r["threads"]), "kind": "reference",
-            "sample": f"oracle/_ref/unet_ref (reference unet.cpp + libtorch CPU): one full step (fwd+5-level loss+bwd+clip+SGD, no augmentation) at "
-                      f"{w}x{h}x{d}, {r['ms_per_step']:.0f} ms, scaled x{scale:.2f} by voxel count to {W}x{H}x{D}",
-            "ms_per_step_sample": r["ms_per_step"]}
+    cmd = [REF_BIN, "time", "--mode", mode, "--in_c", str(IN_C), "--out_c", str(out_c), "--feature", "default", "--dim", *[str(v) for v in dims],
+           "--steps", str(steps), "--warmup", str(warmup), "--threads", str(threads), "--batch", str(batch), "--device", device]
+    if budget_s:
+        cmd += ["--budget_s", str(budget_s)]
+    out = subprocess.check_output(cmd, text=True, timeout=timeout, stderr=subprocess.DEVNULL)
+    return json.loads(out.strip().splitlines()[-1])
 
 
-def run_reference(args, rank):
+def cpu_reference_step(steps, warmup, batch=1, budget_s=None):
+    """The reference training step (unet.cpp unchanged + calc_losses + the restated update) on the host cores at the REAL cfg-2 grid.
+    `steps` is an upper bound; the binary stops taking timed steps when budget_s is spent and reports how many it ran."""
+    r = run_ref_bin("step", OUT_C, (W, H, D), steps, warmup, batch=batch, budget_s=budget_s)
+    if r is None:
+        return None
+    ms = r["ms_per_step"]
+    return {"value": batch * 1000.0 / ms, "unit": UNIT, "cores": int(r["threads"]), "kind": "reference",
+            "sample": f"oracle/_ref/unet_ref = /root/reference/unet.cpp compiled unchanged + the reference's calc_losses, libtorch {r.get('torch', '?')} CPU "
+                      f"(fp32, oneDNN), {r['threads']} threads: {r['steps']} timed optimizer step(s) of {batch} micro-batch(es) after {warmup} warm-up at the "
+                      f"real {W}x{H}x{D} grid, {ms:.0f} ms per optimizer step (fwd + 5-level loss + bwd + clip + SGD).  simulate_modality and "
+                      f"visual_perception_augmentation are NOT in this figure: they need TIPL (un-vendored) and do not compile here; in the "
+                      f"reference they run in worker threads beside the trainer (train.cpp:446-485)",
+            "steps_run": int(r["steps"]), "ms_per_optimizer_step": ms, "micro_batches_per_step": batch}
+
+
+def cpu_augmentation_port_seconds():
+    """The oracle's numpy port of simulate_modality + visual_perception_augmentation on ONE host core at the real grid (the stage the CPU
+    reference figure leaves out).  Reported next to the baseline, never added to it."""
+    try:
+        from oracle import vpa_oracle as V, simulate_oracle as S
+        img, lab = synth_sample(0)
+        t0 = time.perf_counter()
+        im = S.simulate_modality(img[0, 0].copy(), lab[0].copy(), OUT_C, 0)
+        t1 = time.perf_counter()
+        V.augment(dict(V.OPTION_DEFAULTS), im[None].copy(), lab[0].copy(), True, (W, H, D), 0)
+        t2 = time.perf_counter()
+        return {"simulate_modality_s": t1 - t0, "visual_perception_augmentation_s": t2 - t1, "kind": "port", "cores": 1,
+                "what": "oracle/simulate_oracle.py + oracle/vpa_oracle.py (numpy restatements, parity unpinned), one sample at the real grid"}
+    except Exception as ex:
+        return {"failed": str(ex)}
+
+
+def gpu_baseline(steps):
+    """The reference on libtorch CUDA + cuDNN on THIS B200 ('the bar'): the same unet_ref binary with --device cuda,
+    libtorch defaults (cuDNN may use TF32 for convolutions).  cfg-2 training step and cfg-1 inference window."""
+    out = {}
+    try:
+        r = run_ref_bin("step", OUT_C, (W, H, D), max(3, min(steps, 20)), 3, device="cuda", timeout=600)
+        out["train"] = {"value": 1000.0 / r["ms_per_step"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "ms_median": r["ms_median"],
+                        "steps_run": r["steps"], "cudnn_tf32": bool(r["cudnn_tf32"]), "torch": r.get("torch"),
+                        "what": "unet_ref time --mode step --device cuda: H2D of the sample, fwd, 5-level calc_losses, bwd, losses D2H, /batch, clip, SGD "
+                                "(train.cpp:615-706,755-766); no augmentation"}
+    except Exception as ex:
+        out["train"] = {"failed": str(ex)[-300:]}
+    try:
+        r = run_ref_bin("fwd", 1, (W, H, D), max(3, min(steps, 20)), 3, device="cuda", timeout=600)
+        vox = W * H * D / 1e6
+        out["inference"] = {"value": vox / (r["ms_resident"] / 1e3), "unit": "Mvoxel/s", "ms_per_window_resident": r["ms_resident"],
+                            "e2e": {"value": vox / (r["ms_per_step"] / 1e3), "unit": "Mvoxel/s", "ms_per_window": r["ms_per_step"],
+                                    "what": "evaluate.cpp:226-229 per window: H2D, forward()[0], D2H from pageable host memory"},
+                            "cudnn_tf32": bool(r["cudnn_tf32"])}
+    except Exception as ex:
+        out["inference"] = {"failed": str(ex)[-300:]}
+    return out
+
+
+def run_reference(args, rank, world):
     if rank != 0:
         return 0
-    r = cpu_reference_step(max(1, min(args.steps, 2)), max(0, min(args.warmup, 1)))
+    # N GPUs run N micro-batches per optimizer update (weak scaling); the reference's CPU path runs them one after the other
+    est_s = 5.0 * world
+    steps = max(1, min(args.steps, int(CPU_BUDGET_S / est_s)))
+    r = cpu_reference_step(steps, 1, batch=world, budget_s=CPU_BUDGET_S)
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/unet_ref not built (run __graft_entry__.build() where /root/reference exists)"}))
         return 0
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_run"],
+            "steps_requested": args.steps, "warmup": 1, "ms_per_step": r["ms_per_optimizer_step"] / world,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(True, True), "grid": [W, H, D], "in_count": IN_C, "out_count": OUT_C,
-                       "arm": "reference unet.cpp + libtorch CPU (oracle/_ref/unet_ref) on the host cores; simulate_modality and the augmentation "
-                              "(TIPL) are not compilable here, so the CPU step excludes them -- they are in the GPU arm's timed region"},
+                       "micro_batches_per_optimizer_step": world,
+                       "arm": "reference unet.cpp + libtorch CPU (oracle/_ref/unet_ref) on the host cores at the real grid, one process, all host "
+                              "threads; 'steps' is the number of optimizer steps actually timed inside the wall-time budget",
+                       "excluded_stages": "simulate_modality + visual_perception_augmentation (TIPL, not compilable here; worker threads in the reference)"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
+def extra_configs(pkg, torch, comm, world, rank, local_rank, barrier, clocks):
+    """BASELINE.json configs 3, 4, 5 as extra keys (short runs; the headline stays cfg 2).  Every rank takes part."""
+    import numpy as np
+
+    def maxr(v):
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([v], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return v
+
+    def train_cfg(out_c, dims, mb_per_gpu, steps, flop_per_mb):
+        w, h, d = dims
+        net = pkg.UNet3d(IN_C, out_c, None, gpu=local_rank)
+        net.init_params(0)
+        net.set_dim(w, h, d)
+        net.train(True)
+        net.create_optimizer(1e-3)
+        if comm is not None:
+            net.attach_comm(comm, mb_per_gpu)
+        pkg.set_simulate_modality(net, 1)
+        rng = np.random.default_rng(100 + rank)
+        z, y, x = np.meshgrid(np.arange(d, dtype=np.float32), np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+        r = np.sqrt(((z - d / 2) / (0.42 * d)) ** 2 + ((y - h / 2) / (0.40 * h)) ** 2 + ((x - w / 2) / (0.38 * w)) ** 2)
+        img = (np.clip(1.1 - r, 0, 1) + 0.05 * rng.random(r.shape, dtype=np.float32)).astype(np.float32)
+        img /= img.max()
+        lab = np.zeros_like(r)
+        for k in range(1, out_c):
+            lab += (r < 1.0 - (k - 1) * (0.9 / max(out_c - 1, 1)))
+        xh = torch.from_numpy(img[None, None].copy()).pin_memory()
+        lh = torch.from_numpy(lab[None].astype(np.float32)).pin_memory()
+        B = mb_per_gpu * world
+        seq = [0]
+
+        def one_step():
+            # host-buffer path: sample b+1 is uploaded + simulated + augmented on the prefetch stream while micro-batch b trains
+            for b in range(mb_per_gpu):
+                if seq[0] == 0:
+                    pkg.prefetch_augmented(net, xh.numpy(), lh.numpy(), seed=rank, where=0)
+                seq[0] += 1
+                pkg.prefetch_augmented(net, xh.numpy(), lh.numpy(), seed=seq[0] * world + rank, where=0)
+                loss = pkg.train_microbatch_prefetched(net)
+            net.step(B, 1e-3, comm)
+            return loss
+
+        one_step()
+        barrier()
+        clocks.begin()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = one_step()
+        torch.cuda.synchronize()
+        dt = maxr(time.perf_counter() - t0)
+        clocks.end()
+        barrier()
+        skipped = net.last_step_skipped()
+        del net
+        return {"optimizer_steps_per_s": steps / dt, "micro_batches_per_s": steps * B / dt, "ms_per_optimizer_step": dt / steps * 1e3,
+                "micro_batches_per_gpu_per_step": mb_per_gpu, "global_batch": B, "grid": [w, h, d], "out_count": out_c, "steps_timed": steps,
+                "tflops_per_gpu": flop_per_mb * mb_per_gpu * steps / dt / 1e12, "loss": [float(v) for v in loss], "last_step_skipped": bool(skipped),
+                "api": "host buffers: unet3d_prefetch_augmented + unet3d_train_microbatch_prefetched per micro-batch, unet3d_step per update"}
+
+    out = {}
+    try:
+        out["cfg3"] = dict(train_cfg(6, (W, H, D), 8, 3, 1.72e12), workload="cfg3: UNet3d(1,6) multi-class tissue, 160x192x160, 8 micro-batches per GPU "
+                           "per optimizer step (gradient accumulation), fp16 operands")
+        out["cfg4"] = dict(train_cfg(2, (128, 160, 96), 8, 5, 3 * 229.51e9), workload="cfg4: UNet3d(1,2) rodent grid 128x160x96, 8 micro-batches per GPU per "
+                           "optimizer step, one NCCL all-reduce per step when N > 1")
+        # cfg5: the 8 windows (160x192x160 at stride 160,128,160) of one 320^3 volume, window i -> rank i % world, no collective
+        net = pkg.UNet3d(IN_C, 6, None, gpu=local_rank)
+        net.init_params(0)
+        net.set_dim(W, H, D)
+        net.prepare_for_inference()
+        rng = np.random.default_rng(5)
+        mine = pkg.dist.shard_windows(8, world, rank)
+        wins = [torch.from_numpy(rng.random((1, IN_C, D, H, W), dtype=np.float32)).pin_memory() for _ in mine]
+        outs = [torch.empty(1, 6, D, H, W).pin_memory() for _ in range(min(2, len(mine)))]
+        ob = [outs[i % len(outs)].numpy() for i in range(len(mine))]
+        net.evaluate_windows([w_.numpy() for w_ in wins], ob)
+        barrier()
+        clocks.begin()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            net.evaluate_windows([w_.numpy() for w_ in wins], ob)
+        dt = maxr(time.perf_counter() - t0)
+        clocks.end()
+        barrier()
+        out["cfg5"] = {"workload": "cfg5: UNet3d(1,6) 0.5 mm 320^3 volume as 8 windows of 160x192x160 sharded over the GPUs (window i -> rank i % N), "
+                                   "host buffers in, fp32 logits of 6 classes out, no collective",
+                       "value": reps * 8 * W * H * D / 1e6 / dt, "unit": "Mvoxel/s", "ms_per_volume": dt / reps * 1e3, "windows_per_gpu": len(mine),
+                       "h2d_bytes_per_window": IN_C * W * H * D * 4, "d2h_bytes_per_window": 6 * W * H * D * 4,
+                       "api": "unet3d_evaluate_windows (host buffers)"}
+        if world == 1:
+            S = 320
+            net.set_dim(S, S, S)
+            xv = torch.rand(1, IN_C, S, S, S, device="cuda")
+            yv = torch.empty(1, 6, S, S, S, device="cuda")
+            net.device_forward(xv.data_ptr(), [yv.data_ptr()])
+            net.sync()
+            net.timer_start()
+            for _ in range(3):
+                net.device_forward(xv.data_ptr(), [yv.data_ptr()])
+            ms1 = net.timer_stop() / 3
+            out["cfg5"]["single_pass_320"] = {"ms": ms1, "value": S ** 3 / 1e6 / (ms1 / 1e3), "unit": "Mvoxel/s", "tflops": 3830.70e9 / (ms1 / 1e3) / 1e12,
+                                             "what": "the whole 320^3 volume in one forward, device-resident"}
+            del xv, yv
+        del net
+    except Exception as ex:   # extra keys never take the headline down
+        out["extra_configs_error"] = repr(ex)[-400:]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-augment", action="store_true")
     ap.add_argument("--no-simulate", action="store_true", help="skip simulate_modality (train.cpp:459) in front of the augmentation")
     ap.add_argument("--no-inference", action="store_true", help="skip the cfg1 inference leg (profiling runs under ncu)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the libtorch/cuDNN baseline on this GPU")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the cfg 3 / 4 / 5 extra keys")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        return run_reference(args, rank)
+        return run_reference(args, rank, world)
     # libraries (NCCL's version banner, ...) may write to fd 1: keep stdout clean for the ONE JSON line
     sys.stdout.flush()
     json_fd = os.dup(1)
@@ -318,6 +493,9 @@ def main():
         inf.evaluate_windows([x_host.numpy()] * n_inf, outs)
         inf_e2e_ms = (time.perf_counter() - t0) * 1000.0
         barrier()
+    extras = {}
+    if not args.no_extra_configs:
+        extras = extra_configs(pkg, torch, comm, world, rank, local_rank, barrier, clocks)
     clk = clocks.stop()
     if world > 1:
         import torch.distributed as dist
@@ -337,8 +515,13 @@ def main():
         ms_k, n_k, fl_k = prof[3 * i:3 * i + 3]
         fams[name] = {"ms_per_step": ms_k / args.steps, "launches_per_step": n_k / args.steps, "gflop_per_step": fl_k / args.steps / 1e9,
                       "achieved_tflops": (fl_k / 1e12) / (ms_k / 1e3) if ms_k > 0 else None}
-    dom = max(fams, key=lambda k: fams[k]["ms_per_step"])
+    for f in fams.values():
+        f["frac"] = (f["achieved_tflops"] / pk["tf_sustained"]) if f["achieved_tflops"] else None
+    live = {k: f for k, f in fams.items() if f["ms_per_step"] > 0}
+    dom = max(live, key=lambda k: live[k]["ms_per_step"])
+    low = min(live, key=lambda k: live[k]["achieved_tflops"])
     achieved = fams[dom]["achieved_tflops"]
+    tensor_gflop = sum(f["gflop_per_step"] for f in fams.values())
     ncu_summary = {}
     sp = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(sp):
@@ -347,7 +530,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
+        "optimizer_updates_per_s": args.steps / (ms / 1000.0),
         "config": {"workload": workload_name(augment, simulate),
+                   "step_definition": "one batch-1 training step (micro-batch + update); N GPUs run N of them per optimizer update (weak scaling), "
+                                      "so value = N x optimizer_updates_per_s",
                    "grid": [W, H, D], "in_count": IN_C, "out_count": OUT_C, "micro_batches_per_gpu_per_step": 1,
                    "global_batch": world, "parallelism": f"dp{world}", "augmentation": bool(augment), "simulate_modality": bool(simulate),
                    "l2": "no explicit flush: each step streams > 3 GB of activations, far above the 126 MB L2",
@@ -368,13 +554,31 @@ def main():
                      "frac": (achieved / pk["tf_sustained"]) if achieved else None, "peak_source": pk["which"] + " bf16/fp16 sustained",
                      "traffic": ncu_summary.get(dom + "_dram_bytes_per_launch"),
                      "how": "sum of algorithmic FLOPs (2*Cin*Cout*k^3*V_out per layer) / sum of CUDA-event durations of that family's launches inside the timed steps",
+                     "lowest": {"kernel": low, "achieved": fams[low]["achieved_tflops"], "frac": fams[low]["frac"],
+                                "ms_per_step": fams[low]["ms_per_step"]},
+                     "whole_step": {"tensor_gflop_per_step": tensor_gflop, "achieved": tensor_gflop / 1e3 / (ms / args.steps / 1e3),
+                                    "frac": tensor_gflop / 1e3 / (ms / args.steps / 1e3) / pk["tf_sustained"],
+                                    "what": "algorithmic conv FLOPs of one micro-batch / the device-timed step (everything included)"},
                      "families": fams},
     }
+    line["inference"]["roofline"] = {"gflop_per_window": 573.56, "achieved": 573.56 / 1e3 / (inf_ms / n_inf / 1e3), "unit": "TFLOP/s",
+                                     "frac": 573.56 / 1e3 / (inf_ms / n_inf / 1e3) / pk["tf_sustained"]}
+    line.update(extras)
+    if world == 1 and not args.no_gpu_baseline:
+        gb = gpu_baseline(args.steps)
+        line["gpu_baseline"] = gb
+        try:
+            line["gpu_baseline"]["ratio_train_e2e"] = e2e_value / gb["train"]["value"]
+            line["gpu_baseline"]["ratio_inference_resident"] = line["inference"]["value"] / gb["inference"]["value"]
+            line["gpu_baseline"]["ratio_inference_e2e"] = line["inference"]["e2e"]["value"] / gb["inference"]["e2e"]["value"]
+        except Exception:
+            pass
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cb = cpu_reference_step(1, 0)
+            cb = cpu_reference_step(3, 1, budget_s=30.0)
             if cb:
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"]["augmentation_port"] = cpu_augmentation_port_seconds()
         except Exception as ex:  # the baseline is reported, never fatal
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
     emit(line)

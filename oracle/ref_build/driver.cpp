@@ -18,6 +18,7 @@
 //   time  : time forward or a full step on CPU (or cuda when available), print one JSON line
 #include <torch/torch.h>
 #include <ATen/Parallel.h>
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -88,6 +89,13 @@ std::string read_text(const std::string& path) {
     std::stringstream ss;
     ss << in.rdbuf();
     return ss.str();
+}
+
+// -1 = leave libtorch's defaults (cuDNN convolutions may use TF32), 0 = strict fp32, 1 = allow TF32 everywhere
+void set_tf32(int mode) {
+    if (mode < 0) return;
+    at::globalContext().setAllowTF32CuDNN(mode != 0);
+    at::globalContext().setAllowTF32CuBLAS(mode != 0);
 }
 
 struct StepFlags {
@@ -176,6 +184,14 @@ int cmd_dump(const Args& a) {
     fl.dice = a.i("dice", 1) != 0;
     fl.mse = a.i("mse", 1) != 0;
     fl.collapse = int(a.i("collapse", 0));
+    // --device cuda: the SAME reference code on libtorch CUDA + cuDNN (what the north star calls "the reference's own libtorch
+    // implementation"); dump defaults to strict fp32 (--tf32 0) so that it is an fp32 oracle at full-grid sizes in seconds
+    torch::Device dev(a.s("device", "cpu") == "cuda" ? torch::kCUDA : torch::kCPU);
+    if (dev.is_cuda() && !torch::cuda::is_available()) throw std::runtime_error("--device cuda: no CUDA device");
+    set_tf32(int(a.i("tf32", 0)));
+    if (a.has("threads")) at::set_num_threads(int(a.i("threads", 1)));
+    const int logits_levels = int(a.i("logits_levels", 99));   // how many levels' logits to write (full-grid dumps are large)
+    const bool write_after = a.i("write_after", 1) != 0;
 
     auto params = model->parameters();
     if (a.has("params_in")) {
@@ -212,9 +228,10 @@ int cmd_dump(const Args& a) {
 
     if (!train) {
         // evaluate.cpp:223-230 — forward only (NoGradGuard), all heads dumped; the caller uses [0].
-        if (eval_mode) model->prepare_for_inference(torch::kCPU);
+        if (eval_mode) model->prepare_for_inference(dev);
+        else model->to(dev);
         torch::NoGradGuard ng;
-        auto in = torch::from_blob(in_all.data(), {1, in_c, D, H, W}, torch::kFloat32).clone();
+        auto in = torch::from_blob(in_all.data(), {1, in_c, D, H, W}, torch::kFloat32).clone().to(dev);
         if (a.i("dump_acts", 0)) {
             // restated forward (unet.cpp:168-193) with per-level taps, for layer-level debugging
             std::vector<torch::Tensor> skips(model->encoding.size() - 1);
@@ -234,11 +251,13 @@ int cmd_dump(const Args& a) {
         auto outs = model->forward(in);
         man << " \"logits\": [";
         for (size_t k = 0; k < outs.size(); ++k) {
-            write_tensor(outdir + "/logits_" + std::to_string(k) + ".bin", outs[k]);
+            if (int(k) < logits_levels) write_tensor(outdir + "/logits_" + std::to_string(k) + ".bin", outs[k]);
             man << (k ? "," : "") << shape_json(outs[k]);
         }
         man << "]\n}\n";
     } else {
+        model->to(dev);
+        params = model->parameters();
         model->train();
         model->create_optimizer(float(lr0));
         man << " \"losses\": [";
@@ -246,15 +265,20 @@ int cmd_dump(const Args& a) {
             const double lr = lr0 * std::pow(1.0 - double(s) / total_steps, 0.9);  // train.cpp:566
             torch::Tensor logged_sum;
             for (int b = 0; b < batch; ++b) {
-                auto in = torch::from_blob(in_all.data() + size_t(b) * in_c * vox, {1, in_c, D, H, W}, torch::kFloat32).clone();
-                auto tg = torch::from_blob(lab_all.data() + size_t(b) * vox, {1, D, H, W}, torch::kFloat32).clone().to(torch::kLong);
+                auto in = torch::from_blob(in_all.data() + size_t(b) * in_c * vox, {1, in_c, D, H, W}, torch::kFloat32).clone().to(dev);
+                auto tg = torch::from_blob(lab_all.data() + size_t(b) * vox, {1, D, H, W}, torch::kFloat32).clone().to(torch::kLong).to(dev);
                 std::vector<torch::Tensor> logits, lv;
                 auto e = micro_batch(model, in, tg, fl, &logits, &lv, true);
                 logged_sum = logged_sum.defined() ? logged_sum + e : e;
                 if (s == 0 && b == 0) {
-                    for (size_t k = 0; k < logits.size(); ++k)
+                    for (size_t k = 0; k < logits.size() && int(k) < logits_levels; ++k)
                         write_tensor(outdir + "/logits_" + std::to_string(k) + ".bin", logits[k]);
                     write_tensor(outdir + "/level_losses.bin", torch::stack(lv));
+                }
+                if (s == 0) {   // every micro-batch's level losses of the first step (gradient accumulation cases)
+                    char nm[64];
+                    std::snprintf(nm, sizeof nm, "/level_losses_mb%02d.bin", b);
+                    write_tensor(outdir + nm, torch::stack(lv));
                 }
             }
             auto logged = (logged_sum / double(batch)).contiguous();
@@ -270,7 +294,7 @@ int cmd_dump(const Args& a) {
             update(model, batch, lr);
         }
         man << "]\n}\n";
-        for (size_t i = 0; i < params.size(); ++i) {
+        for (size_t i = 0; write_after && i < params.size(); ++i) {
             char nm[64];
             std::snprintf(nm, sizeof nm, "/param_after_%03zu.bin", i);
             write_tensor(outdir + nm, params[i]);
@@ -291,28 +315,50 @@ int cmd_time(const Args& a) {
     const std::string mode = a.s("mode", "fwd");
     const int steps = int(a.i("steps", 3)), warmup = int(a.i("warmup", 1)), batch = int(a.i("batch", 1));
     torch::Device dev(a.s("device", "cpu") == "cuda" ? torch::kCUDA : torch::kCPU);
+    if (dev.is_cuda() && !torch::cuda::is_available()) throw std::runtime_error("--device cuda: no CUDA device");
+    const int tf32 = int(a.i("tf32", -1));
+    set_tf32(tf32);
     StepFlags fl;
     torch::manual_seed(1);
     auto in = torch::rand({1, in_c, D, H, W});
     auto tg = torch::randint(0, std::max(out_c, 1), {1, D, H, W}, torch::kLong);
     std::vector<double> ms;
+    double resident_ms = -1.0;
+    // --budget_s: stop taking timed steps once this much wall time has been spent on them (the reported "steps" is what ran)
+    const double budget_s = a.f("budget_s", 1e30);
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto over_budget = [&]() {
+        return !ms.empty() && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() > budget_s;
+    };
     if (mode == "fwd") {
         model->prepare_for_inference(dev);
         torch::NoGradGuard ng;
-        for (int s = 0; s < warmup + steps; ++s) {
+        for (int s = 0; s < warmup + steps && !over_budget(); ++s) {
             auto t0 = std::chrono::steady_clock::now();
             // evaluate.cpp:226-229: H2D, forward()[0], D2H
             auto r = model->forward(in.to(dev))[0].to(torch::kCPU).contiguous();
             auto t1 = std::chrono::steady_clock::now();
             if (s >= warmup) ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
         }
+        if (dev.is_cuda()) {   // the same forward with the window resident in device memory (no H2D / D2H)
+            auto in_dev = in.to(dev);
+            torch::cuda::synchronize();
+            auto t0 = std::chrono::steady_clock::now();
+            for (int s = 0; s < steps; ++s) auto r = model->forward(in_dev)[0];
+            torch::cuda::synchronize();
+            resident_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / steps;
+        }
     } else {
         model->to(dev);
         model->train();
         model->create_optimizer(1e-3f);
-        for (int s = 0; s < warmup + steps; ++s) {
+        for (int s = 0; s < warmup + steps && !over_budget(); ++s) {
             auto t0 = std::chrono::steady_clock::now();
-            for (int b = 0; b < batch; ++b) micro_batch(model, in.to(dev), tg.to(dev), fl, nullptr, nullptr, true);
+            for (int b = 0; b < batch; ++b) {
+                // train.cpp:615-626: every micro-batch is uploaded from host memory; the logged losses come back (train.cpp:675-681)
+                auto logged = micro_batch(model, in.to(dev), tg.to(dev), fl, nullptr, nullptr, true);
+                logged.to(torch::kCPU);
+            }
             update(model, batch, 1e-3);
             if (dev.is_cuda()) torch::cuda::synchronize();
             auto t1 = std::chrono::steady_clock::now();
@@ -321,10 +367,12 @@ int cmd_time(const Args& a) {
     }
     double sum = 0;
     for (double m : ms) sum += m;
+    std::sort(ms.begin(), ms.end());
     std::printf("{\"mode\": \"%s\", \"threads\": %d, \"dim\": [%ld,%ld,%ld], \"in_c\": %d, \"out_c\": %d, \"batch\": %d, "
-                "\"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.3f, \"device\": \"%s\"}\n",
-                mode.c_str(), threads, long(W), long(H), long(D), in_c, out_c, batch, steps, warmup, sum / ms.size(),
-                dev.is_cuda() ? "cuda" : "cpu");
+                "\"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.3f, \"ms_median\": %.3f, \"ms_resident\": %.3f, \"device\": \"%s\", "
+                "\"tf32\": %d, \"cudnn_tf32\": %d, \"torch\": \"%s\"}\n",
+                mode.c_str(), threads, long(W), long(H), long(D), in_c, out_c, batch, int(ms.size()), warmup, sum / ms.size(), ms[ms.size() / 2],
+                resident_ms, dev.is_cuda() ? "cuda" : "cpu", tf32, int(at::globalContext().allowTF32CuDNN()), TORCH_VERSION);
     return 0;
 }
 

@@ -27,3 +27,9 @@ def bootstrap_nccl(pkg, dist_mod, world, rank):
     comm = ctypes.c_void_p()
     pkg.check(pkg.lib().unet3d_nccl_comm_init(ctypes.byref(comm), world, rank, ids[0]))
     return comm
+
+
+def shard_windows(n_windows, world, rank):
+    """Indices of the inference windows (evaluate.cpp:223-230 iterates model_io[i]) that `rank` forwards: window i -> rank
+    i % world.  No collective: every rank writes its own windows' outputs and the host gathers them."""
+    return [i for i in range(n_windows) if i % world == rank]
