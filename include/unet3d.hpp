@@ -43,7 +43,8 @@ struct UNet3d {
     void get_parameter(int i, float* host) { check(unet3d_get_param(h_, i, host)); }
     void set_parameter(int i, const float* host) { check(unet3d_set_param(h_, i, host)); }
 
-    void train(bool on = true) { check(unet3d_set_mode(h_, on ? 1 : 0)); }           // unet.hpp:58-62
+    void train(bool on = true) { check(unet3d_set_mode(h_, on ? 1 : 2)); }           // unet.hpp:58-62 (train(false) == eval())
+    void eval() { check(unet3d_set_mode(h_, 2)); }
     void prepare_for_inference() { check(unet3d_set_mode(h_, 0)); }                   // unet.cpp:7-22
     void create_optimizer(float learning_rate) { check(unet3d_create_optimizer(h_, learning_rate)); }  // unet.cpp:246-277
     void copy_from(const UNet3d& r) {                                                 // unet.cpp:195-222

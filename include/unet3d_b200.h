@@ -69,9 +69,12 @@ int unet3d_get_momentum(unet3d_t* h, int i, float* host);  /* SGD momentum_buffe
 int unet3d_set_momentum(unet3d_t* h, int i, const float* host);
 int unet3d_init_params(unet3d_t* h, uint64_t seed);        /* torch's default init rule, own RNG stream */
 
-/* train(bool) (unet.hpp:58-62) / prepare_for_inference (unet.cpp:7-22): training != 0 -> training mode;
- * 0 -> eval mode with every BatchNorm3d reduced to y = gamma*x + beta (running stats forced to (0,1), eps 0). */
-int unet3d_set_mode(unet3d_t* h, int training);
+/* train(bool) / eval() (unet.hpp:58-62) and prepare_for_inference (unet.cpp:7-22):
+ *   mode 1 = train(): BatchNorm3d uses batch statistics and updates running_mean / running_var (momentum 0.1, unbiased variance);
+ *   mode 2 = eval():  BatchNorm3d normalises with its running statistics, eps 0 (what the validation replica runs, train.cpp:836);
+ *   mode 0 = prepare_for_inference(): eval() + every BatchNorm3d reset to running_mean 0 / running_var 1, i.e. y = gamma*x + beta.
+ * InstanceNorm3d always uses the statistics of the sample. */
+int unet3d_set_mode(unet3d_t* h, int mode);
 
 /* forward(Tensor{1,in,D,H,W}) -> vector<Tensor> (unet.hpp:51, unet.cpp:168-193).  out_levels[k] receives
  * results[k] ({1,out,D>>k,H>>k,W>>k}); only the first n_levels heads are computed (inference uses
@@ -84,11 +87,16 @@ int unet3d_evaluate_windows(unet3d_t* h, const float* const* in_windows, float* 
 /* one N=1 micro-batch of the training step body, train.cpp:628-706: forward, calc_losses on every
  * deep-supervision level (train.cpp:501-552), level weights (1/2^k)/sum, backward.  Gradients ACCUMULATE
  * across calls until unet3d_step.  loss_out = level-0 {ce, dice, mse} (what the reference logs,
- * train.cpp:675-681); all_level_losses (optional) = 3 floats per level. */
+ * train.cpp:675-681); all_level_losses (optional) = 3 floats per level.
+ * Limit of this build: the fused loss head holds one voxel's class vector in registers and supports out_count <= 32 (the reference
+ * has no such limit; its shipped models use 2..6 classes).  Larger models can be created, loaded and run through
+ * unet3d_forward / unet3d_evaluate_windows, but unet3d_train_microbatch / unet3d_validate fail with
+ * "loss head supports 1..32 output channels". */
 int unet3d_train_microbatch(unet3d_t* h, const float* in, const float* label, int collapse_before, int use_ce, int use_dice,
                             int use_mse, float loss_out[3], float* all_level_losses, int where);
 
-/* validation forward + level-0 calc_losses, no gradient (train.cpp:826-851) */
+/* validation forward + level-0 calc_losses, no gradient (train.cpp:826-851).  Runs with eval() semantics whatever the handle's mode
+ * (BatchNorm3d reads its running statistics, nothing is updated). */
 int unet3d_validate(unet3d_t* h, const float* in, const float* label, int collapse_before, float loss_out[3], int where);
 
 /* create_optimizer(lr) (unet.cpp:246-277): SGD momentum .99, Nesterov, weight decay 3e-5 | 0 groups */
@@ -136,6 +144,11 @@ int unet3d_vpa_augment(unet3d_t* h, const char* const* keys, const float* vals, 
  * and the local distortion foci (x, y, z, radius, magnitude; up to 12).  Any output pointer may be NULL. */
 int vpa_plan_describe(const char* const* keys, const float* vals, int n_opts, int is_label, int w, int h, int d, int channels,
                       uint64_t seed, float M12[12], float persp3[3], int* nfoci, float* foci5);
+
+/* host only: the Perlin background of the same plan (visual_perception_augmentation.cpp:386-418): returns through *applies whether
+ * the stage runs for (options, seed); perm512 = the permutation std::shuffle(p, std::mt19937(seed)) produced, zoom = its drawn zoom. */
+int vpa_plan_perlin(const char* const* keys, const float* vals, int n_opts, int is_label, int w, int h, int d, int channels,
+                    uint64_t seed, int* applies, int* perm512, float* zoom);
 
 /* train.cpp:459-473 + 615-706 in one call: upload the RAW sample once (host pointers, label = float-stored integers), run
  * visual_perception_augmentation on it in HBM (is_label = 1) and feed the result straight into the micro-batch.  Saves the

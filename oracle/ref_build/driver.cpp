@@ -293,7 +293,20 @@ int cmd_dump(const Args& a) {
             }
             update(model, batch, lr);
         }
-        man << "]\n}\n";
+        man << "]";
+        if (a.i("validate", 0)) {
+            // train.cpp:834-840: output_model->eval(); calc_losses(forward(test_in)[0], test_out, out_count) under NoGradGuard
+            torch::NoGradGuard ng;
+            model->eval();
+            auto in = torch::from_blob(in_all.data(), {1, in_c, D, H, W}, torch::kFloat32).clone().to(dev);
+            auto tg = torch::from_blob(lab_all.data(), {1, D, H, W}, torch::kFloat32).clone().to(torch::kLong).to(dev);
+            auto out0 = model->forward(in)[0];
+            auto [ce, dice, mse] = calc_losses(out0, tg, model->out_count);
+            man << ",\n \"validate\": [" << ce.item<float>() << "," << dice.item<float>() << "," << mse.item<float>() << "]";
+            write_tensor(outdir + "/validate_logits_0.bin", out0);
+            write_tensor(outdir + "/validate_losses.bin", torch::stack({ce, dice, mse}));
+        }
+        man << "\n}\n";
         for (size_t i = 0; write_after && i < params.size(); ++i) {
             char nm[64];
             std::snprintf(nm, sizeof nm, "/param_after_%03zu.bin", i);

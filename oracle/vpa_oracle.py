@@ -19,9 +19,11 @@ The CUDA path (unet-studio_b200/csrc/vpa.cu) is tested for exact agreement with 
 Unspecified in the reference itself (C++ argument evaluation order): the three draws of random_location and the
 (location, radius, magnitude) draws of create_distortion_at are taken left to right.
 Deliberate deviations, shared with the CUDA path and documented in DESIGN.md:
-  * per-voxel noise uses a counter-based hash of (seed, index) instead of a sequential mt19937 stream (the
+  * per-voxel noise: by default a counter-based hash of (seed, index); the library option noise_mt19937 = 1 selects the reference
+    CPU path's sequential mt19937 stream bit for bit (noise_field_mt19937).  The default stays the hash (the
     reference's own CUDA path already differs from its CPU path there: curand_init(0,index,0), .cu:64-73);
-  * std::shuffle of the Perlin permutation (implementation-defined) = Fisher-Yates driven by mt19937(seed);
+  * std::shuffle of the Perlin permutation is implementation-defined: restated from libstdc++ 13 (std_shuffle below), which is what
+    the library's host plan calls;
   * a distortion focus voxel itself (length 0, 0/0 in the reference) gets no displacement.
 """
 from __future__ import annotations
@@ -91,6 +93,19 @@ def hash32(x):
     x *= np.uint32(0x846CA68B)
     x ^= x >> np.uint32(16)
     return x
+
+
+def noise_field_mt19937(seed, n, mag):
+    """The reference CPU path's noise stream (visual_perception_augmentation.cpp:252-258): ONE tipl::uniform_dist<float>(0, mag, seed)
+    [TIPL: std::mt19937(seed) + std::uniform_real_distribution<float>] drawn once per voxel, channel after channel.  libstdc++:
+    u = float(word) / 2^32 (clipped below 1), value = (mag - 0) * u + 0, all in float32.  Raw words from numpy's MT19937 with the
+    classic init_genrand seeding (checked against the MT19937 class above in tests/test_vpa_plan_cpu.py)."""
+    bg = np.random.MT19937()
+    bg._legacy_seeding(int(seed) & 0xFFFFFFFF)
+    words = bg.random_raw(n).astype(np.uint32)
+    u = words.astype(F) / F(4294967296.0)
+    u = np.where(u >= F(1.0), np.nextafter(F(1.0), F(0.0)), u).astype(F)
+    return (F(mag) * u).astype(F)
 
 
 def noise_field(seed, n):
@@ -201,13 +216,47 @@ def perlin(x, y, z, p):
     return _lerp(w, y1, y2).astype(F)
 
 
-def perlin_table(seed):
-    p = [i & 255 for i in range(512)]
-    g = MT19937(seed)
-    for i in range(511, 0, -1):
-        j = g() % (i + 1)
+def _lemire_u32(g, rng_range):
+    """libstdc++ >= 11 uniform_int_distribution over a 32-bit engine: Lemire's nearly-divisionless method (bits/uniform_int_dist.h,
+    _S_nd<uint64_t>): uniform integer in [0, rng_range)."""
+    product = g() * rng_range
+    low = product & 0xFFFFFFFF
+    if low < rng_range:
+        threshold = ((1 << 32) - rng_range) % rng_range
+        while low < threshold:
+            product = g() * rng_range
+            low = product & 0xFFFFFFFF
+    return product >> 32
+
+
+def std_shuffle(p, g):
+    """std::shuffle(first, last, std::mt19937) as implemented by libstdc++ 13 (bits/stl_algo.h): because the engine's range (2^32-1)
+    divided by the element count is >= the element count, swap positions are produced TWO per distribution call
+    (__gen_two_uniform_ints: x = uniform[0, b0*b1), (x / b1, x % b1)).  std::shuffle is implementation-defined; the library's host
+    plan calls the real std::shuffle of the same libstdc++, this is its restatement."""
+    n = len(p)
+    if n == 0:
+        return p
+    assert 0xFFFFFFFF // n >= n
+    i = 1
+    if n % 2 == 0:
+        j = _lemire_u32(g, 2)
         p[i], p[j] = p[j], p[i]
+        i += 1
+    while i != n:
+        swap_range = i + 1
+        x = _lemire_u32(g, swap_range * (swap_range + 1))
+        a, b = x // (swap_range + 1), x % (swap_range + 1)
+        p[i], p[a] = p[a], p[i]
+        i += 1
+        p[i], p[b] = p[b], p[i]
+        i += 1
     return p
+
+
+def perlin_table(seed):
+    """visual_perception_augmentation.cpp:388-392: p[i] = i & 255, std::shuffle(p, std::mt19937(seed))."""
+    return std_shuffle([i & 255 for i in range(512)], MT19937(seed))
 
 
 def augment(options, image, label, is_label, shape, seed, trace=None):
@@ -268,7 +317,10 @@ def augment(options, image, label, is_label, shape, seed, trace=None):
             lab[:bot] = 0; img[:, :bot] = 0
     # ---- noise (:252-258)
     if apply("noise"):
-        img += (noise_field(seed, C * V) * opt("noise_mag")).reshape(C, D, H, W)
+        if opt("noise_mt19937") != 0:   # library option: the reference CPU path's sequential stream instead of the counter-based hash
+            img += noise_field_mt19937(seed, C * V, opt("noise_mag")).reshape(C, D, H, W)
+        else:
+            img += (noise_field(seed, C * V) * opt("noise_mag")).reshape(C, D, H, W)
     # ---- lighting (:260-277)
     if apply("ambient"):
         img += rng(0.0, 1.0) * opt("ambient_mag")
@@ -378,6 +430,8 @@ def augment(options, image, label, is_label, shape, seed, trace=None):
         if apply("perlin_texture"):
             p = perlin_table(seed)
             zoom = rng(0.005, 0.05)
+            if trace is not None:
+                trace.update(dict(perlin_perm=list(p), perlin_zoom=zoom))
             bg = np.zeros((D, H, W), F)
             for octave in range(4):
                 po = F(0.5 ** octave)

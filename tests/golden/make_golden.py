@@ -35,6 +35,10 @@ CASES = [
          ce=1, dice=1, mse=0, collapse=2, invalid_labels=False),
     dict(name="f2_train", feature=F2, in_c=1, out_c=2, dim=(24, 16, 16), batch=1, train=1, steps=1,
          ce=1, dice=0, mse=1, collapse=0, invalid_labels=False),
+    # BatchNorm3d in true eval mode: 3 training steps move the running statistics, then the validation forward + level-0 losses
+    # (train.cpp:834-840: output_model->eval(), NoGradGuard) on the first sample
+    dict(name="f2_validate", feature=F2, in_c=1, out_c=2, dim=(24, 16, 16), batch=1, train=1, steps=3, validate=1,
+         ce=1, dice=1, mse=1, collapse=0, invalid_labels=False),
     dict(name="f2_eval", feature=F2, in_c=1, out_c=2, dim=(24, 16, 16), batch=1, train=0, steps=0, eval=1,
          ce=1, dice=1, mse=1, collapse=0, invalid_labels=False),
     dict(name="f1_fwd", feature=F1, in_c=2, out_c=3, dim=(24, 16, 32), batch=1, train=0, steps=0, eval=1, dump_acts=1,
@@ -61,7 +65,10 @@ def synth(rng, in_c, out_c, dim, batch, invalid):
 
 def main():
     subprocess.check_call(["bash", os.path.join(ROOT, "oracle", "build_ref.sh")])
+    only = set(sys.argv[1:])
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         rng = np.random.default_rng(abs(hash(case["name"])) % (2 ** 31) if False else sum(map(ord, case["name"])))
         feature = case["feature"].format(out=case["out_c"])
         ins, labs = synth(rng, case["in_c"], case["out_c"], case["dim"], case["batch"], case["invalid_labels"])
@@ -76,7 +83,7 @@ def main():
                    "--steps", str(max(case["steps"], 1)), "--total_steps", "10", "--lr", "0.01",
                    "--ce", str(case["ce"]), "--dice", str(case["dice"]), "--mse", str(case["mse"]),
                    "--collapse", str(case["collapse"]), "--eval", str(case.get("eval", 0)),
-                   "--dump_acts", str(case.get("dump_acts", 0))]
+                   "--dump_acts", str(case.get("dump_acts", 0)), "--validate", str(case.get("validate", 0))]
             subprocess.check_call(cmd)
             man = json.load(open(os.path.join(td, "manifest.json")))
             out = dict(feature=np.array(feature), input=ins, label=labs,
@@ -95,6 +102,9 @@ def main():
             if case["train"]:
                 out["level_losses"] = np.fromfile(os.path.join(td, "level_losses.bin"), np.float32).reshape(-1, 3)
                 out["logged_losses"] = np.array(man["losses"], np.float32)
+            if case.get("validate"):
+                out["validate_losses"] = np.fromfile(os.path.join(td, "validate_losses.bin"), np.float32)
+                out["validate_logits_0"] = np.fromfile(os.path.join(td, "validate_logits_0.bin"), np.float32)
             for f in os.listdir(td):
                 if f.startswith("act_"):
                     out[f[:-4]] = np.fromfile(os.path.join(td, f), np.float32)

@@ -349,3 +349,54 @@ def test_training_trajectory_tracks_oracle_over_12_steps():
         assert np.allclose(ours, ref, rtol=0, atol=1e-3), (s, ours, ref)   # measured: 4.6e-5 over the 12 steps
     print("12-step trajectory: max |loss - oracle loss| =", worst, "final", ours, ref)
     assert ours[0] < 0.6 * 0.7          # it actually trained (ce well below ln 2)
+
+
+def test_validate_uses_running_statistics_like_the_reference():
+    """unet3d_validate (train.cpp:826-851) after 3 training steps of the BatchNorm net: the reference binary ran eval() + forward()[0]
+    + calc_losses on the first sample (golden f2_validate).  Checks both the handle in training mode (validate must not touch the
+    running statistics) and a copy_from replica in eval() mode (the reference's output_model)."""
+    m = load()
+    z, meta = golden("f2_validate")
+    net = build_from_golden(m, z, meta)
+    net.train(True)
+    net.create_optimizer(meta["lr"])
+    x, lab = z["input"][0:1], z["label"][0:1]
+    for s in range(meta["steps"]):
+        net.train_microbatch(x, lab, meta["collapse"], meta["ce"], meta["dice"], meta["mse"])
+        net.step(1, m.poly_lr(meta["lr"], s, meta["total_steps"]))
+        assert not net.last_step_skipped()
+    v1 = net.validate(x, lab)
+    v2 = net.validate(x, lab)
+    assert np.array_equal(v1, v2), "validate must not change the running statistics"
+    print("validate losses", v1, "reference", z["validate_losses"])
+    np.testing.assert_allclose(v1, z["validate_losses"], rtol=0, atol=3e-3)
+    twin = m.UNet3d(meta["in_c"], meta["out_c"], str(z["feature"]))
+    twin.copy_from(net)            # parameters AND buffers (unet.cpp:195-222)
+    twin.eval()
+    out0 = twin.forward(x, n_levels=1)[0]
+    e = rel(out0, z["validate_logits_0"])
+    print("eval() replica logits rel err", e)
+    assert e < 1e-2, e
+    np.testing.assert_allclose(twin.validate(x, lab), v1, rtol=0, atol=1e-5)
+    # prepare_for_inference resets the buffers: the same replica now gives y = gamma*x + beta
+    twin.prepare_for_inference()
+    out_inf = twin.forward(x, n_levels=1)[0]
+    assert rel(out_inf, z["validate_logits_0"]) > 1e-2
+
+
+def test_validate_default_net_matches_oracle_level0_losses():
+    m = load()
+    W, H, D = 64, 96, 64
+    feature = O.default_feature(2)
+    onet = O.parse_feature(1, 2, feature)
+    P = O.init_params(onet, 4)
+    img, lab = synth_volume(W, H, D, seed=6)
+    net = m.UNet3d(1, 2, feature)
+    net.load_parameters([p.numpy() for p in P])
+    net.set_dim(W, H, D)
+    v = net.validate(img, lab)
+    with torch.no_grad():
+        out0 = O.forward(onet, P, torch.from_numpy(img))[0]
+        ref = torch.stack(O.calc_losses(out0, torch.from_numpy(lab).long(), 2, 0)).numpy()
+    print("validate", v, "oracle", ref)
+    np.testing.assert_allclose(v, ref, rtol=0, atol=2e-3)

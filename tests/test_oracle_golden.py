@@ -80,6 +80,29 @@ def test_step_matches_reference(name):
         assert rel(P[i].numpy(), z[f"after_{i:03d}"]) < 2e-5, (name, i, net.param_names[i])
 
 
+def test_validation_forward_uses_running_statistics():
+    """f2_validate: 3 training steps move the BatchNorm3d running statistics; the validation forward (eval(), NoGradGuard,
+    train.cpp:834-840) then normalises with them.  Pins the oracle's eval mode to the reference binary's output."""
+    z, meta = load("f2_validate")
+    torch.set_num_threads(4)
+    net = O.parse_feature(meta["in_c"], meta["out_c"], str(z["feature"]))
+    n = len(net.param_shapes)
+    P = [torch.from_numpy(z[f"param_{i:03d}"].copy()) for i in range(n)]
+    mom = [None] * n
+    bn = O.init_bn_state(net)
+    x = torch.from_numpy(z["input"][0:1].copy())
+    t = torch.from_numpy(z["label"][0:1].copy()).to(torch.long)
+    for s in range(meta["steps"]):
+        logged, _, _ = O.train_step(net, P, mom, [x], [t], O.poly_lr(meta["lr"], s, meta["total_steps"]), meta["ce"], meta["dice"],
+                                    meta["mse"], meta["collapse"], bn_state=bn)
+        np.testing.assert_allclose(logged.numpy(), z["logged_losses"][s], rtol=2e-4, atol=2e-6)
+    with torch.no_grad():
+        out0 = O.forward(net, P, x, training=False, bn_state=bn)[0]
+        ce, dice, mse = O.calc_losses(out0, t, net.out_count, 0)
+    assert rel(out0.numpy().ravel(), z["validate_logits_0"]) < 5e-5
+    np.testing.assert_allclose(torch.stack([ce, dice, mse]).numpy(), z["validate_losses"], rtol=2e-4, atol=2e-6)
+
+
 def test_parser_errors_match_reference():
     # messages from unet.cpp:53,66,88,117
     with pytest.raises(RuntimeError, match="invalid u-net structure"):

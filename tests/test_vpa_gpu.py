@@ -144,3 +144,26 @@ def test_prefetched_samples_equal_the_fused_call_and_come_out_in_order():
     np.testing.assert_allclose(np.array(got), np.array(ref), rtol=5e-4, atol=5e-5)
     with pytest.raises(m.U3DError, match="no prefetched sample"):
         m.train_microbatch_prefetched(nets[1])
+
+
+def test_mt19937_noise_stream_is_the_reference_cpu_stream():
+    """Library option noise_mt19937 = 1: the noise added per voxel is the reference CPU path's sequential stream
+    (visual_perception_augmentation.cpp:252-258: one uniform_dist<float>(0, noise_mag, seed) drawn voxel after voxel, channel after
+    channel) generated on the GPU in 624-word blocks.  With every other stage off and the identity warp the output is
+    (img + noise) / max per channel, so the stream is checked bit for bit up to the final normalisation."""
+    m = load()
+    W, H, D, C = 24, 20, 16, 2          # 7680 voxels per channel: 12.3 generator blocks per channel, the stream crosses the channel border
+    img, lab = phantom(W, H, D, C, seed=2)
+    o = {"scaling_up": 1.0, "scaling_down": 1.0, "aspect_ratio": 1.0, "noise": 4, "noise_mag": 0.2, "noise_mt19937": 1}
+    seed = 77
+    out_i, out_l = m.vpa_augment(img, lab, o, True, seed)
+    noise = VO.noise_field_mt19937(seed, C * W * H * D, 0.2).reshape(C, D, H, W)
+    want = img + noise
+    want = np.stack([w / w.max() for w in want]).astype(np.float32)
+    np.testing.assert_allclose(out_i, want, rtol=0, atol=1.2e-7)
+    np.testing.assert_array_equal(out_l, lab)
+    ref_i, _ = VO.augment(o, img, lab, True, (W, H, D), seed)
+    np.testing.assert_allclose(out_i, ref_i, rtol=0, atol=1e-6)
+    # and the default (hash) stream is a different one
+    o2 = dict(o); o2["noise_mt19937"] = 0
+    assert np.abs(m.vpa_augment(img, lab, o2, True, seed)[0] - out_i).max() > 1e-3

@@ -52,3 +52,44 @@ def test_unknown_keys_read_as_zero_and_channel_limit():
     assert len(foci) == 0 and (persp == 0).all()
     with pytest.raises(m.U3DError, match="channels"):
         describe(m, {}, 16, 16, 16, 9, 0)
+
+
+@pytest.mark.parametrize("seed", [1, 3, 7, 12345])
+def test_perlin_permutation_is_std_shuffle(seed):
+    """visual_perception_augmentation.cpp:388-392 shuffles the Perlin table with std::shuffle(p, std::mt19937(seed)).  The host plan
+    calls the real std::shuffle; the oracle restates libstdc++'s algorithm (pairs of swap positions per draw, Lemire's bounded
+    integers).  Both must produce the same permutation and the same zoom draw behind it."""
+    m = load()
+    W, H, D = 20, 24, 16
+    rng = np.random.default_rng(seed)
+    img = rng.random((1, D, H, W), dtype=np.float32)
+    lab = (rng.random((D, H, W)) > 0.5).astype(np.float32)
+    options = dict(VO.OPTION_DEFAULTS)
+    options["perlin_texture"] = 4
+    tr = {}
+    VO.augment(options, img, lab, True, (W, H, D), seed, trace=tr)
+    keys = [k.encode() for k in options]
+    karr = (ctypes.c_char_p * len(keys))(*keys)
+    varr = (ctypes.c_float * len(keys))(*[float(v) for v in options.values()])
+    perm = (ctypes.c_int * 512)()
+    applies = ctypes.c_int(0)
+    zoom = ctypes.c_float(0)
+    m.check(m.lib().vpa_plan_perlin(karr, varr, len(keys), 1, W, H, D, 1, ctypes.c_uint64(seed), ctypes.byref(applies), perm,
+                                    ctypes.byref(zoom)))
+    assert applies.value == 1
+    assert list(perm) == tr["perlin_perm"]
+    assert sorted(perm) == sorted(i & 255 for i in range(512))
+    assert zoom.value == np.float32(tr["perlin_zoom"])
+
+
+def test_oracle_mt19937_words_and_uniform_float_match_the_scalar_restatement():
+    """noise_field_mt19937 takes its raw words from numpy's MT19937 (legacy init_genrand seeding); they must be std::mt19937's
+    words (restated scalar class MT19937, known answer: the 10000th output of mt19937(5489) is 4123659995, ISO C++ [rand.predef])."""
+    g = VO.MT19937(5489)
+    for _ in range(9999):
+        g()
+    assert g() == 4123659995
+    for seed in (0, 1, 77, 2 ** 31 + 5):
+        ud = VO.UniformDist(0.0, 0.2, seed)
+        want = np.array([ud() for _ in range(1500)], np.float32)     # crosses two 624-word regenerations
+        np.testing.assert_array_equal(VO.noise_field_mt19937(seed, 1500, 0.2), want)

@@ -171,8 +171,8 @@ int unet3d_init_params(unet3d_t* h, uint64_t seed) {
     GUARD_END
 }
 
-int unet3d_set_mode(unet3d_t* h, int training) {
-    GUARD_BEGIN NEED(h) return h->m->set_mode(training);
+int unet3d_set_mode(unet3d_t* h, int mode) {
+    GUARD_BEGIN NEED(h) return h->m->set_mode(mode);
     GUARD_END
 }
 
@@ -212,9 +212,18 @@ int unet3d_step(unet3d_t* h, int batch_size, double lr, void* nccl_comm) {
     GUARD_END
 }
 
-double unet3d_last_grad_norm(const unet3d_t* h) { return h && h->m ? h->m->last_grad_norm : -1.0; }
-int unet3d_last_step_skipped(const unet3d_t* h) { return h && h->m ? h->m->last_step_skipped : -1; }
-float unet3d_loss_scale(const unet3d_t* h) { return h && h->m ? h->m->loss_scale : -1.f; }
+double unet3d_last_grad_norm(const unet3d_t* h) {
+    if (!h || !h->m || h->m->resolve_status()) return -1.0;
+    return h->m->last_grad_norm;
+}
+int unet3d_last_step_skipped(const unet3d_t* h) {
+    if (!h || !h->m || h->m->resolve_status()) return -1;
+    return h->m->last_step_skipped;
+}
+float unet3d_loss_scale(const unet3d_t* h) {
+    if (!h || !h->m || h->m->resolve_status()) return -1.f;
+    return h->m->loss_scale;
+}
 int unet3d_set_loss_scale(unet3d_t* h, float s) {
     if (!h || !h->m) return 1;
     h->m->loss_scale = s;
@@ -267,15 +276,19 @@ static size_t sample_ws_need(int w, int h, int d, int channels) {
     return std::max(u3d::vpa_workspace_bytes(w, h, d, channels), u3d::simulate_workspace_bytes(w, h, d)) + stage;
 }
 
-static int ensure_model_ws(Model* m, size_t need) {
-    if (m->vpa_ws_bytes >= need) return 0;
+// Two workspaces per handle: one for the calls that run on the main stream, one for the prefetch stream (stream3), so a prefetch in
+// flight never shares scratch (displacement field, min/max cells, tissue planes) with a main-stream sample call.
+static int ensure_model_ws(Model* m, size_t need, bool prefetch = false) {
+    void*& ws = prefetch ? m->pf_ws : m->vpa_ws;
+    size_t& bytes = prefetch ? m->pf_ws_bytes : m->vpa_ws_bytes;
+    if (bytes >= need) return 0;
     cudaStreamSynchronize(m->stream);
     if (m->stream3) cudaStreamSynchronize(m->stream3);
-    if (m->vpa_ws) cudaFree(m->vpa_ws);
-    m->vpa_ws = nullptr;
-    m->vpa_ws_bytes = 0;
-    if (cudaMalloc(&m->vpa_ws, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
-    m->vpa_ws_bytes = need;
+    if (ws) cudaFree(ws);
+    ws = nullptr;
+    bytes = 0;
+    if (cudaMalloc(&ws, need) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+    bytes = need;
     return 0;
 }
 
@@ -306,11 +319,11 @@ static int sim_impl(float* t1w, const float* label, unsigned max_label, unsigned
 }
 
 // the fused / prefetched sample calls run simulate_modality first when the handle asks for it (train.cpp:459-462)
-static int sim_stage(Model* m, float* din, const float* dlab, uint64_t seed, cudaStream_t stream) {
+static int sim_stage(Model* m, float* din, const float* dlab, uint64_t seed, cudaStream_t stream, void* ws) {
     if (!m->sim_mode) return 0;
     if (m->in_count != 1) { set_error("simulate_modality needs a single-channel image"); return 1; }
     return sim_impl(din, m->sim_mode == 1 ? dlab : nullptr, unsigned(m->out_count), unsigned(seed), m->dim[0], m->dim[1], m->dim[2], 1,
-                    m->vpa_ws, stream, &m->launches);
+                    ws, stream, &m->launches);
 }
 
 static int vpa_impl(const char* const* keys, const float* vals, int n_opts, float* image, float* label, int is_label, int w, int h,
@@ -388,7 +401,7 @@ int unet3d_train_microbatch_augmented(unet3d_t* h, const char* const* keys, cons
         set_error("unet3d_train_microbatch_augmented: upload failed");
         return 1;
     }
-    if (sim_stage(m, din, dlab, seed, m->stream)) return 1;
+    if (sim_stage(m, din, dlab, seed, m->stream, m->vpa_ws)) return 1;
     if (vpa_impl(keys, vals, n_opts, din, dlab, 1, w, hgt, d, channels, seed, 1, m->vpa_ws, m->stream, &m->launches)) return 1;
     return m->train_microbatch(din, dlab, collapse_before, use_ce, use_dice, use_mse, loss_out3, nullptr, 1);
     GUARD_END
@@ -405,15 +418,15 @@ int unet3d_prefetch_augmented(unet3d_t* h, const char* const* keys, const float*
     if (m->prefetch_slot(&din, &dlab, &slot)) return 1;
     const int w = m->dim[0], hgt = m->dim[1], d = m->dim[2], channels = m->in_count;
     const size_t V = size_t(w) * hgt * d;
-    if (ensure_model_ws(m, sample_ws_need(w, hgt, d, channels))) return 1;
+    if (ensure_model_ws(m, sample_ws_need(w, hgt, d, channels), true)) return 1;
     const cudaMemcpyKind kind = where == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     if (cudaMemcpyAsync(din, image, size_t(channels) * V * 4, kind, m->stream3) != cudaSuccess ||
         cudaMemcpyAsync(dlab, label, V * 4, kind, m->stream3) != cudaSuccess) {
         set_error("unet3d_prefetch_augmented: copy failed");
         return 1;
     }
-    if (sim_stage(m, din, dlab, seed, m->stream3)) return 1;
-    if (vpa_impl(keys, vals, n_opts, din, dlab, 1, w, hgt, d, channels, seed, 1, m->vpa_ws, m->stream3, &m->launches)) return 1;
+    if (sim_stage(m, din, dlab, seed, m->stream3, m->pf_ws)) return 1;
+    if (vpa_impl(keys, vals, n_opts, din, dlab, 1, w, hgt, d, channels, seed, 1, m->pf_ws, m->stream3, &m->launches)) return 1;
     if (cudaEventRecord(m->ev_sample[slot], m->stream3) != cudaSuccess) { set_error("unet3d_prefetch_augmented: event"); return 1; }
     m->pf_mark(slot);
     return 0;
@@ -480,6 +493,19 @@ int vpa_plan_describe(const char* const* keys, const float* vals, int n_opts, in
             foci5[5 * f + 3] = plan.foci[f].radius;
             foci5[5 * f + 4] = plan.foci[f].mag;
         }
+    return 0;
+    GUARD_END
+}
+
+int vpa_plan_perlin(const char* const* keys, const float* vals, int n_opts, int is_label, int w, int h, int d, int channels,
+                    uint64_t seed, int* applies, int* perm512, float* zoom) {
+    GUARD_BEGIN
+    u3d::VpaPlan plan;
+    if (u3d::vpa_make_plan(keys, vals, n_opts, is_label, w, h, d, channels, seed, plan)) return 1;
+    if (applies) *applies = plan.perlin;
+    if (perm512 && plan.perlin)
+        for (int i = 0; i < 512; ++i) perm512[i] = int(plan.perm[i]);
+    if (zoom) *zoom = plan.perlin ? plan.zoom : 0.f;
     return 0;
     GUARD_END
 }

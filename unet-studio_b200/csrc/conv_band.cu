@@ -701,10 +701,15 @@ __global__ void pack_weights_band_kernel(const __grid_constant__ PackDesc d) {
                 if (d.band_taps[t].dz == oz && d.band_taps[t].dy == oy && d.band_taps[t].dx == ox) tap = t;
             const int s = ks < d.nch[0] ? 0 : 1;
             const int kk = (ks - (s ? d.nch[0] : 0)) * 16 + kg * 8 + k8;
-            if (tap >= 0 && kk < d.k_real[s] && nn < d.n_real) {
-                const int kidx = d.k_off[s] + kk, nidx = d.n_off + nn;
+            int kidx = 0, part = 0;
+            bool kok;
+            if (d.split_k > 0 && s == 0) { kok = kk < 3 * d.split_k; part = kk / d.split_k; kidx = d.k_off[0] + kk % d.split_k; }   // PackDesc::split_k
+            else { kok = kk < d.k_real[s]; kidx = d.k_off[s] + kk; }
+            if (tap >= 0 && kok && nn < d.n_real) {
+                const int nidx = d.n_off + nn;
                 const long long a = d.n_is_A ? nidx : kidx, b = d.n_is_A ? kidx : nidx;
                 v = d.w[(a * d.dimB + b) * d.ktaps + d.tap_ref[tap]];
+                if (part == 2) v -= __half2float(__float2half_rn(v));
             }
         }
         static_cast<__half*>(d.out)[i] = __float2half_rn(v);

@@ -89,6 +89,12 @@ __global__ void finalize_stats_kernel(const float* __restrict__ partials, int ro
     }
 }
 
+// BatchNorm3d in eval mode (running statistics, eps 0: unet.cpp:80-84): rstd[c] = 1/sqrt(running_var[c])
+__global__ void rstd_from_var_kernel(const float* __restrict__ var, float* __restrict__ rstd, int C, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) rstd[c] = rsqrtf(var[c] + eps);
+}
+
 // Generic two-value per-channel reduction over a [V][Cp] tensor.  MODE 0: (x, x^2).
 // MODE 1 (norm/act backward): dz = dy*act'(z), xhat = (x-mean)*rstd -> (dz, dz*xhat).
 struct ReduceArgs {
@@ -579,6 +585,12 @@ int finalize_stats_launch(const float* partials, int rows, int ntot, int C, doub
                           float* running_mean, float* running_var, float momentum, cudaStream_t s) {
     finalize_stats_kernel<<<(C * 32 + 127) / 128, 128, 0, s>>>(partials, rows, ntot, C, count, eps, mean, rstd, running_mean,
                                                           running_var, momentum);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int rstd_from_var_launch(const float* var, float* rstd, int C, float eps, cudaStream_t s) {
+    rstd_from_var_kernel<<<(C + 127) / 128, 128, 0, s>>>(var, rstd, C, eps);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -13,6 +13,8 @@ int channel_stats_launch(const void* x, long long V, int C, int Cp, float* parti
 // partial rows [rows][2][ntot] -> mean, rstd = 1/sqrt(var_biased + eps); optional BatchNorm running-stat update
 int finalize_stats_launch(const float* partials, int rows, int ntot, int C, double count, float eps, float* mean, float* rstd,
                           float* running_mean, float* running_var, float momentum, cudaStream_t s);
+// rstd[c] = 1/sqrt(var[c] + eps)  (BatchNorm3d eval mode with running statistics)
+int rstd_from_var_launch(const float* var, float* rstd, int C, float eps, cudaStream_t s);
 // y = act(gamma*(x-mean)*rstd + beta); mean/rstd may be null (affine only: BatchNorm eval after prepare_for_inference)
 int norm_act_fwd_launch(const void* x, void* y, long long V, int C, int Cp, int has_norm, int act, const float* mean,
                         const float* rstd, const float* gamma, const float* beta, cudaStream_t s);

@@ -9,6 +9,40 @@
 namespace u3d {
 namespace {
 
+// first-layer precision: the input as fp16 hi + lo pairs in the padded channels, [hi (C) | lo (C) | hi (C) | 0...]
+__global__ void pack_act_split_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int Cp, long long V) {
+    for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < V; vox += (long long)gridDim.x * blockDim.x) {
+        __align__(16) __half row[64];
+        for (int c = 0; c < Cp; ++c) row[c] = __float2half_rn(0.f);
+        for (int c = 0; c < C; ++c) {
+            const float x = in[(long long)c * V + vox];
+            const __half hi = __float2half_rn(x);
+            row[c] = hi;
+            row[C + c] = __float2half_rn(x - __half2float(hi));
+            row[2 * C + c] = hi;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + vox * Cp);
+        for (int q = 0; q < Cp / 8; ++q) dst[q] = reinterpret_cast<const uint4*>(row)[q];
+    }
+}
+
+// weight value of K index kk of source s for the pack kernels (PackDesc::split_k)
+__device__ __forceinline__ bool pack_k_lookup(const PackDesc& d, int s, int kk, int& kidx, int& part) {
+    part = 0;
+    if (d.split_k > 0 && s == 0) {
+        if (kk >= 3 * d.split_k) return false;
+        part = kk / d.split_k;
+        kidx = d.k_off[0] + kk % d.split_k;
+        return true;
+    }
+    if (kk >= d.k_real[s]) return false;
+    kidx = d.k_off[s] + kk;
+    return true;
+}
+__device__ __forceinline__ float pack_k_value(float w, int part) {
+    return part == 2 ? w - __half2float(__float2half_rn(w)) : w;
+}
+
 template <bool BF16>
 __global__ void pack_act_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, int Cp, long long V) {
     // thread = voxel: reads its C planar fp32 values (coalesced per channel plane), writes the whole padded NDHWC row (Cp * 2 bytes,
@@ -74,10 +108,11 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackDesc d) {
             nn = nn % d.stack_cp;
         }
         float v = 0.f;
-        if (ref >= 0 && kk < d.k_real[s] && nn < d.n_real) {
-            const int kidx = d.k_off[s] + kk, nidx = d.n_off + nn;
+        int kidx = 0, part = 0;
+        if (ref >= 0 && nn < d.n_real && pack_k_lookup(d, s, kk, kidx, part)) {
+            const int nidx = d.n_off + nn;
             const long long a = d.n_is_A ? nidx : kidx, b = d.n_is_A ? kidx : nidx;
-            v = d.w[(a * d.dimB + b) * d.ktaps + ref];
+            v = pack_k_value(d.w[(a * d.dimB + b) * d.ktaps + ref], part);
         }
         if (d.out_bf16)
             static_cast<__nv_bfloat16*>(d.out)[i] = __float2bfloat16_rn(v);
@@ -102,7 +137,13 @@ int pack_weights_launch(const PackDesc& d, cudaStream_t stream) {
     return 0;
 }
 
-int pack_act_launch(const float* in, void* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream) {
+int pack_act_launch(const float* in, void* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream, int split) {
+    if (split) {
+        if (bf16 || 3 * C > Cp || Cp > 64) { set_error("pack_act: split needs fp16 and 3*C <= Cp <= 64"); return 1; }
+        pack_act_split_kernel<<<grid_for(V, 256), 256, 0, stream>>>(in, static_cast<__half*>(out), C, Cp, V);
+        U3D_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     if (bf16)
         pack_act_kernel<true><<<grid_for(V, 256), 256, 0, stream>>>(in, static_cast<uint4*>(out), C, Cp, V);
     else

@@ -232,9 +232,10 @@ Model::Model(int in_c, int out_c, const std::string& feature, bool host_only_)
     cudaMalloc(&d_chunks, chunks.size() * sizeof(SgdChunk));
     cudaMemcpy(d_chunks, chunks.data(), chunks.size() * sizeof(SgdChunk), cudaMemcpyHostToDevice);
     cudaMalloc(&d_status, sizeof(SgdStatus));
-    cudaMalloc(&d_loss_acc, sizeof(double) * 8 * 80);
-    cudaMalloc(&d_loss_part, sizeof(float) * 8 * size_t(loss_part_rows()) * loss_part_cols());
-    cudaMalloc(&d_losses, sizeof(float) * 8 * 3 * 2);
+    const size_t nl = std::max<size_t>(output.size(), 1);   // per-level loss scratch, sized from the number of deep-supervision heads
+    cudaMalloc(&d_loss_acc, sizeof(double) * nl * 80);
+    cudaMalloc(&d_loss_part, sizeof(float) * nl * size_t(loss_part_rows()) * loss_part_cols());
+    cudaMalloc(&d_losses, sizeof(float) * nl * 3 * 2);
 }
 
 Model::~Model() {
@@ -248,9 +249,12 @@ Model::~Model() {
     if (stream4) { cudaStreamSynchronize(stream4); cudaStreamDestroy(stream4); }
     if (ev_ar_ready) cudaEventDestroy(ev_ar_ready);
     if (ev_ar_done) cudaEventDestroy(ev_ar_done);
+    if (ev_status) cudaEventDestroy(ev_status);
+    if (h_status) cudaFreeHost(h_status);
     free_plan();
     cudaFree(d_params); cudaFree(d_grads); cudaFree(d_mom);
     if (vpa_ws) cudaFree(vpa_ws);
+    if (pf_ws) cudaFree(pf_ws);
     for (auto b : d_buffers) cudaFree(b);
     cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_loss_part); cudaFree(d_losses);
     if (stream3) { cudaStreamSynchronize(stream3); cudaStreamDestroy(stream3); }
@@ -358,13 +362,23 @@ int Model::set_dim(int w, int h, int d) {
     return 0;
 }
 
-int Model::set_mode(int train) {
-    if ((train != 0) != training) {
-        cudaSetDevice(device);
+int Model::set_mode(int mode) {
+    if (mode < 0 || mode > 2) { set_error("set_mode: 0 = prepare_for_inference, 1 = train, 2 = eval"); return 1; }
+    const bool train = mode == 1;
+    cudaSetDevice(device);
+    if (train != training) {
         cudaStreamSynchronize(stream);
         free_plan();
     }
-    training = train != 0;
+    training = train;
+    bn_running = mode == 2;
+    if (mode == 0) {   // unet.cpp:14-21: running_mean.zero_(), running_var.fill_(1)
+        for (size_t i = 0; i < d_buffers.size(); ++i) {
+            std::vector<float> h(size_t(buffer_len[i]), (i & 1) ? 1.f : 0.f);
+            M_CUDA(cudaMemcpyAsync(d_buffers[i], h.data(), h.size() * 4, cudaMemcpyHostToDevice, stream));
+            M_CUDA(cudaStreamSynchronize(stream));
+        }
+    }
     return 0;
 }
 
@@ -480,6 +494,7 @@ int Model::build_steps() {
                 const bool next_norm = i + 1 < blk.mods.size() &&
                                        (blk.mods[i + 1].kind == ModuleDef::NORM || (blk.mods[i + 1].kind == ModuleDef::BNORM && training));
                 s.stats = next_norm && !g.transposed;
+                s.drop_bias = head_level < 0 && i + 1 < blk.mods.size() && blk.mods[i + 1].kind == ModuleDef::NORM;
                 if (head_level >= 0) {
                     if (blk.mods.size() != 1) { fail = true; why = "the output token must be a single conv"; break; }
                     s.head_level = head_level;
@@ -538,6 +553,14 @@ int Model::build_steps() {
         if (!fail && !tail[l].mods.empty()) cur = run_block(tail[l], cur, -1, -1);
     }
     if (fail) { set_error(why); return 1; }
+    // first-layer precision: when every consumer of the network input is a conv reading it as its first source and
+    // the padded channels have room, the input is stored as fp16 hi + lo pairs and the consumer's weights are packed to match
+    static const bool no_split = std::getenv("U3D_NO_SPLIT_INPUT") != nullptr;
+    split_input = !no_split && 3 * in_count <= tens[0].Cp;
+    for (const Step& s : steps) {
+        if (s.in1 == 0) split_input = false;
+        if (s.in0 == 0 && s.kind != Step::CONV) split_input = false;
+    }
     return 0;
 }
 
@@ -608,13 +631,14 @@ int Model::ensure_plan() {
                 s.fpacks[i].w = param_ptr(s.p_w);
                 s.fpacks[i].out = blob;
                 s.fpacks[i].out_bf16 = 0;
+                if (split_input && s.in0 == 0) s.fpacks[i].split_k = in_count;
                 ConvProblem& P = s.fprobs[i];
                 P.src0 = tens[s.in0].p;
                 P.c0p = tens[s.in0].Cp;
                 if (s.in1 >= 0) { P.src1 = tens[s.in1].p; P.c1p = tens[s.in1].Cp; }
                 P.dst = s.head_level >= 0 ? static_cast<void*>(logits[s.head_level]) : tens[s.out].p;
                 P.wpack = blob;
-                P.bias = param_ptr(s.p_b);
+                P.bias = s.drop_bias ? nullptr : param_ptr(s.p_b);
             }
             if (tr) {
                 void* dy = s.head_level >= 0 ? dlogits[s.head_level] : tens[s.out].grad;
@@ -702,7 +726,7 @@ int Model::repack() {
 // ------------------------------------------------------------------------------------------------
 // forward (unet.cpp:168-193)
 // ------------------------------------------------------------------------------------------------
-int Model::run_forward(int levels_wanted) {
+int Model::run_forward(int levels_wanted, bool bn_eval) {
     for (auto& s : steps) {
         if (s.kind == Step::CONV) {
             if (s.head_level >= levels_wanted) continue;
@@ -728,7 +752,12 @@ int Model::run_forward(int levels_wanted) {
             const Ten& a = tens[s.in0];
             const float* gamma = s.norm ? param_ptr(s.p_g) : nullptr;
             const float* beta = s.norm ? param_ptr(s.p_g + 1) : nullptr;
-            if (s.norm == 1 || (s.norm == 2 && training)) {
+            if (s.norm == 2 && (bn_eval || bn_running)) {
+                // eval(): y = gamma*(x - running_mean)/sqrt(running_var) + beta, eps 0 (unet.cpp:80-84; validation, train.cpp:836)
+                M_CHECK(rstd_from_var_launch(d_buffers[s.buf0 + 1], s.rstd, a.C, 0.f, stream));
+                M_CHECK(norm_act_fwd_launch(a.p, tens[s.out].p, a.V(), a.C, a.Cp, 1, s.act, d_buffers[s.buf0], s.rstd, gamma, beta, stream));
+                launches += 2;
+            } else if (s.norm == 1 || (s.norm == 2 && training)) {
                 int rows = last_stat_rows, ntot = last_stat_ntot;
                 if (!s.stats_from_conv) {
                     M_CHECK(channel_stats_launch(a.p, a.V(), a.C, a.Cp, d_partials, &rows, stream));
@@ -766,7 +795,7 @@ int Model::upload_input(const float* in, int where) {
         M_CUDA(cudaMemcpyAsync(d_in_f32, in, size_t(in_count) * V0 * 4, cudaMemcpyHostToDevice, stream));
         src = d_in_f32;
     }
-    M_CHECK(pack_act_launch(src, tens[0].p, in_count, tens[0].Cp, V0, false, stream));
+    M_CHECK(pack_act_launch(src, tens[0].p, in_count, tens[0].Cp, V0, false, stream, split_input ? 1 : 0));
     ++launches;
     return 0;
 }
@@ -836,7 +865,7 @@ int Model::evaluate_windows(const float* const* in_windows, float* const* out_wi
         const int s = i & 1;
         if (i + 1 < n_windows) upload(i + 1);
         cudaStreamWaitEvent(stream, ev_up[s], 0);
-        rc = pack_act_launch(ew_in[s], tens[0].p, in_count, tens[0].Cp, V0, false, stream);
+        rc = pack_act_launch(ew_in[s], tens[0].p, in_count, tens[0].Cp, V0, false, stream, split_input ? 1 : 0);
         ++launches;
         cudaEventRecord(ev_packed[s], stream);
         if (!rc) rc = run_forward(1);
@@ -966,6 +995,7 @@ int Model::run_backward() {
 int Model::train_microbatch(const float* in, const float* label, int collapse_before, int use_ce, int use_dice, int use_mse,
                             float* loss_out3, float* all_levels, int where) {
     if (!training) { set_error("train_microbatch needs training mode (unet3d_set_mode(h, 1))"); return 1; }
+    M_CHECK(resolve_status());   // the loss scale may change with the last update's overflow flag
     M_CHECK(ensure_plan());
     M_CHECK(repack());
     const int L = int(output.size());
@@ -1082,7 +1112,7 @@ int Model::validate(const float* in, const float* label, int collapse_before, fl
         M_CUDA(cudaMemcpyAsync(d_label, label, size_t(V0) * 4, cudaMemcpyHostToDevice, stream));
         lab = d_label;
     }
-    M_CHECK(run_forward(1));
+    M_CHECK(run_forward(1, true));   // output_model->eval() (train.cpp:836): BatchNorm3d reads its running statistics, nothing is updated
     LossLevel Q{};
     Q.logits = logits[0]; Q.label = lab; Q.dlogits = nullptr;
     Q.C = out_count; Q.Cp = pad16(out_count); Q.collapse_before = collapse_before;

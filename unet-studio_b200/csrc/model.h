@@ -47,6 +47,8 @@ struct Step {
     LayerGeom g{};
     int p_w = -1, p_b = -1;
     bool stats = false;        // epilogue emits the statistics of the norm that follows
+    bool drop_bias = false;    // InstanceNorm3d follows: the bias is not added (the norm removes any per-channel constant and the bias
+                               // gradient is exactly zero), so the fp16 raw output is not rounded relative to an information-free offset
     std::vector<ConvProblem> fprobs;
     std::vector<PackDesc> fpacks;
     int fkc = 0;
@@ -83,6 +85,7 @@ class Model {
     int dim[3] = {192, 224, 192};  // W, H, D
     float voxel_size[3] = {1.f, 1.f, 1.f};
     bool training = true;
+    bool bn_running = false;       // eval() without prepare_for_inference: BatchNorm3d normalises with its running statistics (eps 0)
 
     std::vector<BlockDef> encoding, decoding, output, tail;
     std::vector<ParamInfo> params;
@@ -135,6 +138,8 @@ class Model {
     long long launches = 0;          // kernels launched by this handle (bench "gpu_launches")
     void* vpa_ws = nullptr;          // augmentation workspace (unet3d_vpa_augment)
     size_t vpa_ws_bytes = 0;
+    void* pf_ws = nullptr;           // the same for the prefetch stream (unet3d_prefetch_augmented)
+    size_t pf_ws_bytes = 0;
     int sim_mode = 0;                // simulate_modality before augmentation in the fused / prefetched sample calls: 0 off, 1 labelled, 2 image only
 
     int init_params(uint64_t seed);
@@ -142,7 +147,7 @@ class Model {
     int set_param(int i, const float* host);
     int set_momentum(int i, const float* host);
     int set_dim(int w, int h, int d);
-    int set_mode(int train);
+    int set_mode(int mode);   // 1 train(), 0 prepare_for_inference() (BatchNorm buffers reset to (0,1)), 2 eval() (running statistics)
     // where: 0 = host pointers, 1 = device pointers
     int forward(const float* in, float* const* out_levels, int n_levels, int where);
     int train_microbatch(const float* in, const float* label, int collapse_before, int use_ce, int use_dice, int use_mse,
@@ -173,7 +178,11 @@ class Model {
     void prof_end(cudaStream_t on = nullptr);
     int prof_read(double out[18], int reset);  // per kind: {ms, launches, algorithmic FLOPs}
     int n_levels() const { return int(output.size()); }
-    bool planned_for_pack() const { return planned && !packs_dirty; }   // blobs exist and hold the pre-update weights
+    bool planned_for_pack_blobs() const { return planned; }   // the plan's weight blobs exist
+    int resolve_status();            // waits for the last update's status read-back (lazy; see step.cpp)
+    SgdStatus* h_status = nullptr;   // pinned
+    cudaEvent_t ev_status = nullptr;
+    bool status_pending = false;
 
   private:
     std::vector<Ten> tens;
@@ -184,6 +193,7 @@ class Model {
     std::vector<int> head_step;      // per level: index of the head conv in `steps` (-1 = none)
     bool planned = false, planned_training = false;
     bool packs_dirty = true;
+    bool split_input = false;        // network input stored as fp16 [hi | lo | hi] in the padded channels (PackDesc::split_k)
     float* d_in_f32 = nullptr;
     float* d_label = nullptr;
     float* d_partials = nullptr;
@@ -208,7 +218,7 @@ class Model {
     int alloc(void** p, size_t bytes);
     int repack();
     int repack_on(cudaStream_t s);
-    int run_forward(int levels_wanted);
+    int run_forward(int levels_wanted, bool bn_eval = false);   // bn_eval: BatchNorm3d uses (and does not update) its running statistics
     int run_backward();
     int upload_input(const float* in, int where);
     float* param_ptr(int i) { return d_params + params[i].offset; }

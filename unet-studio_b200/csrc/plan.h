@@ -25,6 +25,9 @@ struct PackDesc {
     int banded;              // 1: x-banded layout of conv_band.cu ([9 (dz,dy)][K chunk][kx 2,1,0,zero][band_co])
     int band_co;
     ConvTap band_taps[27];   // the problem's tap offsets (which reference tap each (dz,dy,dx) offset reads)
+    int split_k;             // > 0 (first layer of the network, source 0 only): K channel kk = g*split_k + c carries reference input channel c;
+                             // g = 0, 1: fp16(w), g = 2: fp16(w - fp16(w)).  With the input packed as [hi | lo | hi] (pack_act_launch split = 1) the
+                             // layer computes w_hi*x_hi + w_hi*x_lo + w_lo*x_hi = w*x to ~22 bits in the spare padded channels
 };
 size_t pack_bytes_band(const PackDesc& d);
 int pack_weights_band_launch(const PackDesc& d, cudaStream_t stream);
@@ -32,7 +35,8 @@ size_t pack_bytes(const PackDesc& d);
 int pack_weights_launch(const PackDesc& d, cudaStream_t stream);
 
 // NCDHW fp32 (reference order, train.cpp:619-621) <-> NDHWC 16-bit with channels zero-padded to Cp
-int pack_act_launch(const float* in, void* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream);
+// split != 0 (needs 3*C <= Cp): channels [0,C) = fp16(x), [C,2C) = fp16(x - fp16(x)), [2C,3C) = fp16(x) again (see PackDesc::split_k)
+int pack_act_launch(const float* in, void* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream, int split = 0);
 int unpack_act_launch(const void* in, float* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream);
 
 struct LayerGeom {

@@ -32,19 +32,55 @@ int Model::attach_comm(void* comm, int microbatches_per_step) {
     return 0;
 }
 
+// The status of an update (pre-clip gradient norm, overflow flag) is read back lazily: Model::step only enqueues the copy into pinned
+// host memory; the first caller that needs it (the next micro-batch for its loss scale, the next step, or the accessors) waits.
+int Model::resolve_status() {
+    if (!status_pending) return 0;
+    cudaSetDevice(device);
+    if (cudaEventSynchronize(ev_status) != cudaSuccess) { set_error("step: status read-back failed"); return 1; }
+    status_pending = false;
+    const unsigned int code = read_device_error();
+    if (code) { set_error("device pipeline timeout code " + std::to_string(code)); return 1; }
+    const SgdStatus& st = *h_status;
+    last_grad_norm = std::sqrt(st.sumsq);
+    last_step_skipped = (st.nonfinite != 0 || !std::isfinite(st.sumsq)) ? 1 : 0;
+    if (loss_scale_max == 0.f) loss_scale_max = loss_scale;
+    if (last_step_skipped) {
+        loss_scale = std::max(1.0f, loss_scale / 16.0f);   // fp16 gradient overflow: drop the scale, the update was skipped on the device
+        good_steps = 0;
+    } else {
+        mom_initialized = true;
+        if (++good_steps >= 500 && loss_scale < loss_scale_max) { loss_scale *= 2.0f; good_steps = 0; }
+    }
+    return 0;
+}
+
 int Model::step(int batch_size, double lr, void* nccl_comm) {
     if (!optimizer_created) { set_error("create_optimizer has not been called"); return 1; }
     if (batch_size < 1) { set_error("batch_size must be >= 1"); return 1; }
     cudaSetDevice(device);
-    if (loss_scale == 0.f) { set_error("step called before any micro-batch"); return 1; }
+    if (resolve_status()) return 1;
+    if (dp_comm != nullptr && nccl_comm != nullptr && nccl_comm != dp_comm) {
+        set_error("unet3d_step: the communicator differs from the one given to unet3d_attach_comm");
+        return 1;
+    }
+    // a rank that ran no micro-batch in this step (batch_size < world: the reference uses min(gpus, batch) workers, train.cpp:592) still
+    // takes part in the collectives with its zero gradients
+    if (loss_scale == 0.f && ensure_plan()) return 1;
+    if (dp_tail_reduced && cudaStreamWaitEvent(stream, ev_ar_done, 0) != cudaSuccess) { set_error("step: event"); return 1; }
     if (nccl_comm != nullptr) {
-        // the tail bucket may already have been reduced on stream4 during the backward pass (Model::run_backward)
-        const size_t count = dp_tail_reduced ? size_t(dp_split) : size_t(flat_n);
-        if (count) {
-            ncclResult_t r = ncclAllReduce(d_grads, d_grads, count, ncclFloat, ncclSum, static_cast<ncclComm_t>(nccl_comm), stream);
-            if (r != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(r)); return 1; }
-        }
-        if (dp_tail_reduced && cudaStreamWaitEvent(stream, ev_ar_done, 0) != cudaSuccess) { set_error("step: event"); return 1; }
+        // every rank issues the SAME collective sequence whatever it did in its backward passes.  Attached handles: tail bucket
+        // [dp_split, flat_n) then prefix [0, dp_split); the tail may already be in flight on stream4 (Model::run_backward).  A rank that
+        // declared more micro-batches than it ran reduces the tail here.  Un-attached handles: one all-reduce of the whole buffer.
+        ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
+        const bool split = dp_comm != nullptr && dp_split_step >= 0 && dp_split > 0 && dp_split < flat_n;
+        ncclResult_t r = ncclSuccess;
+        if (split) {
+            if (!dp_tail_reduced) r = ncclAllReduce(d_grads + dp_split, d_grads + dp_split, size_t(flat_n - dp_split), ncclFloat, ncclSum, comm, stream);
+            if (r == ncclSuccess) r = ncclAllReduce(d_grads, d_grads, size_t(dp_split), ncclFloat, ncclSum, comm, stream);
+        } else
+            r = ncclAllReduce(d_grads, d_grads, size_t(flat_n), ncclFloat, ncclSum, comm, stream);
+        if (r != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(r)); return 1; }
     }
     dp_tail_reduced = false;
     dp_seen = 0;
@@ -53,31 +89,24 @@ int Model::step(int batch_size, double lr, void* nccl_comm) {
                         d_status, stream))
         return 1;
     launches += 2;
+    if (!h_status) {
+        if (cudaMallocHost(reinterpret_cast<void**>(&h_status), sizeof(SgdStatus)) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_status, cudaEventDisableTiming) != cudaSuccess) { set_error("step: pinned status"); return 1; }
+    }
+    if (cudaMemcpyAsync(h_status, d_status, sizeof(SgdStatus), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaEventRecord(ev_status, stream) != cudaSuccess) { set_error("step: status copy"); return 1; }
+    status_pending = true;
     // re-pack the fp16 weight blobs right away on the side stream: ordered after the update, overlapping whatever the main stream does
-    // next (read-back below, the next sample's upload and augmentation); the next forward joins it (Model::repack)
+    // next (the next sample's upload and augmentation); the next forward joins it (Model::repack).  A skipped update (gradient
+    // overflow) leaves the weights unchanged, so the re-pack is then merely redundant.
     static const bool no_side = std::getenv("U3D_ONE_STREAM") != nullptr;
-    bool async_pack = false;
-    if (planned_for_pack() && stream2 != nullptr && !no_side) {
+    packs_dirty = true;
+    if (planned_for_pack_blobs() && stream2 != nullptr && !no_side) {
         if (cudaEventRecord(ev_fork, stream) != cudaSuccess || cudaStreamWaitEvent(stream2, ev_fork, 0) != cudaSuccess) { set_error("step: event"); return 1; }
         if (repack_on(stream2)) return 1;
         if (cudaEventRecord(ev_pack, stream2) != cudaSuccess) { set_error("step: event"); return 1; }
         pack_pending = true;
-        async_pack = true;
-    }
-    SgdStatus st{};
-    cudaError_t e = cudaMemcpyAsync(&st, d_status, sizeof(st), cudaMemcpyDeviceToHost, stream);
-    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return 1; }
-    if (sync()) return 1;
-    last_grad_norm = std::sqrt(st.sumsq);
-    last_step_skipped = (st.nonfinite != 0 || !std::isfinite(st.sumsq)) ? 1 : 0;
-    if (loss_scale_max == 0.f) loss_scale_max = loss_scale;
-    if (last_step_skipped) {
-        loss_scale = std::max(1.0f, loss_scale / 16.0f);   // fp16 gradient overflow: drop the scale, skip this update
-        good_steps = 0;
-    } else {
-        mom_initialized = true;
-        if (++good_steps >= 500 && loss_scale < loss_scale_max) { loss_scale *= 2.0f; good_steps = 0; }
-        packs_dirty = !async_pack;
+        packs_dirty = false;
     }
     return 0;
 }

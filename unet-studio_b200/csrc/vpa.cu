@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <algorithm>
 #include <random>
 #include <string>
 #include <vector>
@@ -124,7 +125,7 @@ int vpa_make_plan(const char* const* keys, const float* vals, int n_opts, int is
         float b = one() * 0.5f;
         P.bot = int(std::fabs(b * float(D)));
     }
-    if (apply("noise")) { P.noise = 1; P.noise_mag = opt("noise_mag"); }
+    if (apply("noise")) { P.noise = 1; P.noise_mag = opt("noise_mag"); P.noise_mt = opt("noise_mt19937") != 0.f ? 1 : 0; }
     if (apply("ambient")) { P.ambient = 1; P.ambient_add = range(0.0f, 1.0f) * opt("ambient_mag"); }
     if (apply("diffuse")) {
         P.diffuse = 1;
@@ -197,11 +198,8 @@ int vpa_make_plan(const char* const* keys, const float* vals, int n_opts, int is
         if (apply("perlin_texture")) {
             P.perlin = 1;
             for (int i = 0; i < 512; ++i) P.perm[i] = i & 255;
-            std::mt19937 g(seed);
-            for (int i = 511; i > 0; --i) {
-                const uint32_t j = uint32_t(g()) % uint32_t(i + 1);
-                std::swap(P.perm[i], P.perm[j]);
-            }
+            // the reference's own call (visual_perception_augmentation.cpp:392); this host code is built against the same libstdc++
+            std::shuffle(P.perm, P.perm + 512, std::mt19937(uint32_t(seed)));
             P.zoom = range(0.005f, 0.05f);
             P.perlin_upper = range(0.0f, 1.0f) * opt("perlin_texture_mag");
         }
@@ -277,8 +275,47 @@ __global__ void k_scale(const float* __restrict__ src, float* __restrict__ dst, 
     }
 }
 
+// std::mt19937(seed) output words 0..n-1 (tempered), for the bit-exact noise stream of the reference CPU path
+// (visual_perception_augmentation.cpp:254-257: ONE uniform_dist drawn voxel after voxel, channel after channel).  The recurrence is
+// sequential across 624-word blocks; inside a block word i needs the OLD words i, i+1 and, for i < 227, the old word i+397, else the
+// NEW word i-227: three dependent phases [0,227) [227,454) [454,624) of one CTA.  ~1.2 ms for a 160x192x160 volume on the prefetch
+// stream; the default noise is the counter-based hash (no sequential dependency).
+__global__ void __launch_bounds__(256) k_mt19937_words(uint32_t* __restrict__ out, long long n, uint32_t seed) {
+    __shared__ uint32_t mt[624];
+    __shared__ uint32_t nw[624];
+    if (threadIdx.x == 0) {
+        mt[0] = seed;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + uint32_t(i);
+    }
+    __syncthreads();
+    auto twist = [](uint32_t a, uint32_t b) {
+        const uint32_t y = (a & 0x80000000u) | (b & 0x7FFFFFFFu);
+        return (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+    };
+    const int t = threadIdx.x;
+    for (long long base = 0; base < n; base += 624) {
+        if (t < 227) nw[t] = mt[t + 397] ^ twist(mt[t], mt[t + 1]);
+        __syncthreads();
+        if (t < 227) nw[227 + t] = nw[t] ^ twist(mt[227 + t], mt[228 + t]);
+        __syncthreads();
+        if (t < 169) nw[454 + t] = nw[227 + t] ^ twist(mt[454 + t], mt[455 + t]);
+        else if (t == 169) nw[623] = nw[396] ^ twist(mt[623], nw[0]);
+        __syncthreads();
+        for (int i = t; i < 624; i += 256) {
+            uint32_t y = nw[i];
+            mt[i] = y;
+            y ^= y >> 11;
+            y ^= (y << 7) & 0x9D2C5680u;
+            y ^= (y << 15) & 0xEFC60000u;
+            y ^= y >> 18;
+            if (base + i < n) out[base + i] = y;
+        }
+        __syncthreads();
+    }
+}
+
 // crop / truncation / noise / ambient / diffuse / specular, in the reference's order, in place
-__global__ void k_pre(float* __restrict__ img, float* __restrict__ lab, const __grid_constant__ VpaPlan P) {
+__global__ void k_pre(float* __restrict__ img, float* __restrict__ lab, const uint32_t* __restrict__ mt_words, const __grid_constant__ VpaPlan P) {
     const long long V = 1LL * P.W * P.H * P.D;
     const uint32_t key = hash32(P.seed);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
@@ -310,7 +347,12 @@ __global__ void k_pre(float* __restrict__ img, float* __restrict__ lab, const __
             float v = img[c * V + i];
             if (c == 0 && crop_hit) v = P.crop_value;
             if (trunc) v = 0.f;
-            if (P.noise) {
+            if (P.noise && P.noise_mt) {
+                // libstdc++ uniform_real_distribution<float>(0, mag): u = float(word) / 2^32 clipped below 1, value = mag * u
+                float u = __fmul_rn(__uint2float_rn(mt_words[c * V + i]), 2.3283064365386963e-10f);
+                if (u >= 1.0f) u = 0.99999994f;
+                v = __fadd_rn(v, __fmul_rn(P.noise_mag, u));
+            } else if (P.noise) {
                 const uint32_t h = hash32(uint32_t(c * V + i) ^ key);
                 v += float(h >> 8) * (1.0f / 16777216.0f) * P.noise_mag;
             }
@@ -581,7 +623,13 @@ int vpa_run(const VpaPlan& P, float* image, float* label, void* workspace, cudaS
     } else
         U3D_CUDA_CHECK(cudaMemcpyAsync(wimg, image, size_t(C) * V * 4, cudaMemcpyDeviceToDevice, s));
     if (P.crop || P.trunc || P.noise || P.ambient || P.diffuse || P.specular) {
-        k_pre<<<vgrid(V), 256, 0, s>>>(wimg, wlab, P);
+        uint32_t* mt_words = nullptr;
+        if (P.noise && P.noise_mt) {   // `out` is not written before k_warp: stage the C*V generator words there
+            mt_words = reinterpret_cast<uint32_t*>(out);
+            k_mt19937_words<<<1, 256, 0, s>>>(mt_words, C * V, P.seed);
+            ++nl;
+        }
+        k_pre<<<vgrid(V), 256, 0, s>>>(wimg, wlab, mt_words, P);
         ++nl;
     }
     k_warp<<<vgrid(V), 256, 0, s>>>(wimg, wlab, out, olab, chmax, P);

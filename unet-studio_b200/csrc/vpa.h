@@ -21,6 +21,7 @@ struct VpaPlan {
     float crop_value;
     int trunc, top, bot;
     int noise;
+    int noise_mt;          // library option noise_mt19937: the reference CPU path's sequential std::mt19937 stream (bit-exact) instead of the hash
     float noise_mag;
     int ambient;
     float ambient_add;

@@ -116,12 +116,19 @@ class UNet3d:
         self.dim = (int(w), int(h), int(d))
 
     def train(self, on=True):
+        """unet.hpp:58-62: train(False) is eval() (BatchNorm3d reads its running statistics)."""
         from . import check
-        check(self._lib.unet3d_set_mode(self._h, 1 if on else 0))
+        check(self._lib.unet3d_set_mode(self._h, 1 if on else 2))
 
     def prepare_for_inference(self):
-        """unet.cpp:7-22."""
-        self.train(False)
+        """unet.cpp:7-22 (eval + every BatchNorm3d reset to running_mean 0 / running_var 1)."""
+        from . import check
+        check(self._lib.unet3d_set_mode(self._h, 0))
+
+    def eval(self):
+        """torch Module::eval(): BatchNorm3d normalises with its tracked running statistics (the validation replica, train.cpp:836)."""
+        from . import check
+        check(self._lib.unet3d_set_mode(self._h, 2))
 
     # ---- forward / training ----
     def _level_shape(self, k):
