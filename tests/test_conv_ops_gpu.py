@@ -30,14 +30,14 @@ CASES = [
     ("k3s2_odd_dims", 0, 3, 2, 16, 0, 24, (15, 9, 7)),
     ("ct_64_32_odd", 1, 2, 2, 64, 0, 32, (7, 5, 3)),
     ("k3s1_320", 0, 3, 1, 32, 0, 320, (8, 8, 4)),
-    # >= 32768 voxels, K,N <= 32: these go through the halo-block kernel (conv_halo.cu), incl. ragged tile edges
-    ("halo_16_16", 0, 3, 1, 16, 0, 16, (40, 36, 28)),
-    ("halo_cat16_16", 0, 3, 1, 16, 16, 16, (64, 32, 20)),
-    ("halo_32_32", 0, 3, 1, 32, 0, 32, (36, 40, 24)),
-    ("halo_1_16", 0, 3, 1, 1, 0, 16, (48, 32, 24)),
-    ("halo_cat16_16_to32", 0, 3, 1, 12, 9, 24, (33, 35, 30)),
-    ("halo_cat32_32_k64", 0, 3, 1, 32, 32, 32, (40, 28, 30)),
-    ("halo_64_16_k64", 0, 3, 1, 64, 0, 16, (34, 33, 31)),
+    # >= 32768 voxels, K <= 64, N <= 32: the x-banded kernel (conv_band.cu; K = 64 as two passes), incl. ragged tile edges
+    ("big_16_16", 0, 3, 1, 16, 0, 16, (40, 36, 28)),
+    ("big_cat16_16", 0, 3, 1, 16, 16, 16, (64, 32, 20)),
+    ("big_32_32", 0, 3, 1, 32, 0, 32, (36, 40, 24)),
+    ("big_1_16", 0, 3, 1, 1, 0, 16, (48, 32, 24)),
+    ("big_cat16_16_to32", 0, 3, 1, 12, 9, 24, (33, 35, 30)),
+    ("big_cat32_32_k64", 0, 3, 1, 32, 32, 32, (40, 28, 30)),
+    ("big_64_16_k64", 0, 3, 1, 64, 0, 16, (34, 33, 31)),
     # x-banded kernel (conv_band.cu) and N-stacked wgrad (conv_wgrad_band.cu): ragged tiles in x, y and z chunks
     ("band_16_16_ragged", 0, 3, 1, 16, 0, 16, (37, 29, 33)),
     ("band_32_32_ragged", 0, 3, 1, 32, 0, 32, (41, 30, 27)),
@@ -147,7 +147,29 @@ def test_opt_in_z_stacked_band_kernel_matches_too():
     if os.environ.get("U3D_ZBAND"):
         pytest.skip("already inside the child run")
     env = dict(os.environ, U3D_ZBAND="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k", "k3s1_16_16 or k3s1_1_16 or halo_16_16 or halo_1_16 or band_16_16_ragged or band_5_20"],
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k", "k3s1_16_16 or k3s1_1_16 or big_16_16 or big_1_16 or band_16_16_ragged or band_5_20"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+def test_fallback_kernels_under_the_debug_switches():
+    """The generic gather kernel (conv_igemm) and the generic split-K weight gradient (conv_wgrad) are what remains when a problem is
+    not eligible for the specialised kernels (or the driver lacks cuTensorMapEncodeTiled).  With U3D_NO_BAND / U3D_NO_S2 / U3D_NO_TMA /
+    U3D_NO_WBAND set (read once per process) every case of this file must still pass through them: a representative subset here."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("U3D_NO_TMA"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, U3D_NO_BAND="1", U3D_NO_S2="1", U3D_NO_TMA="1", U3D_NO_WBAND="1")
+    pick = "k3s1_16_16 or k3s1_cat32_32 or k3s2_16_32 or k3s1_64_64 or k1_256_6 or ct_32_16 or ct_64_32_odd or k3s2_odd_dims or big_cat16_16_to32 or band_5_20 or s2_9_24_odd"
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k", "(test_conv_forward or test_conv_backward) and (" + pick + ")"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+    # and with only the TMA kernel removed the banded / s2 kernels keep running next to the gather fallback
+    env = dict(os.environ, U3D_NO_TMA="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k", "test_conv_forward and (k3s1_64_64 or k3s2_128_256 or ct_256_256 or s2_32_64_tma)"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -93,7 +93,7 @@ extern "C" int u3d_op_conv_forward(int transposed, int ks, int stride, int cin0,
     std::vector<ConvProblem> probs;
     std::vector<PackDesc> packs;
     int kc = 0;
-    plan_forward(g, probs, packs, kc, (!planar_fp32 && (conv_halo_wants_kc16(ks, stride, transposed, pad16(cin0) + (cin1 ? pad16(cin1) : 0), pad16(cout), Vout) ||
+    plan_forward(g, probs, packs, kc, (!planar_fp32 && (conv_band_wants_kc16(ks, stride, transposed, pad16(cin0) + (cin1 ? pad16(cin1) : 0), pad16(cout), Vout) ||
                                                         conv_s2_wants_kc16(ks, stride, transposed, pad16(cin0), cin1 ? 2 : 1, pad16(cout), Vout))) ? 16 : 0);
     DevBuf dx0, dx1, dw, db, dy, dstats, dyf;
     OP_CHECK(upload_act(dx0, x0, cin0, Vin, false, s));
@@ -173,7 +173,7 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
         std::vector<ConvProblem> probs;
         std::vector<PackDesc> packs;
         int kc = 0;
-        plan_dgrad(g, src, probs, packs, kc, conv_halo_wants_kc16(ks, stride, transposed, pad16(cout), pad16(cin[src]), Vin) ? 16 : 0);
+        plan_dgrad(g, src, probs, packs, kc, conv_band_wants_kc16(ks, stride, transposed, pad16(cout), pad16(cin[src]), Vin) ? 16 : 0);
         const bool acc = src == 0 && (accumulate_gx0 & 1);
         if (acc) OP_CHECK(upload_act(dgx[src], gx[src], cin[src], Vin, false, s));
         else {

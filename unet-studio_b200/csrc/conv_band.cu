@@ -736,7 +736,7 @@ int pack_weights_band_launch(const PackDesc& d, cudaStream_t stream) {
 
 // planner hook: k3 s1 layer with 16|32 padded input channels (both sources together) and 16|32 padded output channels
 bool conv_band_wants(int k_channels_padded, int n_channels_padded, long long voxels) {
-    static const bool disabled = std::getenv("U3D_NO_BAND") != nullptr || std::getenv("U3D_NO_HALO") != nullptr;
+    static const bool disabled = std::getenv("U3D_NO_BAND") != nullptr;
     return !disabled && (k_channels_padded == 16 || k_channels_padded == 32) && (n_channels_padded == 16 || n_channels_padded == 32) &&
            voxels >= 32768;
 }

@@ -423,16 +423,13 @@ unsigned int read_device_error() {
     if (v) return v;
     v = read_device_error_wgrad();
     if (v) return v;
-    v = read_device_error_halo();
-    if (v) return v;
     v = read_device_error_tma();
     if (v) return v;
     v = read_device_error_band();
     if (v) return v;
     v = read_device_error_wband();
     if (v) return v;
-    v = read_device_error_s2();
-    return v ? v : read_device_error_rows();
+    return read_device_error_s2();
 }
 
 int conv_igemm_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, ConvProblem*, cudaStream_t stream) {

@@ -9,6 +9,7 @@
 #include <random>
 #include <sstream>
 #include <stdexcept>
+#include <unordered_map>
 
 namespace u3d {
 
@@ -71,89 +72,123 @@ static int to_int(const std::string& s) {
     }
 }
 
-// Appends the modules of one '+'-separated token; returns the output channel count.
-static int create_layer(BlockDef& blk, const std::string& def, int in_c) {
-    std::map<std::string, std::string> kv;
-    for (const auto& arg : split(def, ',')) {
-        const size_t pos = arg.find_first_of("0123456789");
-        if (pos != std::string::npos) kv[arg.substr(0, pos)] = arg.substr(pos);
-        else kv[arg] = "1";
+// ---- token grammar -------------------------------------------------------------------------------------------------------------
+// A token is a comma-separated attribute list; an attribute is NAME or NAME<digits...> (everything from the first digit on is the
+// value; a bare name has the value "1").  The first rule of kLayerRules whose key is present decides the module, then the first
+// activation key present appends an activation (same precedence as unet.cpp:38-98).
+namespace {
+
+class Token {
+  public:
+    explicit Token(const std::string& text) : text_(text) {
+        for (const std::string& a : split(text, ',')) {
+            const size_t digit = a.find_first_of("0123456789");
+            if (digit == std::string::npos) attr_[a] = "1";
+            else attr_[a.substr(0, digit)] = a.substr(digit);
+        }
     }
-    int out_c = in_c;
+    bool has(const char* key) const { return attr_.find(key) != attr_.end(); }
+    int number(const char* key, int fallback) const {
+        const auto it = attr_.find(key);
+        return it == attr_.end() ? fallback : to_int(it->second);
+    }
+    // what the reference names in "unknown layer: ..." (unet.cpp:87): the first key of its std::unordered_map, or the raw text
+    std::string some_key() const { return attr_.empty() ? text_ : attr_.begin()->first; }
+
+  private:
+    std::string text_;
+    std::unordered_map<std::string, std::string> attr_;   // same container as the reference so begin() names the same key
+};
+
+struct LayerRule {
+    const char* key;
+    ModuleDef::Kind kind;
+    bool has_channels;          // the key's number is the output channel count
+    int ks, stride;             // defaults when the token does not say
+    bool (*geometry_ok)(int ks, int stride);
+    const char* geometry_error;
+};
+bool convt_geometry(int ks, int stride) { return ks == 2 && stride == 2; }
+bool conv_geometry(int ks, int stride) { return (ks == 1 && stride == 1) || (ks == 3 && (stride == 1 || stride == 2)); }
+const LayerRule kLayerRules[] = {
+    {"max_pool", ModuleDef::MAXPOOL, false, 0, 0, nullptr, nullptr},
+    {"upsample", ModuleDef::UPSAMPLE, false, 0, 0, nullptr, nullptr},
+    {"conv_trans", ModuleDef::CONVT, true, 2, 2, convt_geometry, "conv_trans supports only ks2 stride2"},
+    {"conv", ModuleDef::CONV, true, 3, 1, conv_geometry, "conv supports only ks1 stride1, ks3 stride1, and ks3 stride2"},
+    {"norm", ModuleDef::NORM, false, 0, 0, nullptr, nullptr},
+    {"bnorm", ModuleDef::BNORM, false, 0, 0, nullptr, nullptr},
+};
+const struct { const char* key; ModuleDef::Kind kind; } kActivationRules[] = {
+    {"relu", ModuleDef::RELU}, {"leaky_relu", ModuleDef::LEAKY}, {"elu", ModuleDef::ELU}};
+
+// Appends the modules one token stands for; returns the channel count behind it.
+int append_token(BlockDef& blk, const std::string& text, int in_c) {
+    const Token tok(text);
+    const LayerRule* rule = nullptr;
+    for (const LayerRule& r : kLayerRules)
+        if (tok.has(r.key)) { rule = &r; break; }
+    if (!rule) throw std::runtime_error("unknown layer: " + tok.some_key());
     ModuleDef m;
-    if (kv.count("max_pool")) {
-        m.kind = ModuleDef::MAXPOOL; m.cin = m.cout = in_c;
-        blk.mods.push_back(m);
-    } else if (kv.count("upsample")) {
-        m.kind = ModuleDef::UPSAMPLE; m.cin = m.cout = in_c;
-        blk.mods.push_back(m);
-    } else if (kv.count("conv_trans")) {
-        out_c = to_int(kv["conv_trans"]);
-        const int ks = kv.count("ks") ? to_int(kv["ks"]) : 2;
-        const int stride = kv.count("stride") ? to_int(kv["stride"]) : 2;
-        if (ks != 2 || stride != 2) throw std::runtime_error("conv_trans supports only ks2 stride2");
-        m.kind = ModuleDef::CONVT; m.cin = in_c; m.cout = out_c; m.ks = 2; m.stride = 2;
-        blk.mods.push_back(m);
-    } else if (kv.count("conv")) {
-        out_c = to_int(kv["conv"]);
-        const int ks = kv.count("ks") ? to_int(kv["ks"]) : 3;
-        const int stride = kv.count("stride") ? to_int(kv["stride"]) : 1;
-        if (!((ks == 1 && stride == 1) || (ks == 3 && (stride == 1 || stride == 2))))
-            throw std::runtime_error("conv supports only ks1 stride1, ks3 stride1, and ks3 stride2");
-        m.kind = ModuleDef::CONV; m.cin = in_c; m.cout = out_c; m.ks = ks; m.stride = stride;
-        blk.mods.push_back(m);
-    } else if (kv.count("norm")) {
-        m.kind = ModuleDef::NORM; m.cin = m.cout = in_c;
-        blk.mods.push_back(m);
-    } else if (kv.count("bnorm")) {
-        m.kind = ModuleDef::BNORM; m.cin = m.cout = in_c;
-        blk.mods.push_back(m);
-    } else {
-        throw std::runtime_error("unknown layer: " + (kv.empty() ? def : kv.begin()->first));
+    m.kind = rule->kind;
+    m.cin = in_c;
+    m.cout = rule->has_channels ? tok.number(rule->key, 0) : in_c;
+    if (rule->geometry_ok) {
+        m.ks = tok.number("ks", rule->ks);
+        m.stride = tok.number("stride", rule->stride);
+        if (!rule->geometry_ok(m.ks, m.stride)) throw std::runtime_error(rule->geometry_error);
     }
-    ModuleDef a;
-    a.cin = a.cout = out_c;
-    if (kv.count("relu")) { a.kind = ModuleDef::RELU; blk.mods.push_back(a); }
-    else if (kv.count("leaky_relu")) { a.kind = ModuleDef::LEAKY; blk.mods.push_back(a); }
-    else if (kv.count("elu")) { a.kind = ModuleDef::ELU; blk.mods.push_back(a); }
-    return out_c;
+    blk.mods.push_back(m);
+    for (const auto& a : kActivationRules)
+        if (tok.has(a.key)) {
+            ModuleDef act;
+            act.kind = a.kind;
+            act.cin = act.cout = m.cout;
+            blk.mods.push_back(act);
+            break;
+        }
+    return m.cout;
 }
 
+}  // namespace
+
+// Line i of the feature string is encoder level i for the first n/2+1 lines; the remaining lines are the decoder levels from the
+// deepest up (unet.cpp:103-166).  In a decoder line the token equal to the LAST token of the LAST line is that level's output
+// head; tokens in front of it form the level's decoder block (fed by cat{skip, x}), tokens behind it the up-sampling tail.
 Model::Model(int in_c, int out_c, const std::string& feature, bool host_only_)
     : host_only(host_only_), in_count(in_c), out_count(out_c), architecture(feature) {
-    const auto lines = split_lines(feature);
+    const std::vector<std::string> lines = split_lines(feature);
     if (lines.size() < 3) throw std::runtime_error("invalid u-net structure");
-    const size_t enc_count = lines.size() / 2 + 1;
-    std::vector<std::vector<std::string>> enc_tokens, dec_tokens;
-    for (size_t i = 0; i < lines.size(); ++i) (i < enc_count ? enc_tokens : dec_tokens).push_back(split(lines[i], '+'));
-    encoding.resize(enc_tokens.size());
-    int channel = in_c;
-    std::vector<int> skip_channels(enc_tokens.size());
-    for (size_t l = 0; l < enc_tokens.size(); ++l) {
-        encoding[l].name = "encode" + std::to_string(l);
-        for (const auto& tok : enc_tokens[l]) channel = create_layer(encoding[l], tok, channel);
-        skip_channels[l] = channel;
-    }
-    const int n_dec = int(dec_tokens.size());
+    const int n_enc = int(lines.size()) / 2 + 1, n_dec = int(lines.size()) - n_enc;
+    const std::vector<std::string> last_line = split(lines.back(), '+');
+    if (last_line.empty()) throw std::runtime_error("invalid u-net structure");
+    const std::string head_token = last_line.back();
+    encoding.resize(n_enc);
     decoding.resize(n_dec);
     output.resize(n_dec);
     tail.resize(n_dec);
-    if (dec_tokens.back().empty()) throw std::runtime_error("invalid u-net structure");
-    const std::string out_token = dec_tokens.back().back();
-    for (int level = n_dec - 1; level >= 0; --level) {
-        const auto& tokens = dec_tokens[n_dec - 1 - level];
-        decoding[level].name = "decode" + std::to_string(level);
-        output[level].name = "output" + std::to_string(level);
-        tail[level].name = "decode_tail" + std::to_string(level);
-        bool after_out = false;
-        channel += skip_channels[level];
-        for (const auto& tok : tokens) {
-            if (tok == out_token) {
-                create_layer(output[level], tok, channel);
-                after_out = true;
-                continue;
-            }
-            channel = create_layer(after_out ? tail[level] : decoding[level], tok, channel);
+    std::vector<int> width_at(n_enc, 0);   // channels leaving encoder level l (= the skip connection's width)
+    int width = in_c;
+    for (int li = 0; li < int(lines.size()); ++li) {
+        const std::vector<std::string> pieces = split(lines[li], '+');
+        if (li < n_enc) {
+            encoding[li].name = "encode" + std::to_string(li);
+            for (const std::string& t : pieces) width = append_token(encoding[li], t, width);
+            width_at[li] = width;
+            continue;
+        }
+        const int level = int(lines.size()) - 1 - li;
+        const std::string tag = std::to_string(level);
+        decoding[level].name = "decode" + tag;
+        output[level].name = "output" + tag;
+        tail[level].name = "decode_tail" + tag;
+        width += width_at[level];
+        BlockDef* sink = &decoding[level];
+        for (const std::string& t : pieces) {
+            if (t == head_token) {
+                append_token(output[level], t, width);   // the head does not change the width of the trunk
+                sink = &tail[level];
+            } else
+                width = append_token(*sink, t, width);
         }
     }
     // registration order == parameters() order == tensorN order (unet.cpp:130,160-164)
@@ -616,7 +651,7 @@ int Model::ensure_plan() {
         if (s.kind == Step::CONV) {
             {
                 const long long vox = 1LL * s.g.out_d * s.g.out_h * s.g.out_w;
-                const bool halo = s.head_level < 0 && conv_halo_wants_kc16(s.g.ks, s.g.stride, s.g.transposed,
+                const bool halo = s.head_level < 0 && conv_band_wants_kc16(s.g.ks, s.g.stride, s.g.transposed,
                                                                            pad16(s.g.cin[0]) + (s.g.cin[1] ? pad16(s.g.cin[1]) : 0), pad16(s.g.cout), vox);
                 const bool s2 = s.head_level < 0 && conv_s2_wants_kc16(s.g.ks, s.g.stride, s.g.transposed, pad16(s.g.cin[0]), s.g.cin[1] ? 2 : 1,
                                                                        pad16(s.g.cout), vox);
@@ -655,7 +690,7 @@ int Model::ensure_plan() {
                     Step::DG& D = s.dg[src];
                     {
                         const long long vox = 1LL * s.g.in_d * s.g.in_h * s.g.in_w;
-                        const bool halo = conv_halo_wants_kc16(s.g.ks, s.g.stride, s.g.transposed, pad16(s.g.cout), pad16(s.g.cin[src]), vox);
+                        const bool halo = conv_band_wants_kc16(s.g.ks, s.g.stride, s.g.transposed, pad16(s.g.cout), pad16(s.g.cin[src]), vox);
                         plan_dgrad(s.g, src, D.probs, D.packs, D.kc, halo ? 16 : 0);
                     }
                     for (size_t i = 0; i < D.probs.size(); ++i) {
@@ -918,7 +953,7 @@ int Model::run_backward() {
             // flat gradient, so it can overlap the data gradient below (the small deep-level launches fill the SMs the other leaves idle)
             WgradLaunch wc{};
             bool all_rows = !s.wg.empty();
-            for (const auto& wp : s.wg) all_rows = all_rows && (conv_wgrad_band_eligible(wp) || conv_wgrad_rows_eligible(wp));
+            for (const auto& wp : s.wg) all_rows = all_rows && conv_wgrad_band_eligible(wp);
             cudaStream_t ws = two_streams ? stream2 : stream;
             if (two_streams) {
                 M_CUDA(cudaEventRecord(ev_fork, stream));

@@ -116,10 +116,8 @@ struct WgradLaunch {
 int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch& cfg, WgradProblem* dev_scratch,
                       cudaStream_t stream);
 
-bool conv_halo_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
-int conv_halo_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
-int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);  // halo, TMA or gather kernel
-int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);  // profile family conv_launch will use: 0 igemm, 2 halo, 4 tma, 5 band
+int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);  // band, s2, TMA or gather kernel (dispatch.cpp)
+int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);  // profile family conv_launch will use: 0 igemm, 2 s2, 4 tma, 5 band
 bool conv_band_wants(int k_channels_padded, int n_channels_padded, long long voxels);
 bool conv_s2_wants_kc16(int ks, int stride, int transposed, int cin_padded, int n_sources, int cout_padded, long long out_voxels);
 bool conv_s2_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
@@ -132,17 +130,13 @@ bool conv_tma_available();   // the driver exposes cuTensorMapEncodeTiled and th
 bool conv_tma_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);
 int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);
 unsigned int read_device_error_tma();
-bool conv_halo_wants_kc16(int ks, int stride, int transposed, int k_channels_padded, int n_channels_padded, long long voxels);
-unsigned int read_device_error_halo();
+bool conv_band_wants_kc16(int ks, int stride, int transposed, int k_channels_padded, int n_channels_padded, long long voxels);
 
 bool conv_wgrad_band_eligible(const WgradProblem& P);
 int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream);
 unsigned int read_device_error_wband();
-bool conv_wgrad_rows_eligible(const WgradProblem& P);
-int conv_wgrad_rows_launch(const WgradProblem& P, cudaStream_t stream);
-// row-stacked halo kernel per eligible problem, generic kernel for the rest; *launches = kernels launched
+// N-stacked band kernel per eligible problem, generic kernel for the rest; *launches = kernels launched
 int conv_wgrad_dispatch(const std::vector<WgradProblem>& probs, const WgradLaunch& cfg, cudaStream_t stream, int* launches);
-unsigned int read_device_error_rows();
 
 int device_sm_count();
 unsigned int read_device_error();  // first non-zero mbarrier-timeout code of any kernel TU (0 = ok)
