@@ -113,6 +113,40 @@ float unet3d_loss_scale(const unet3d_t* h);
 int unet3d_set_loss_scale(unet3d_t* h, float s);
 long long unet3d_launch_count(const unet3d_t* h);  /* kernels launched by this handle so far */
 
+/* ---- model file (.nz): load_from_file / save_to_file, main.cpp:157-233 -------------------------------------------------------
+ * A gzip stream of MATLAB Level-4 MAT matrices: channels, architecture, dimension, voxel_size, fov_strategy, preproc, orientation,
+ * postproc, training_errors, testing_errors, [single_component_label], tensor{i} = parameters()[i] as rows = numel/size(0),
+ * cols = size(0) in native element order.  The Level-4 container is pinned against scipy.io (tests/test_modelfile_cpu.py); TIPL's
+ * "sloped" integer encoding of tensor{i} is NOT vendored (parity unpinned): the reader converts any numeric type and applies
+ * "<name>.slope" / "<name>.inter" companions if present, the writer stores fp32 exactly.
+ * unet3d_load_from_file constructs the model from the file's channels + architecture (same errors as unet3d_create;
+ * "invalid format" / "tensor size mismatch at tensorN ..." like main.cpp:166,177,199) and leaves it in training mode (main.cpp:193). */
+int unet3d_load_from_file(const char* file_name, int gpu, unet3d_t** out);
+int unet3d_save_to_file(unet3d_t* h, const char* file_name);
+/* train.cpp:787,945-957 keep the SGD state next to the model as <model>.opt via torch::save (a libtorch pickle archive); here the
+ * momentum buffers go into the same .nz container (momentum{i} + sgd_state). */
+int unet3d_save_optimizer(unet3d_t* h, const char* file_name);
+int unet3d_load_optimizer(unet3d_t* h, const char* file_name);
+/* raw export of the same logical layout: <directory>/tensor{i}.bin (fp32, native order) + <directory>/model.json */
+int unet3d_export_raw(unet3d_t* h, const char* directory);
+/* metadata strings of UNet3dImpl (unet.hpp:18): key = "preproc" | "postproc" | "orientation" | "fov_strategy" */
+int unet3d_set_info(unet3d_t* h, const char* key, const char* value);
+int unet3d_get_info(unet3d_t* h, const char* key, char* buf, size_t buflen);
+/* training_errors / testing_errors (unet.hpp:22; 3 floats ce, dice, mse per step).  get returns the number of steps stored. */
+int unet3d_set_errors(unet3d_t* h, int testing, const float* ce_dice_mse, int n_steps);
+int unet3d_get_errors(unet3d_t* h, int testing, float* ce_dice_mse, int max_steps);
+
+/* the container itself, host only (no GPU): type = Level-4 code (0 f64, 10 f32, 20 i32, 30 i16, 40 u16, 50 u8, +1 = text) */
+typedef struct u3d_nz u3d_nz_t;
+int u3d_nz_create(u3d_nz_t** out);
+int u3d_nz_load(const char* path, u3d_nz_t** out);
+int u3d_nz_save(const u3d_nz_t* f, const char* path);
+void u3d_nz_free(u3d_nz_t* f);
+int u3d_nz_count(const u3d_nz_t* f);
+int u3d_nz_info(const u3d_nz_t* f, int i, char* name, size_t name_len, int* type, int* rows, int* cols);
+int u3d_nz_add(u3d_nz_t* f, const char* name, int type, int rows, int cols, const void* data);   /* column-major data */
+int u3d_nz_read_f32(const u3d_nz_t* f, const char* name, float* out, size_t n);
+
 /* copy_from (unet.cpp:195-222): parameters/buffers of identical size, dim, voxel_size; works across GPUs */
 int unet3d_copy_from(unet3d_t* dst, const unet3d_t* src);
 int unet3d_sync(unet3d_t* h);

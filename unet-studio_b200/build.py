@@ -56,7 +56,7 @@ def build(verbose=False, force=False):
                 print(out)
     objs = [os.path.join(OBJ, s + ".o") for s in srcs]
     if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lnccl", "-L/usr/lib/x86_64-linux-gnu"]
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lnccl", "-lz", "-L/usr/lib/x86_64-linux-gnu"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

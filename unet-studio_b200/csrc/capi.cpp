@@ -8,8 +8,11 @@
 #include "model.h"
 #include "vpa.h"
 #include "simulate.h"
+#include "modelfile.h"
 #include <algorithm>
+#include <memory>
 #include <mutex>
+#include <vector>
 #include <map>
 
 namespace u3d {
@@ -255,6 +258,157 @@ int unet3d_profile(unet3d_t* h, int enable) {
 int unet3d_profile_read(unet3d_t* h, double out18[18], int reset) {
     GUARD_BEGIN NEED(h) return h->m->prof_read(out18, reset);
     GUARD_END
+}
+
+// ---- model file (.nz), main.cpp:157-233 -------------------------------------------------------------------
+
+struct u3d_nz {
+    u3d::NzFile* f;
+};
+
+int u3d_nz_create(u3d_nz_t** out) {
+    GUARD_BEGIN
+    if (!out) { set_error("null argument"); return 1; }
+    *out = new u3d_nz{u3d::nz_new()};
+    return 0;
+    GUARD_END
+}
+int u3d_nz_load(const char* path, u3d_nz_t** out) {
+    GUARD_BEGIN
+    if (!out || !path) { set_error("null argument"); return 1; }
+    u3d_nz* z = new u3d_nz{u3d::nz_new()};
+    if (u3d::nz_load(path, *z->f)) { u3d::nz_delete(z->f); delete z; return 1; }
+    *out = z;
+    return 0;
+    GUARD_END
+}
+void u3d_nz_free(u3d_nz_t* z) {
+    if (!z) return;
+    u3d::nz_delete(z->f);
+    delete z;
+}
+int u3d_nz_save(const u3d_nz_t* z, const char* path) {
+    GUARD_BEGIN
+    if (!z || !path) { set_error("null argument"); return 1; }
+    return u3d::nz_save(*z->f, path);
+    GUARD_END
+}
+int u3d_nz_count(const u3d_nz_t* z) { return z ? u3d::nz_count(*z->f) : -1; }
+int u3d_nz_info(const u3d_nz_t* z, int i, char* name, size_t name_len, int* type, int* rows, int* cols) {
+    GUARD_BEGIN
+    if (!z) { set_error("null argument"); return 1; }
+    std::string n;
+    int t = 0, r = 0, c = 0;
+    if (u3d::nz_info(*z->f, i, n, t, r, c)) return 1;
+    if (name && name_len) { std::strncpy(name, n.c_str(), name_len - 1); name[name_len - 1] = 0; }
+    if (type) *type = t;
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+    return 0;
+    GUARD_END
+}
+int u3d_nz_add(u3d_nz_t* z, const char* name, int type, int rows, int cols, const void* data) {
+    GUARD_BEGIN
+    if (!z || !name || (!data && rows * cols > 0)) { set_error("null argument"); return 1; }
+    return u3d::nz_add(*z->f, name, type, rows, cols, data);
+    GUARD_END
+}
+int u3d_nz_read_f32(const u3d_nz_t* z, const char* name, float* out, size_t n) {
+    GUARD_BEGIN
+    if (!z || !name) { set_error("null argument"); return 1; }
+    std::vector<float> v;
+    if (u3d::nz_read_f32(*z->f, name, v)) return 1;
+    if (v.size() != n) { set_error("matrix " + std::string(name) + " has " + std::to_string(v.size()) + " elements"); return 1; }
+    if (n) std::memcpy(out, v.data(), n * 4);
+    return 0;
+    GUARD_END
+}
+
+int unet3d_load_from_file(const char* file_name, int gpu, unet3d_t** out) {
+    GUARD_BEGIN
+    if (!file_name || !out) { set_error("null argument"); return 1; }
+    std::unique_ptr<u3d::NzFile, void (*)(u3d::NzFile*)> f(u3d::nz_new(), u3d::nz_delete);
+    if (u3d::nz_load(file_name, *f)) return 1;
+    int in_c = 1, out_c = 1;
+    std::string arch;
+    if (u3d::nz_model_header(*f, in_c, out_c, arch)) return 1;
+    unet3d_t* h = nullptr;
+    if (unet3d_create(in_c, out_c, arch.c_str(), gpu, &h)) return 1;
+    if (u3d::nz_to_model(*f, *h->m)) { unet3d_destroy(h); return 1; }
+    *out = h;
+    return 0;
+    GUARD_END
+}
+int unet3d_save_to_file(unet3d_t* h, const char* file_name) {
+    GUARD_BEGIN NEED(h)
+    if (!file_name) { set_error("null argument"); return 1; }
+    std::unique_ptr<u3d::NzFile, void (*)(u3d::NzFile*)> f(u3d::nz_new(), u3d::nz_delete);
+    if (u3d::model_to_nz(*h->m, *f)) return 1;
+    return u3d::nz_save(*f, file_name);
+    GUARD_END
+}
+int unet3d_save_optimizer(unet3d_t* h, const char* file_name) {
+    GUARD_BEGIN NEED(h)
+    if (!file_name) { set_error("null argument"); return 1; }
+    std::unique_ptr<u3d::NzFile, void (*)(u3d::NzFile*)> f(u3d::nz_new(), u3d::nz_delete);
+    if (u3d::model_momentum_to_nz(*h->m, *f)) return 1;
+    return u3d::nz_save(*f, file_name);
+    GUARD_END
+}
+int unet3d_load_optimizer(unet3d_t* h, const char* file_name) {
+    GUARD_BEGIN NEED(h)
+    if (!file_name) { set_error("null argument"); return 1; }
+    std::unique_ptr<u3d::NzFile, void (*)(u3d::NzFile*)> f(u3d::nz_new(), u3d::nz_delete);
+    if (u3d::nz_load(file_name, *f)) return 1;
+    return u3d::nz_to_model_momentum(*f, *h->m);
+    GUARD_END
+}
+int unet3d_export_raw(unet3d_t* h, const char* directory) {
+    GUARD_BEGIN NEED(h)
+    if (!directory) { set_error("null argument"); return 1; }
+    return u3d::model_export_raw(*h->m, directory);
+    GUARD_END
+}
+static std::string* info_field(Model* m, const char* key) {
+    const std::string k = key ? key : "";
+    if (k == "preproc") return &m->preproc;
+    if (k == "postproc") return &m->postproc;
+    if (k == "orientation") return &m->orientation;
+    if (k == "fov_strategy") return &m->fov_strategy;
+    return nullptr;
+}
+int unet3d_set_info(unet3d_t* h, const char* key, const char* value) {
+    GUARD_BEGIN NEED(h)
+    std::string* f = info_field(h->m, key);
+    if (!f || !value) { set_error("unet3d_set_info: key must be preproc, postproc, orientation or fov_strategy"); return 1; }
+    *f = value;
+    return 0;
+    GUARD_END
+}
+int unet3d_get_info(unet3d_t* h, const char* key, char* buf, size_t buflen) {
+    GUARD_BEGIN NEED(h)
+    const std::string* f = info_field(h->m, key);
+    if (!f) { set_error("unet3d_get_info: key must be preproc, postproc, orientation or fov_strategy"); return 1; }
+    if (!buf || buflen < f->size() + 1) { set_error("buffer too small"); return int(f->size() + 1); }
+    std::memcpy(buf, f->c_str(), f->size() + 1);
+    return 0;
+    GUARD_END
+}
+int unet3d_set_errors(unet3d_t* h, int testing, const float* ce_dice_mse, int n_steps) {
+    GUARD_BEGIN NEED(h)
+    if (n_steps < 0 || (n_steps && !ce_dice_mse)) { set_error("null argument"); return 1; }
+    auto& v = testing ? h->m->testing_errors : h->m->training_errors;
+    v.assign(ce_dice_mse, ce_dice_mse + size_t(3) * n_steps);
+    return 0;
+    GUARD_END
+}
+int unet3d_get_errors(unet3d_t* h, int testing, float* ce_dice_mse, int max_steps) {
+    if (!h || !h->m) return -1;
+    const auto& v = testing ? h->m->testing_errors : h->m->training_errors;
+    const int n = int(v.size() / 3);
+    if (ce_dice_mse)
+        for (int i = 0; i < std::min(n, max_steps) * 3; ++i) ce_dice_mse[i] = v[size_t(i)];
+    return n;
 }
 
 int unet3d_sync(unet3d_t* h) {

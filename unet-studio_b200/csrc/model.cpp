@@ -1175,6 +1175,7 @@ int Model::copy_from(const Model& src) {
         M_CUDA(cudaMemcpyPeerAsync(d_buffers[i], device, src.d_buffers[i], src.device, size_t(buffer_len[i]) * 4, stream));
     }
     for (int k = 0; k < 3; ++k) { voxel_size[k] = src.voxel_size[k]; }
+    fov_strategy = src.fov_strategy; postproc = src.postproc; preproc = src.preproc;   // unet.cpp:217-221
     M_CHECK(set_dim(src.dim[0], src.dim[1], src.dim[2]));
     M_CUDA(cudaStreamSynchronize(stream));
     packs_dirty = true;

@@ -84,6 +84,12 @@ class Model {
     std::string architecture;
     int dim[3] = {192, 224, 192};  // W, H, D
     float voxel_size[3] = {1.f, 1.f, 1.f};
+    // model-file metadata (unet.hpp:18-23; defaults of the constructor, unet.cpp:110-112)
+    std::string preproc, postproc = "softmax+create_mask+argmax", orientation, fov_strategy = "align_top";
+    std::vector<float> testing_errors, training_errors;   // 3 floats (ce, dice, mse) per step
+    std::vector<int> single_component_label;
+    const float* params_base() const { return d_params; }
+    const float* momentum_base() const { return d_mom; }
     bool training = true;
     bool bn_running = false;       // eval() without prepare_for_inference: BatchNorm3d normalises with its running statistics (eps 0)
 

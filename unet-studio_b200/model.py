@@ -49,6 +49,50 @@ class UNet3d:
         self.levels = L.unet3d_levels(self._h)
         self.dim = (192, 224, 192)  # unet.hpp:38
 
+    @classmethod
+    def _from_handle(cls, h, gpu=0):
+        """Wraps a handle made by the library (unet3d_load_from_file)."""
+        from . import lib
+        self = cls.__new__(cls)
+        self._lib = L = lib()
+        L.unet3d_param_name.restype = ctypes.c_char_p
+        L.unet3d_architecture.restype = ctypes.c_char_p
+        L.unet3d_last_grad_norm.restype = ctypes.c_double
+        L.unet3d_loss_scale.restype = ctypes.c_float
+        L.unet3d_param_total.restype = ctypes.c_longlong
+        L.unet3d_launch_count.restype = ctypes.c_longlong
+        L.unet3d_destroy.restype = None
+        self._h = h
+        self.in_count, self.out_count = L.unet3d_in_count(h), L.unet3d_out_count(h)
+        self.architecture, self.gpu = L.unet3d_architecture(h).decode(), gpu
+        self.levels = L.unet3d_levels(h)
+        d = (ctypes.c_int * 3)()
+        L.unet3d_get_dim(h, d)
+        self.dim = (d[0], d[1], d[2])
+        return self
+
+    def get_info(self, key):
+        from . import check
+        buf = ctypes.create_string_buffer(65536)
+        check(self._lib.unet3d_get_info(self._h, key.encode(), buf, ctypes.c_size_t(len(buf))))
+        return buf.value.decode()
+
+    def set_info(self, key, value):
+        from . import check
+        check(self._lib.unet3d_set_info(self._h, key.encode(), value.encode()))
+
+    def set_errors(self, testing, errors):
+        from . import check
+        e = np.ascontiguousarray(errors, np.float32).reshape(-1, 3)
+        check(self._lib.unet3d_set_errors(self._h, int(bool(testing)), _fp(e), int(e.shape[0])))
+
+    def get_errors(self, testing):
+        n = self._lib.unet3d_get_errors(self._h, int(bool(testing)), None, 0)
+        e = np.zeros((max(n, 0), 3), np.float32)
+        if n > 0:
+            self._lib.unet3d_get_errors(self._h, int(bool(testing)), _fp(e), n)
+        return e
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
