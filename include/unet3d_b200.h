@@ -84,6 +84,25 @@ int unet3d_forward(unet3d_t* h, const float* in, float* const* out_levels, int n
 /* the inference window loop, evaluate.cpp:223-230: out_windows[i] = forward(in_windows[i])[0] */
 int unet3d_evaluate_windows(unet3d_t* h, const float* const* in_windows, float* const* out_windows, int n_windows, int where);
 
+/* One whole volume through evaluate (evaluate.cpp:195-230, 274): the volume ({in,d,hgt,w} fp32, any size) is covered by windows of
+ * the model grid (unet3d_set_dim) at the given stride per axis (<= 0: the window size, i.e. no overlap; the last window of an axis
+ * is shifted inward to end at the border; a smaller volume is zero-padded at the far end), every window runs forward()[0], and the
+ * default postproc "softmax+create_mask+argmax" (unet.cpp:112) runs on the GPU over the re-assembled volume: probabilities of
+ * overlapping windows are averaged, fg_prob = 1 - p(channel 0), label = fg_prob > mask_threshold ? arg-max channel : 0
+ * (evaluate.cpp:315-319).  label_out: 1 byte per voxel; fg_prob_out ({d,hgt,w} fp32) and label_prob_out ({out,d,hgt,w} fp32) may
+ * be NULL.  The window cutting / re-assembly / postproc arithmetic of the reference lives in TIPL (not vendored): parity unpinned,
+ * semantics restated in oracle/postproc_oracle.py.  out_count <= 32. */
+int unet3d_evaluate_volume(unet3d_t* h, const float* volume, int w, int hgt, int d, int stride_x, int stride_y, int stride_z,
+                           float mask_threshold, uint8_t* label_out, float* fg_prob_out, float* label_prob_out, int where, int* n_windows);
+/* host only: the window start positions unet3d_evaluate_volume uses along one axis; returns their number */
+int unet3d_window_origins(int volume_dim, int window_dim, int stride, int* origins, int max_origins);
+/* standalone "softmax+create_mask+argmax" on host logits ({channels, voxels} fp32 planar) */
+int u3d_postproc(const float* logits, int channels, long long voxels, float mask_threshold, uint8_t* label_out, float* fg_prob_out,
+                 float* label_prob_out, int gpu);
+/* resampling to / from the model grid (the step in front of the windows; tipl::scale-style index mapping dst*src_dim/dst_dim):
+ * trilinear for images, nearest for label maps.  Host buffers {channels, d, h, w}. */
+int u3d_resample(const float* src, int channels, int sw, int sh, int sd, float* dst, int dw, int dh, int dd, int nearest, int gpu);
+
 /* one N=1 micro-batch of the training step body, train.cpp:628-706: forward, calc_losses on every
  * deep-supervision level (train.cpp:501-552), level weights (1/2^k)/sum, backward.  Gradients ACCUMULATE
  * across calls until unet3d_step.  loss_out = level-0 {ce, dice, mse} (what the reference logs,
@@ -98,6 +117,14 @@ int unet3d_train_microbatch(unet3d_t* h, const float* in, const float* label, in
 /* validation forward + level-0 calc_losses, no gradient (train.cpp:826-851).  Runs with eval() semantics whatever the handle's mode
  * (BatchNorm3d reads its running statistics, nothing is updated). */
 int unet3d_validate(unet3d_t* h, const float* in, const float* label, int collapse_before, float loss_out[3], int where);
+
+/* The reference validates on its own replica (output_model) in its own thread, beside the trainer (train.cpp:826-851, 773-776).
+ * Same structure here: a second handle (unet3d_copy_from under the caller's mutex) owns its own CUDA stream, so its validation
+ * runs beside the training handle's kernels on the same GPU.  unet3d_validate_async only enqueues (host pointers with where = 0
+ * must stay valid until unet3d_validate_result returns; pinned memory keeps the upload asynchronous); unet3d_validate_result waits
+ * for that handle's stream alone and returns the level-0 {ce, dice, mse}. */
+int unet3d_validate_async(unet3d_t* h, const float* in, const float* label, int collapse_before, int where);
+int unet3d_validate_result(unet3d_t* h, float loss_out[3]);
 
 /* create_optimizer(lr) (unet.cpp:246-277): SGD momentum .99, Nesterov, weight decay 3e-5 | 0 groups */
 int unet3d_create_optimizer(unet3d_t* h, float learning_rate);

@@ -89,3 +89,16 @@ def test_create_without_gpu_fails_loudly():
     m = load()
     with pytest.raises(m.U3DError, match="no CPU fallback"):
         m.UNet3d(1, 2)
+
+
+def test_window_origins_cover_the_volume_host_only():
+    """unet3d_window_origins (host only): windows at 0, stride, ... plus the one ending at the border; every voxel covered."""
+    from oracle import postproc_oracle as PO
+    m = load()
+    for vdim, wdim, stride in ((320, 160, 0), (320, 192, 128), (100, 160, 0), (161, 160, 80), (160, 160, 0), (500, 96, 64)):
+        o = m.window_origins(vdim, wdim, stride)
+        assert o == PO.window_origins(vdim, wdim, stride)
+        covered = set()
+        for s in o:
+            covered.update(range(s, min(s + wdim, vdim)))
+        assert covered == set(range(vdim)) and all(s + wdim <= max(vdim, wdim) for s in o)

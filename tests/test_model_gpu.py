@@ -400,3 +400,44 @@ def test_validate_default_net_matches_oracle_level0_losses():
         ref = torch.stack(O.calc_losses(out0, torch.from_numpy(lab).long(), 2, 0)).numpy()
     print("validate", v, "oracle", ref)
     np.testing.assert_allclose(v, ref, rtol=0, atol=2e-3)
+
+
+def test_validation_replica_runs_beside_the_trainer():
+    """train.cpp:773-776, 826-851: the trainer copies its weights into output_model (copy_from) and a second thread validates on that
+    replica while training continues.  Two handles on one GPU, two host threads: the asynchronous validation of the replica, started
+    before a block of training steps and collected after it, equals a plain validation of the same weights."""
+    import threading
+    m = load()
+    W, H, D = 64, 64, 64
+    feature = O.default_feature(2)
+    img, lab = synth_volume(W, H, D, seed=8)
+    trainer = m.UNet3d(1, 2, feature)
+    trainer.init_params(6)
+    trainer.set_dim(W, H, D)
+    trainer.train(True)
+    trainer.create_optimizer(1e-2)
+    replica = m.UNet3d(1, 2, feature)
+    replica.copy_from(trainer)
+    replica.train(False)
+    want = replica.validate(img, lab)
+    got = {}
+
+    def validator():
+        for k in range(4):
+            replica.validate_async(img, lab)
+            got[k] = replica.validate_result()
+
+    t = threading.Thread(target=validator)
+    t.start()
+    for s in range(6):                      # the trainer keeps stepping on its own stream meanwhile
+        trainer.train_microbatch(img, lab)
+        trainer.step(1, 1e-2)
+        assert not trainer.last_step_skipped()
+    t.join()
+    for k in range(4):
+        assert np.array_equal(got[k], want), (k, got[k], want)
+    # after the next copy_from the replica sees the trained weights
+    replica.copy_from(trainer)
+    replica.train(False)
+    after = replica.validate(img, lab)
+    assert after[0] < want[0], (after, want)

@@ -36,4 +36,5 @@ from .model import UNet3d, default_feature, poly_lr  # noqa: E402,F401
 from .vpa import (vpa_augment, vpa_augment_on, train_microbatch_augmented, prefetch_augmented, train_microbatch_prefetched,  # noqa: E402,F401
                   simulate_modality, simulate_modality_on, set_simulate_modality, OPTION_DEFAULTS)  # noqa: E402,F401
 from .modelfile import NzFile, load_from_file, save_to_file, save_optimizer, load_optimizer, export_raw  # noqa: E402,F401
+from .postproc import evaluate_volume, window_origins, postproc, resample  # noqa: E402,F401
 from . import dist  # noqa: E402,F401

@@ -9,6 +9,7 @@
 #include "vpa.h"
 #include "simulate.h"
 #include "modelfile.h"
+#include "postproc.h"
 #include <algorithm>
 #include <memory>
 #include <mutex>
@@ -202,6 +203,15 @@ int unet3d_validate(unet3d_t* h, const float* in, const float* label, int collap
     GUARD_END
 }
 
+int unet3d_validate_async(unet3d_t* h, const float* in, const float* label, int collapse_before, int where) {
+    GUARD_BEGIN NEED(h) return h->m->validate(in, label, collapse_before, nullptr, where);
+    GUARD_END
+}
+int unet3d_validate_result(unet3d_t* h, float loss_out[3]) {
+    GUARD_BEGIN NEED(h) return h->m->validate_result(loss_out);
+    GUARD_END
+}
+
 int unet3d_create_optimizer(unet3d_t* h, float learning_rate) {
     GUARD_BEGIN NEED(h)
     h->m->optimizer_created = true;
@@ -257,6 +267,69 @@ int unet3d_profile(unet3d_t* h, int enable) {
 }
 int unet3d_profile_read(unet3d_t* h, double out18[18], int reset) {
     GUARD_BEGIN NEED(h) return h->m->prof_read(out18, reset);
+    GUARD_END
+}
+
+int unet3d_evaluate_volume(unet3d_t* h, const float* volume, int w, int hgt, int d, int stride_x, int stride_y, int stride_z,
+                           float mask_threshold, uint8_t* label_out, float* fg_prob_out, float* label_prob_out, int where, int* n_windows) {
+    GUARD_BEGIN NEED(h)
+    return h->m->evaluate_volume(volume, w, hgt, d, stride_x, stride_y, stride_z, mask_threshold, label_out, fg_prob_out, label_prob_out,
+                                 where, n_windows);
+    GUARD_END
+}
+
+int unet3d_window_origins(int volume_dim, int window_dim, int stride, int* origins, int max_origins) {
+    const std::vector<int> o = u3d::window_origins(volume_dim, window_dim, stride);
+    for (size_t i = 0; i < o.size() && int(i) < max_origins; ++i) origins[i] = o[i];
+    return int(o.size());
+}
+
+int u3d_postproc(const float* logits, int channels, long long voxels, float mask_threshold, uint8_t* label_out, float* fg_prob_out,
+                 float* label_prob_out, int gpu) {
+    GUARD_BEGIN
+    if (!logits || !label_out || channels < 1 || voxels < 1) { set_error("u3d_postproc: invalid argument"); return 1; }
+    if (cudaSetDevice(gpu) != cudaSuccess) { set_error("no CUDA device: libunet3d_b200 has no CPU fallback"); return 1; }
+    float* buf = nullptr;
+    const size_t V = size_t(voxels);
+    if (cudaMalloc(reinterpret_cast<void**>(&buf), (size_t(2 * channels + 2) * V) * 4 + V) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+    float* d_log = buf;
+    float* d_acc = d_log + size_t(channels) * V;
+    float* d_cnt = d_acc + size_t(channels) * V;
+    float* d_fg = d_cnt + V;
+    uint8_t* d_lab = reinterpret_cast<uint8_t*>(d_fg + V);
+    int rc = 0;
+    cudaMemcpy(d_log, logits, size_t(channels) * V * 4, cudaMemcpyHostToDevice);
+    cudaMemset(d_acc, 0, (size_t(channels) + 1) * V * 4);
+    // one "window" covering the whole buffer, viewed as a 1-D volume
+    if (voxels >= (1LL << 31)) { set_error("u3d_postproc: too many voxels"); rc = 1; }
+    else rc = u3d::softmax_accumulate_launch(d_log, d_acc, d_cnt, channels, int(voxels), 1, 1, int(voxels), 1, 1, 0, 0, 0, nullptr);
+    if (!rc) rc = u3d::mask_argmax_launch(d_acc, d_cnt, d_lab, d_fg, channels, voxels, mask_threshold, label_prob_out != nullptr, nullptr);
+    if (!rc) {
+        cudaMemcpy(label_out, d_lab, V, cudaMemcpyDeviceToHost);
+        if (fg_prob_out) cudaMemcpy(fg_prob_out, d_fg, V * 4, cudaMemcpyDeviceToHost);
+        if (label_prob_out) cudaMemcpy(label_prob_out, d_acc, size_t(channels) * V * 4, cudaMemcpyDeviceToHost);
+        if (cudaDeviceSynchronize() != cudaSuccess) { set_error("u3d_postproc: device error"); rc = 1; }
+    }
+    cudaFree(buf);
+    return rc;
+    GUARD_END
+}
+
+int u3d_resample(const float* src, int channels, int sw, int sh, int sd, float* dst, int dw, int dh, int dd, int nearest, int gpu) {
+    GUARD_BEGIN
+    if (!src || !dst || channels < 1 || sw < 1 || sh < 1 || sd < 1 || dw < 1 || dh < 1 || dd < 1) { set_error("u3d_resample: invalid argument"); return 1; }
+    if (cudaSetDevice(gpu) != cudaSuccess) { set_error("no CUDA device: libunet3d_b200 has no CPU fallback"); return 1; }
+    const size_t SV = size_t(sw) * sh * sd * channels, DV = size_t(dw) * dh * dd * channels;
+    float* buf = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&buf), (SV + DV) * 4) != cudaSuccess) { set_error("cudaMalloc failed"); return 1; }
+    cudaMemcpy(buf, src, SV * 4, cudaMemcpyHostToDevice);
+    int rc = u3d::resample_launch(buf, buf + SV, channels, sw, sh, sd, dw, dh, dd, nearest, nullptr);
+    if (!rc) {
+        cudaMemcpy(dst, buf + SV, DV * 4, cudaMemcpyDeviceToHost);
+        if (cudaDeviceSynchronize() != cudaSuccess) { set_error("u3d_resample: device error"); rc = 1; }
+    }
+    cudaFree(buf);
+    return rc;
     GUARD_END
 }
 

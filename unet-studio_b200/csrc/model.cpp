@@ -1,4 +1,5 @@
 #include "model.h"
+#include "postproc.h"
 
 #include <nccl.h>
 
@@ -284,6 +285,7 @@ Model::~Model() {
     if (stream4) { cudaStreamSynchronize(stream4); cudaStreamDestroy(stream4); }
     if (ev_ar_ready) cudaEventDestroy(ev_ar_ready);
     if (ev_ar_done) cudaEventDestroy(ev_ar_done);
+    if (h_val) cudaFreeHost(h_val);
     if (ev_status) cudaEventDestroy(ev_status);
     if (h_status) cudaFreeHost(h_status);
     free_plan();
@@ -295,6 +297,7 @@ Model::~Model() {
     if (stream3) { cudaStreamSynchronize(stream3); cudaStreamDestroy(stream3); }
     for (int i = 0; i < 2; ++i) { if (ev_sample[i]) cudaEventDestroy(ev_sample[i]); if (pf_in[i]) cudaFree(pf_in[i]); }
     for (int i = 0; i < 2; ++i) { if (ew_in[i]) cudaFree(ew_in[i]); if (ew_out[i]) cudaFree(ew_out[i]); }
+    if (ev_buf) cudaFree(ev_buf);
     if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -920,6 +923,60 @@ int Model::evaluate_windows(const float* const* in_windows, float* const* out_wi
     return rc;
 }
 
+// evaluate.cpp:195-230 + 274 for one volume: cut windows (handle_fov_pre), forward()[0] per window, softmax, re-assemble
+// (handle_fov_post), create_mask, argmax.  The TIPL side of this is un-vendored: see postproc.cu for the assumed semantics.
+int Model::evaluate_volume(const float* volume, int vw, int vh, int vd, int sx, int sy, int sz, float threshold, uint8_t* label_out,
+                           float* fg_out, float* prob_out, int where, int* n_windows_out) {
+    if (vw < 1 || vh < 1 || vd < 1 || !volume || !label_out) { set_error("evaluate_volume: invalid argument"); return 1; }
+    M_CHECK(ensure_plan());
+    M_CHECK(repack());
+    if (!logits[0]) { set_error("undefined output at level 0"); return 1; }
+    const int ww = dim[0], wh = dim[1], wd = dim[2], C = out_count;
+    const long long VV = 1LL * vw * vh * vd, WV = 1LL * ww * wh * wd;
+    // device layout: [volume in_count*VV] [window in_count*WV] [acc C*VV] [cnt VV] [fg VV] [labels VV bytes]
+    const size_t need = (size_t(in_count) * VV + size_t(in_count) * WV + size_t(C) * VV + 2 * size_t(VV)) * 4 + size_t(VV) + 256;
+    if (ev_bytes < need) {
+        M_CUDA(cudaStreamSynchronize(stream));
+        if (ev_buf) cudaFree(ev_buf);
+        ev_buf = nullptr; ev_bytes = 0;
+        M_CUDA(cudaMalloc(reinterpret_cast<void**>(&ev_buf), need));
+        ev_bytes = need;
+    }
+    float* d_vol = ev_buf;
+    float* d_win = d_vol + size_t(in_count) * VV;
+    float* d_acc = d_win + size_t(in_count) * WV;
+    float* d_cnt = d_acc + size_t(C) * VV;
+    float* d_fg = d_cnt + VV;
+    uint8_t* d_lab = reinterpret_cast<uint8_t*>(d_fg + VV);
+    const float* vol = volume;
+    if (where == 0) {
+        M_CUDA(cudaMemcpyAsync(d_vol, volume, size_t(in_count) * VV * 4, cudaMemcpyHostToDevice, stream));
+        vol = d_vol;
+    }
+    M_CUDA(cudaMemsetAsync(d_acc, 0, (size_t(C) + 1) * VV * 4, stream));
+    const std::vector<int> ox = window_origins(vw, ww, sx), oy = window_origins(vh, wh, sy), oz = window_origins(vd, wd, sz);
+    int n = 0;
+    for (int z : oz)
+        for (int y : oy)
+            for (int x : ox) {
+                M_CHECK(crop_window_launch(vol, d_win, in_count, vw, vh, vd, ww, wh, wd, x, y, z, stream));
+                M_CHECK(pack_act_launch(d_win, tens[0].p, in_count, tens[0].Cp, WV, false, stream, split_input ? 1 : 0));
+                M_CHECK(run_forward(1));
+                M_CHECK(softmax_accumulate_launch(logits[0], d_acc, d_cnt, C, vw, vh, vd, ww, wh, wd, x, y, z, stream));
+                launches += 3;
+                ++n;
+            }
+    M_CHECK(mask_argmax_launch(d_acc, d_cnt, d_lab, d_fg, C, VV, threshold, prob_out != nullptr, stream));
+    ++launches;
+    if (n_windows_out) *n_windows_out = n;
+    const cudaMemcpyKind k = where == 0 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    M_CUDA(cudaMemcpyAsync(label_out, d_lab, size_t(VV), k, stream));
+    if (fg_out) M_CUDA(cudaMemcpyAsync(fg_out, d_fg, size_t(VV) * 4, k, stream));
+    if (prob_out) M_CUDA(cudaMemcpyAsync(prob_out, d_acc, size_t(C) * VV * 4, k, stream));
+    if (where == 0) return sync();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward (autograd of the step body, train.cpp:706)
 // ------------------------------------------------------------------------------------------------
@@ -1156,8 +1213,21 @@ int Model::validate(const float* in, const float* label, int collapse_before, fl
     Q.acc = d_loss_acc; Q.part = d_loss_part; Q.out3 = d_losses;
     M_CHECK(loss_level_launch(Q, stream));
     launches += 3;
-    M_CUDA(cudaMemcpyAsync(loss_out3, d_losses, 12, cudaMemcpyDeviceToHost, stream));
-    return sync();
+    if (!h_val) M_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_val), 16));
+    M_CUDA(cudaMemcpyAsync(h_val, d_losses, 12, cudaMemcpyDeviceToHost, stream));
+    val_pending = true;
+    if (loss_out3 == nullptr) return 0;   // asynchronous form: the caller collects the losses with validate_result()
+    return validate_result(loss_out3);
+}
+
+// second half of the asynchronous validation: waits for this handle's stream only (a training handle on the same GPU keeps running)
+int Model::validate_result(float* loss_out3) {
+    if (!val_pending) { set_error("validate_result without a pending unet3d_validate_async"); return 1; }
+    cudaSetDevice(device);
+    M_CHECK(sync());
+    val_pending = false;
+    if (loss_out3) std::memcpy(loss_out3, h_val, 12);
+    return 0;
 }
 
 int Model::copy_from(const Model& src) {

@@ -158,10 +158,19 @@ class Model {
     int forward(const float* in, float* const* out_levels, int n_levels, int where);
     int train_microbatch(const float* in, const float* label, int collapse_before, int use_ce, int use_dice, int use_mse,
                          float* loss_out3, float* all_levels, int where);
-    int validate(const float* in, const float* label, int collapse_before, float* loss_out3, int where);
+    int validate(const float* in, const float* label, int collapse_before, float* loss_out3, int where);   // loss_out3 == nullptr: asynchronous
+    int validate_result(float* loss_out3);
+    float* h_val = nullptr;          // pinned result of the last validation
+    bool val_pending = false;
     // evaluate.cpp:223-230 over a list of windows; host pointers: upload of window i+1 and download of window i-1 overlap the
     // forward of window i (two staging slots each way, copy streams = the side streams that are idle during inference)
     int evaluate_windows(const float* const* in_windows, float* const* out_windows, int n_windows, int where);
+    // evaluate one whole volume (any size): windows of the model grid, forward()[0] per window, softmax + re-assembly +
+    // create_mask + argmax on the device (postproc.cu); label_out = 1 byte per voxel, fg_out / prob_out optional
+    int evaluate_volume(const float* volume, int vw, int vh, int vd, int stride_x, int stride_y, int stride_z, float threshold,
+                        uint8_t* label_out, float* fg_out, float* prob_out, int where, int* n_windows_out);
+    float* ev_buf = nullptr;         // device: volume in, window in, accumulators, count, fg, labels
+    size_t ev_bytes = 0;
     float* ew_in[2] = {nullptr, nullptr};
     float* ew_out[2] = {nullptr, nullptr};
     size_t ew_in_bytes = 0, ew_out_bytes = 0;

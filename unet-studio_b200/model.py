@@ -233,6 +233,19 @@ class UNet3d:
         check(self._lib.unet3d_validate(self._h, _fp(x), _fp(label), int(collapse_before), _fp(out), 0))
         return out
 
+    def validate_async(self, x, label, collapse_before=0):
+        """Enqueues the validation on this handle's own stream and returns; keep x / label alive until validate_result()."""
+        from . import check
+        self._val_keep = (np.ascontiguousarray(x, np.float32), np.ascontiguousarray(label, np.float32))
+        check(self._lib.unet3d_validate_async(self._h, _fp(self._val_keep[0]), _fp(self._val_keep[1]), int(collapse_before), 0))
+
+    def validate_result(self):
+        from . import check
+        out = np.zeros(3, np.float32)
+        check(self._lib.unet3d_validate_result(self._h, _fp(out)))
+        self._val_keep = None
+        return out
+
     def attach_comm(self, nccl_comm, microbatches_per_step=1):
         from . import check
         check(self._lib.unet3d_attach_comm(self._h, nccl_comm, int(microbatches_per_step)))
