@@ -229,13 +229,16 @@ def test_gradients_match_fp16_emulating_oracle_tightly(name):
     total.backward()
     num = den = 0.0
     worst = 0.0
+    per = []
     for i in range(n):
         g = net.get_grad(i)
         gr = P[i].grad.numpy() if P[i].grad is not None else np.zeros_like(g)
         num += float(((g - gr).astype(np.float64) ** 2).sum()); den += float((gr.astype(np.float64) ** 2).sum())
         if np.linalg.norm(gr) > 1e-3 and not onet.param_names[i].endswith(".bias"):
             worst = max(worst, rel(g, gr))
+            per.append((rel(g, gr), onet.param_names[i], float(np.linalg.norm(gr))))
     print(name, "vs fp16-emulating oracle: global grad rel err", np.sqrt(num / den), "worst weight tensor", worst)
+    print("   per tensor (rel err, name, |g|):", sorted(per, reverse=True)[:6])
     assert np.sqrt(num / den) < 1.2e-2, np.sqrt(num / den)
     assert worst < 5e-2, worst
 

@@ -679,43 +679,6 @@ __global__ void __launch_bounds__(kZThreads, 1) conv_zband_kernel(const __grid_c
     if (warp == 12) tmem_dealloc(tmem_base, 512);
 }
 
-// ---- weight pack: reference fp32 tensor -> [9 (dz,dy)][KS][2 k-groups][NB = 4*CO columns][8] fp16, columns = kernel column
-// kx = 2,1,0 then a zero block; the (dz,dy,dx) offsets come from the problem's own tap list (forward: k-1, dgrad: 1-k) ----
-__global__ void pack_weights_band_kernel(const __grid_constant__ PackDesc d) {
-    const int KS = d.nch[0] + d.nch[1];
-    const int NB = 4 * d.band_co;
-    const long long total = 9LL * KS * 2 * NB * 8;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long r = i;
-        const int k8 = int(r % 8); r /= 8;
-        const int col = int(r % NB); r /= NB;
-        const int kg = int(r % 2); r /= 2;
-        const int ks = int(r % KS); r /= KS;
-        const int t9 = int(r);
-        const int blk = col / d.band_co, nn = col % d.band_co;
-        float v = 0.f;
-        if (blk < 3) {
-            const int oz = t9 / 3 - 1, oy = t9 % 3 - 1, ox = (2 - blk) - 1;   // input offset of this block relative to the output voxel
-            int tap = -1;
-            for (int t = 0; t < 27; ++t)
-                if (d.band_taps[t].dz == oz && d.band_taps[t].dy == oy && d.band_taps[t].dx == ox) tap = t;
-            const int s = ks < d.nch[0] ? 0 : 1;
-            const int kk = (ks - (s ? d.nch[0] : 0)) * 16 + kg * 8 + k8;
-            int kidx = 0, part = 0;
-            bool kok;
-            if (d.split_k > 0 && s == 0) { kok = kk < 3 * d.split_k; part = kk / d.split_k; kidx = d.k_off[0] + kk % d.split_k; }   // PackDesc::split_k
-            else { kok = kk < d.k_real[s]; kidx = d.k_off[s] + kk; }
-            if (tap >= 0 && kok && nn < d.n_real) {
-                const int nidx = d.n_off + nn;
-                const long long a = d.n_is_A ? nidx : kidx, b = d.n_is_A ? kidx : nidx;
-                v = d.w[(a * d.dimB + b) * d.ktaps + d.tap_ref[tap]];
-                if (part == 2) v -= __half2float(__float2half_rn(v));
-            }
-        }
-        static_cast<__half*>(d.out)[i] = __float2half_rn(v);
-    }
-}
-
 }  // namespace
 
 unsigned int read_device_error_band() {
@@ -726,13 +689,6 @@ unsigned int read_device_error_band() {
 
 size_t pack_bytes_band(const PackDesc& d) { return size_t(9) * (d.nch[0] + d.nch[1]) * 2 * (4 * d.band_co) * 8 * 2; }
 
-int pack_weights_band_launch(const PackDesc& d, cudaStream_t stream) {
-    const long long total = (long long)pack_bytes_band(d) / 2;
-    const int grid = int(std::min<long long>((total + 255) / 256, 148 * 4));
-    pack_weights_band_kernel<<<grid, 256, 0, stream>>>(d);
-    U3D_CUDA_CHECK(cudaGetLastError());
-    return 0;
-}
 
 // planner hook: k3 s1 layer with 16|32 padded input channels (both sources together) and 16|32 padded output channels
 bool conv_band_wants(int k_channels_padded, int n_channels_padded, long long voxels) {

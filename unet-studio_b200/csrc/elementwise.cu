@@ -107,7 +107,12 @@ struct ReduceArgs {
     float* partials;     // [grid][2][Cp]
     long long V;
     int C, Cp, has_norm, act;
-    float dy_scale;      // unused
+    // MODE 1 with counter != nullptr: the block that finishes last also reduces the partial rows (fixed order => deterministic) into
+    // sums[2][Cp] and adds them to the gamma / beta gradients -- no separate finalize launch
+    unsigned int* counter;
+    float* sums;
+    float* dgamma;
+    float* dbeta;
 };
 
 template <int MODE>
@@ -187,6 +192,50 @@ __global__ void channel_reduce_kernel(const ReduceArgs a) {
         float acc = 0.f;
         for (int r = 0; r < k; ++r) acc += sm[size_t(r) * a.Cp * 2 + i];
         a.partials[size_t(blockIdx.x) * 2 * a.Cp + i] = acc;
+    }
+    if constexpr (MODE == 1) {
+        if (a.counter == nullptr) return;
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (t == 0) s_last = atomicAdd(a.counter, 1u) == gridDim.x - 1 ? 1 : 0;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const int ncol = 2 * a.Cp, rows = int(gridDim.x);
+        double* red = reinterpret_cast<double*>(sm);   // blockDim.x doubles fit: the dynamic buffer holds 16 floats per thread
+        auto emit = [&](int col, double tot) {
+            a.sums[col] = float(tot);
+            const int c = col < a.Cp ? col : col - a.Cp;
+            if (c < a.C) {
+                if (col < a.Cp) { if (a.dbeta) a.dbeta[c] += float(tot); }
+                else if (a.dgamma) a.dgamma[c] += float(tot);
+            }
+        };
+        if (ncol <= int(blockDim.x)) {
+            const int G = int(blockDim.x) / ncol;        // row groups; thread (g, col) walks rows g, g+G, ...
+            const int col = t % ncol, g = t / ncol;
+            double acc = 0;
+            if (g < G) {
+#pragma unroll 4
+                for (int r = g; r < rows; r += G) acc += double(__ldcg(a.partials + size_t(r) * ncol + col));
+            }
+            red[t] = acc;
+            __syncthreads();
+            if (g == 0) {
+                double tot = 0;
+                for (int q = 0; q < G; ++q) tot += red[q * ncol + col];
+                emit(col, tot);
+            }
+        } else {
+            for (int col = t; col < ncol; col += blockDim.x) {
+                double tot = 0;
+#pragma unroll 4
+                for (int r = 0; r < rows; ++r) tot += double(__ldcg(a.partials + size_t(r) * ncol + col));
+                emit(col, tot);
+            }
+        }
+        if (t == 0) *a.counter = 0u;
     }
 }
 
@@ -607,16 +656,19 @@ int norm_act_fwd_launch(const void* x, void* y, long long V, int C, int Cp, int 
 
 int norm_act_bwd_launch(const void* x, const void* dy, void* dx, long long V, int C, int Cp, int has_norm, int act,
                         const float* mean, const float* rstd, const float* gamma, const float* beta, float* partials,
-                        float* sums, float* dgamma, float* dbeta, cudaStream_t s) {
+                        float* sums, float* dgamma, float* dbeta, cudaStream_t s, unsigned int* counter) {
     if (has_norm) {
         ReduceArgs r{};
         r.x = static_cast<const uint4*>(x); r.dy = static_cast<const uint4*>(dy); r.V = V; r.C = C; r.Cp = Cp;
         r.has_norm = 1; r.act = act; r.mean = mean; r.rstd = rstd; r.gamma = gamma; r.beta = beta; r.partials = partials;
+        r.counter = counter; r.sums = sums; r.dgamma = dgamma; r.dbeta = dbeta;
         int rows = 0;
         if (reduce_launch(1, r, &rows, s)) return 1;
-        if (2 * Cp > 1024) { set_error("norm_act_bwd_launch: more than 512 padded channels"); return 1; }
-        finalize_bwd_sums_kernel<<<1, 1024, 0, s>>>(partials, rows, Cp, C, sums, dgamma, dbeta);
-        U3D_CUDA_CHECK(cudaGetLastError());
+        if (counter == nullptr) {
+            if (2 * Cp > 1024) { set_error("norm_act_bwd_launch: more than 512 padded channels"); return 1; }
+            finalize_bwd_sums_kernel<<<1, 1024, 0, s>>>(partials, rows, Cp, C, sums, dgamma, dbeta);
+            U3D_CUDA_CHECK(cudaGetLastError());
+        }
     }
     BwdApplyArgs a{};
     a.x = static_cast<const uint4*>(x); a.dy = static_cast<const uint4*>(dy); a.dx = static_cast<uint4*>(dx);

@@ -86,12 +86,13 @@ __global__ void unpack_act_kernel(const uint4* __restrict__ in, float* __restric
     }
 }
 
-__global__ void pack_weights_kernel(const __grid_constant__ PackDesc d) {
+// generic blob: element i of [tap][chunk][ntile][kc/8][n][8]; (vblock, nvblocks) = this block's position in the job's virtual grid
+__device__ __forceinline__ void pack_generic_body(const PackDesc& d, uint32_t vblock, uint32_t nvblocks) {
     // 32-bit index arithmetic (a pack has < 2^31 elements): the six div/mod per element dominated this kernel in 64 bit
     const uint32_t nch = uint32_t(d.nch[0] + d.nch[1]);
     const uint32_t ntile = uint32_t(d.ntile), ntiles = uint32_t(d.ntiles), kg_n = uint32_t(d.kc / 8);
     const uint32_t total = uint32_t(d.ntaps) * nch * ntiles * ntile * uint32_t(d.kc);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = vblock * blockDim.x + threadIdx.x; i < total; i += nvblocks * blockDim.x) {
         uint32_t r = i;
         const int k8 = int(r & 7u); r >>= 3;
         const int n = int(r % ntile); r /= ntile;
@@ -121,6 +122,58 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackDesc d) {
     }
 }
 
+// banded blob of conv_band.cu: [9 (dz,dy)][KS][2 k-groups][NB = 4*CO columns][8] fp16, columns = kernel column kx = 2,1,0 then a zero
+// block; the (dz,dy,dx) offsets come from the problem's own tap list (forward: k-1, dgrad: 1-k)
+__device__ __forceinline__ void pack_band_body(const PackDesc& d, uint32_t vblock, uint32_t nvblocks) {
+    const int KS = d.nch[0] + d.nch[1];
+    const int NB = 4 * d.band_co;
+    const uint32_t total = uint32_t(9 * KS * 2 * NB * 8);
+    for (uint32_t i = vblock * blockDim.x + threadIdx.x; i < total; i += nvblocks * blockDim.x) {
+        uint32_t r = i;
+        const int k8 = int(r % 8); r /= 8;
+        const int col = int(r % NB); r /= NB;
+        const int kg = int(r % 2); r /= 2;
+        const int ks = int(r % KS); r /= KS;
+        const int t9 = int(r);
+        const int blk = col / d.band_co, nn = col % d.band_co;
+        float v = 0.f;
+        if (blk < 3) {
+            const int oz = t9 / 3 - 1, oy = t9 % 3 - 1, ox = (2 - blk) - 1;   // input offset of this block relative to the output voxel
+            int tap = -1;
+            for (int t = 0; t < 27; ++t)
+                if (d.band_taps[t].dz == oz && d.band_taps[t].dy == oy && d.band_taps[t].dx == ox) tap = t;
+            const int s = ks < d.nch[0] ? 0 : 1;
+            const int kk = (ks - (s ? d.nch[0] : 0)) * 16 + kg * 8 + k8;
+            int kidx = 0, part = 0;
+            if (tap >= 0 && nn < d.n_real && pack_k_lookup(d, s, kk, kidx, part)) {
+                const int nidx = d.n_off + nn;
+                const long long a = d.n_is_A ? nidx : kidx, b = d.n_is_A ? kidx : nidx;
+                v = pack_k_value(d.w[(a * d.dimB + b) * d.ktaps + d.tap_ref[tap]], part);
+            }
+        }
+        static_cast<__half*>(d.out)[i] = __float2half_rn(v);
+    }
+}
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackDesc d) {
+    if (d.banded) pack_band_body(d, blockIdx.x, gridDim.x);
+    else pack_generic_body(d, blockIdx.x, gridDim.x);
+}
+
+// every weight blob of a model in ONE launch (the re-pack after each optimizer step was 69 launches of a few microseconds of work
+// each): job j owns the blocks [first_block[j], first_block[j+1])
+__global__ void pack_all_kernel(const PackDesc* __restrict__ descs, const int* __restrict__ first_block, int njobs) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {   // last job whose first block is <= blockIdx.x
+        const int mid = (lo + hi + 1) >> 1;
+        if (first_block[mid] <= int(blockIdx.x)) lo = mid; else hi = mid - 1;
+    }
+    const PackDesc& d = descs[lo];
+    const uint32_t vb = blockIdx.x - uint32_t(first_block[lo]), nvb = uint32_t(first_block[lo + 1] - first_block[lo]);
+    if (d.banded) pack_band_body(d, vb, nvb);
+    else pack_generic_body(d, vb, nvb);
+}
+
 inline int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = 148LL * 16;
@@ -130,9 +183,21 @@ inline int grid_for(long long total, int block) {
 }  // namespace
 
 int pack_weights_launch(const PackDesc& d, cudaStream_t stream) {
-    if (d.banded) return pack_weights_band_launch(d, stream);
     const long long total = (long long)pack_bytes(d) / 2;
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(d);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int pack_job_blocks(const PackDesc& d) {
+    const long long total = (long long)pack_bytes(d) / 2;
+    const long long b = (total + 256 * 8 - 1) / (256 * 8);   // ~8 elements per thread
+    return int(b < 1 ? 1 : (b > 4096 ? 4096 : b));
+}
+
+int pack_all_launch(const PackDesc* descs_dev, const int* first_block_dev, int njobs, int total_blocks, cudaStream_t stream) {
+    if (njobs <= 0) return 0;
+    pack_all_kernel<<<total_blocks, 256, 0, stream>>>(descs_dev, first_block_dev, njobs);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

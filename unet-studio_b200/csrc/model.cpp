@@ -268,6 +268,8 @@ Model::Model(int in_c, int out_c, const std::string& feature, bool host_only_)
     cudaMalloc(&d_chunks, chunks.size() * sizeof(SgdChunk));
     cudaMemcpy(d_chunks, chunks.data(), chunks.size() * sizeof(SgdChunk), cudaMemcpyHostToDevice);
     cudaMalloc(&d_status, sizeof(SgdStatus));
+    cudaMalloc(&d_counter, 16);
+    cudaMemsetAsync(d_counter, 0, 16, stream);
     const size_t nl = std::max<size_t>(output.size(), 1);   // per-level loss scratch, sized from the number of deep-supervision heads
     cudaMalloc(&d_loss_acc, sizeof(double) * nl * 80);
     cudaMalloc(&d_loss_part, sizeof(float) * nl * size_t(loss_part_rows()) * loss_part_cols());
@@ -293,6 +295,7 @@ Model::~Model() {
     if (vpa_ws) cudaFree(vpa_ws);
     if (pf_ws) cudaFree(pf_ws);
     for (auto b : d_buffers) cudaFree(b);
+    cudaFree(d_counter);
     cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_loss_part); cudaFree(d_losses);
     if (stream3) { cudaStreamSynchronize(stream3); cudaStreamDestroy(stream3); }
     for (int i = 0; i < 2; ++i) { if (ev_sample[i]) cudaEventDestroy(ev_sample[i]); if (pf_in[i]) cudaFree(pf_in[i]); }
@@ -308,7 +311,53 @@ int Model::alloc(void** p, size_t bytes) {
     return 0;
 }
 
+void Model::drop_graphs() {
+    for (auto& g : graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+}
+
+int Model::graph_run(const std::vector<uint64_t>& key, const std::function<int()>& body) {
+    static const bool disabled = std::getenv("U3D_NO_GRAPH") != nullptr;
+    if (disabled || prof_on) return body();
+    GraphEntry* e = nullptr;
+    for (auto& g : graphs)
+        if (g.key == key) { e = &g; break; }
+    if (!e) {   // first sight: enqueue normally (lazy allocations, function attributes, tensor-map encodes happen here)
+        if (graphs.size() >= 16) drop_graphs();
+        GraphEntry n;
+        n.key = key;
+        graphs.push_back(n);
+        return body();
+    }
+    if (e->bad) return body();
+    if (!e->exec) {
+        const long long l0 = launches;
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); e->bad = true; return body(); }
+        const int rc = body();
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+        if (rc != 0 || ce != cudaSuccess || g == nullptr) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            e->bad = true;
+            launches = l0;
+            if (rc != 0) return 1;
+            return body();   // nothing ran during the failed capture
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&e->exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) { cudaGetLastError(); e->exec = nullptr; e->bad = true; launches = l0; return body(); }
+        e->n_launches = launches - l0;
+        launches = l0;
+    }
+    M_CUDA(cudaGraphLaunch(e->exec, stream));
+    launches += e->n_launches;
+    return 0;
+}
+
 void Model::free_plan() {
+    drop_graphs();
     if (stream2) cudaStreamSynchronize(stream2);   // an asynchronous re-pack may still be writing the blobs freed below
     pack_pending = false;
     for (void* p : owned) cudaFree(p);
@@ -319,6 +368,7 @@ void Model::free_plan() {
     dlogits.clear();
     level_dims.clear();
     d_in_f32 = d_label = d_partials = d_sums = nullptr;
+    d_pack_descs = nullptr; d_pack_first = nullptr; n_pack_jobs = n_pack_blocks = 0;
     d_scratch = nullptr;
     d_splitk = nullptr;
     splitk_bytes = 0;
@@ -719,6 +769,27 @@ int Model::ensure_plan() {
             M_CHECK(alloc(reinterpret_cast<void**>(&s.idx), tens[s.out].V() * tens[s.out].Cp * sizeof(int)));
         }
     }
+    {   // job table of the one-launch weight re-pack
+        std::vector<PackDesc> jobs;
+        std::vector<int> first(1, 0);
+        for (auto& s : steps) {
+            if (s.kind != Step::CONV) continue;
+            for (auto& k : s.fpacks) jobs.push_back(k);
+            for (int src = 0; src < 2; ++src)
+                for (auto& k : s.dg[src].packs) jobs.push_back(k);
+        }
+        for (auto& k : jobs) first.push_back(first.back() + pack_job_blocks(k));
+        n_pack_jobs = int(jobs.size());
+        n_pack_blocks = first.back();
+        d_pack_descs = nullptr; d_pack_first = nullptr;
+        if (n_pack_jobs) {
+            M_CHECK(alloc(reinterpret_cast<void**>(&d_pack_descs), jobs.size() * sizeof(PackDesc)));
+            M_CHECK(alloc(reinterpret_cast<void**>(&d_pack_first), first.size() * sizeof(int)));
+            M_CUDA(cudaMemcpyAsync(d_pack_descs, jobs.data(), jobs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, stream));
+            M_CUDA(cudaMemcpyAsync(d_pack_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            M_CUDA(cudaStreamSynchronize(stream));   // the host vectors go out of scope
+        }
+    }
     grad_written.assign(tens.size(), 0);
     // data-parallel overlap split: the first conv (forward order) that has >= 5 % of the parameters in front of it.  In the default net
     // that is encode4's first conv: levels 0-3 hold 6 % of the parameters but the last ~20 % of the backward time.
@@ -741,12 +812,8 @@ int Model::ensure_plan() {
 }
 
 int Model::repack_on(cudaStream_t on) {
-    for (auto& s : steps) {
-        if (s.kind != Step::CONV) continue;
-        for (auto& k : s.fpacks) { M_CHECK(pack_weights_launch(k, on)); ++launches; }
-        for (int src = 0; src < 2; ++src)
-            for (auto& k : s.dg[src].packs) { M_CHECK(pack_weights_launch(k, on)); ++launches; }
-    }
+    M_CHECK(pack_all_launch(d_pack_descs, d_pack_first, n_pack_jobs, n_pack_blocks, on));
+    ++launches;
     return 0;
 }
 
@@ -843,8 +910,15 @@ int Model::forward(const float* in, float* const* out_levels, int n_levels_wante
     M_CHECK(repack());
     const int L = int(output.size());
     if (n_levels_wanted < 1 || n_levels_wanted > L) { set_error("levels wanted out of range"); return 1; }
-    M_CHECK(upload_input(in, where));
-    M_CHECK(run_forward(n_levels_wanted));
+    const float* fsrc = in;
+    if (where == 0) {
+        M_CUDA(cudaMemcpyAsync(d_in_f32, in, size_t(in_count) * tens[0].V() * 4, cudaMemcpyHostToDevice, stream));
+        fsrc = d_in_f32;
+    }
+    M_CHECK(graph_run({2u, uint64_t(reinterpret_cast<uintptr_t>(fsrc)), uint64_t(n_levels_wanted), uint64_t(bn_running ? 1 : 0)}, [&]() -> int {
+        M_CHECK(upload_input(fsrc, 1));
+        return run_forward(n_levels_wanted);
+    }));
     for (int l = 0; l < n_levels_wanted; ++l) {
         if (!out_levels || !out_levels[l]) continue;
         if (!logits[l]) { set_error("undefined deep supervision output at level " + std::to_string(l)); return 1; }
@@ -903,10 +977,13 @@ int Model::evaluate_windows(const float* const* in_windows, float* const* out_wi
         const int s = i & 1;
         if (i + 1 < n_windows) upload(i + 1);
         cudaStreamWaitEvent(stream, ev_up[s], 0);
-        rc = pack_act_launch(ew_in[s], tens[0].p, in_count, tens[0].Cp, V0, false, stream, split_input ? 1 : 0);
-        ++launches;
+        // packing the slot into the NDHWC input + the forward: one captured graph per staging slot
+        rc = graph_run({3u, uint64_t(reinterpret_cast<uintptr_t>(ew_in[s])), uint64_t(bn_running ? 1 : 0)}, [&]() -> int {
+            M_CHECK(pack_act_launch(ew_in[s], tens[0].p, in_count, tens[0].Cp, V0, false, stream, split_input ? 1 : 0));
+            ++launches;
+            return run_forward(1);
+        });
         cudaEventRecord(ev_packed[s], stream);
-        if (!rc) rc = run_forward(1);
         if (rc) break;
         if (i >= 2) cudaStreamWaitEvent(stream, ev_down[s], 0);  // the slot's previous window has left for the host
         cudaMemcpyAsync(ew_out[s], logits[0], out_bytes, cudaMemcpyDeviceToDevice, stream);
@@ -983,11 +1060,6 @@ int Model::evaluate_volume(const float* volume, int vw, int vh, int vd, int sx, 
 int Model::run_backward() {
     static const bool no_side = std::getenv("U3D_ONE_STREAM") != nullptr;
     const bool two_streams = !no_side && !prof_on && stream2 != nullptr;   // the per-family event profile needs serial kernels
-    ++dp_seen;
-    if (dp_comm != nullptr && dp_seen > dp_microbatches) {
-        set_error("more micro-batches in this step than declared in unet3d_attach_comm (the tail gradient bucket is already reduced)");
-        return 1;
-    }
     const bool dp_overlap_now = dp_comm != nullptr && stream4 != nullptr && dp_split_step >= 0 && dp_seen == dp_microbatches && !no_side;
     std::fill(grad_written.begin(), grad_written.end(), 0);
     // fused heads: the loss-gradient kernel (launched before this function) already stored dL/dx of the head input
@@ -1060,8 +1132,8 @@ int Model::run_backward() {
                 const float* beta = s.norm ? param_ptr(s.p_g + 1) : nullptr;
                 M_CHECK(norm_act_bwd_launch(a.p, o.grad, target, a.V(), a.C, a.Cp, s.norm ? 1 : 0, s.act, s.mean, s.rstd, gamma, beta,
                                             d_partials, d_sums, s.norm ? grad_ptr(s.p_g) : nullptr,
-                                            s.norm ? grad_ptr(s.p_g + 1) : nullptr, stream));
-                launches += s.norm ? 3 : 1;
+                                            s.norm ? grad_ptr(s.p_g + 1) : nullptr, stream, d_counter));
+                launches += s.norm ? 2 : 1;
             } else if (s.kind == Step::MAXPOOL) {
                 M_CHECK(maxpool_bwd_launch(o.grad, s.idx, target, o.Cp, o.d, o.h, o.w, stream));
                 ++launches;
@@ -1101,45 +1173,64 @@ int Model::train_microbatch(const float* in, const float* label, int collapse_be
     }
     if (collapse_before < 0 || collapse_before >= std::max(out_count, 1)) { set_error("invalid collapse_before"); return 1; }
     const long long V0 = tens[0].V();
-    M_CHECK(upload_input(in, where));
+    const float* src = in;
     const float* lab = label;
     if (where == 0) {
+        M_CUDA(cudaMemcpyAsync(d_in_f32, in, size_t(in_count) * V0 * 4, cudaMemcpyHostToDevice, stream));
         M_CUDA(cudaMemcpyAsync(d_label, label, size_t(V0) * 4, cudaMemcpyHostToDevice, stream));
+        src = d_in_f32;
         lab = d_label;
     }
-    M_CHECK(run_forward(L));
-    float weight_sum = 0.f;
-    for (int k = 0; k < L; ++k) weight_sum += 1.0f / float(1 << k);
-    const float inv_weight_sum = 1.0f / weight_sum;
-    const bool any = use_ce || use_dice || use_mse;
-    for (int k = 0; k < L; ++k) {
-        LossLevel Q{};
-        Q.logits = logits[k]; Q.label = lab; Q.dlogits = dlogits[k];
-        Q.C = out_count; Q.Cp = pad16(out_count); Q.collapse_before = collapse_before;
-        Q.d = level_dims[3 * k]; Q.h = level_dims[3 * k + 1]; Q.w = level_dims[3 * k + 2];
-        Q.H0 = dim[1]; Q.W0 = dim[0]; Q.shift = k;
-        const float nw = (1.0f / float(1 << k)) * inv_weight_sum;
-        Q.w_ce = (use_ce || !any) ? nw : 0.f;   // "if(!level_loss.defined()) level_loss = ce" (train.cpp:696-697)
-        Q.w_dice = use_dice ? nw : 0.f;
-        Q.w_mse = use_mse ? nw : 0.f;
-        Q.loss_scale = loss_scale;
-        Q.acc = d_loss_acc + 80 * k;
-        Q.part = d_loss_part + size_t(k) * loss_part_rows() * loss_part_cols();
-        Q.out3 = d_losses + 3 * k;
-        HeadFuse Hd{};
-        const Step* hs = head_step[k] >= 0 ? &steps[head_step[k]] : nullptr;
-        if (hs && hs->head_bwd_fused) {
-            const Ten& a = tens[hs->in0];
-            Hd.x = a.p; Hd.xc = a.C; Hd.xcp = a.Cp;
-            Hd.w = param_ptr(hs->p_w);
-            Hd.dx = a.grad; Hd.dx_accum = 0;
-            Hd.dw = grad_ptr(hs->p_w); Hd.db = grad_ptr(hs->p_b);
-            M_CHECK(loss_level_launch(Q, &Hd, stream));
-        } else
-            M_CHECK(loss_level_launch(Q, stream));
-        launches += 4;
+    ++dp_seen;
+    if (dp_comm != nullptr && dp_seen > dp_microbatches) {
+        set_error("more micro-batches in this step than declared in unet3d_attach_comm (the tail gradient bucket is already reduced)");
+        return 1;
     }
-    M_CHECK(run_backward());
+    auto enqueue = [&]() -> int {
+        M_CHECK(upload_input(src, 1));
+        M_CHECK(run_forward(L));
+        float weight_sum = 0.f;
+        for (int k = 0; k < L; ++k) weight_sum += 1.0f / float(1 << k);
+        const float inv_weight_sum = 1.0f / weight_sum;
+        const bool any = use_ce || use_dice || use_mse;
+        for (int k = 0; k < L; ++k) {
+            LossLevel Q{};
+            Q.logits = logits[k]; Q.label = lab; Q.dlogits = dlogits[k];
+            Q.C = out_count; Q.Cp = pad16(out_count); Q.collapse_before = collapse_before;
+            Q.d = level_dims[3 * k]; Q.h = level_dims[3 * k + 1]; Q.w = level_dims[3 * k + 2];
+            Q.H0 = dim[1]; Q.W0 = dim[0]; Q.shift = k;
+            const float nw = (1.0f / float(1 << k)) * inv_weight_sum;
+            Q.w_ce = (use_ce || !any) ? nw : 0.f;   // "if(!level_loss.defined()) level_loss = ce" (train.cpp:696-697)
+            Q.w_dice = use_dice ? nw : 0.f;
+            Q.w_mse = use_mse ? nw : 0.f;
+            Q.loss_scale = loss_scale;
+            Q.acc = d_loss_acc + 80 * k;
+            Q.part = d_loss_part + size_t(k) * loss_part_rows() * loss_part_cols();
+            Q.out3 = d_losses + 3 * k;
+            HeadFuse Hd{};
+            const Step* hs = head_step[k] >= 0 ? &steps[head_step[k]] : nullptr;
+            if (hs && hs->head_bwd_fused) {
+                const Ten& a = tens[hs->in0];
+                Hd.x = a.p; Hd.xc = a.C; Hd.xcp = a.Cp;
+                Hd.w = param_ptr(hs->p_w);
+                Hd.dx = a.grad; Hd.dx_accum = 0;
+                Hd.dw = grad_ptr(hs->p_w); Hd.db = grad_ptr(hs->p_b);
+                M_CHECK(loss_level_launch(Q, &Hd, stream));
+            } else
+                M_CHECK(loss_level_launch(Q, stream));
+            launches += 4;
+        }
+        return run_backward();
+    };
+    // the data-parallel overlap issues an NCCL collective from inside the backward pass: enqueued normally
+    if (dp_comm == nullptr) {
+        uint32_t ls_bits;
+        std::memcpy(&ls_bits, &loss_scale, 4);
+        const std::vector<uint64_t> key = {1u, uint64_t(reinterpret_cast<uintptr_t>(src)), uint64_t(reinterpret_cast<uintptr_t>(lab)),
+                                           uint64_t(collapse_before), uint64_t((use_ce ? 1 : 0) | (use_dice ? 2 : 0) | (use_mse ? 4 : 0)), ls_bits};
+        M_CHECK(graph_run(key, enqueue));
+    } else
+        M_CHECK(enqueue());
     std::vector<float> h(size_t(3) * L);
     M_CUDA(cudaMemcpyAsync(h.data(), d_losses, h.size() * 4, cudaMemcpyDeviceToHost, stream));
     M_CHECK(sync());

@@ -1,6 +1,7 @@
 // Host-side UNet3d: feature_string parser, layer graph, memory plan and the forward / backward /
 // optimizer executors that drive the sm_100a kernels.  Mirrors UNet3dImpl (/root/reference/unet.hpp:13-70).
 #pragma once
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -192,6 +193,19 @@ class Model {
     void prof_begin(int kind, double flops, cudaStream_t on = nullptr);
     void prof_end(cudaStream_t on = nullptr);
     int prof_read(double out[18], int reset);  // per kind: {ms, launches, algorithmic FLOPs}
+    // CUDA graphs: the kernel sequence of a micro-batch / an inference forward is fixed for a plan, so its second occurrence with the
+    // same buffers is captured (stream capture of the ordinary enqueue code, side stream included) and replayed afterwards: one
+    // graph launch instead of ~250 kernel launches whose host cost paced the small deep-level kernels.  Keyed by the device pointers
+    // and flags baked into the kernel arguments; dropped with the plan.  U3D_NO_GRAPH=1 disables.
+    struct GraphEntry {
+        std::vector<uint64_t> key;
+        cudaGraphExec_t exec = nullptr;
+        long long n_launches = 0;
+        bool bad = false;     // capture failed once: keep enqueuing normally
+    };
+    std::vector<GraphEntry> graphs;
+    int graph_run(const std::vector<uint64_t>& key, const std::function<int()>& body);
+    void drop_graphs();
     int n_levels() const { return int(output.size()); }
     bool planned_for_pack_blobs() const { return planned; }   // the plan's weight blobs exist
     int resolve_status();            // waits for the last update's status read-back (lazy; see step.cpp)
@@ -208,6 +222,9 @@ class Model {
     std::vector<int> head_step;      // per level: index of the head conv in `steps` (-1 = none)
     bool planned = false, planned_training = false;
     bool packs_dirty = true;
+    PackDesc* d_pack_descs = nullptr;   // every weight blob of the plan (forward then data-gradient packs of each conv), one launch
+    int* d_pack_first = nullptr;
+    int n_pack_jobs = 0, n_pack_blocks = 0;
     bool split_input = false;        // network input stored as fp16 [hi | lo | hi] in the padded channels (PackDesc::split_k)
     float* d_in_f32 = nullptr;
     float* d_label = nullptr;
@@ -223,6 +240,7 @@ class Model {
     SgdChunk* d_chunks = nullptr;
     int n_chunks = 0;
     SgdStatus* d_status = nullptr;
+    unsigned int* d_counter = nullptr;   // "last block finalizes" ticket of the norm-backward reduction (reset by that block)
     int last_stat_rows = 0, last_stat_ntot = 0;
     std::vector<char> grad_written;
     std::vector<void*> owned;        // every cudaMalloc of the plan

@@ -30,9 +30,11 @@ struct PackDesc {
                              // layer computes w_hi*x_hi + w_hi*x_lo + w_lo*x_hi = w*x to ~22 bits in the spare padded channels
 };
 size_t pack_bytes_band(const PackDesc& d);
-int pack_weights_band_launch(const PackDesc& d, cudaStream_t stream);
 size_t pack_bytes(const PackDesc& d);
 int pack_weights_launch(const PackDesc& d, cudaStream_t stream);
+// all blobs of a model in one launch: descs_dev[njobs], first_block_dev[njobs + 1] (prefix sums of pack_job_blocks)
+int pack_job_blocks(const PackDesc& d);
+int pack_all_launch(const PackDesc* descs_dev, const int* first_block_dev, int njobs, int total_blocks, cudaStream_t stream);
 
 // NCDHW fp32 (reference order, train.cpp:619-621) <-> NDHWC 16-bit with channels zero-padded to Cp
 // split != 0 (needs 3*C <= Cp): channels [0,C) = fp16(x), [C,2C) = fp16(x - fp16(x)), [2C,3C) = fp16(x) again (see PackDesc::split_k)
