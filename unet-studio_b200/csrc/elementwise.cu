@@ -3,6 +3,7 @@
 // (/root/reference/unet.cpp:74-98), MaxPool3d(2,2) with indices and nearest Upsample x2 (unet.cpp:38-44).
 // One thread moves one 16-byte chunk (8 channels of one voxel); reductions keep a fixed channel chunk per
 // thread so no atomics are needed until the per-block partial rows.
+#include <algorithm>
 #include <string>
 
 #include "common.cuh"
@@ -217,8 +218,16 @@ __global__ void channel_reduce_kernel(const ReduceArgs a) {
             const int col = t % ncol, g = t / ncol;
             double acc = 0;
             if (g < G) {
-#pragma unroll 4
-                for (int r = g; r < rows; r += G) acc += double(__ldcg(a.partials + size_t(r) * ncol + col));
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;   // four independent chains in a fixed pattern (deterministic)
+                int r = g;
+                for (; r + 3 * G < rows; r += 4 * G) {
+                    a0 += double(__ldcg(a.partials + size_t(r) * ncol + col));
+                    a1 += double(__ldcg(a.partials + size_t(r + G) * ncol + col));
+                    a2 += double(__ldcg(a.partials + size_t(r + 2 * G) * ncol + col));
+                    a3 += double(__ldcg(a.partials + size_t(r + 3 * G) * ncol + col));
+                }
+                for (; r < rows; r += G) a0 += double(__ldcg(a.partials + size_t(r) * ncol + col));
+                acc = (a0 + a1) + (a2 + a3);
             }
             red[t] = acc;
             __syncthreads();
@@ -615,7 +624,13 @@ static int reduce_launch(int mode, const ReduceArgs& a, int* rows, cudaStream_t 
     const int k = nch >= 256 ? 1 : 256 / nch;
     const int block = nch * k;
     long long want = (a.V + k - 1) / k;
-    const int grid = int(want < 1 ? 1 : (want > reduce_rows_max() ? reduce_rows_max() : want));
+    int grid = int(want < 1 ? 1 : (want > reduce_rows_max() ? reduce_rows_max() : want));
+    if (mode == 1 && a.counter != nullptr) {
+        // the block that finishes last sums the partial rows: keep its per-thread chain (rows * 2*Cp / block) at ~40 loads.  The wide
+        // layers are the small deep-level tensors, which a few dozen blocks stream in a microsecond anyway.
+        const int cap = std::max(8, 40 * block / (2 * a.Cp));
+        grid = std::min(grid, cap);
+    }
     const size_t smem = size_t(k) * a.Cp * 2 * sizeof(float);
     if (mode == 0) channel_reduce_kernel<0><<<grid, block, smem, s>>>(a);
     else channel_reduce_kernel<1><<<grid, block, smem, s>>>(a);

@@ -10,19 +10,32 @@ namespace u3d {
 namespace {
 
 // first-layer precision: the input as fp16 hi + lo pairs in the padded channels, [hi (C) | lo (C) | hi (C) | 0...]
-__global__ void pack_act_split_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int Cp, long long V) {
+__global__ void pack_act_split_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, int Cp, long long V) {
+    const int nch = Cp / 8;
     for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < V; vox += (long long)gridDim.x * blockDim.x) {
-        __align__(16) __half row[64];
-        for (int c = 0; c < Cp; ++c) row[c] = __float2half_rn(0.f);
-        for (int c = 0; c < C; ++c) {
-            const float x = in[(long long)c * V + vox];
-            const __half hi = __float2half_rn(x);
-            row[c] = hi;
-            row[C + c] = __float2half_rn(x - __half2float(hi));
-            row[2 * C + c] = hi;
+        for (int chunk = 0; chunk < nch; ++chunk) {
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (chunk * 8 < 3 * C) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int ch = chunk * 8 + j;
+                    float v = 0.f;
+                    if (ch < 3 * C) {
+                        const int part = ch / C;
+                        const float x = in[(long long)(ch - part * C) * V + vox];   // re-reads of the same address hit L1
+                        const float hi = __half2float(__float2half_rn(x));
+                        v = part == 1 ? x - hi : hi;
+                    }
+                    f[j] = v;
+                }
+                q.x = pack2<false>(f[0], f[1]);
+                q.y = pack2<false>(f[2], f[3]);
+                q.z = pack2<false>(f[4], f[5]);
+                q.w = pack2<false>(f[6], f[7]);
+            }
+            out[vox * nch + chunk] = q;
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + vox * Cp);
-        for (int q = 0; q < Cp / 8; ++q) dst[q] = reinterpret_cast<const uint4*>(row)[q];
     }
 }
 
@@ -205,7 +218,7 @@ int pack_all_launch(const PackDesc* descs_dev, const int* first_block_dev, int n
 int pack_act_launch(const float* in, void* out, int C, int Cp, long long V, bool bf16, cudaStream_t stream, int split) {
     if (split) {
         if (bf16 || 3 * C > Cp || Cp > 64) { set_error("pack_act: split needs fp16 and 3*C <= Cp <= 64"); return 1; }
-        pack_act_split_kernel<<<grid_for(V, 256), 256, 0, stream>>>(in, static_cast<__half*>(out), C, Cp, V);
+        pack_act_split_kernel<<<grid_for(V, 256), 256, 0, stream>>>(in, static_cast<uint4*>(out), C, Cp, V);
         U3D_CUDA_CHECK(cudaGetLastError());
         return 0;
     }

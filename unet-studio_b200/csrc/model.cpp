@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <random>
@@ -338,6 +339,7 @@ int Model::graph_run(const std::vector<uint64_t>& key, const std::function<int()
         cudaGraph_t g = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(stream, &g);
         if (rc != 0 || ce != cudaSuccess || g == nullptr) {
+            if (std::getenv("U3D_GRAPH_DEBUG")) std::fprintf(stderr, "u3d: graph capture failed (rc %d, %s)\n", rc, cudaGetErrorString(ce));
             cudaGetLastError();
             if (g) cudaGraphDestroy(g);
             e->bad = true;
@@ -350,6 +352,7 @@ int Model::graph_run(const std::vector<uint64_t>& key, const std::function<int()
         if (ie != cudaSuccess) { cudaGetLastError(); e->exec = nullptr; e->bad = true; launches = l0; return body(); }
         e->n_launches = launches - l0;
         launches = l0;
+        if (std::getenv("U3D_GRAPH_DEBUG")) std::fprintf(stderr, "u3d: captured a graph of %lld launches (kind %llu)\n", e->n_launches, (unsigned long long)key[0]);
     }
     M_CUDA(cudaGraphLaunch(e->exec, stream));
     launches += e->n_launches;
