@@ -511,7 +511,8 @@ def main():
     e2e_value = world * args.steps / (e2e_ms / 1000.0)
     vox = W * H * D
     fams = {}
-    for i, name in enumerate(("conv_igemm_kernel", "conv_wgrad_kernel", "conv_halo_s2_kernel", "conv_wgrad_band_kernel", "conv_tma_kernel", "conv_band_kernel")):
+    for i, name in enumerate(("conv_igemm_kernel", "conv_wgrad_kernel", "conv_s2_kernel", "conv_wgrad_band_kernel", "conv_tma_kernel", "conv_band_kernel",
+                              "conv_wgrad_quad_kernel")):
         ms_k, n_k, fl_k = prof[3 * i:3 * i + 3]
         fams[name] = {"ms_per_step": ms_k / args.steps, "launches_per_step": n_k / args.steps, "gflop_per_step": fl_k / args.steps / 1e9,
                       "achieved_tflops": (fl_k / 1e12) / (ms_k / 1e3) if ms_k > 0 else None}

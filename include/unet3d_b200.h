@@ -182,11 +182,11 @@ int unet3d_timer_start(unet3d_t* h);
 int unet3d_timer_stop(unet3d_t* h, float* ms);
 
 /* Per-launch CUDA-event profile of the tensor-core kernels on the handle's stream (for the bench roofline):
- * out18 = {ms, launches, algorithmic FLOPs} for each of conv_igemm, conv_wgrad, conv_halo, conv_wgrad_rows, conv_tma and one
- * reserved family (in this order)
+ * out24 = {ms, launches, algorithmic FLOPs} for each of conv_igemm, conv_wgrad, conv_s2, conv_wgrad_band, conv_tma, conv_band,
+ * conv_wgrad_quad and one reserved family (in this order)
  * since the last reset; algorithmic FLOPs = 2*Cin*Cout*k^3*V_out per layer. */
 int unet3d_profile(unet3d_t* h, int enable);
-int unet3d_profile_read(unet3d_t* h, double out18[18], int reset);
+int unet3d_profile_read(unet3d_t* h, double out24[24], int reset);
 
 /* visual_perception_augmentation(options, image, label, is_label, shape, seed) (train.hpp:43-48,
  * visual_perception_augmentation.cpp:163-438): in place on `image` ({channels,D,H,W} fp32 = tipl::image<3> with the

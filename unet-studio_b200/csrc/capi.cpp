@@ -265,8 +265,8 @@ int unet3d_profile(unet3d_t* h, int enable) {
     return 0;
     GUARD_END
 }
-int unet3d_profile_read(unet3d_t* h, double out18[18], int reset) {
-    GUARD_BEGIN NEED(h) return h->m->prof_read(out18, reset);
+int unet3d_profile_read(unet3d_t* h, double out24[24], int reset) {
+    GUARD_BEGIN NEED(h) return h->m->prof_read(out24, reset);
     GUARD_END
 }
 

@@ -429,6 +429,8 @@ unsigned int read_device_error() {
     if (v) return v;
     v = read_device_error_wband();
     if (v) return v;
+    v = read_device_error_wquad();
+    if (v) return v;
     return read_device_error_s2();
 }
 

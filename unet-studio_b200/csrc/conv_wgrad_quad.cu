@@ -1,0 +1,283 @@
+// Weight gradient of the 16-channel 3x3x3 stride-1 convolutions of the full-resolution level ("quad" kernel: 2 x 2 output rows
+// against 4 x 4 input rows per MMA pair).
+//
+//   dW[co][ci][dz,dy,dx] = sum_v x[v + (dz,dy,dx)][ci] * g[v][co]          (g = gradient of the conv output)
+//
+// Both operands are NDHWC rows, i.e. MN-major with the reduction index (voxels along x) strided by one voxel row of 32 bytes: exactly
+// the SWIZZLE_32B MN-major canonical layout (8 voxels x 32 B per atom, next 8 voxels 256 B further).  Measured
+// (tools/mma_mn_bench.cu, profiles/r02_mma_mn_bench.txt): an MN-major tcgen05.mma M = 128, K = 16 costs 114 clk for EVERY N <= 192
+// and 128 clk at N = 256, in every swizzle mode, so the only lever is useful work per instruction.  conv_wgrad_band.cu stacks
+// (8 x rows) x (3 g rows x 3 dx copies): 9 of its 24 (row, row) pairs are taps, 1 MMA per g row and 16 voxels.  Here
+//   M = 8 atoms = (ay' in {0,1}) x (az in 0..3) x 16 ci     x rows of FOUR planes z0-1..z0+2, two y rows  -> two accumulators
+//                                                           D1 (y rows y-1, y) and D2 (y rows y+1, y+2)
+//   N = 12 atoms = (by in {0,1}) x (bz in {0,1}) x (3 copies shifted by dx) x 16 co = 192
+//   tap (dz, dy) = (az - bz - 1, ay - by - 1): 36 of the 64 (x row, g row) pairs are taps (each of the 9 (dz,dy) taps four times,
+//   once per g row), 2 MMAs per FOUR g rows and 16 voxels = half the instructions of the band kernel at the same 114 clk.
+// The CTA owns a column (32 voxels in x, 2 planes in z) and marches along y two rows at a time through a ring of x row pairs
+// (each pair = 2 y rows x 4 planes, laid out [y][plane] so that the 8 atoms of an operand are 1 KB apart) and a ring of g slots
+// (4 rows x 3 copies).  Accumulators live in TMEM for the CTA's whole life; one epilogue adds the 36 useful blocks into the
+// reference-layout gradient with fp32 atomics.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "u3d.h"
+
+namespace u3d {
+namespace {
+
+constexpr int kQThreads = 32 * 13;     // warps 0-3 epilogue, 4-11 producers, 12 MMA issuer
+constexpr int kQProducers = 256;
+constexpr int kQXSlots = 4, kQYSlots = 3;
+constexpr int kQXT = 32;               // voxels per tile along x = two K steps
+constexpr uint32_t kQRow = kQXT * 32u; // bytes of one atom row (32 voxels x 16 channels fp16)
+constexpr uint32_t kQXSlotB = 8 * kQRow, kQYSlotB = 12 * kQRow;
+constexpr uint32_t kQOffY = kQXSlots * kQXSlotB;
+constexpr uint32_t kQOffBars = kQOffY + kQYSlots * kQYSlotB;
+constexpr size_t kQSmem = kQOffBars + 8 * (2 * kQXSlots + 2 * kQYSlots + 1) + 16 + 1024;   // + slack for the 1024-byte alignment
+
+struct WQParams {
+    WgradProblem P;
+    int tiles_x, zpairs, ychunks, ylen, total_items;
+};
+
+__device__ __forceinline__ uint64_t desc_sw32_mn(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= uint64_t((addr & 0x3FFFF) >> 4);
+    d |= uint64_t((lbo >> 4) & 0x3FFF) << 16;
+    d |= uint64_t((sbo >> 4) & 0x3FFF) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(6) << 61;   // SWIZZLE_32B
+    return d;
+}
+// SWIZZLE_32B: the two 16-byte halves of a 32-byte row are exchanged in rows 4..7 of every 8-row (256-byte) atom
+__device__ __forceinline__ uint32_t sw32(uint32_t addr) { return addr ^ (((addr >> 7) & 1u) << 4); }
+
+__global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __grid_constant__ WQParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t bars = sbase + kQOffBars;
+    auto xfull = [&](int s) { return bars + 8u * s; };
+    auto xempty = [&](int s) { return bars + 8u * (kQXSlots + s); };
+    auto yfull = [&](int s) { return bars + 8u * (2 * kQXSlots + s); };
+    auto yempty = [&](int s) { return bars + 8u * (2 * kQXSlots + kQYSlots + s); };
+    const uint32_t done_bar = bars + 8u * (2 * kQXSlots + 2 * kQYSlots);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kQOffBars + 8u * (2 * kQXSlots + 2 * kQYSlots + 1));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kQXSlots; ++s) { mbar_init(xfull(s), kQProducers); mbar_init(xempty(s), 1); }
+        for (int s = 0; s < kQYSlots; ++s) { mbar_init(yfull(s), kQProducers); mbar_init(yempty(s), 1); }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 12) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const WgradProblem& P = p.P;
+    const int D = P.t_d, H = P.t_h, W = P.t_w;
+    const bool has_work = int(blockIdx.x) < p.total_items;
+
+    if (warp >= 4 && warp < 12) {
+        // ===================================== producers =====================================
+        const int t = threadIdx.x - 128;
+        const uint8_t* const xsrc = static_cast<const uint8_t*>(P.T) + P.t_coff * 2;
+        const uint8_t* const gsrc = static_cast<const uint8_t*>(P.U) + P.u_coff * 2;
+        const long long xpitch = (long long)P.t_cp * 2, gpitch = (long long)P.u_cp * 2;
+        uint32_t xcnt = 0, ycnt = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int rem = item;
+            const int yc = rem % p.ychunks; rem /= p.ychunks;
+            const int tx = rem % p.tiles_x;
+            const int zp = rem / p.tiles_x;
+            const int x0 = tx * kQXT, z0 = zp * 2, y0 = yc * p.ylen;
+            const int y1 = min(H, y0 + p.ylen);
+            const int ns = (y1 - y0 + 1) / 2;
+            for (int pr = 0; pr <= ns; ++pr) {
+                {   // x pair pr: rows y0 + 2 pr - 1 + r (r = 0, 1) of the planes z0 - 1 + az (az = 0..3); row index in the slot = r*4 + az
+                    const int slot = xcnt % kQXSlots;
+                    mbar_wait(xempty(slot), ((xcnt / kQXSlots) & 1) ^ 1, 0x3500u | slot);
+                    const uint32_t blk = sbase + slot * kQXSlotB;
+                    // 8 rows x 32 voxels x 2 chunks = 512 copies: two per thread
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int idx = t + k * kQProducers;
+                        const int cg = idx & 1, lx = (idx >> 1) & 31, row = idx >> 6;
+                        const int az = row & 3, r = row >> 2;
+                        const int gz = z0 - 1 + az, gy = y0 + 2 * pr - 1 + r, gx = x0 + lx;
+                        const bool ok = (unsigned)gz < (unsigned)D && (unsigned)gy < (unsigned)H && gx < W;
+                        const uint8_t* src = ok ? xsrc + (((long long)gz * H + gy) * W + gx) * xpitch + cg * 16 : xsrc;
+                        cp_async16(sw32(blk + uint32_t(row) * kQRow + uint32_t(lx) * 32u + uint32_t(cg) * 16u), src, ok ? 16u : 0u);
+                    }
+                    cp_async_mbar_arrive(xfull(slot));
+                    ++xcnt;
+                }
+                if (pr < ns) {   // g slot pr: rows y0 + 2 pr + by of the planes z0 + bz, three copies shifted by dx = -1, 0, +1
+                    const int slot = ycnt % kQYSlots;
+                    mbar_wait(yempty(slot), ((ycnt / kQYSlots) & 1) ^ 1, 0x3600u | slot);
+                    const uint32_t blk = sbase + kQOffY + slot * kQYSlotB;
+                    // 4 rows x 32 voxels x 2 chunks = 256 sources, each copied three times
+                    const int cg = t & 1, lx = (t >> 1) & 31, rw = t >> 6;   // rw = by*2 + bz
+                    const int bz = rw & 1, by = rw >> 1;
+                    const int gz = z0 + bz, gy = y0 + 2 * pr + by;
+                    const bool rok = gz < D && gy < y1;     // rows past the chunk belong to the next item
+                    const uint8_t* const s0 = gsrc + (((long long)(rok ? gz : 0) * H + (rok ? gy : 0)) * W) * gpitch + cg * 16;
+#pragma unroll
+                    for (int dxc = 0; dxc < 3; ++dxc) {     // copy dxc holds g[x' - dx], dx = dxc - 1
+                        const int gx = x0 + lx - (dxc - 1);
+                        const bool ok = rok && (unsigned)gx < (unsigned)W;
+                        cp_async16_ca(sw32(blk + uint32_t(rw * 3 + dxc) * kQRow + uint32_t(lx) * 32u + uint32_t(cg) * 16u),
+                                      ok ? s0 + (long long)gx * gpitch : gsrc, ok ? 16u : 0u);
+                    }
+                    cp_async_mbar_arrive(yfull(slot));
+                    ++ycnt;
+                }
+            }
+        }
+        cp_async_wait<0>();
+    } else if (warp == 12) {
+        // ===================================== MMA issuer =====================================
+        if (has_work) {
+            const uint32_t idesc = umma_idesc(128, 192, 0, 0, 1, 1);    // both operands MN-major
+            const uint32_t d1 = tmem_base, d2 = tmem_base + 256u;
+            uint32_t xcnt = 0, ycnt = 0;
+            bool first = true;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int yc = item % p.ychunks;
+                const int y0 = yc * p.ylen, y1 = min(H, y0 + p.ylen);
+                const int ns = (y1 - y0 + 1) / 2;
+#pragma unroll 1
+                for (int j = 0; j < ns; ++j, ++ycnt) {
+                    const uint32_t c1 = xcnt + j, c2 = c1 + 1;
+                    mbar_wait(xfull(c1 % kQXSlots), (c1 / kQXSlots) & 1, 0x3701u);
+                    mbar_wait(xfull(c2 % kQXSlots), (c2 / kQXSlots) & 1, 0x3702u);
+                    mbar_wait(yfull(ycnt % kQYSlots), (ycnt / kQYSlots) & 1, 0x3703u);
+                    fence_proxy_async();
+                    tc_fence_after();
+                    const uint64_t a1 = desc_sw32_mn(sbase + (c1 % kQXSlots) * kQXSlotB, kQRow, 256u);
+                    const uint64_t a2 = desc_sw32_mn(sbase + (c2 % kQXSlots) * kQXSlotB, kQRow, 256u);
+                    const uint64_t b = desc_sw32_mn(sbase + kQOffY + (ycnt % kQYSlots) * kQYSlotB, kQRow, 256u);
+                    const bool f = first;
+                    first = false;
+                    if (elect_one()) {
+                        if (f) { umma_f16_first(d1, a1, b, idesc); umma_f16_first(d2, a2, b, idesc); }
+                        else { umma_f16_acc(d1, a1, b, idesc); umma_f16_acc(d2, a2, b, idesc); }
+                        umma_f16_acc(d1, a1 + 32u, b + 32u, idesc);      // second K step: 16 voxels = 512 bytes further
+                        umma_f16_acc(d2, a2 + 32u, b + 32u, idesc);
+                        umma_commit(yempty(ycnt % kQYSlots));
+                        umma_commit(xempty(c1 % kQXSlots));              // pair j: last used here (as the D1 operand)
+                        if (j == ns - 1) umma_commit(xempty(c2 % kQXSlots));
+                    }
+                    __syncwarp();
+                }
+                xcnt += uint32_t(ns + 1);
+            }
+            if (elect_one()) umma_commit(done_bar);
+        }
+        __syncwarp();
+    } else if (has_work) {
+        // ===================================== epilogue (once) ================================
+        mbar_wait(done_bar, 0, 0x3800u);
+        tc_fence_after();
+        const int m = threadIdx.x;                 // accumulator row = TMEM lane
+        const int g = m >> 4, ci = m & 15;
+        const int az = g & 3, ayp = g >> 2;        // atom g = ay' * 4 + az
+        const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
+        const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
+        const bool ci_ok = ci < P.t_creal;
+#pragma unroll 1
+        for (int acc = 0; acc < 2; ++acc) {
+            const int ay = acc * 2 + ayp;
+#pragma unroll 1
+            for (int rw = 0; rw < 4; ++rw) {       // g row rw = by * 2 + bz
+                const int bz = rw & 1, by = rw >> 1;
+                const int dzi = az - bz, dyi = ay - by;    // = dz + 1, dy + 1
+                const bool ok = ci_ok && dzi >= 0 && dzi <= 2 && dyi >= 0 && dyi <= 2;
+#pragma unroll 1
+                for (int dxc = 0; dxc < 3; ++dxc) {
+                    float v[16];
+                    tmem_ld16(t_row + uint32_t(acc * 256 + (rw * 3 + dxc) * 16), v);   // warp-collective: every lane takes part
+                    if (ok) {
+                        const int tap = (dzi * 3 + dyi) * 3 + dxc;
+                        float* dwrow = P.dw + size_t(P.w_moff + ci) * P.w_ktaps + tap;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < P.u_creal) atomicAdd(dwrow + size_t(P.w_noff + j) * nstride, v[j]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+unsigned int read_device_error_wquad() {
+    unsigned int v = 0;
+    cudaMemcpyFromSymbol(&v, g_dev_error, sizeof(v));
+    return v;
+}
+
+bool conv_wgrad_quad_eligible(const WgradProblem& P) {
+    static const bool disabled = std::getenv("U3D_NO_WQUAD") != nullptr || std::getenv("U3D_NO_WBAND") != nullptr;
+    if (disabled) return false;
+    if (P.ntaps != 27 || P.tstride != 1 || P.w_ktaps != 27) return false;
+    if (P.t_c != 16 || P.u_c != 16) return false;
+    if (P.t_d != P.ld || P.t_h != P.lh || P.t_w != P.lw) return false;
+    if (1LL * P.ld * P.lh * P.lw < 32768) return false;
+    if ((P.t_cp * 2) % 32 || (P.u_cp * 2) % 32 || (P.t_coff * 2) % 32 || (P.u_coff * 2) % 32) return false;   // 16-byte chunks of a 32-byte channel row
+    if ((reinterpret_cast<uintptr_t>(P.T) & 15) || (reinterpret_cast<uintptr_t>(P.U) & 15)) return false;
+    for (int t = 0; t < 27; ++t)   // forward tap order (kz,ky,kx) with offsets k-1 and identity tap_ref
+        if (P.taps[t].dz != t / 9 - 1 || P.taps[t].dy != (t / 3) % 3 - 1 || P.taps[t].dx != t % 3 - 1 || P.tap_ref[t] != t) return false;
+    return true;
+}
+
+int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream) {
+    WQParams wp;
+    std::memset(&wp, 0, sizeof(wp));
+    wp.P = P;
+    wp.tiles_x = (P.lw + kQXT - 1) / kQXT;
+    wp.zpairs = (P.ld + 1) / 2;
+    const int sms = device_sm_count();
+    const long long cols = 1LL * wp.tiles_x * wp.zpairs;
+    // y chunk length: even, balances (items per wave) against the one extra x pair every chunk loads
+    int best_yc = 1;
+    double best_eff = -1;
+    for (int yc = 1; yc <= std::max(1, P.lh / 8); ++yc) {
+        int yl = (P.lh + yc - 1) / yc;
+        yl += yl & 1;
+        const int yc_eff = (P.lh + yl - 1) / yl;
+        const long long items = cols * yc_eff;
+        const long long waves = (items + sms - 1) / sms;
+        const double eff = double(items) / double(waves * sms) * double(yl) / double(yl + 2);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_yc = yc_eff; }
+    }
+    int yl = (P.lh + best_yc - 1) / best_yc;
+    yl += yl & 1;
+    wp.ylen = yl;
+    wp.ychunks = (P.lh + yl - 1) / yl;
+    wp.total_items = int(cols * wp.ychunks);
+    const int grid = std::max(1, std::min(wp.total_items, sms));
+    static bool attr_set = false;
+    if (!attr_set) {
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kQSmem)));
+        attr_set = true;
+    }
+    conv_wgrad_quad_kernel<<<grid, kQThreads, kQSmem, stream>>>(wp);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace u3d

@@ -1,7 +1,8 @@
 // Kernel selection for one conv / weight-gradient problem set (model.cpp and the op-level API call only these).
 //   forward + data gradient:  conv_band (k3 s1, <= 32 channels) -> conv_s2 (stride-2 forward, 16 input channels) -> conv_tma -> conv_igemm
-//   weight gradient:          conv_wgrad_band (k3 s1) per eligible problem, conv_wgrad (generic split-K) for the rest
-// U3D_NO_BAND / U3D_NO_S2 / U3D_NO_TMA / U3D_NO_WBAND take a family out (tests/test_conv_ops_gpu.py runs the fallbacks that way).
+//   weight gradient:          conv_wgrad_quad (k3 s1, 16 x 16 channels) -> conv_wgrad_band (k3 s1) per eligible problem, conv_wgrad
+//                             (generic split-K) for the rest
+// U3D_NO_BAND / U3D_NO_S2 / U3D_NO_TMA / U3D_NO_WQUAD / U3D_NO_WBAND take a family out (tests/test_conv_ops_gpu.py runs the fallbacks that way).
 #include <cstdlib>
 
 #include "u3d.h"
@@ -35,7 +36,10 @@ int conv_wgrad_dispatch(const std::vector<WgradProblem>& probs, const WgradLaunc
     std::vector<WgradProblem> rest;
     int n = 0;
     for (const auto& P : probs) {
-        if (conv_wgrad_band_eligible(P)) {
+        if (conv_wgrad_quad_eligible(P)) {
+            if (conv_wgrad_quad_launch(P, stream)) return 1;
+            ++n;
+        } else if (conv_wgrad_band_eligible(P)) {
             if (conv_wgrad_band_launch(P, stream)) return 1;
             ++n;
         } else

@@ -493,14 +493,14 @@ void Model::prof_end(cudaStream_t on) {
     cudaEventRecord(prof_ev[prof_used + 1], on ? on : stream);
     prof_used += 2;
 }
-int Model::prof_read(double out[18], int reset) {
+int Model::prof_read(double out[24], int reset) {
     cudaSetDevice(device);
     M_CUDA(cudaStreamSynchronize(stream));
-    for (int i = 0; i < 18; ++i) out[i] = 0;
+    for (int i = 0; i < 24; ++i) out[i] = 0;
     for (size_t i = 0; i + 1 < prof_used; i += 2) {
         float ms = 0.f;
         M_CUDA(cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]));
-        const int k = 3 * std::min(prof_kind[i / 2], 5);
+        const int k = 3 * std::min(prof_kind[i / 2], 7);
         out[k] += ms;
         out[k + 1] += 1;
         out[k + 2] += prof_flops[i / 2];
@@ -1084,14 +1084,17 @@ int Model::run_backward() {
             // weight gradient on the side stream: it only reads x and dy (both final here) and adds into this layer's slice of the
             // flat gradient, so it can overlap the data gradient below (the small deep-level launches fill the SMs the other leaves idle)
             WgradLaunch wc{};
-            bool all_rows = !s.wg.empty();
-            for (const auto& wp : s.wg) all_rows = all_rows && conv_wgrad_band_eligible(wp);
+            bool all_rows = !s.wg.empty(), all_quad = !s.wg.empty();
+            for (const auto& wp : s.wg) {
+                all_quad = all_quad && conv_wgrad_quad_eligible(wp);
+                all_rows = all_rows && (conv_wgrad_band_eligible(wp) || conv_wgrad_quad_eligible(wp));
+            }
             cudaStream_t ws = two_streams ? stream2 : stream;
             if (two_streams) {
                 M_CUDA(cudaEventRecord(ev_fork, stream));
                 M_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0));
             }
-            prof_begin(all_rows ? 3 : 1, s.flops, ws);
+            prof_begin(all_quad ? 6 : all_rows ? 3 : 1, s.flops, ws);
             int nl = 0;
             M_CHECK(conv_wgrad_dispatch(s.wg, wc, ws, &nl));
             prof_end(ws);

@@ -184,7 +184,7 @@ class Model {
     int timer_stop(float* ms);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // per-launch CUDA-event profile of the tensor-core kernels (bench.py roofline):
-    // kind 0 = conv_igemm, 1 = conv_wgrad, 2 = conv_halo, 3 = conv_wgrad_rows, 4 = conv_tma
+    // kind 0 = conv_igemm, 1 = conv_wgrad, 2 = conv_s2, 3 = conv_wgrad_band, 4 = conv_tma, 5 = conv_band, 6 = conv_wgrad_quad
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int> prof_kind;
@@ -192,7 +192,7 @@ class Model {
     size_t prof_used = 0;
     void prof_begin(int kind, double flops, cudaStream_t on = nullptr);
     void prof_end(cudaStream_t on = nullptr);
-    int prof_read(double out[18], int reset);  // per kind: {ms, launches, algorithmic FLOPs}
+    int prof_read(double out[24], int reset);  // per kind (8): {ms, launches, algorithmic FLOPs}
     // CUDA graphs: the kernel sequence of a micro-batch / an inference forward is fixed for a plan, so its second occurrence with the
     // same buffers is captured (stream capture of the ordinary enqueue code, side stream included) and replayed afterwards: one
     // graph launch instead of ~250 kernel launches whose host cost paced the small deep-level kernels.  Keyed by the device pointers

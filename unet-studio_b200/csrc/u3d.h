@@ -132,6 +132,9 @@ int conv_tma_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg
 unsigned int read_device_error_tma();
 bool conv_band_wants_kc16(int ks, int stride, int transposed, int k_channels_padded, int n_channels_padded, long long voxels);
 
+bool conv_wgrad_quad_eligible(const WgradProblem& P);   // 16 x 16 channels, k3 s1, big volume: 2 x 2 g rows per MMA pair (conv_wgrad_quad.cu)
+int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream);
+unsigned int read_device_error_wquad();
 bool conv_wgrad_band_eligible(const WgradProblem& P);
 int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream);
 unsigned int read_device_error_wband();

@@ -299,7 +299,7 @@ class UNet3d:
 
     def profile_read(self, reset=True):
         from . import check
-        out = (ctypes.c_double * 18)()
+        out = (ctypes.c_double * 24)()
         check(self._lib.unet3d_profile_read(self._h, out, int(reset)))
         return [float(v) for v in out]
 
