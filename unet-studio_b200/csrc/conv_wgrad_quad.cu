@@ -31,16 +31,15 @@ namespace {
 constexpr int kQThreads = 32 * 13;     // warps 0-3 epilogue, 4-11 producers, 12 MMA issuer
 constexpr int kQProducers = 256;
 constexpr int kQXSlots = 4, kQYSlots = 3;
-constexpr int kQXT = 32;               // voxels per tile along x = two K steps
-constexpr uint32_t kQRow = kQXT * 32u; // bytes of one atom row (32 voxels x 16 channels fp16)
-constexpr uint32_t kQXSlotB = 8 * kQRow, kQYSlotB = 12 * kQRow;
-constexpr uint32_t kQOffY = kQXSlots * kQXSlotB;
-constexpr uint32_t kQOffBars = kQOffY + kQYSlots * kQYSlotB;
-constexpr size_t kQSmem = kQOffBars + 8 * (2 * kQXSlots + 2 * kQYSlots + 1) + 16 + 1024;   // + slack for the 1024-byte alignment
+// tile width along x (xt voxels = xt/16 K steps per ring slot) is chosen per problem: a slot must carry enough MMA time (114 clk per
+// instruction) to cover the L2 latency of the slot being refilled -- with 32 voxels (456 clk per step) the ring ran dry
 
 struct WQParams {
     WgradProblem P;
     int tiles_x, zpairs, ychunks, ylen, total_items;
+    int xt;                    // voxels per tile along x (multiple of 16)
+    uint32_t row_b;            // bytes of one atom row = xt * 32
+    uint32_t xslot_b, yslot_b, off_y, off_bars;
 };
 
 __device__ __forceinline__ uint64_t desc_sw32_mn(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -61,13 +60,15 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
     uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t bars = sbase + kQOffBars;
+    const uint32_t bars = sbase + p.off_bars;
+    const uint32_t kQRow = p.row_b, kQXSlotB = p.xslot_b, kQYSlotB = p.yslot_b, kQOffY = p.off_y;
+    const int kQXT = p.xt;
     auto xfull = [&](int s) { return bars + 8u * s; };
     auto xempty = [&](int s) { return bars + 8u * (kQXSlots + s); };
     auto yfull = [&](int s) { return bars + 8u * (2 * kQXSlots + s); };
     auto yempty = [&](int s) { return bars + 8u * (2 * kQXSlots + kQYSlots + s); };
     const uint32_t done_bar = bars + 8u * (2 * kQXSlots + 2 * kQYSlots);
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kQOffBars + 8u * (2 * kQXSlots + 2 * kQYSlots + 1));
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kQXSlots + 2 * kQYSlots + 1));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kQXSlots; ++s) { mbar_init(xfull(s), kQProducers); mbar_init(xempty(s), 1); }
@@ -107,16 +108,19 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
                     const int slot = xcnt % kQXSlots;
                     mbar_wait(xempty(slot), ((xcnt / kQXSlots) & 1) ^ 1, 0x3500u | slot);
                     const uint32_t blk = sbase + slot * kQXSlotB;
-                    // 8 rows x 32 voxels x 2 chunks = 512 copies: two per thread
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int idx = t + k * kQProducers;
-                        const int cg = idx & 1, lx = (idx >> 1) & 31, row = idx >> 6;
+                    // 8 rows x xt voxels x 2 chunks: producer warp w copies row w
+                    {
+                        const int row = t >> 5;
                         const int az = row & 3, r = row >> 2;
-                        const int gz = z0 - 1 + az, gy = y0 + 2 * pr - 1 + r, gx = x0 + lx;
-                        const bool ok = (unsigned)gz < (unsigned)D && (unsigned)gy < (unsigned)H && gx < W;
-                        const uint8_t* src = ok ? xsrc + (((long long)gz * H + gy) * W + gx) * xpitch + cg * 16 : xsrc;
-                        cp_async16(sw32(blk + uint32_t(row) * kQRow + uint32_t(lx) * 32u + uint32_t(cg) * 16u), src, ok ? 16u : 0u);
+                        const int gz = z0 - 1 + az, gy = y0 + 2 * pr - 1 + r;
+                        const bool rok = (unsigned)gz < (unsigned)D && (unsigned)gy < (unsigned)H;
+                        const uint8_t* const rsrc = xsrc + (((long long)(rok ? gz : 0) * H + (rok ? gy : 0)) * W + x0) * xpitch;
+                        const uint32_t rdst = blk + uint32_t(row) * kQRow;
+                        for (int idx = lane; idx < 2 * kQXT; idx += 32) {
+                            const int cg = idx & 1, lx = idx >> 1;
+                            const bool ok = rok && x0 + lx < W;
+                            cp_async16(sw32(rdst + uint32_t(idx) * 16u), ok ? rsrc + (long long)lx * xpitch + cg * 16 : xsrc, ok ? 16u : 0u);
+                        }
                     }
                     cp_async_mbar_arrive(xfull(slot));
                     ++xcnt;
@@ -125,18 +129,21 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
                     const int slot = ycnt % kQYSlots;
                     mbar_wait(yempty(slot), ((ycnt / kQYSlots) & 1) ^ 1, 0x3600u | slot);
                     const uint32_t blk = sbase + kQOffY + slot * kQYSlotB;
-                    // 4 rows x 32 voxels x 2 chunks = 256 sources, each copied three times
-                    const int cg = t & 1, lx = (t >> 1) & 31, rw = t >> 6;   // rw = by*2 + bz
+                    // 4 rows x xt voxels x 2 chunks, each copied three times: producer warps w and w + 4 share row w & 3
+                    const int rw = (t >> 5) & 3;             // rw = by*2 + bz
                     const int bz = rw & 1, by = rw >> 1;
                     const int gz = z0 + bz, gy = y0 + 2 * pr + by;
                     const bool rok = gz < D && gy < y1;     // rows past the chunk belong to the next item
-                    const uint8_t* const s0 = gsrc + (((long long)(rok ? gz : 0) * H + (rok ? gy : 0)) * W) * gpitch + cg * 16;
+                    const uint8_t* const s0 = gsrc + (((long long)(rok ? gz : 0) * H + (rok ? gy : 0)) * W) * gpitch;
+                    for (int idx = lane + 32 * (t >> 7); idx < 2 * kQXT; idx += 64) {
+                        const int cg = idx & 1, lx = idx >> 1;
 #pragma unroll
-                    for (int dxc = 0; dxc < 3; ++dxc) {     // copy dxc holds g[x' - dx], dx = dxc - 1
-                        const int gx = x0 + lx - (dxc - 1);
-                        const bool ok = rok && (unsigned)gx < (unsigned)W;
-                        cp_async16_ca(sw32(blk + uint32_t(rw * 3 + dxc) * kQRow + uint32_t(lx) * 32u + uint32_t(cg) * 16u),
-                                      ok ? s0 + (long long)gx * gpitch : gsrc, ok ? 16u : 0u);
+                        for (int dxc = 0; dxc < 3; ++dxc) {     // copy dxc holds g[x' - dx], dx = dxc - 1
+                            const int gx = x0 + lx - (dxc - 1);
+                            const bool ok = rok && (unsigned)gx < (unsigned)W;
+                            cp_async16_ca(sw32(blk + uint32_t(rw * 3 + dxc) * kQRow + uint32_t(idx) * 16u),
+                                          ok ? s0 + (long long)gx * gpitch + cg * 16 : gsrc, ok ? 16u : 0u);
+                        }
                     }
                     cp_async_mbar_arrive(yfull(slot));
                     ++ycnt;
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
             const uint32_t d1 = tmem_base, d2 = tmem_base + 256u;
             uint32_t xcnt = 0, ycnt = 0;
             bool first = true;
+            const uint32_t ksteps = uint32_t(kQXT / 16);
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 const int yc = item % p.ychunks;
                 const int y0 = yc * p.ylen, y1 = min(H, y0 + p.ylen);
@@ -171,8 +179,11 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
                     if (elect_one()) {
                         if (f) { umma_f16_first(d1, a1, b, idesc); umma_f16_first(d2, a2, b, idesc); }
                         else { umma_f16_acc(d1, a1, b, idesc); umma_f16_acc(d2, a2, b, idesc); }
-                        umma_f16_acc(d1, a1 + 32u, b + 32u, idesc);      // second K step: 16 voxels = 512 bytes further
-                        umma_f16_acc(d2, a2 + 32u, b + 32u, idesc);
+#pragma unroll 1
+                        for (uint32_t ks = 1; ks < ksteps; ++ks) {       // next K step: 16 voxels = 512 bytes further
+                            umma_f16_acc(d1, a1 + 32u * ks, b + 32u * ks, idesc);
+                            umma_f16_acc(d2, a2 + 32u * ks, b + 32u * ks, idesc);
+                        }
                         umma_commit(yempty(ycnt % kQYSlots));
                         umma_commit(xempty(c1 % kQXSlots));              // pair j: last used here (as the D1 operand)
                         if (j == ns - 1) umma_commit(xempty(c2 % kQXSlots));
@@ -248,6 +259,25 @@ int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream) {
     WQParams wp;
     std::memset(&wp, 0, sizeof(wp));
     wp.P = P;
+    {   // widest tile that fits (4 x slots of 8 rows + 3 g slots of 12 rows), least padding of the last tile first
+        int best = 32;
+        double best_cost = 1e30;
+        for (int xt = 32; xt <= 96; xt += 16) {
+            const size_t need = size_t(kQXSlots * 8 + kQYSlots * 12) * xt * 32 + 2048;
+            if (need > 225 * 1024) break;
+            const int tiles = (P.lw + xt - 1) / xt;
+            const double cost = double(tiles) * xt / double(P.lw) + 4.0 / xt;   // padded work + a penalty for short slots
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = xt; }
+        }
+        wp.xt = best;
+    }
+    const int kQXT = wp.xt;
+    wp.row_b = uint32_t(kQXT) * 32u;
+    wp.xslot_b = 8 * wp.row_b;
+    wp.yslot_b = 12 * wp.row_b;
+    wp.off_y = kQXSlots * wp.xslot_b;
+    wp.off_bars = wp.off_y + kQYSlots * wp.yslot_b;
+    const size_t kQSmem = wp.off_bars + 8 * (2 * kQXSlots + 2 * kQYSlots + 1) + 16 + 1024;   // + slack for the 1024-byte alignment
     wp.tiles_x = (P.lw + kQXT - 1) / kQXT;
     wp.zpairs = (P.ld + 1) / 2;
     const int sms = device_sm_count();
@@ -272,7 +302,7 @@ int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream) {
     const int grid = std::max(1, std::min(wp.total_items, sms));
     static bool attr_set = false;
     if (!attr_set) {
-        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kQSmem)));
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     conv_wgrad_quad_kernel<<<grid, kQThreads, kQSmem, stream>>>(wp);
