@@ -128,7 +128,7 @@ int main() {
                    maxerr, cudaGetErrorString(e));
         }
         // ---- timing
-        for (int m : {64, 128})
+        for (int m : {128})
             for (int n : {16, 32, 48, 64, 96, 128, 144, 192, 256}) {
                 if (n % cw && cw > 16 && n % 16) continue;
                 if (n < cw && n % 16) continue;
@@ -142,6 +142,16 @@ int main() {
                            2.0 * m * n * 16 / (double(h[1]) / c.iters), cudaGetErrorString(e));
                     if (e != cudaSuccess) return 1;
                 }
+            }
+        // ---- atom strides that are NOT multiples of 128 bytes (are the 114 clk a bank-conflict artefact of the strides above?)
+        for (int pad : {0, 32, 64, 96})
+            for (int n : {48, 192}) {
+                Cfg c{128, n, cw, 40 * row + pad, 24 * row + pad, 2048, 0};
+                bench<<<1, 128, 200 * 1024>>>(c, d, dout, da, db, nvox);
+                cudaError_t e = cudaDeviceSynchronize();
+                long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+                printf("cw %2d M 128 N %3d atom strides %d / %d bytes (pad %d): %.1f clk/mma (%s)\n", cw, n, c.a_lbo, c.b_lbo, pad,
+                       double(h[1]) / c.iters, cudaGetErrorString(e));
             }
         cudaFree(da); cudaFree(db);
     }

@@ -13,10 +13,12 @@
 //   N = 12 atoms = (by in {0,1}) x (bz in {0,1}) x (3 copies shifted by dx) x 16 co = 192
 //   tap (dz, dy) = (az - bz - 1, ay - by - 1): 36 of the 64 (x row, g row) pairs are taps (each of the 9 (dz,dy) taps four times,
 //   once per g row), 2 MMAs per FOUR g rows and 16 voxels = half the instructions of the band kernel at the same 114 clk.
-// The CTA owns a column (32 voxels in x, 2 planes in z) and marches along y two rows at a time through a ring of x row pairs
-// (each pair = 2 y rows x 4 planes, laid out [y][plane] so that the 8 atoms of an operand are 1 KB apart) and a ring of g slots
-// (4 rows x 3 copies).  Accumulators live in TMEM for the CTA's whole life; one epilogue adds the 36 useful blocks into the
-// reference-layout gradient with fp32 atomics.
+// The CTA owns a column (xt voxels in x, 2 planes in z) and marches along y two rows at a time through a ring of x row pairs
+// (each pair = 4 planes x 2 y rows = ONE tensor-map box, so the 8 atoms of an operand are one row apart) and a ring of g slots
+// (3 boxes of 2 planes x 2 rows, fetched at x - dx).  Everything arrives by TMA (cp.async.bulk.tensor with the 32-byte hardware
+// swizzle): the first version fed the rings with 16-byte cp.async like conv_wgrad_band and both kernels stopped at ~12.5 bytes per
+// clock and SM of shared-memory fill (profiles/r02_ncu_wgrad_quad_cpasync.md), far below what the MMAs consume.  Accumulators live
+// in TMEM for the CTA's whole life; one epilogue adds the 36 useful blocks into the reference-layout gradient with fp32 atomics.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -28,11 +30,22 @@
 namespace u3d {
 namespace {
 
-constexpr int kQThreads = 32 * 13;     // warps 0-3 epilogue, 4-11 producers, 12 MMA issuer
-constexpr int kQProducers = 256;
+constexpr int kQThreads = 32 * 6;      // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer
+constexpr int kQIssuerWarp = 5;
 constexpr int kQXSlots = 4, kQYSlots = 3;
 // tile width along x (xt voxels = xt/16 K steps per ring slot) is chosen per problem: a slot must carry enough MMA time (114 clk per
 // instruction) to cover the L2 latency of the slot being refilled -- with 32 voxels (456 clk per step) the ring ran dry
+
+struct alignas(64) WQMaps {
+    CUtensorMap x, g;          // dims (16 ch, W, H, D) over the channel slice of each tensor, SWIZZLE_32B; boxes (16, xt, 2, 4) / (16, xt, 2, 2)
+};
+
+__device__ __forceinline__ void tma_box_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 
 struct WQParams {
     WgradProblem P;
@@ -51,10 +64,7 @@ __device__ __forceinline__ uint64_t desc_sw32_mn(uint32_t addr, uint32_t lbo, ui
     d |= uint64_t(6) << 61;   // SWIZZLE_32B
     return d;
 }
-// SWIZZLE_32B: the two 16-byte halves of a 32-byte row are exchanged in rows 4..7 of every 8-row (256-byte) atom
-__device__ __forceinline__ uint32_t sw32(uint32_t addr) { return addr ^ (((addr >> 7) & 1u) << 4); }
-
-__global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __grid_constant__ WQParams p) {
+__global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __grid_constant__ WQParams p, const __grid_constant__ WQMaps maps) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -71,12 +81,12 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kQXSlots + 2 * kQYSlots + 1));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kQXSlots; ++s) { mbar_init(xfull(s), kQProducers); mbar_init(xempty(s), 1); }
-        for (int s = 0; s < kQYSlots; ++s) { mbar_init(yfull(s), kQProducers); mbar_init(yempty(s), 1); }
+        for (int s = 0; s < kQXSlots; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 1); }
+        for (int s = 0; s < kQYSlots; ++s) { mbar_init(yfull(s), 1); mbar_init(yempty(s), 1); }
         mbar_init(done_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 12) {
+    if (warp == kQIssuerWarp) {
         tmem_alloc(smem_u32(tmem_ptr_smem), 512);
         tmem_relinquish();
     }
@@ -88,70 +98,41 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
     const int D = P.t_d, H = P.t_h, W = P.t_w;
     const bool has_work = int(blockIdx.x) < p.total_items;
 
-    if (warp >= 4 && warp < 12) {
-        // ===================================== producers =====================================
-        const int t = threadIdx.x - 128;
-        const uint8_t* const xsrc = static_cast<const uint8_t*>(P.T) + P.t_coff * 2;
-        const uint8_t* const gsrc = static_cast<const uint8_t*>(P.U) + P.u_coff * 2;
-        const long long xpitch = (long long)P.t_cp * 2, gpitch = (long long)P.u_cp * 2;
-        uint32_t xcnt = 0, ycnt = 0;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            int rem = item;
-            const int yc = rem % p.ychunks; rem /= p.ychunks;
-            const int tx = rem % p.tiles_x;
-            const int zp = rem / p.tiles_x;
-            const int x0 = tx * kQXT, z0 = zp * 2, y0 = yc * p.ylen;
-            const int y1 = min(H, y0 + p.ylen);
-            const int ns = (y1 - y0 + 1) / 2;
-            for (int pr = 0; pr <= ns; ++pr) {
-                {   // x pair pr: rows y0 + 2 pr - 1 + r (r = 0, 1) of the planes z0 - 1 + az (az = 0..3); row index in the slot = r*4 + az
-                    const int slot = xcnt % kQXSlots;
-                    mbar_wait(xempty(slot), ((xcnt / kQXSlots) & 1) ^ 1, 0x3500u | slot);
-                    const uint32_t blk = sbase + slot * kQXSlotB;
-                    // 8 rows x xt voxels x 2 chunks: producer warp w copies row w
-                    {
-                        const int row = t >> 5;
-                        const int az = row & 3, r = row >> 2;
-                        const int gz = z0 - 1 + az, gy = y0 + 2 * pr - 1 + r;
-                        const bool rok = (unsigned)gz < (unsigned)D && (unsigned)gy < (unsigned)H;
-                        const uint8_t* const rsrc = xsrc + (((long long)(rok ? gz : 0) * H + (rok ? gy : 0)) * W + x0) * xpitch;
-                        const uint32_t rdst = blk + uint32_t(row) * kQRow;
-                        for (int idx = lane; idx < 2 * kQXT; idx += 32) {
-                            const int cg = idx & 1, lx = idx >> 1;
-                            const bool ok = rok && x0 + lx < W;
-                            cp_async16(sw32(rdst + uint32_t(idx) * 16u), ok ? rsrc + (long long)lx * xpitch + cg * 16 : xsrc, ok ? 16u : 0u);
-                        }
+    if (warp == 4) {
+        // ===================================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            uint32_t xcnt = 0, ycnt = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int rem = item;
+                const int yc = rem % p.ychunks; rem /= p.ychunks;
+                const int tx = rem % p.tiles_x;
+                const int zp = rem / p.tiles_x;
+                const int x0 = tx * kQXT, z0 = zp * 2, y0 = yc * p.ylen;
+                const int y1 = min(H, y0 + p.ylen);
+                const int ns = (y1 - y0 + 1) / 2;
+                for (int pr = 0; pr <= ns; ++pr) {
+                    {   // x pair pr: planes z0-1..z0+2, rows y0 + 2 pr - 1, y0 + 2 pr; row index in the slot = az*2 + ay'.  Out of range = 0.
+                        const int slot = xcnt % kQXSlots;
+                        mbar_wait(xempty(slot), ((xcnt / kQXSlots) & 1) ^ 1, 0x3500u | slot);
+                        mbar_arrive_expect_tx(xfull(slot), kQXSlotB);
+                        tma_box_4d(sbase + slot * kQXSlotB, &maps.x, xfull(slot), 0, x0, y0 + 2 * pr - 1, z0 - 1);
+                        ++xcnt;
                     }
-                    cp_async_mbar_arrive(xfull(slot));
-                    ++xcnt;
-                }
-                if (pr < ns) {   // g slot pr: rows y0 + 2 pr + by of the planes z0 + bz, three copies shifted by dx = -1, 0, +1
-                    const int slot = ycnt % kQYSlots;
-                    mbar_wait(yempty(slot), ((ycnt / kQYSlots) & 1) ^ 1, 0x3600u | slot);
-                    const uint32_t blk = sbase + kQOffY + slot * kQYSlotB;
-                    // 4 rows x xt voxels x 2 chunks, each copied three times: producer warps w and w + 4 share row w & 3
-                    const int rw = (t >> 5) & 3;             // rw = by*2 + bz
-                    const int bz = rw & 1, by = rw >> 1;
-                    const int gz = z0 + bz, gy = y0 + 2 * pr + by;
-                    const bool rok = gz < D && gy < y1;     // rows past the chunk belong to the next item
-                    const uint8_t* const s0 = gsrc + (((long long)(rok ? gz : 0) * H + (rok ? gy : 0)) * W) * gpitch;
-                    for (int idx = lane + 32 * (t >> 7); idx < 2 * kQXT; idx += 64) {
-                        const int cg = idx & 1, lx = idx >> 1;
+                    if (pr < ns) {   // g slot pr: copy dxc holds g[x' - dx] (dx = dxc - 1) of the rows y0 + 2 pr + by, planes z0 + bz
+                        const int slot = ycnt % kQYSlots;
+                        mbar_wait(yempty(slot), ((ycnt / kQYSlots) & 1) ^ 1, 0x3600u | slot);
+                        mbar_arrive_expect_tx(yfull(slot), kQYSlotB);
+                        const uint32_t blk = sbase + kQOffY + slot * kQYSlotB;
 #pragma unroll
-                        for (int dxc = 0; dxc < 3; ++dxc) {     // copy dxc holds g[x' - dx], dx = dxc - 1
-                            const int gx = x0 + lx - (dxc - 1);
-                            const bool ok = rok && (unsigned)gx < (unsigned)W;
-                            cp_async16_ca(sw32(blk + uint32_t(rw * 3 + dxc) * kQRow + uint32_t(idx) * 16u),
-                                          ok ? s0 + (long long)gx * gpitch + cg * 16 : gsrc, ok ? 16u : 0u);
-                        }
+                        for (int dxc = 0; dxc < 3; ++dxc)
+                            tma_box_4d(blk + uint32_t(dxc) * 4u * kQRow, &maps.g, yfull(slot), 0, x0 - (dxc - 1), y0 + 2 * pr, z0);
+                        ++ycnt;
                     }
-                    cp_async_mbar_arrive(yfull(slot));
-                    ++ycnt;
                 }
             }
         }
-        cp_async_wait<0>();
-    } else if (warp == 12) {
+        __syncwarp();
+    } else if (warp == kQIssuerWarp) {
         // ===================================== MMA issuer =====================================
         if (has_work) {
             const uint32_t idesc = umma_idesc(128, 192, 0, 0, 1, 1);    // both operands MN-major
@@ -169,7 +150,6 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
                     mbar_wait(xfull(c1 % kQXSlots), (c1 / kQXSlots) & 1, 0x3701u);
                     mbar_wait(xfull(c2 % kQXSlots), (c2 / kQXSlots) & 1, 0x3702u);
                     mbar_wait(yfull(ycnt % kQYSlots), (ycnt / kQYSlots) & 1, 0x3703u);
-                    fence_proxy_async();
                     tc_fence_after();
                     const uint64_t a1 = desc_sw32_mn(sbase + (c1 % kQXSlots) * kQXSlotB, kQRow, 256u);
                     const uint64_t a2 = desc_sw32_mn(sbase + (c2 % kQXSlots) * kQXSlotB, kQRow, 256u);
@@ -201,7 +181,7 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
         tc_fence_after();
         const int m = threadIdx.x;                 // accumulator row = TMEM lane
         const int g = m >> 4, ci = m & 15;
-        const int az = g & 3, ayp = g >> 2;        // atom g = ay' * 4 + az
+        const int az = g >> 1, ayp = g & 1;        // atom g = az * 2 + ay' (box order: x fastest, then y, then z)
         const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
         const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
         const bool ci_ok = ci < P.t_creal;
@@ -209,14 +189,14 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
         for (int acc = 0; acc < 2; ++acc) {
             const int ay = acc * 2 + ayp;
 #pragma unroll 1
-            for (int rw = 0; rw < 4; ++rw) {       // g row rw = by * 2 + bz
-                const int bz = rw & 1, by = rw >> 1;
+            for (int rw = 0; rw < 4; ++rw) {       // g row rw = bz * 2 + by
+                const int bz = rw >> 1, by = rw & 1;
                 const int dzi = az - bz, dyi = ay - by;    // = dz + 1, dy + 1
                 const bool ok = ci_ok && dzi >= 0 && dzi <= 2 && dyi >= 0 && dyi <= 2;
 #pragma unroll 1
                 for (int dxc = 0; dxc < 3; ++dxc) {
                     float v[16];
-                    tmem_ld16(t_row + uint32_t(acc * 256 + (rw * 3 + dxc) * 16), v);   // warp-collective: every lane takes part
+                    tmem_ld16(t_row + uint32_t(acc * 256 + (dxc * 4 + rw) * 16), v);   // warp-collective: every lane takes part
                     if (ok) {
                         const int tap = (dzi * 3 + dyi) * 3 + dxc;
                         float* dwrow = P.dw + size_t(P.w_moff + ci) * P.w_ktaps + tap;
@@ -230,9 +210,38 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem_base, 512);
+    if (warp == kQIssuerWarp) tmem_dealloc(tmem_base, 512);
 }
 
+}  // namespace
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn quad_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+int encode_rows(CUtensorMap* m, const void* base, int coff, int cp, int W, int H, int D, int xt, int bz) {
+    const cuuint64_t gdim[4] = {16, cuuint64_t(W), cuuint64_t(H), cuuint64_t(D)};
+    const cuuint64_t gstr[3] = {cuuint64_t(cp) * 2, cuuint64_t(cp) * 2 * W, cuuint64_t(cp) * 2 * W * H};
+    const cuuint32_t box[4] = {16, cuuint32_t(xt), 2, cuuint32_t(bz)};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    void* p = const_cast<uint8_t*>(static_cast<const uint8_t*>(base) + size_t(coff) * 2);
+    const CUresult r = quad_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_wgrad_quad_launch: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r))); return 1; }
+    return 0;
+}
 }  // namespace
 
 unsigned int read_device_error_wquad() {
@@ -243,7 +252,7 @@ unsigned int read_device_error_wquad() {
 
 bool conv_wgrad_quad_eligible(const WgradProblem& P) {
     static const bool disabled = std::getenv("U3D_NO_WQUAD") != nullptr || std::getenv("U3D_NO_WBAND") != nullptr;
-    if (disabled) return false;
+    if (disabled || quad_encode_fn() == nullptr) return false;
     if (P.ntaps != 27 || P.tstride != 1 || P.w_ktaps != 27) return false;
     if (P.t_c != 16 || P.u_c != 16) return false;
     if (P.t_d != P.ld || P.t_h != P.lh || P.t_w != P.lw) return false;
@@ -305,7 +314,10 @@ int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream) {
         U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    conv_wgrad_quad_kernel<<<grid, kQThreads, kQSmem, stream>>>(wp);
+    WQMaps maps;
+    if (encode_rows(&maps.x, P.T, P.t_coff, P.t_cp, P.t_w, P.t_h, P.t_d, kQXT, 4)) return 1;
+    if (encode_rows(&maps.g, P.U, P.u_coff, P.u_cp, P.lw, P.lh, P.ld, kQXT, 2)) return 1;
+    conv_wgrad_quad_kernel<<<grid, kQThreads, kQSmem, stream>>>(wp, maps);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
