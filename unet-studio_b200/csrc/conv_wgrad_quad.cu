@@ -37,7 +37,8 @@ constexpr int kQXSlots = 4, kQYSlots = 3;
 // instruction) to cover the L2 latency of the slot being refilled -- with 32 voxels (456 clk per step) the ring ran dry
 
 struct alignas(64) WQMaps {
-    CUtensorMap x, g;          // dims (16 ch, W, H, D) over the channel slice of each tensor, SWIZZLE_32B; boxes (16, xt, 2, 4) / (16, xt, 2, 2)
+    CUtensorMap x, g, gh;      // dims (16 ch, W, H, D) over the channel slice of each tensor, SWIZZLE_32B; boxes (16, xt, 2, 4) / (16, xt, 2, 2)
+                               // and the one-voxel halo columns of g (16, 1, 2, 2)
 };
 
 __device__ __forceinline__ void tma_box_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -64,6 +65,9 @@ __device__ __forceinline__ uint64_t desc_sw32_mn(uint32_t addr, uint32_t lbo, ui
     d |= uint64_t(6) << 61;   // SWIZZLE_32B
     return d;
 }
+// SWIZZLE_32B: the two 16-byte halves of a 32-byte row are exchanged in rows 4..7 of every 8-row (256-byte) atom
+__device__ __forceinline__ uint32_t sw32(uint32_t addr) { return addr ^ (((addr >> 7) & 1u) << 4); }
+
 __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __grid_constant__ WQParams p, const __grid_constant__ WQMaps maps) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -77,12 +81,13 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
     auto xempty = [&](int s) { return bars + 8u * (kQXSlots + s); };
     auto yfull = [&](int s) { return bars + 8u * (2 * kQXSlots + s); };
     auto yempty = [&](int s) { return bars + 8u * (2 * kQXSlots + kQYSlots + s); };
-    const uint32_t done_bar = bars + 8u * (2 * kQXSlots + 2 * kQYSlots);
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kQXSlots + 2 * kQYSlots + 1));
+    auto ycopy = [&](int s) { return bars + 8u * (2 * kQXSlots + 2 * kQYSlots + s); };   // the shifted copies of a g slot are in place
+    const uint32_t done_bar = bars + 8u * (2 * kQXSlots + 3 * kQYSlots);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bars + 8u * (2 * kQXSlots + 3 * kQYSlots + 1));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kQXSlots; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 1); }
-        for (int s = 0; s < kQYSlots; ++s) { mbar_init(yfull(s), 1); mbar_init(yempty(s), 1); }
+        for (int s = 0; s < kQYSlots; ++s) { mbar_init(yfull(s), 1); mbar_init(yempty(s), 1); mbar_init(ycopy(s), 128); }
         mbar_init(done_bar, 1);
         fence_barrier_init();
     }
@@ -118,14 +123,14 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
                         tma_box_4d(sbase + slot * kQXSlotB, &maps.x, xfull(slot), 0, x0, y0 + 2 * pr - 1, z0 - 1);
                         ++xcnt;
                     }
-                    if (pr < ns) {   // g slot pr: copy dxc holds g[x' - dx] (dx = dxc - 1) of the rows y0 + 2 pr + by, planes z0 + bz
+                    if (pr < ns) {   // g slot pr: rows y0 + 2 pr + by of the planes z0 + bz (row bz*2 + by) -> middle copy (dx = 0) + halo columns
                         const int slot = ycnt % kQYSlots;
                         mbar_wait(yempty(slot), ((ycnt / kQYSlots) & 1) ^ 1, 0x3600u | slot);
-                        mbar_arrive_expect_tx(yfull(slot), kQYSlotB);
+                        mbar_arrive_expect_tx(yfull(slot), 4u * kQRow + 256u);
                         const uint32_t blk = sbase + kQOffY + slot * kQYSlotB;
-#pragma unroll
-                        for (int dxc = 0; dxc < 3; ++dxc)
-                            tma_box_4d(blk + uint32_t(dxc) * 4u * kQRow, &maps.g, yfull(slot), 0, x0 - (dxc - 1), y0 + 2 * pr, z0);
+                        tma_box_4d(blk + 4u * kQRow, &maps.g, yfull(slot), 0, x0, y0 + 2 * pr, z0);
+                        tma_box_4d(blk + 12u * kQRow, &maps.gh, yfull(slot), 0, x0 - 1, y0 + 2 * pr, z0);
+                        tma_box_4d(blk + 12u * kQRow + 128u, &maps.gh, yfull(slot), 0, x0 + kQXT, y0 + 2 * pr, z0);
                         ++ycnt;
                     }
                 }
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
                     const uint32_t c1 = xcnt + j, c2 = c1 + 1;
                     mbar_wait(xfull(c1 % kQXSlots), (c1 / kQXSlots) & 1, 0x3701u);
                     mbar_wait(xfull(c2 % kQXSlots), (c2 / kQXSlots) & 1, 0x3702u);
-                    mbar_wait(yfull(ycnt % kQYSlots), (ycnt / kQYSlots) & 1, 0x3703u);
+                    mbar_wait(ycopy(ycnt % kQYSlots), (ycnt / kQYSlots) & 1, 0x3703u);
                     tc_fence_after();
                     const uint64_t a1 = desc_sw32_mn(sbase + (c1 % kQXSlots) * kQXSlotB, kQRow, 256u);
                     const uint64_t a2 = desc_sw32_mn(sbase + (c2 % kQXSlots) * kQXSlotB, kQRow, 256u);
@@ -176,6 +181,47 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
         }
         __syncwarp();
     } else if (has_work) {
+        // ============ g replication during the march: the copy engine delivers every g row ONCE (the dx = 0 copy + two halo columns);
+        // the copies shifted by dx = -1 / +1 are made here, shared memory to shared memory, by the warps that otherwise only wait for
+        // the epilogue.  The fill rate of the rings (~15 bytes per clock and SM with 32-byte rows, TMA or cp.async alike), not the
+        // tensor pipe, paces this kernel: three fetched copies were 60 % of the fill.
+        {
+            uint32_t ycnt = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int yc = item % p.ychunks;
+                const int y0 = yc * p.ylen, y1 = min(H, y0 + p.ylen);
+                const int ns = (y1 - y0 + 1) / 2;
+#pragma unroll 1
+                for (int j = 0; j < ns; ++j, ++ycnt) {
+                    const int slot = ycnt % kQYSlots;
+                    mbar_wait(yfull(slot), (ycnt / kQYSlots) & 1, 0x3900u | slot);
+                    const uint32_t blk = sbase + kQOffY + slot * kQYSlotB;
+                    const uint32_t mid = blk + uint32_t(4 + warp) * kQRow;        // warp w copies g row w
+                    const uint32_t lo = blk + uint32_t(warp) * kQRow;             // dxc = 0: g[x' + 1]
+                    const uint32_t hi = blk + uint32_t(8 + warp) * kQRow;         // dxc = 2: g[x' - 1]
+                    const uint32_t halo = blk + 12u * kQRow + uint32_t(warp) * 32u;   // left column; right column 128 bytes further
+                    for (int idx = lane; idx < 2 * kQXT; idx += 32) {
+                        const uint32_t cgo = uint32_t(idx & 1) * 16u;
+                        const int xv = idx >> 1;
+                        uint4 v;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sw32(mid + uint32_t(idx) * 16u)));
+                        // this voxel is g[x'] for x' = xv - 1 of the lo copy and x' = xv + 1 of the hi copy
+                        if (xv >= 1) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sw32(lo + uint32_t(idx - 2) * 16u)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                        if (xv + 1 < kQXT) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sw32(hi + uint32_t(idx + 2) * 16u)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                        if (xv == 0) {   // hi copy voxel 0 = left halo column
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sw32(halo + cgo)));
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sw32(hi + cgo)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                        }
+                        if (xv == kQXT - 1) {   // lo copy last voxel = right halo column
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sw32(halo + 128u + cgo)));
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sw32(lo + uint32_t(idx) * 16u)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                        }
+                    }
+                    fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's operand reads
+                    mbar_arrive(ycopy(slot));
+                }
+            }
+        }
         // ===================================== epilogue (once) ================================
         mbar_wait(done_bar, 0, 0x3800u);
         tc_fence_after();
@@ -231,7 +277,7 @@ EncodeTiledFn quad_encode_fn() {
     }
     return fn;
 }
-int encode_rows(CUtensorMap* m, const void* base, int coff, int cp, int W, int H, int D, int xt, int bz) {
+int encode_rows(CUtensorMap* m, const void* base, int coff, int cp, int W, int H, int D, int xt, int bz) {   // box (16, xt, 2, bz)
     const cuuint64_t gdim[4] = {16, cuuint64_t(W), cuuint64_t(H), cuuint64_t(D)};
     const cuuint64_t gstr[3] = {cuuint64_t(cp) * 2, cuuint64_t(cp) * 2 * W, cuuint64_t(cp) * 2 * W * H};
     const cuuint32_t box[4] = {16, cuuint32_t(xt), 2, cuuint32_t(bz)};
@@ -272,7 +318,7 @@ int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream) {
         int best = 32;
         double best_cost = 1e30;
         for (int xt = 32; xt <= 96; xt += 16) {
-            const size_t need = size_t(kQXSlots * 8 + kQYSlots * 12) * xt * 32 + 2048;
+            const size_t need = size_t(kQXSlots * 8 + kQYSlots * 12) * xt * 32 + kQYSlots * 256 + 2048;
             if (need > 225 * 1024) break;
             const int tiles = (P.lw + xt - 1) / xt;
             const double cost = double(tiles) * xt / double(P.lw) + 4.0 / xt;   // padded work + a penalty for short slots
@@ -283,10 +329,10 @@ int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream) {
     const int kQXT = wp.xt;
     wp.row_b = uint32_t(kQXT) * 32u;
     wp.xslot_b = 8 * wp.row_b;
-    wp.yslot_b = 12 * wp.row_b;
+    wp.yslot_b = 12 * wp.row_b + 256;   // + the two halo columns (4 rows x 32 bytes each)
     wp.off_y = kQXSlots * wp.xslot_b;
     wp.off_bars = wp.off_y + kQYSlots * wp.yslot_b;
-    const size_t kQSmem = wp.off_bars + 8 * (2 * kQXSlots + 2 * kQYSlots + 1) + 16 + 1024;   // + slack for the 1024-byte alignment
+    const size_t kQSmem = wp.off_bars + 8 * (2 * kQXSlots + 3 * kQYSlots + 1) + 16 + 1024;   // + slack for the 1024-byte alignment
     wp.tiles_x = (P.lw + kQXT - 1) / kQXT;
     wp.zpairs = (P.ld + 1) / 2;
     const int sms = device_sm_count();
@@ -317,6 +363,7 @@ int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream) {
     WQMaps maps;
     if (encode_rows(&maps.x, P.T, P.t_coff, P.t_cp, P.t_w, P.t_h, P.t_d, kQXT, 4)) return 1;
     if (encode_rows(&maps.g, P.U, P.u_coff, P.u_cp, P.lw, P.lh, P.ld, kQXT, 2)) return 1;
+    if (encode_rows(&maps.gh, P.U, P.u_coff, P.u_cp, P.lw, P.lh, P.ld, 1, 2)) return 1;
     conv_wgrad_quad_kernel<<<grid, kQThreads, kQSmem, stream>>>(wp, maps);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
