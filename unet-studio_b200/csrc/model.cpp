@@ -473,6 +473,21 @@ int Model::set_mode(int mode) {
     return 0;
 }
 
+// U3D_TRACE_LAUNCHES=<file>: one line per tensor-kernel launch site (layer, pass, kernel family, problem count, algorithmic FLOPs), in
+// launch order -- joined with an ncu launch list of the same run (one stream, no graphs) it gives the per-layer tensor-pipe table
+void Model::trace_launch(const Step& s, const char* pass, int kind, int nprob, double flops) {
+    static const char* path = std::getenv("U3D_TRACE_LAUNCHES");
+    if (!path) return;
+    static FILE* f = std::fopen(path, "w");
+    if (!f) return;
+    static const char* fam[] = {"conv_igemm", "conv_wgrad", "conv_s2", "conv_wgrad_band", "conv_tma", "conv_band", "conv_wgrad_quad", "?"};
+    const ParamInfo& p = params[size_t(s.p_w)];
+    std::fprintf(f, "%s\t%s\t%s\t%d\t%.6g\tcin=%d+%d cout=%d k%d s%d%s out=%dx%dx%d\n", p.name.c_str(), pass, fam[kind & 7], nprob, flops, s.g.cin[0],
+                 s.g.cin[1], s.g.cout, s.g.ks, s.g.stride, s.g.transposed ? " transposed" : "", s.g.out_w, s.g.out_h, s.g.out_d);
+    std::fflush(f);
+    trace_marker_launch(std::strcmp(pass, "wgrad") == 0 && stream2 && !std::getenv("U3D_ONE_STREAM") ? stream2 : stream);
+}
+
 void Model::prof_begin(int kind, double flops, cudaStream_t on) {
     if (!prof_on) return;
     if (prof_used + 2 > prof_ev.size()) {
@@ -851,6 +866,7 @@ int Model::run_forward(int levels_wanted, bool bn_eval) {
             cfg.stats_grid_out = &rows;
             if (s.stats) cfg.stats_partials = d_partials;
             cfg.splitk_scratch = d_splitk; cfg.splitk_scratch_bytes = splitk_bytes;
+            trace_launch(s, "fwd", conv_kernel_kind(s.fprobs, cfg), int(s.fprobs.size()), s.flops);
             prof_begin(conv_kernel_kind(s.fprobs, cfg), s.flops);
             M_CHECK(conv_launch(s.fprobs, cfg, stream));
             prof_end();
@@ -1094,6 +1110,7 @@ int Model::run_backward() {
                 M_CUDA(cudaEventRecord(ev_fork, stream));
                 M_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0));
             }
+            trace_launch(s, "wgrad", all_quad ? 6 : all_rows ? 3 : 1, int(s.wg.size()), s.flops);
             prof_begin(all_quad ? 6 : all_rows ? 3 : 1, s.flops, ws);
             int nl = 0;
             M_CHECK(conv_wgrad_dispatch(s.wg, wc, ws, &nl));
@@ -1106,6 +1123,8 @@ int Model::run_backward() {
                 cfg.kc = s.dg[src].kc;
                 cfg.epi = grad_written[ins[src]] ? EPI_ACCUM16 : EPI_STORE16;
                 cfg.splitk_scratch = d_splitk; cfg.splitk_scratch_bytes = splitk_bytes;
+                trace_launch(s, src ? "dgrad1" : "dgrad0", conv_kernel_kind(s.dg[src].probs, cfg), int(s.dg[src].probs.size()),
+                             s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
                 prof_begin(conv_kernel_kind(s.dg[src].probs, cfg), s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
                 M_CHECK(conv_launch(s.dg[src].probs, cfg, stream));
                 prof_end();

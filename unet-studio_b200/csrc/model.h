@@ -190,6 +190,7 @@ class Model {
     std::vector<int> prof_kind;
     std::vector<double> prof_flops;
     size_t prof_used = 0;
+    void trace_launch(const Step& s, const char* pass, int kind, int nprob, double flops);
     void prof_begin(int kind, double flops, cudaStream_t on = nullptr);
     void prof_end(cudaStream_t on = nullptr);
     int prof_read(double out[24], int reset);  // per kind (8): {ms, launches, algorithmic FLOPs}

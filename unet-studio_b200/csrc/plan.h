@@ -33,6 +33,7 @@ size_t pack_bytes_band(const PackDesc& d);
 size_t pack_bytes(const PackDesc& d);
 int pack_weights_launch(const PackDesc& d, cudaStream_t stream);
 // all blobs of a model in one launch: descs_dev[njobs], first_block_dev[njobs + 1] (prefix sums of pack_job_blocks)
+void trace_marker_launch(cudaStream_t stream);
 int pack_job_blocks(const PackDesc& d);
 int pack_all_launch(const PackDesc* descs_dev, const int* first_block_dev, int njobs, int total_blocks, cudaStream_t stream);
 
