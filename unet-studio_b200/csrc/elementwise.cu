@@ -4,6 +4,7 @@
 // One thread moves one 16-byte chunk (8 channels of one voxel); reductions keep a fixed channel chunk per
 // thread so no atomics are needed until the per-block partial rows.
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -355,7 +356,8 @@ struct BwdApplyArgs {
     int C, Cp, has_norm, act;
 };
 
-__global__ void norm_act_bwd_apply_kernel(const BwdApplyArgs a) {
+template <bool FAST, int NCH, int MINB>
+__global__ void __launch_bounds__(256, MINB) norm_act_bwd_apply_kernel(const BwdApplyArgs a) {
     extern __shared__ float sm[];
     float* sc = sm;
     float* sh = sc + a.Cp;
@@ -382,32 +384,35 @@ __global__ void norm_act_bwd_apply_kernel(const BwdApplyArgs a) {
     const int smod = int(stride % nch);
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int ch = int(i % nch);
-    if (smod == 0) {
+    if constexpr (FAST) {
         // the grid stride is a multiple of the channel groups: every chunk of this thread has the same 8 channels -> coefficients
         // live in registers (the shared-memory version issued 96 LDS per iteration and was LSU-bound, not HBM-bound)
-        float csc[8], csh[8], cmu[8], crs[8], cm1[8], cm2[8];
-        bool creal[8];
+        // dx = sc*(dz - m1 - xhat*m2) with xhat = (x - mu)*rs  ==  G*dz + P*x + Q, four coefficients per channel instead of six
+        // (G = sc with a norm, 1 without, 0 for a padded channel): fewer registers -> three blocks per SM instead of two
+        // (sc = gamma*rstd with a norm, 1 without; 0 here for a padded channel, whose output must be 0)
+        float csc[8], csh[8], cp[8], cq[8];
+        const bool hn = a.has_norm != 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = ch * 8 + j;
-            csc[j] = sc[c]; csh[j] = sh[c]; cmu[j] = mu[c]; crs[j] = rs[c]; cm1[j] = m1[c]; cm2[j] = m2[c];
-            creal[j] = c < a.C;
+            const bool real = c < a.C;
+            csc[j] = real ? sc[c] : 0.f; csh[j] = sh[c];
+            cp[j] = (real && hn) ? -sc[c] * m2[c] * rs[c] : 0.f;
+            cq[j] = (real && hn) ? sc[c] * (m2[c] * rs[c] * mu[c] - m1[c]) : 0.f;
         }
-        const bool hn = a.has_norm != 0;
         const int act = a.act;
-        // four chunks per iteration: the eight 16-byte loads are issued before the first result is needed (the kernel was
-        // latency-bound at ~3.7 TB/s with two)
-        for (; i < total; i += 4 * stride) {
-            uint4 rx[4], rd[4];
-            bool ok[4];
+        // NCH chunks per iteration: the 2*NCH 16-byte loads are issued before the first result is needed
+        for (; i < total; i += NCH * stride) {
+            uint4 rx[NCH], rd[NCH];
+            bool ok[NCH];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < NCH; ++u) {
                 const long long iu = i + u * stride;
                 ok[u] = iu < total;
                 if (ok[u]) { rx[u] = a.x[iu]; rd[u] = a.dy[iu]; }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < NCH; ++u) {
                 if (!ok[u]) continue;
                 float x[8], d[8];
                 unpack8(rx[u], x);
@@ -416,14 +421,13 @@ __global__ void norm_act_bwd_apply_kernel(const BwdApplyArgs a) {
                 for (int j = 0; j < 8; ++j) {
                     const float z = csc[j] * x[j] + csh[j];
                     const float dz = d[j] * act_grad(z, act);
-                    const float xh = (x[j] - cmu[j]) * crs[j];
-                    d[j] = creal[j] ? (hn ? csc[j] * (dz - cm1[j] - xh * cm2[j]) : dz) : 0.f;
+                    d[j] = csc[j] * dz + (cp[j] * x[j] + cq[j]);
                 }
                 store8(a.dx + i + u * stride, d);
             }
         }
         return;
-    }
+    } else {
     auto one = [&](int chq, float (&x)[8], float (&d)[8]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -452,6 +456,7 @@ __global__ void norm_act_bwd_apply_kernel(const BwdApplyArgs a) {
             store8(a.dx + i2, d2);
         }
         ch = ch2 + smod; if (ch >= nch) ch -= nch;
+    }
     }
 }
 
@@ -689,7 +694,14 @@ int norm_act_bwd_launch(const void* x, const void* dy, void* dx, long long V, in
     a.x = static_cast<const uint4*>(x); a.dy = static_cast<const uint4*>(dy); a.dx = static_cast<uint4*>(dx);
     a.V = V; a.C = C; a.Cp = Cp; a.has_norm = has_norm; a.act = act;
     a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.beta = beta; a.sums = sums;
-    norm_act_bwd_apply_kernel<<<ew_grid(V * (Cp / 8), 256), 256, size_t(6) * Cp * sizeof(float), s>>>(a);
+    const int grid = ew_grid(V * (Cp / 8), 256);
+    static const int variant = std::getenv("U3D_APPLY_VARIANT") ? std::atoi(std::getenv("U3D_APPLY_VARIANT")) : 0;
+    const size_t sm = size_t(6) * Cp * sizeof(float);
+    if ((1LL * grid * 256) % (Cp / 8) != 0) norm_act_bwd_apply_kernel<false, 2, 2><<<grid, 256, sm, s>>>(a);
+    else if (variant == 1) norm_act_bwd_apply_kernel<true, 2, 3><<<grid, 256, sm, s>>>(a);
+    else if (variant == 2) norm_act_bwd_apply_kernel<true, 3, 3><<<grid, 256, sm, s>>>(a);
+    else if (variant == 3) norm_act_bwd_apply_kernel<true, 2, 4><<<grid, 256, sm, s>>>(a);
+    else norm_act_bwd_apply_kernel<true, 4, 2><<<grid, 256, sm, s>>>(a);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
