@@ -320,17 +320,6 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
             for (int gz = z0; gz < z1; ++gz, ++acc_cnt) {
                 const size_t vox0 = (size_t(gz) * H + gy) * W + gx0;
                 const uint32_t acc = acc_cnt & 3u;
-                // norm-backward mode: the raw activations of this row (G voxels x CO channels = 128 bytes) are fetched BEFORE waiting for
-                // the accumulator, so their latency hides behind the MMAs instead of stalling the TMEM drain
-                uint4 xpre[G * CO / 8];
-                if (nbx != nullptr) {
-#pragma unroll
-                    for (int q = 0; q < G * CO / 8; ++q) {
-                        const int xo = q / (CO / 8);
-                        const bool rvq = rv_xy && gx0 + xo < W;
-                        xpre[q] = rvq ? __ldg(reinterpret_cast<const uint4*>(nbx + (vox0 + xo) * dst_pitch) + (q % (CO / 8))) : make_uint4(0u, 0u, 0u, 0u);
-                    }
-                }
                 mbar_wait(tfull_bar(acc), (acc_cnt >> 2) & 1, 0x2500u | acc);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16) + acc * uint32_t(N);
@@ -364,7 +353,8 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                             out[1] = q1v;
                             if (want_stats && nbx != nullptr) {
                                 // norm-backward sums of the layer in front: dz = dy * act'(z), (sum dz, sum dz * xhat)
-                                const uint4 x0v = xpre[xo * (CO / 8) + c0 / 8], x1v = xpre[xo * (CO / 8) + c0 / 8 + 1];
+                                const uint4* xr = reinterpret_cast<const uint4*>(nbx + (vox0 + xo) * dst_pitch + c0 * 2);
+                                const uint4 x0v = __ldg(xr), x1v = __ldg(xr + 1);
                                 const uint32_t xw[8] = {x0v.x, x0v.y, x0v.z, x0v.w, x1v.x, x1v.y, x1v.z, x1v.w};
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
