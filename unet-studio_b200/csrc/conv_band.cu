@@ -47,12 +47,7 @@ struct BParams {
     uint32_t slot_bytes, w_bytes, off_w, off_stats, off_bars;
     float* stats;
     int epi;
-    NormBwdFuse nb;        // nb.x_raw != nullptr: the statistics are the norm-backward sums (u3d.h)
 };
-
-__device__ __forceinline__ float band_act_grad(float z, int act) {   // ActKind: 1 relu, 2 leaky_relu(0.01), 3 elu
-    return act == 1 ? (z > 0.f ? 1.f : 0.f) : act == 2 ? (z > 0.f ? 1.f : 0.01f) : act == 3 ? (z > 0.f ? 1.f : __expf(z)) : 1.f;
-}
 
 template <int HALF, int BIT>
 __device__ __forceinline__ void halve_step_b(float (&a)[16], float (&q)[16], int lane) {
@@ -108,18 +103,6 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 8 * CO + CO; i += kBThreads) sstats[i] = 0.f;
-    if (p.nb.x_raw != nullptr) {   // z = sc*x + sh, xhat = rs*x - murs per channel (padded channels: dy is 0 there)
-        float* co = sstats + 9 * CO;
-        for (int c = threadIdx.x; c < CO; c += kBThreads) {
-            const bool real = c < p.P.n_real;
-            const float rs = real ? p.nb.rstd[c] : 0.f, mu = real ? p.nb.mean[c] : 0.f;
-            const float sc = real ? p.nb.gamma[c] * rs : 0.f;
-            co[c] = sc;
-            co[CO + c] = real ? p.nb.beta[c] - mu * sc : 0.f;
-            co[2 * CO + c] = rs;
-            co[3 * CO + c] = mu * rs;
-        }
-    }
     if (warp == 12) {
         tmem_alloc(smem_u32(tmem_ptr_smem), 4 * N);
         tmem_relinquish();
@@ -301,9 +284,6 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const bool want_stats = p.stats != nullptr;
         const bool accum = p.epi == EPI_ACCUM16;
-        const uint8_t* const nbx = p.nb.x_raw ? static_cast<const uint8_t*>(p.nb.x_raw) + P.dst_coff * 2 : nullptr;
-        const float* const nco = sstats + 9 * CO;
-        const int nact = p.nb.act;
         const int hy = 1 + r / HQ, hq = r % HQ;
         const bool row_in_tile = r < p.TY * HQ && hq < p.TX / G;
         uint8_t* const dst = static_cast<uint8_t*>(P.dst) + P.dst_coff * 2;
@@ -351,24 +331,7 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                             q1v.z = pack2<false>(v[12], v[13]); q1v.w = pack2<false>(v[14], v[15]);
                             out[0] = q0v;
                             out[1] = q1v;
-                            if (want_stats && nbx != nullptr) {
-                                // norm-backward sums of the layer in front: dz = dy * act'(z), (sum dz, sum dz * xhat)
-                                const uint4* xr = reinterpret_cast<const uint4*>(nbx + (vox0 + xo) * dst_pitch + c0 * 2);
-                                const uint4 x0v = __ldg(xr), x1v = __ldg(xr + 1);
-                                const uint32_t xw[8] = {x0v.x, x0v.y, x0v.z, x0v.w, x1v.x, x1v.y, x1v.z, x1v.w};
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float2 xf = unpack2<false>(xw[j]);
-#pragma unroll
-                                    for (int h = 0; h < 2; ++h) {
-                                        const int c = c0 + 2 * j + h;
-                                        const float x = h ? xf.y : xf.x;
-                                        const float dz = v[2 * j + h] * band_act_grad(fmaf(nco[c], x, nco[CO + c]), nact);
-                                        ssum[c] += dz;
-                                        ssq[c] = fmaf(dz, fmaf(nco[2 * CO + c], x, -nco[3 * CO + c]), ssq[c]);
-                                    }
-                                }
-                            } else if (want_stats) {
+                            if (want_stats) {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) {
                                     ssum[c0 + j] += v[j];
@@ -831,7 +794,7 @@ static int conv_band_launch_one(const ConvProblem& Pin, const ConvLaunch& cfg, b
     static const bool use_zband = std::getenv("U3D_ZBAND") != nullptr;
     const bool zband = use_zband && bp.CO == 16 && bp.KS == 1 && P.c1p == 0;
     bp.w_bytes = zband ? kZWBytes : uint32_t(9 * bp.KS * 2 * bp.NB * 16);
-    const uint32_t stats_bytes = uint32_t((zband ? 17 : 13) * bp.CO * 4);
+    const uint32_t stats_bytes = uint32_t((zband ? 17 : 9) * bp.CO * 4);
     bp.nslots = int(std::min<size_t>(kMaxSlots, (size_t(222) * 1024 - bp.w_bytes - stats_bytes) / bp.slot_bytes));
     if (bp.nslots < (zband ? 3 : 4)) { set_error("conv_band_launch: plane ring does not fit in shared memory"); return 1; }
     bp.off_w = bp.nslots * bp.slot_bytes;
@@ -841,10 +804,6 @@ static int conv_band_launch_one(const ConvProblem& Pin, const ConvLaunch& cfg, b
     if (smem > 227 * 1024) { set_error("conv_band_launch: tile does not fit in shared memory"); return 1; }
     bp.epi = cfg.epi;
     bp.stats = stats ? cfg.stats_partials : nullptr;
-    if (stats && cfg.norm_bwd != nullptr) {
-        if (zband) { set_error("conv_band_launch: norm-backward statistics are not available in the z-stacked variant"); return 1; }
-        bp.nb = *cfg.norm_bwd;
-    }
     const int grid = std::max(1, std::min(bp.total_items, sms));
     if (cfg.stats_grid_out) *cfg.stats_grid_out = grid;
     if (zband) {

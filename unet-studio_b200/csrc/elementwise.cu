@@ -676,13 +676,8 @@ int norm_act_fwd_launch(const void* x, void* y, long long V, int C, int Cp, int 
 
 int norm_act_bwd_launch(const void* x, const void* dy, void* dx, long long V, int C, int Cp, int has_norm, int act,
                         const float* mean, const float* rstd, const float* gamma, const float* beta, float* partials,
-                        float* sums, float* dgamma, float* dbeta, cudaStream_t s, unsigned int* counter, int prefused_rows) {
-    if (has_norm && prefused_rows > 0) {
-        // the partial rows (sum dz, sum dz*xhat) were produced by the epilogue of the data gradient that wrote dy (NormBwdFuse)
-        if (2 * Cp > 1024) { set_error("norm_act_bwd_launch: more than 512 padded channels"); return 1; }
-        finalize_bwd_sums_kernel<<<1, 1024, 0, s>>>(partials, prefused_rows, Cp, C, sums, dgamma, dbeta);
-        U3D_CUDA_CHECK(cudaGetLastError());
-    } else if (has_norm) {
+                        float* sums, float* dgamma, float* dbeta, cudaStream_t s, unsigned int* counter) {
+    if (has_norm) {
         ReduceArgs r{};
         r.x = static_cast<const uint4*>(x); r.dy = static_cast<const uint4*>(dy); r.V = V; r.C = C; r.Cp = Cp;
         r.has_norm = 1; r.act = act; r.mean = mean; r.rstd = rstd; r.gamma = gamma; r.beta = beta; r.partials = partials;

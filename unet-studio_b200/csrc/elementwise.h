@@ -21,7 +21,7 @@ int norm_act_fwd_launch(const void* x, void* y, long long V, int C, int Cp, int 
 // dx from dy through act and (instance|batch N=1) norm; dgamma/dbeta += (accumulated across micro-batches)
 int norm_act_bwd_launch(const void* x, const void* dy, void* dx, long long V, int C, int Cp, int has_norm, int act,
                         const float* mean, const float* rstd, const float* gamma, const float* beta, float* partials,
-                        float* sums, float* dgamma, float* dbeta, cudaStream_t s, unsigned int* counter = nullptr, int prefused_rows = 0);
+                        float* sums, float* dgamma, float* dbeta, cudaStream_t s, unsigned int* counter = nullptr);
 // out[c] += sum_v x[v][c]   (bias gradients)
 int colsum_accumulate_launch(const void* x, long long V, int C, int Cp, float* partials, float* out, cudaStream_t s);
 

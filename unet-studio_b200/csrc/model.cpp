@@ -371,7 +371,6 @@ void Model::free_plan() {
     dlogits.clear();
     level_dims.clear();
     d_in_f32 = d_label = d_partials = d_sums = nullptr;
-    d_partials_nb = nullptr;
     d_pack_descs = nullptr; d_pack_first = nullptr; n_pack_jobs = n_pack_blocks = 0;
     d_scratch = nullptr;
     d_splitk = nullptr;
@@ -692,7 +691,6 @@ int Model::ensure_plan() {
     const int rows = std::max(reduce_rows_max(), device_sm_count());
     M_CHECK(alloc(reinterpret_cast<void**>(&d_partials), size_t(rows) * 2 * std::max(max_cp, 512) * 4));
     M_CHECK(alloc(reinterpret_cast<void**>(&d_sums), size_t(2) * max_cp * 4));
-    if (tr) M_CHECK(alloc(reinterpret_cast<void**>(&d_partials_nb), size_t(rows) * 2 * 64 * 4));
     if (tr) {
         M_CHECK(alloc(&d_scratch, max_bytes));
         scratch_bytes = max_bytes;
@@ -787,34 +785,6 @@ int Model::ensure_plan() {
             }
         } else if (s.kind == Step::MAXPOOL) {
             M_CHECK(alloc(reinterpret_cast<void**>(&s.idx), tens[s.out].V() * tens[s.out].Cp * sizeof(int)));
-        }
-    }
-    if (tr) {
-        // norm-backward fusion: a norm+activation whose output has exactly one consumer, a conv whose data gradient runs through the
-        // banded kernel, gets its backward sums from that kernel's epilogue
-        static const bool no_fuse = std::getenv("U3D_NO_NORM_BWD_FUSE") != nullptr;
-        std::vector<int> consumers(tens.size(), 0);
-        for (const Step& s : steps) {
-            if (s.in0 >= 0) ++consumers[s.in0];
-            if (s.in1 >= 0) ++consumers[s.in1];
-        }
-        for (size_t qi = 0; qi < steps.size() && !no_fuse; ++qi) {
-            Step& q = steps[qi];
-            if (q.kind != Step::NORMACT || !q.norm || q.out < 0 || consumers[q.out] != 1) continue;
-            for (size_t ci = 0; ci < steps.size(); ++ci) {
-                Step& c = steps[ci];
-                if (c.kind != Step::CONV || c.head_level >= 0) continue;
-                for (int src = 0; src < 2; ++src) {
-                    if ((src ? c.in1 : c.in0) != q.out || c.dg[src].probs.size() != 1) continue;
-                    ConvLaunch cfg{};
-                    cfg.kc = c.dg[src].kc;
-                    cfg.epi = EPI_STORE16;
-                    if (!conv_band_eligible(c.dg[src].probs, cfg)) continue;
-                    if (tens[q.in0].Cp != tens[q.out].Cp) continue;
-                    q.bwd_fused_conv = int(ci); q.bwd_fused_src = src;
-                    c.fuse_norm_bwd[src] = int(qi);
-                }
-            }
         }
     }
     {   // job table of the one-launch weight re-pack
@@ -1153,23 +1123,12 @@ int Model::run_backward() {
                 cfg.kc = s.dg[src].kc;
                 cfg.epi = grad_written[ins[src]] ? EPI_ACCUM16 : EPI_STORE16;
                 cfg.splitk_scratch = d_splitk; cfg.splitk_scratch_bytes = splitk_bytes;
-                NormBwdFuse nbf{};
-                int nbf_rows = 0;
-                if (s.fuse_norm_bwd[src] >= 0 && cfg.epi == EPI_STORE16) {
-                    Step& q = steps[size_t(s.fuse_norm_bwd[src])];
-                    nbf.x_raw = tens[q.in0].p; nbf.mean = q.mean; nbf.rstd = q.rstd;
-                    nbf.gamma = param_ptr(q.p_g); nbf.beta = param_ptr(q.p_g + 1); nbf.act = q.act;
-                    cfg.norm_bwd = &nbf;
-                    cfg.stats_partials = d_partials_nb;
-                    cfg.stats_grid_out = &nbf_rows;
-                }
                 trace_launch(s, src ? "dgrad1" : "dgrad0", conv_kernel_kind(s.dg[src].probs, cfg), int(s.dg[src].probs.size()),
                              s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
                 prof_begin(conv_kernel_kind(s.dg[src].probs, cfg), s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
                 M_CHECK(conv_launch(s.dg[src].probs, cfg, stream));
                 prof_end();
                 ++launches;
-                if (cfg.norm_bwd) steps[size_t(s.fuse_norm_bwd[src])].bwd_fused_rows = nbf_rows;
                 grad_written[ins[src]] = 1;
             }
             if (dp_overlap_now && si == dp_split_step) {
@@ -1197,9 +1156,8 @@ int Model::run_backward() {
                 const float* gamma = s.norm ? param_ptr(s.p_g) : nullptr;
                 const float* beta = s.norm ? param_ptr(s.p_g + 1) : nullptr;
                 M_CHECK(norm_act_bwd_launch(a.p, o.grad, target, a.V(), a.C, a.Cp, s.norm ? 1 : 0, s.act, s.mean, s.rstd, gamma, beta,
-                                            s.bwd_fused_rows > 0 ? d_partials_nb : d_partials, d_sums, s.norm ? grad_ptr(s.p_g) : nullptr,
-                                            s.norm ? grad_ptr(s.p_g + 1) : nullptr, stream, d_counter, s.bwd_fused_rows));
-                s.bwd_fused_rows = 0;
+                                            d_partials, d_sums, s.norm ? grad_ptr(s.p_g) : nullptr,
+                                            s.norm ? grad_ptr(s.p_g + 1) : nullptr, stream, d_counter));
                 launches += s.norm ? 2 : 1;
             } else if (s.kind == Step::MAXPOOL) {
                 M_CHECK(maxpool_bwd_launch(o.grad, s.idx, target, o.Cp, o.d, o.h, o.w, stream));

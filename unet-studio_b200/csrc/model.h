@@ -69,11 +69,6 @@ struct Step {
     float* rstd = nullptr;
     int buf0 = -1;
     bool stats_from_conv = false;
-    // backward: the (sum dz, sum dz*xhat) partial rows of this norm come from the epilogue of the data gradient of its only consumer
-    // (conv step bwd_fused_conv, source bwd_fused_src) instead of a separate pass over x and dy
-    int bwd_fused_conv = -1, bwd_fused_src = 0;
-    int fuse_norm_bwd[2] = {-1, -1};   // CONV: the NORMACT step whose backward sums the data gradient wrt source 0 / 1 emits
-    int bwd_fused_rows = 0;            // partial rows written by that launch in the current backward pass
     // MAXPOOL
     int* idx = nullptr;
 };
@@ -235,7 +230,6 @@ class Model {
     float* d_in_f32 = nullptr;
     float* d_label = nullptr;
     float* d_partials = nullptr;
-    float* d_partials_nb = nullptr;  // partial rows of the fused norm-backward sums (own buffer: lives from a data gradient to the norm backward behind it)
     float* d_sums = nullptr;
     void* d_scratch = nullptr;       // gradient staging for multi-consumer tensors
     float* d_splitk = nullptr;       // fp32 slices of the deterministic split-K convs of the deep levels (conv_tma.cu)

@@ -67,26 +67,12 @@ struct ConvProblem {
     int shuffle_nreal;     // real channels per parity block
 };
 
-// Norm-backward statistics fused into a data-gradient epilogue: the launch writes dy = d(activated tensor); the tensor in front of
-// that activation is x_raw with InstanceNorm/BatchNorm coefficients (mean, rstd, gamma, beta) and activation `act`.  Instead of
-// (sum y, sum y^2) the per-CTA partial rows then hold (sum dz, sum dz*xhat), dz = dy*act'(z), xhat = (x - mean)*rstd: what
-// channel_reduce_kernel<1> computes in a separate pass over x and dy.
-struct NormBwdFuse {
-    const void* x_raw;     // same geometry / channel pitch as the destination
-    const float* mean;
-    const float* rstd;
-    const float* gamma;
-    const float* beta;
-    int act;               // ActKind
-};
-
 struct ConvLaunch {
     int kc;                // K chunk (16, 32 or 64 channels)
     int a_bf16, b_bf16;    // operand formats (0 = fp16, 1 = bf16)
     int out_bf16;          // 16-bit output format
     EpiMode epi;
     float* stats_partials; // [grid][2][ntile*ntiles] or nullptr (single-problem launches only)
-    const NormBwdFuse* norm_bwd;   // with stats_partials (conv_band only): emit the norm-backward sums instead of the forward statistics
     int* stats_grid_out;   // host pointer: receives the grid size used (number of partial rows)
     float* splitk_scratch; // optional fp32 scratch for the deterministic split-K of conv_tma (deep levels); nullptr = no split-K
     size_t splitk_scratch_bytes;
