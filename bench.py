@@ -300,6 +300,18 @@ def extra_configs(pkg, torch, comm, world, rank, local_rank, barrier, clocks):
                        "h2d_bytes_per_window": IN_C * W * H * D * 4, "d2h_bytes_per_window": 6 * W * H * D * 4,
                        "api": "unet3d_evaluate_windows (host buffers)"}
         if world == 1:
+            # the same volume through unet3d_evaluate_volume: windows cut, forwarded, soft-maxed, re-assembled and arg-maxed on the GPU;
+            # 1 byte per voxel comes back instead of 6 x 4
+            vol = torch.from_numpy(rng.random((IN_C, 320, 320, 320), dtype=np.float32)).pin_memory()
+            pkg.evaluate_volume(net, vol.numpy(), (160, 128, 160), 0.5, want_fg=False)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                _, _, _, nwin = pkg.evaluate_volume(net, vol.numpy(), (160, 128, 160), 0.5, want_fg=False)
+            dtl = time.perf_counter() - t0
+            out["cfg5"]["label_map"] = {"value": reps * 320 ** 3 / 1e6 / dtl, "unit": "Mvoxel/s", "ms_per_volume": dtl / reps * 1e3, "windows": nwin,
+                                        "h2d_bytes_per_volume": IN_C * 320 ** 3 * 4, "d2h_bytes_per_volume": 320 ** 3,
+                                        "api": "unet3d_evaluate_volume (host volume in, uint8 label map out; softmax + create_mask + argmax on the GPU)"}
+            del vol
             S = 320
             net.set_dim(S, S, S)
             xv = torch.rand(1, IN_C, S, S, S, device="cuda")
