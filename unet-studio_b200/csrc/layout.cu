@@ -1,6 +1,7 @@
 // Layout kernels: reference NCDHW fp32 <-> internal NDHWC 16-bit (channels padded to 16), and the
 // weight pack from the reference parameter layout (tensorN order/shape, /root/reference/main.cpp:193-204)
 // into the canonical UMMA B-operand blobs consumed by conv_igemm.cu.
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -168,8 +169,100 @@ __device__ __forceinline__ void pack_band_body(const PackDesc& d, uint32_t vbloc
     }
 }
 
+// Tiled form of the generic blob for the plain (not parity-stacked, not split) case.  pack_generic_body reads one fp32 per element at
+// a stride of ktaps floats (108 bytes for 3x3x3): every 4-byte read is its own 32-byte sector and the re-pack of the whole net spent
+// ~200 us on that gather.  Here a block stages a CONTIGUOUS piece of the reference tensor in shared memory (coalesced reads) and
+// writes 16-byte pieces [8 k] that are contiguous over n (coalesced writes):
+//   n indexes dimA (forward conv weights [Cout][Cin][taps]):      tile = 4 n x (kc k x taps), contiguous per n
+//   n indexes dimB (data-gradient packs, transposed conv weights): tile = 8 k x (32 n x taps), contiguous per k
+constexpr int kPackTileFloats = 4 * 64 * 27;   // 27.6 KB of shared memory
+__device__ __forceinline__ bool pack_tiled_ok(const PackDesc& d) {
+    return !d.banded && d.stack_cp == 0 && d.split_k == 0 && !d.out_bf16 && d.kc * d.ktaps * 4 <= kPackTileFloats && 8 * 32 * d.ktaps <= kPackTileFloats &&
+           d.ntile % 8 == 0;
+}
+__device__ __forceinline__ void pack_tiled_body(const PackDesc& d, uint32_t vblock, uint32_t nvblocks, float* sm) {
+    const int nch = d.nch[0] + d.nch[1];
+    const int kg_n = d.kc / 8;
+    const int ktaps = d.ktaps;
+    __half* const out = static_cast<__half*>(d.out);
+    if (d.n_is_A) {
+        const int n4s = d.ntile / 4;
+        const int tiles = nch * d.ntiles * n4s;
+        const int run = d.kc * ktaps;                  // floats per n
+        for (int tile = int(vblock); tile < tiles; tile += int(nvblocks)) {
+            const int n4 = tile % n4s;
+            const int nt = (tile / n4s) % d.ntiles;
+            const int ch = tile / (n4s * d.ntiles);
+            const int s = ch < d.nch[0] ? 0 : 1;
+            const int kk0 = (ch - (s ? d.nch[0] : 0)) * d.kc;
+            const int kvalid = min(d.kc, d.k_real[s] - kk0);          // may be <= 0: an all-padding chunk
+            __syncthreads();
+            for (int e = threadIdx.x; e < 4 * run; e += blockDim.x) {
+                const int i = e / run, r = e - i * run;
+                const int nn = nt * d.ntile + n4 * 4 + i;
+                float v = 0.f;
+                if (nn < d.n_real && r < kvalid * ktaps) v = d.w[(size_t(d.n_off + nn) * d.dimB + d.k_off[s] + kk0) * ktaps + r];
+                sm[e] = v;
+            }
+            __syncthreads();
+            const int pieces = d.ntaps * kg_n * 4;
+            for (int q = threadIdx.x; q < pieces; q += blockDim.x) {
+                const int i = q & 3;
+                const int kg = (q >> 2) % kg_n;
+                const int tap = (q >> 2) / kg_n;
+                const int ref = d.tap_ref[tap];
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = ref >= 0 ? sm[i * run + (kg * 8 + j) * ktaps + ref] : 0.f;
+                uint4 o;
+                o.x = pack2<false>(f[0], f[1]); o.y = pack2<false>(f[2], f[3]); o.z = pack2<false>(f[4], f[5]); o.w = pack2<false>(f[6], f[7]);
+                const size_t idx = ((((size_t(tap) * nch + ch) * d.ntiles + nt) * kg_n + kg) * d.ntile + (n4 * 4 + i)) * 8;
+                *reinterpret_cast<uint4*>(out + idx) = o;
+            }
+        }
+    } else {
+        const int n32s = (d.ntile + 31) / 32;
+        const int tiles = nch * d.ntiles * kg_n * n32s;
+        for (int tile = int(vblock); tile < tiles; tile += int(nvblocks)) {
+            const int n32 = tile % n32s;
+            const int kg = (tile / n32s) % kg_n;
+            const int nt = (tile / (n32s * kg_n)) % d.ntiles;
+            const int ch = tile / (n32s * kg_n * d.ntiles);
+            const int s = ch < d.nch[0] ? 0 : 1;
+            const int kk0 = (ch - (s ? d.nch[0] : 0)) * d.kc + kg * 8;
+            const int nbase = nt * d.ntile + n32 * 32;                 // first n of this tile
+            const int ncount = min(32, d.ntile - n32 * 32);
+            const int run = 32 * ktaps;                                // floats per k (stride in shared memory)
+            const int nvalid = min(ncount, d.n_real - nbase);          // may be <= 0
+            __syncthreads();
+            for (int e = threadIdx.x; e < 8 * ncount * ktaps; e += blockDim.x) {
+                const int j = e / (ncount * ktaps), r = e - j * (ncount * ktaps);
+                float v = 0.f;
+                if (kk0 + j < d.k_real[s] && r < nvalid * ktaps) v = d.w[(size_t(d.k_off[s] + kk0 + j) * d.dimB + d.n_off + nbase) * ktaps + r];
+                sm[j * run + r] = v;
+            }
+            __syncthreads();
+            const int pieces = d.ntaps * ncount;
+            for (int q = threadIdx.x; q < pieces; q += blockDim.x) {
+                const int n = q % ncount;
+                const int tap = q / ncount;
+                const int ref = d.tap_ref[tap];
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = ref >= 0 ? sm[j * run + n * ktaps + ref] : 0.f;
+                uint4 o;
+                o.x = pack2<false>(f[0], f[1]); o.y = pack2<false>(f[2], f[3]); o.z = pack2<false>(f[4], f[5]); o.w = pack2<false>(f[6], f[7]);
+                const size_t idx = ((((size_t(tap) * nch + ch) * d.ntiles + nt) * kg_n + kg) * d.ntile + (n32 * 32 + n)) * 8;
+                *reinterpret_cast<uint4*>(out + idx) = o;
+            }
+        }
+    }
+}
+
 __global__ void pack_weights_kernel(const __grid_constant__ PackDesc d) {
+    __shared__ float sm[kPackTileFloats];
     if (d.banded) pack_band_body(d, blockIdx.x, gridDim.x);
+    else if (pack_tiled_ok(d) && !d.force_elementwise) pack_tiled_body(d, blockIdx.x, gridDim.x, sm);
     else pack_generic_body(d, blockIdx.x, gridDim.x);
 }
 
@@ -181,9 +274,11 @@ __global__ void pack_all_kernel(const PackDesc* __restrict__ descs, const int* _
         const int mid = (lo + hi + 1) >> 1;
         if (first_block[mid] <= int(blockIdx.x)) lo = mid; else hi = mid - 1;
     }
+    __shared__ float sm[kPackTileFloats];
     const PackDesc& d = descs[lo];
     const uint32_t vb = blockIdx.x - uint32_t(first_block[lo]), nvb = uint32_t(first_block[lo + 1] - first_block[lo]);
     if (d.banded) pack_band_body(d, vb, nvb);
+    else if (pack_tiled_ok(d) && !d.force_elementwise) pack_tiled_body(d, vb, nvb, sm);
     else pack_generic_body(d, vb, nvb);
 }
 
@@ -197,7 +292,14 @@ inline int grid_for(long long total, int block) {
 
 }  // namespace
 
-int pack_weights_launch(const PackDesc& d, cudaStream_t stream) {
+bool pack_force_elementwise() {
+    static const bool v = std::getenv("U3D_PACK_ELEMENTWISE") != nullptr;
+    return v;
+}
+
+int pack_weights_launch(const PackDesc& din, cudaStream_t stream) {
+    PackDesc d = din;
+    d.force_elementwise = pack_force_elementwise() ? 1 : 0;
     const long long total = (long long)pack_bytes(d) / 2;
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(d);
     U3D_CUDA_CHECK(cudaGetLastError());

@@ -787,6 +787,15 @@ int Model::ensure_plan() {
             M_CHECK(alloc(reinterpret_cast<void**>(&s.idx), tens[s.out].V() * tens[s.out].Cp * sizeof(int)));
         }
     }
+    {   // concat convs whose source 0 (the skip tensor) is also consumed by another conv: their skip gradient can be deferred
+        skip_has_other_consumer.assign(steps.size(), 0);
+        for (size_t ci = 0; ci < steps.size(); ++ci) {
+            const Step& c = steps[ci];
+            if (c.kind != Step::CONV || c.in1 < 0) continue;
+            for (size_t oi = 0; oi < steps.size(); ++oi)
+                if (oi != ci && steps[oi].kind == Step::CONV && oi < ci && (steps[oi].in0 == c.in0 || steps[oi].in1 == c.in0)) skip_has_other_consumer[ci] = 1;
+        }
+    }
     {   // job table of the one-launch weight re-pack
         std::vector<PackDesc> jobs;
         std::vector<int> first(1, 0);
@@ -796,7 +805,10 @@ int Model::ensure_plan() {
             for (int src = 0; src < 2; ++src)
                 for (auto& k : s.dg[src].packs) jobs.push_back(k);
         }
-        for (auto& k : jobs) first.push_back(first.back() + pack_job_blocks(k));
+        for (auto& k : jobs) {
+            k.force_elementwise = pack_force_elementwise() ? 1 : 0;
+            first.push_back(first.back() + pack_job_blocks(k));
+        }
         n_pack_jobs = int(jobs.size());
         n_pack_blocks = first.back();
         d_pack_descs = nullptr; d_pack_first = nullptr;
@@ -1084,8 +1096,40 @@ int Model::run_backward() {
     // fused heads: the loss-gradient kernel (launched before this function) already stored dL/dx of the head input
     for (const Step& s : steps)
         if (s.kind == Step::CONV && s.head_bwd_fused) grad_written[s.in0] = 1;
+    // data gradient of conv step s wrt its source src (store, or read-add-store when the tensor already holds a contribution)
+    auto launch_dgrad = [&](Step& s, int src) -> int {
+        const int t = src ? s.in1 : s.in0;
+        ConvLaunch cfg{};
+        cfg.kc = s.dg[src].kc;
+        cfg.epi = grad_written[t] ? EPI_ACCUM16 : EPI_STORE16;
+        cfg.splitk_scratch = d_splitk; cfg.splitk_scratch_bytes = splitk_bytes;
+        const double fl = s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]);
+        trace_launch(s, src ? "dgrad1" : "dgrad0", conv_kernel_kind(s.dg[src].probs, cfg), int(s.dg[src].probs.size()), fl);
+        prof_begin(conv_kernel_kind(s.dg[src].probs, cfg), fl);
+        M_CHECK(conv_launch(s.dg[src].probs, cfg, stream));
+        prof_end();
+        ++launches;
+        grad_written[t] = 1;
+        return 0;
+    };
+    // A skip tensor receives two data gradients: from the decoder conv that consumes it (early in this loop) and from the next encoder
+    // level's stride-2 conv (late).  The stride-2 data gradient scatters 32-byte rows (parity-stacked epilogue) and is bound by that
+    // traffic; as a read-add-store it moves it twice.  So the decoder conv's skip gradient is DEFERRED until just before the skip
+    // tensor's producer runs its backward: the scatter kernel stores, the dense kernel (MMA-bound, the extra read is free) accumulates.
+    static const bool no_defer = std::getenv("U3D_NO_DEFER_SKIP") != nullptr;
+    std::vector<int> deferred;   // conv steps whose source-0 data gradient is pending
     for (int si = int(steps.size()) - 1; si >= 0; --si) {
         Step& s = steps[si];
+        if (s.out >= 0 && !deferred.empty()) {
+            for (size_t k = 0; k < deferred.size();) {
+                Step& c = steps[size_t(deferred[k])];
+                if (c.in0 == s.out) {
+                    M_CHECK(launch_dgrad(c, 0));
+                    deferred.erase(deferred.begin() + long(k));
+                } else
+                    ++k;
+            }
+        }
         if (s.kind == Step::CONV && s.head_bwd_fused) continue;
         if (s.kind == Step::CONV) {
             const bool head = s.head_level >= 0;
@@ -1119,17 +1163,11 @@ int Model::run_backward() {
             const int ins[2] = {s.in0, s.in1};
             for (int src = 0; src < 2; ++src) {
                 if (ins[src] < 0 || !tens[ins[src]].needs_grad) continue;
-                ConvLaunch cfg{};
-                cfg.kc = s.dg[src].kc;
-                cfg.epi = grad_written[ins[src]] ? EPI_ACCUM16 : EPI_STORE16;
-                cfg.splitk_scratch = d_splitk; cfg.splitk_scratch_bytes = splitk_bytes;
-                trace_launch(s, src ? "dgrad1" : "dgrad0", conv_kernel_kind(s.dg[src].probs, cfg), int(s.dg[src].probs.size()),
-                             s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
-                prof_begin(conv_kernel_kind(s.dg[src].probs, cfg), s.flops * double(s.g.cin[src]) / double(s.g.cin[0] + s.g.cin[1]));
-                M_CHECK(conv_launch(s.dg[src].probs, cfg, stream));
-                prof_end();
-                ++launches;
-                grad_written[ins[src]] = 1;
+                if (src == 0 && s.in1 >= 0 && !no_defer && !grad_written[s.in0] && skip_has_other_consumer[size_t(si)]) {
+                    deferred.push_back(si);
+                    continue;
+                }
+                M_CHECK(launch_dgrad(s, src));
             }
             if (dp_overlap_now && si == dp_split_step) {
                 // every contribution to the tail bucket has been issued: weight gradients on stream2, bias / norm / head gradients on
@@ -1173,6 +1211,7 @@ int Model::run_backward() {
             grad_written[s.in0] = 1;
         }
     }
+    for (int k : deferred) M_CHECK(launch_dgrad(steps[size_t(k)], 0));   // (a producer that was never reached)
     if (two_streams) {   // the update (and the next forward) must see every weight gradient
         M_CUDA(cudaEventRecord(ev_join, stream2));
         M_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));

@@ -244,6 +244,7 @@ class Model {
     unsigned int* d_counter = nullptr;   // "last block finalizes" ticket of the norm-backward reduction (reset by that block)
     int last_stat_rows = 0, last_stat_ntot = 0;
     std::vector<char> grad_written;
+    std::vector<char> skip_has_other_consumer;   // per step: concat conv whose skip tensor feeds an earlier conv as well (deferred skip gradient)
     std::vector<void*> owned;        // every cudaMalloc of the plan
 
     void free_plan();

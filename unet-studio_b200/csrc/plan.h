@@ -25,6 +25,7 @@ struct PackDesc {
     int banded;              // 1: x-banded layout of conv_band.cu ([9 (dz,dy)][K chunk][kx 2,1,0,zero][band_co])
     int band_co;
     ConvTap band_taps[27];   // the problem's tap offsets (which reference tap each (dz,dy,dx) offset reads)
+    int force_elementwise;   // debug (U3D_PACK_ELEMENTWISE): one thread per blob element instead of the shared-memory tiled form
     int split_k;             // > 0 (first layer of the network, source 0 only): K channel kk = g*split_k + c carries reference input channel c;
                              // g = 0, 1: fp16(w), g = 2: fp16(w - fp16(w)).  With the input packed as [hi | lo | hi] (pack_act_launch split = 1) the
                              // layer computes w_hi*x_hi + w_hi*x_lo + w_lo*x_hi = w*x to ~22 bits in the spare padded channels
@@ -34,6 +35,7 @@ size_t pack_bytes(const PackDesc& d);
 int pack_weights_launch(const PackDesc& d, cudaStream_t stream);
 // all blobs of a model in one launch: descs_dev[njobs], first_block_dev[njobs + 1] (prefix sums of pack_job_blocks)
 void trace_marker_launch(cudaStream_t stream);
+bool pack_force_elementwise();
 int pack_job_blocks(const PackDesc& d);
 int pack_all_launch(const PackDesc* descs_dev, const int* first_block_dev, int njobs, int total_blocks, cudaStream_t stream);
 
