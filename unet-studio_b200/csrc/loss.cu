@@ -322,7 +322,7 @@ __global__ void head_fwd_kernel(const uint4* __restrict__ x, const float* __rest
 // backward: dlogits stay in registers; dx[v][k] = sum_c dl[c] W[c][k] (fp16, store or accumulate), dW[c][k] += dl[c] x[v][k],
 // db[c] += dl[c].  Replaces loss_grad + the head's dgrad / wgrad / bias-gradient launches and the dlogits round trip.
 template <int CT, int XCP>
-__global__ void __launch_bounds__(128) loss_grad_head_kernel(const LossLevel L, const HeadFuse Hd) {
+__global__ void __launch_bounds__(128, (CT * XCP <= 64 ? 5 : 3)) loss_grad_head_kernel(const LossLevel L, const HeadFuse Hd) {
     const long long nv = (long long)L.d * L.h * L.w;
     const int cb = L.collapse_before;
     const int Cc = cb ? L.C - cb + 1 : L.C;
@@ -345,14 +345,20 @@ __global__ void __launch_bounds__(128) loss_grad_head_kernel(const LossLevel L, 
     const float invZ = 1.f / float(Cc - 1 > 1 ? Cc - 1 : 1);
     const uint4* xin = static_cast<const uint4*>(Hd.x);
     uint4* dxo = static_cast<uint4*>(Hd.dx);
-    float aw[CT][XCP], ab[CT];
+    // one thread per (voxel, group of 8 head-input channels): the XCP/8 threads of a voxel evaluate its softmax gradient redundantly
+    // (a few classes) but each owns 16 bytes of x / dx, so a warp's loads and stores are contiguous and a thread carries CT*8 weight-
+    // gradient accumulators instead of CT*XCP (the one-thread-per-voxel form needed 167 registers: 19 % occupancy, 2.1 TB/s)
+    constexpr int GP = XCP / 8;
+    const int g = int(threadIdx.x) % GP;
+    float aw[CT][8], ab[CT];
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
         ab[c] = 0.f;
 #pragma unroll
-        for (int k = 0; k < XCP; ++k) aw[c][k] = 0.f;
+        for (int k = 0; k < 8; ++k) aw[c][k] = 0.f;
     }
-    for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < nv; vox += (long long)gridDim.x * blockDim.x) {
+    const long long vstride = (long long)gridDim.x * (blockDim.x / GP);
+    for (long long vox = blockIdx.x * (long long)(blockDim.x / GP) + threadIdx.x / GP; vox < nv; vox += vstride) {
         int x = 0, y = 0, z = 0;
         if (L.shift != 0) {   // level 0 reads label[vox] directly; deeper levels need (x,y,z) (32-bit: a level has < 2^31 voxels)
             const unsigned uv = unsigned(vox);
@@ -361,59 +367,54 @@ __global__ void __launch_bounds__(128) loss_grad_head_kernel(const LossLevel L, 
             y = int(q % unsigned(L.h));
             z = int(q / unsigned(L.h));
         }
+        const uint4 qx = xin[vox * GP + g];
+        uint4 qd = make_uint4(0u, 0u, 0u, 0u);
+        if (Hd.dx_accum) qd = dxo[vox * GP + g];
         Voxel<CT> o;
         eval_voxel<CT>(L, vox, x, y, z, o);
         float dlo[CT];
         voxel_grad<CT>(L, o, sI, sK, inv_n, invZ, dlo);
+        const uint32_t u[4] = {qx.x, qx.y, qx.z, qx.w};
+        const uint32_t ud[4] = {qd.x, qd.y, qd.z, qd.w};
+        float xv[8], dv[8];
 #pragma unroll
-        for (int g = 0; g < XCP / 8; ++g) {
-            const uint4 qx = xin[vox * (XCP / 8) + g];
-            const uint32_t u[4] = {qx.x, qx.y, qx.z, qx.w};
-            float xv[8], dv[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack2<false>(u[j]);
-                xv[2 * j] = f.x;
-                xv[2 * j + 1] = f.y;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) dv[k] = 0.f;
-            if (Hd.dx_accum) {
-                const uint4 qd = dxo[vox * (XCP / 8) + g];
-                const uint32_t ud[4] = {qd.x, qd.y, qd.z, qd.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = unpack2<false>(ud[j]);
-                    dv[2 * j] = f.x;
-                    dv[2 * j + 1] = f.y;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < CT; ++c) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    dv[k] = fmaf(dlo[c], sw[c * XCP + g * 8 + k], dv[k]);
-                    aw[c][g * 8 + k] = fmaf(dlo[c], xv[k], aw[c][g * 8 + k]);
-                }
-            }
-            uint4 qo;
-            qo.x = pack2<false>(dv[0], dv[1]); qo.y = pack2<false>(dv[2], dv[3]);
-            qo.z = pack2<false>(dv[4], dv[5]); qo.w = pack2<false>(dv[6], dv[7]);
-            dxo[vox * (XCP / 8) + g] = qo;
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2<false>(u[j]);
+            xv[2 * j] = f.x;
+            xv[2 * j + 1] = f.y;
+            const float2 fd = unpack2<false>(ud[j]);
+            dv[2 * j] = fd.x;
+            dv[2 * j + 1] = fd.y;
         }
 #pragma unroll
-        for (int c = 0; c < CT; ++c) ab[c] += dlo[c];
+        for (int c = 0; c < CT; ++c) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                dv[k] = fmaf(dlo[c], sw[c * XCP + g * 8 + k], dv[k]);
+                aw[c][k] = fmaf(dlo[c], xv[k], aw[c][k]);
+            }
+        }
+        uint4 qo;
+        qo.x = pack2<false>(dv[0], dv[1]); qo.y = pack2<false>(dv[2], dv[3]);
+        qo.z = pack2<false>(dv[4], dv[5]); qo.w = pack2<false>(dv[6], dv[7]);
+        dxo[vox * GP + g] = qo;
+        if (g == 0) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) ab[c] += dlo[c];
+        }
     }
-    const int lane = threadIdx.x & 31;
+    // lanes with the same channel group: lane % GP == g  ->  butterfly over the lane bits above log2(GP)
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
 #pragma unroll
-        for (int k = 0; k < XCP; ++k) {
-            const float v = warp_sum(aw[c][k]);
-            if (lane == 0) atomicAdd(&sacc[c * XCP + k], v);
+        for (int k = 0; k < 8; ++k) {
+            float v = aw[c][k];
+#pragma unroll
+            for (int o = 16; o >= GP; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) < GP) atomicAdd(&sacc[c * XCP + g * 8 + k], v);
         }
         const float vb = warp_sum(ab[c]);
-        if (lane == 0) atomicAdd(&sacc[CT * XCP + c], vb);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[CT * XCP + c], vb);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < CT * XCP; i += blockDim.x) {
@@ -466,8 +467,8 @@ int loss_level_launch(const LossLevel& L, const HeadFuse* Hd, cudaStream_t s) {
     loss_finalize_kernel<<<1, 960, 0, s>>>(L, grid);
     if (Hd != nullptr) {
         if (!head_bwd_supported(L.C, Hd->xcp)) { set_error("loss_level_launch: unsupported fused head shape"); return 1; }
-        long long gh = (nv + 127) / 128;
-        const int gridh = int(gh < 1 ? 1 : (gh > 148 * 8 ? 148 * 8 : gh));
+        long long gh = (nv * (Hd->xcp / 8) + 127) / 128;
+        const int gridh = int(gh < 1 ? 1 : (gh > 148 * 16 ? 148 * 16 : gh));
         const int ct = L.C <= 2 ? 2 : L.C <= 4 ? 4 : 8;
         if (ct == 2 && Hd->xcp == 16) loss_grad_head_kernel<2, 16><<<gridh, 128, 0, s>>>(L, *Hd);
         else if (ct == 2) loss_grad_head_kernel<2, 32><<<gridh, 128, 0, s>>>(L, *Hd);
