@@ -631,9 +631,9 @@ static int reduce_launch(int mode, const ReduceArgs& a, int* rows, cudaStream_t 
     long long want = (a.V + k - 1) / k;
     int grid = int(want < 1 ? 1 : (want > reduce_rows_max() ? reduce_rows_max() : want));
     if (mode == 1 && a.counter != nullptr) {
-        // the block that finishes last sums the partial rows: keep its per-thread chain (rows * 2*Cp / block) at ~40 loads.  The wide
+        // the block that finishes last sums the partial rows: keep its per-thread chain (rows * 2*Cp / block) at ~80 loads.  The wide
         // layers are the small deep-level tensors, which a few dozen blocks stream in a microsecond anyway.
-        const int cap = std::max(8, 40 * block / (2 * a.Cp));
+        const int cap = std::max(8, 80 * block / (2 * a.Cp));
         grid = std::min(grid, cap);
     }
     const size_t smem = size_t(k) * a.Cp * 2 * sizeof(float);
