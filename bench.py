@@ -391,7 +391,7 @@ def main():
     x_host = torch.from_numpy(img).pin_memory()
     l_host = torch.from_numpy(lab).pin_memory()
     x_dev, l_dev = x_host.cuda(), l_host.cuda()
-    total_steps = 1000
+    total_steps = 100000
     step_no = [0]
     pending = [False]   # a prefetched sample is waiting in the handle
 
@@ -446,6 +446,33 @@ def main():
     barrier()
     clocks.end()
     launches = net.launch_count() - launches0
+    # ---------------- the same loop over a longer window (the contract times exactly --steps; a 20-step window is 0.15 s) ----------------
+    n_sus = max(200, args.steps)
+    barrier()
+    clocks.begin()
+    net.timer_start()
+    for _ in range(n_sus):
+        one_step_device()
+    ms_sus = net.timer_stop()
+    barrier()
+    clocks.end()
+    # ---------------- N > 1: the same steps WITHOUT the gradient all-reduce (replicas may drift apart: timing only) = what the
+    # collective costs on top of the compute, i.e. its exposed (non-overlapped) time plus the SM share it takes from the backward pass
+    ms_noar = None
+    if world > 1:
+        net.attach_comm(None, 1)
+        real_comm, comm = comm, None
+        for _ in range(3):
+            one_step_device()
+        barrier()
+        net.timer_start()
+        for _ in range(args.steps):
+            one_step_device()
+        ms_noar = net.timer_stop()
+        barrier()
+        comm = real_comm
+        if not os.environ.get("U3D_NO_AR_OVERLAP"):
+            net.attach_comm(comm, 1)
     # ---------------- per-family attribution: the same steps again with a CUDA-event pair around every tensor-kernel launch.  The
     # library serialises the weight-gradient side stream while profiling, so these per-kernel times are not the concurrent ones ----
     net.profile(True)
@@ -468,9 +495,9 @@ def main():
     barrier()
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms, e2e_s * 1000.0], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s * 1000.0, ms_sus, ms_noar], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        ms, e2e_ms, ms_sus, ms_noar = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     else:
         e2e_ms = e2e_s * 1000.0
     # ---------------- inference (BASELINE configs[0]/[4] building block): forward()[0] of one 160x192x160 window per GPU ----------------
@@ -544,6 +571,8 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
         "optimizer_updates_per_s": args.steps / (ms / 1000.0),
+        "sustained": {"steps": n_sus, "ms_per_step": ms_sus / n_sus, "value": world * n_sus / (ms_sus / 1000.0), "unit": UNIT,
+                      "what": "the same device-timed loop over a longer window, right after the contract's --steps window"},
         "config": {"workload": workload_name(augment, simulate),
                    "step_definition": "one batch-1 training step (micro-batch + update); N GPUs run N of them per optimizer update (weak scaling), "
                                       "so value = N x optimizer_updates_per_s",
@@ -576,6 +605,11 @@ def main():
     }
     line["inference"]["roofline"] = {"gflop_per_window": 573.56, "achieved": 573.56 / 1e3 / (inf_ms / n_inf / 1e3), "unit": "TFLOP/s",
                                      "frac": 573.56 / 1e3 / (inf_ms / n_inf / 1e3) / pk["tf_sustained"]}
+    if ms_noar is not None:
+        line["allreduce"] = {"ms_per_step_with": ms / args.steps, "ms_per_step_without": ms_noar / args.steps,
+                             "cost_ms_per_step": (ms - ms_noar) / args.steps, "bytes_per_step": 15023818 * 4,
+                             "what": "device-timed step with and without the NCCL gradient all-reduce (max over ranks): the difference is the "
+                                     "collective's exposed time plus the SM share it takes from the overlapped backward pass"}
     line.update(extras)
     if world == 1 and not args.no_gpu_baseline:
         gb = gpu_baseline(args.steps)
