@@ -1091,6 +1091,7 @@ int Model::evaluate_volume(const float* volume, int vw, int vh, int vd, int sx, 
 int Model::run_backward() {
     static const bool no_side = std::getenv("U3D_ONE_STREAM") != nullptr;
     const bool two_streams = !no_side && !prof_on && stream2 != nullptr;   // the per-family event profile needs serial kernels
+    bool dp_tail_launched = false;
     const bool dp_overlap_now = dp_comm != nullptr && stream4 != nullptr && dp_split_step >= 0 && dp_seen == dp_microbatches && !no_side;
     std::fill(grad_written.begin(), grad_written.end(), 0);
     // fused heads: the loss-gradient kernel (launched before this function) already stored dL/dx of the head input
@@ -1181,8 +1182,7 @@ int Model::run_backward() {
                 const ncclResult_t nr = ncclAllReduce(d_grads + dp_split, d_grads + dp_split, size_t(flat_n - dp_split), ncclFloat, ncclSum,
                                                       static_cast<ncclComm_t>(dp_comm), stream4);
                 if (nr != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(nr)); return 1; }
-                M_CUDA(cudaEventRecord(ev_ar_done, stream4));
-                dp_tail_reduced = true;
+                dp_tail_launched = true;
             }
         } else {
             if (!grad_written[s.out]) continue;
@@ -1212,6 +1212,12 @@ int Model::run_backward() {
         }
     }
     for (int k : deferred) M_CHECK(launch_dgrad(steps[size_t(k)], 0));   // (a producer that was never reached)
+    if (dp_tail_launched) {
+        // the tail bucket's all-reduce joins the main stream at the end of the backward pass (it ran beside the first encoder levels'
+        // backward).  Joining here rather than in unet3d_step keeps the whole micro-batch one fork/join region: capturable as a graph.
+        M_CUDA(cudaEventRecord(ev_ar_done, stream4));
+        M_CUDA(cudaStreamWaitEvent(stream, ev_ar_done, 0));
+    }
     if (two_streams) {   // the update (and the next forward) must see every weight gradient
         M_CUDA(cudaEventRecord(ev_join, stream2));
         M_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
@@ -1286,15 +1292,21 @@ int Model::train_microbatch(const float* in, const float* label, int collapse_be
         }
         return run_backward();
     };
-    // the data-parallel overlap issues an NCCL collective from inside the backward pass: enqueued normally
-    if (dp_comm == nullptr) {
+    // with an attached communicator the LAST micro-batch of a step carries the tail bucket's all-reduce on a forked stream (NCCL
+    // collectives are capturable; every rank captures and replays the same sequence): a different graph than the other micro-batches
+    static const bool no_side_dp = std::getenv("U3D_ONE_STREAM") != nullptr;
+    static const bool no_nccl_graph = std::getenv("U3D_NO_NCCL_GRAPH") != nullptr;
+    const bool overlap_now = dp_comm != nullptr && stream4 != nullptr && dp_split_step >= 0 && dp_seen == dp_microbatches && !no_side_dp;
+    if (dp_comm == nullptr || !no_nccl_graph) {
         uint32_t ls_bits;
         std::memcpy(&ls_bits, &loss_scale, 4);
         const std::vector<uint64_t> key = {1u, uint64_t(reinterpret_cast<uintptr_t>(src)), uint64_t(reinterpret_cast<uintptr_t>(lab)),
-                                           uint64_t(collapse_before), uint64_t((use_ce ? 1 : 0) | (use_dice ? 2 : 0) | (use_mse ? 4 : 0)), ls_bits};
+                                           uint64_t(collapse_before), uint64_t((use_ce ? 1 : 0) | (use_dice ? 2 : 0) | (use_mse ? 4 : 0)), ls_bits,
+                                           uint64_t(overlap_now ? 1 : 0), uint64_t(reinterpret_cast<uintptr_t>(dp_comm))};
         M_CHECK(graph_run(key, enqueue));
     } else
         M_CHECK(enqueue());
+    if (overlap_now) dp_tail_reduced = true;   // (host state: also on a graph replay)
     std::vector<float> h(size_t(3) * L);
     M_CUDA(cudaMemcpyAsync(h.data(), d_losses, h.size() * 4, cudaMemcpyDeviceToHost, stream));
     M_CHECK(sync());

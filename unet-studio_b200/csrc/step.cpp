@@ -67,7 +67,7 @@ int Model::step(int batch_size, double lr, void* nccl_comm) {
     // a rank that ran no micro-batch in this step (batch_size < world: the reference uses min(gpus, batch) workers, train.cpp:592) still
     // takes part in the collectives with its zero gradients
     if (loss_scale == 0.f && ensure_plan()) return 1;
-    if (dp_tail_reduced && cudaStreamWaitEvent(stream, ev_ar_done, 0) != cudaSuccess) { set_error("step: event"); return 1; }
+    // (a tail bucket reduced during the backward pass has already joined the main stream at the end of that pass)
     if (nccl_comm != nullptr) {
         // every rank issues the SAME collective sequence whatever it did in its backward passes.  Attached handles: tail bucket
         // [dp_split, flat_n) then prefix [0, dp_split); the tail may already be in flight on stream4 (Model::run_backward).  A rank that
