@@ -83,3 +83,40 @@ def test_sharding_covers_every_microbatch_once():
         for batch in (1, 3, 8, 13):
             got = sorted(b for r in range(world) for b in D.shard_microbatches(batch, world, r))
             assert got == list(range(batch))
+
+
+def _window_worker(rank, world, port, out):
+    """Inference sharding: every rank forwards its own windows (oracle forward on CPU), rank 0 gathers; no data-path collective."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("u3d_dist", os.path.join(root, "unet-studio_b200", "dist.py"))
+    D = importlib.util.module_from_spec(spec); spec.loader.exec_module(D)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    net = O.parse_feature(1, 2, FEATURE)
+    P = O.init_params(net, 3)
+    mine = D.shard_windows(5, world, rank)
+    with torch.no_grad():
+        res = {i: O.forward(net, P, _data(200 + i)[0])[0] for i in mine}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)          # the HOST gathers the outputs (evaluate.cpp:228-229 copies them into model_io)
+    if rank == 0:
+        merged = {}
+        for g in gathered:
+            merged.update(g)
+        assert sorted(merged) == list(range(5))
+        np.save(out, torch.stack([merged[i] for i in range(5)]).numpy())
+    dist.destroy_process_group()
+
+
+def test_window_sharding_equals_the_sequential_window_loop(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "w.npy")
+    mp.spawn(_window_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    net = O.parse_feature(1, 2, FEATURE)
+    P = O.init_params(net, 3)
+    with torch.no_grad():
+        want = torch.stack([O.forward(net, P, _data(200 + i)[0])[0] for i in range(5)]).numpy()
+    np.testing.assert_array_equal(got, want)
