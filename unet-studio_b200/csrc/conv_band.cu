@@ -65,19 +65,7 @@ __device__ __forceinline__ void halve_step_b(float (&a)[16], float (&q)[16], int
 
 // ACC = read-add-store epilogue (skip connections sum two data gradients): its own instantiation, because it prefetches the old
 // row before waiting for the accumulator and the extra registers must not burden the store-only path
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// EARLY: the whole accumulator row (N columns) is read with ONE wait and the accumulator is handed back to the MMA issuer before the
-// bias / pack / store / statistics work (opt-in experiment, U3D_BAND_EARLY=1)
-template <int G, int CO, int KS, bool ACC, bool EARLY = false>
+template <int G, int CO, int KS, bool ACC>
 __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_constant__ BParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int N = G * CO;            // accumulator columns (64)
@@ -328,25 +316,13 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                 mbar_wait(tfull_bar(acc), (acc_cnt >> 2) & 1, 0x2500u | acc);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16) + acc * uint32_t(N);
-                uint32_t raw[EARLY ? N / 16 : 1][16];
-                if constexpr (EARLY) {
-#pragma unroll
-                    for (int q = 0; q < N / 16; ++q) tmem_ld16_nowait(t_row + uint32_t(q * 16), raw[q]);
-                    tmem_wait_ld();
-                    tc_fence_before();
-                    mbar_arrive(tempty_bar(acc));
-                }
 #pragma unroll
                 for (int xo = 0; xo < G; ++xo) {
                     const bool rv = rv_xy && gx0 + xo < W;
 #pragma unroll
                     for (int c0 = 0; c0 < CO; c0 += 16) {
                         float v[16];
-                        if constexpr (EARLY) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[(xo * CO + c0) / 16][j]);
-                        } else
-                            tmem_ld16(t_row + uint32_t(xo * CO + c0), v);
+                        tmem_ld16(t_row + uint32_t(xo * CO + c0), v);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] += sbias[c0 + j];
                         uint4* out = reinterpret_cast<uint4*>(dst + (vox0 + xo) * dst_pitch + c0 * 2);
@@ -378,10 +354,8 @@ __global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_co
                         }
                     }
                 }
-                if constexpr (!EARLY) {
-                    tc_fence_before();
-                    mbar_arrive(tempty_bar(acc));
-                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));
             }
         }
         if (want_stats) {
@@ -754,22 +728,20 @@ bool conv_band_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch&
     return true;
 }
 
-template <int G, int CO, int KS, bool ACC, bool EARLY = false>
+template <int G, int CO, int KS, bool ACC>
 static int launch_band_ta(const BParams& bp, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<G, CO, KS, ACC, EARLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<G, CO, KS, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    conv_band_kernel<G, CO, KS, ACC, EARLY><<<grid, kBThreads, smem, stream>>>(bp);
+    conv_band_kernel<G, CO, KS, ACC><<<grid, kBThreads, smem, stream>>>(bp);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 template <int G, int CO, int KS>
 static int launch_band_t(const BParams& bp, int grid, size_t smem, cudaStream_t stream) {
-    static const bool early = std::getenv("U3D_BAND_EARLY") != nullptr;
     if (bp.epi == EPI_ACCUM16) return launch_band_ta<G, CO, KS, true>(bp, grid, smem, stream);
-    if (early) return launch_band_ta<G, CO, KS, false, true>(bp, grid, smem, stream);
     return launch_band_ta<G, CO, KS, false>(bp, grid, smem, stream);
 }
 
