@@ -64,7 +64,8 @@ struct HeadFuse {
 };
 bool head_fwd_supported(int C, int xcp);
 bool head_bwd_supported(int C, int xcp);
-int head_fwd_launch(const void* x, int xc, int xcp, const float* w, const float* b, float* logits, int C, long long nv, cudaStream_t s);
+int head_fwd_launch(const void* x, int xc, int xcp, const float* w, const float* b, float* logits, int C, long long nv, cudaStream_t s,
+                    const SrcTransform* xf = nullptr);
 // loss of one level with the gradient pushed straight through the head (no dlogits tensor); Hd == nullptr = plain loss
 int loss_level_launch(const LossLevel& L, const HeadFuse* Hd, cudaStream_t s);
 

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "elementwise.h"
+#include "xform.cuh"
 
 namespace u3d {
 namespace {
@@ -286,11 +287,17 @@ __global__ void loss_grad_kernel(const LossLevel L) {
 
 // ---- 1x1 output head fused with the loss gradient (levels whose head input has <= 32 channels: bandwidth-bound) ----
 // forward: logits[c][v] = b[c] + sum_k W[c][k] x[v][k]            (unet.cpp:186-187, Conv3d k1 of the output token)
+// xf.enabled: x is the RAW output of the last conv; its norm + activation is applied here (and the activated voxels stored to
+// xf.writeback for the backward pass) -- see SrcTransform in u3d.h
 template <int XCP>
 __global__ void head_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                                float* __restrict__ logits, int C, int xc, long long nv) {
+                                float* __restrict__ logits, int C, int xc, long long nv, const SrcTransform xf) {
     __shared__ float sw[kMaxC * XCP];
     __shared__ float sb[kMaxC];
+    __shared__ float ssc[XCP], ssh[XCP];
+    if (xf.enabled)
+        for (int i = threadIdx.x; i < XCP; i += blockDim.x) xf_coef1(xf, i, ssc[i], ssh[i]);
+    uint4* const wb = xf.enabled ? static_cast<uint4*>(xf.writeback) : nullptr;
     for (int i = threadIdx.x; i < C * XCP; i += blockDim.x) {
         const int c = i / XCP, k = i % XCP;
         sw[i] = k < xc ? w[c * xc + k] : 0.f;
@@ -301,7 +308,11 @@ __global__ void head_fwd_kernel(const uint4* __restrict__ x, const float* __rest
         float xv[XCP];
 #pragma unroll
         for (int g = 0; g < XCP / 8; ++g) {
-            const uint4 q = x[vox * (XCP / 8) + g];
+            uint4 q = x[vox * (XCP / 8) + g];
+            if (xf.enabled) {
+                q = xf_apply(q, ssc + g * 8, ssh + g * 8, xf.act);
+                if (wb != nullptr) wb[vox * (XCP / 8) + g] = q;
+            }
             const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -437,12 +448,15 @@ bool head_bwd_supported(int C, int xcp) {
     return C <= 8 && ct * xcp <= 128;
 }
 
-int head_fwd_launch(const void* x, int xc, int xcp, const float* w, const float* b, float* logits, int C, long long nv, cudaStream_t s) {
+int head_fwd_launch(const void* x, int xc, int xcp, const float* w, const float* b, float* logits, int C, long long nv, cudaStream_t s,
+                    const SrcTransform* xfp) {
+    SrcTransform xf{};
+    if (xfp) xf = *xfp;
     if (!head_fwd_supported(C, xcp)) { set_error("head_fwd_launch: unsupported shape"); return 1; }
     long long g = (nv + 255) / 256;
     const int grid = int(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
-    if (xcp == 16) head_fwd_kernel<16><<<grid, 256, 0, s>>>(static_cast<const uint4*>(x), w, b, logits, C, xc, nv);
-    else head_fwd_kernel<32><<<grid, 256, 0, s>>>(static_cast<const uint4*>(x), w, b, logits, C, xc, nv);
+    if (xcp == 16) head_fwd_kernel<16><<<grid, 256, 0, s>>>(static_cast<const uint4*>(x), w, b, logits, C, xc, nv, xf);
+    else head_fwd_kernel<32><<<grid, 256, 0, s>>>(static_cast<const uint4*>(x), w, b, logits, C, xc, nv, xf);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -787,6 +787,39 @@ int Model::ensure_plan() {
             M_CHECK(alloc(reinterpret_cast<void**>(&s.idx), tens[s.out].V() * tens[s.out].Cp * sizeof(int)));
         }
     }
+    // Norm + activation folded into the consumers: when every reader of an activated tensor is a kernel whose producers
+    // are threads (conv_band, conv_s2, head_fwd), the norm_act_fwd pass is dropped; the readers take the raw tensor and apply
+    // scale/shift/activation while staging.  In training the first reader also stores the activated voxels, because the weight
+    // gradients (copy-engine fed) and the fused head backward read the materialised tensor.
+    for (size_t ni = 0; ni < steps.size(); ++ni) {
+        Step& n = steps[ni];
+        if (n.kind != Step::NORMACT) continue;
+        bool ok = true;
+        std::vector<std::pair<size_t, int>> readers;
+        for (size_t ci = 0; ci < steps.size() && ok; ++ci) {
+            Step& c = steps[ci];
+            if (c.in0 != n.out && c.in1 != n.out) continue;
+            if (c.kind != Step::CONV || (c.in0 == n.out && c.in1 == n.out)) { ok = false; break; }
+            const int src = c.in0 == n.out ? 0 : 1;
+            if (c.head_level >= 0) ok = c.head_fwd_fused;
+            else {
+                ConvLaunch cfg{};
+                cfg.kc = c.fkc;
+                cfg.epi = EPI_STORE16;
+                ok = conv_supports_xf(c.fprobs, cfg, src);
+            }
+            readers.push_back({ci, src});
+        }
+        if (!ok || readers.empty()) continue;
+        n.elided = true;
+        for (size_t r = 0; r < readers.size(); ++r) {
+            Step& c = steps[readers[r].first];
+            const int src = readers[r].second;
+            c.xf_from[src] = int(ni);
+            c.xf_write[src] = tr && r == 0;
+            for (auto& P : c.fprobs) (src == 0 ? P.src0 : P.src1) = tens[n.in0].p;
+        }
+    }
     {   // concat convs whose source 0 (the skip tensor) is also consumed by another conv: their skip gradient can be deferred
         skip_has_other_consumer.assign(steps.size(), 0);
         for (size_t ci = 0; ci < steps.size(); ++ci) {
@@ -865,12 +898,29 @@ int Model::run_forward(int levels_wanted, bool bn_eval) {
     for (auto& s : steps) {
         if (s.kind == Step::CONV) {
             if (s.head_level >= levels_wanted) continue;
+            SrcTransform xf[2] = {};
+            for (int src = 0; src < 2; ++src) {
+                if (s.xf_from[src] < 0) continue;
+                const Step& n = steps[s.xf_from[src]];
+                xf[src].enabled = 1;
+                xf[src].C = tens[n.in0].C;
+                xf[src].has_norm = n.cur_has_norm;
+                xf[src].act = n.act;
+                xf[src].mean = n.cur_mean;
+                xf[src].rstd = n.cur_rstd;
+                xf[src].gamma = n.norm ? param_ptr(n.p_g) : nullptr;
+                xf[src].beta = n.norm ? param_ptr(n.p_g + 1) : nullptr;
+                xf[src].writeback = s.xf_write[src] ? tens[n.out].p : nullptr;
+            }
             if (s.head_fwd_fused) {
                 const Ten& a = tens[s.in0];
-                M_CHECK(head_fwd_launch(a.p, a.C, a.Cp, param_ptr(s.p_w), param_ptr(s.p_b), logits[s.head_level], s.g.cout, a.V(), stream));
+                const void* x = s.xf_from[0] >= 0 ? tens[steps[s.xf_from[0]].in0].p : a.p;
+                M_CHECK(head_fwd_launch(x, a.C, a.Cp, param_ptr(s.p_w), param_ptr(s.p_b), logits[s.head_level], s.g.cout, a.V(), stream,
+                                        s.xf_from[0] >= 0 ? &xf[0] : nullptr));
                 ++launches;
                 continue;
             }
+            for (auto& P : s.fprobs) { P.xf[0] = xf[0]; P.xf[1] = xf[1]; }
             ConvLaunch cfg{};
             cfg.kc = s.fkc;
             cfg.epi = s.head_level >= 0 ? EPI_PLANAR32 : EPI_STORE16;
@@ -891,8 +941,9 @@ int Model::run_forward(int levels_wanted, bool bn_eval) {
             if (s.norm == 2 && (bn_eval || bn_running)) {
                 // eval(): y = gamma*(x - running_mean)/sqrt(running_var) + beta, eps 0 (unet.cpp:80-84; validation, train.cpp:836)
                 M_CHECK(rstd_from_var_launch(d_buffers[s.buf0 + 1], s.rstd, a.C, 0.f, stream));
-                M_CHECK(norm_act_fwd_launch(a.p, tens[s.out].p, a.V(), a.C, a.Cp, 1, s.act, d_buffers[s.buf0], s.rstd, gamma, beta, stream));
-                launches += 2;
+                s.cur_mean = d_buffers[s.buf0]; s.cur_rstd = s.rstd; s.cur_has_norm = 1;
+                if (!s.elided) M_CHECK(norm_act_fwd_launch(a.p, tens[s.out].p, a.V(), a.C, a.Cp, 1, s.act, d_buffers[s.buf0], s.rstd, gamma, beta, stream));
+                launches += s.elided ? 1 : 2;
             } else if (s.norm == 1 || (s.norm == 2 && training)) {
                 int rows = last_stat_rows, ntot = last_stat_ntot;
                 if (!s.stats_from_conv) {
@@ -904,12 +955,16 @@ int Model::run_forward(int levels_wanted, bool bn_eval) {
                 float* rv = (s.norm == 2) ? d_buffers[s.buf0 + 1] : nullptr;
                 M_CHECK(finalize_stats_launch(d_partials, rows, ntot, a.C, double(a.V()), s.norm == 1 ? 1e-5f : 0.f, s.mean, s.rstd,
                                               rm, rv, 0.1f, stream));
-                M_CHECK(norm_act_fwd_launch(a.p, tens[s.out].p, a.V(), a.C, a.Cp, 1, s.act, s.mean, s.rstd, gamma, beta, stream));
-                launches += 2;
+                s.cur_mean = s.mean; s.cur_rstd = s.rstd; s.cur_has_norm = 1;
+                if (!s.elided) M_CHECK(norm_act_fwd_launch(a.p, tens[s.out].p, a.V(), a.C, a.Cp, 1, s.act, s.mean, s.rstd, gamma, beta, stream));
+                launches += s.elided ? 1 : 2;
             } else {
                 // no norm, or BatchNorm after prepare_for_inference (mean 0, var 1, eps 0 => y = gamma*x + beta; unet.cpp:7-22)
-                M_CHECK(norm_act_fwd_launch(a.p, tens[s.out].p, a.V(), a.C, a.Cp, s.norm ? 1 : 0, s.act, nullptr, nullptr, gamma, beta, stream));
-                ++launches;
+                s.cur_mean = nullptr; s.cur_rstd = nullptr; s.cur_has_norm = s.norm ? 1 : 0;
+                if (!s.elided) {
+                    M_CHECK(norm_act_fwd_launch(a.p, tens[s.out].p, a.V(), a.C, a.Cp, s.norm ? 1 : 0, s.act, nullptr, nullptr, gamma, beta, stream));
+                    ++launches;
+                }
             }
         } else if (s.kind == Step::MAXPOOL) {
             const Ten& o = tens[s.out];
