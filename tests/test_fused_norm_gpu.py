@@ -1,7 +1,7 @@
-"""Norm + activation folded into the consumers (SrcTransform): conv_band / conv_s2 / head_fwd apply
-gamma*rstd*(x - mean) + beta and the activation of unet.cpp:74-98 while they stage their operand, and the separate norm_act_fwd pass
-over the full-resolution tensors disappears.  The arithmetic is norm_act_fwd_kernel's, operation for operation, so the folded path
-must give BIT-identical forward results to the unfolded one (U3D_NO_XF=1, read once per process -> child process)."""
+"""Norm + activation folded into the output head (SrcTransform): head_fwd_kernel applies gamma*rstd*(x - mean) + beta
+and the activation of unet.cpp:74-98 itself when it is the only reader of the activated tensor, and the separate norm_act_fwd pass over
+that full-resolution tensor disappears.  The arithmetic is norm_act_fwd_kernel's, operation for operation, so the folded path must give
+BIT-identical forward results to the unfolded one (U3D_NO_XF=1, read once per process -> child process)."""
 import os
 import subprocess
 import sys
@@ -14,12 +14,11 @@ from tests._pkg import load
 
 pytestmark = pytest.mark.gpu
 
-W, H, D = 64, 64, 64   # level 1 = 32^3 = 32768 voxels: the banded kernel runs on levels 0 and 1
+W, H, D = 64, 64, 64
 NETS = {
     # the default architecture (InstanceNorm3d + LeakyReLU, skips, stride-2 down, transpose-conv up)
     "default": (1, 3, None),
     # BatchNorm3d + ReLU / ELU, max_pool / upsample: batch statistics in training, running statistics in eval
-    # (the ELU tensor feeds max_pool and the up-sampled one is not a conv output: those two keep their separate pass)
     "bn_relu_elu": (2, 2, "conv16,ks3,stride1+bnorm,relu+conv16,ks3,stride1+bnorm,elu\n"
                           "max_pool+conv32,ks3,stride1+bnorm,relu+upsample\n"
                           "conv16,ks3,stride1+bnorm,relu+conv16,ks3,stride1+norm,leaky_relu+conv2,ks1,stride1"),

@@ -28,15 +28,12 @@
 #include "common.cuh"
 #include "plan.h"
 #include "u3d.h"
-#include "xform.cuh"
 
 namespace u3d {
 namespace {
 
 constexpr int kBThreads = 32 * 14;
 constexpr int kBProducers = 256;
-constexpr int band_producers(bool xf) { return xf ? 384 : 256; }
-constexpr int band_threads(bool xf) { return 128 + band_producers(xf) + 64; }
 constexpr int kMaxSlots = 8;   // ring of input z-planes: 3 in use + (nslots - 3) in flight
 
 struct BParams {
@@ -68,15 +65,8 @@ __device__ __forceinline__ void halve_step_b(float (&a)[16], float (&q)[16], int
 
 // ACC = read-add-store epilogue (skip connections sum two data gradients): its own instantiation, because it prefetches the old
 // row before waiting for the accumulator and the extra registers must not burden the store-only path
-// XF = the producers stage the planes through registers (ld.global -> norm + activation of SrcTransform -> st.shared, optionally the
-// activated voxels back to global memory) instead of cp.async: the separate norm_act_fwd pass over the source disappears
-template <int G, int CO, int KS, bool ACC, bool XF>
-__global__ void __launch_bounds__(band_threads(XF), 1) conv_band_kernel(const __grid_constant__ BParams p) {
-    // the XF variant has 12 producer warps instead of 8: its producers also run the transform and their instruction latency per plane,
-    // not the tensor pipe, is what bounds it
-    constexpr int NPROD = band_producers(XF);       // producer threads
-    constexpr int IW = 4 + NPROD / 32;              // first MMA issuer warp
-    constexpr int NTHREADS = band_threads(XF);
+template <int G, int CO, int KS, bool ACC>
+__global__ void __launch_bounds__(kBThreads, 1) conv_band_kernel(const __grid_constant__ BParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int N = G * CO;            // accumulator columns (64)
     constexpr int XI = G + 2;
@@ -104,18 +94,18 @@ __global__ void __launch_bounds__(band_threads(XF), 1) conv_band_kernel(const __
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < kSlots; ++s) {
-            mbar_init(full_bar(s), XF ? NPROD / 32 : NPROD);
+            mbar_init(full_bar(s), kBProducers);
             mbar_init(empty_bar(s), 2);
         }
         for (uint32_t a = 0; a < 4; ++a) {
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 128);
         }
-        mbar_init(wfull_bar, NPROD);
+        mbar_init(wfull_bar, kBProducers);
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < 8 * CO + CO; i += NTHREADS) sstats[i] = 0.f;
-    if (warp == IW) {
+    for (int i = threadIdx.x; i < 8 * CO + CO; i += kBThreads) sstats[i] = 0.f;
+    if (warp == 12) {
         tmem_alloc(smem_u32(tmem_ptr_smem), 4 * N);
         tmem_relinquish();
     }
@@ -126,12 +116,12 @@ __global__ void __launch_bounds__(band_threads(XF), 1) conv_band_kernel(const __
     const ConvProblem& P = p.P;
     const int D = P.in_d, H = P.in_h, W = P.in_w;
 
-    if (warp >= 4 && warp < IW) {
+    if (warp >= 4 && warp < 12) {
         // ===================================== producers =====================================
         const int t = threadIdx.x - 128;
         {   // resident weights
             const uint8_t* wsrc = static_cast<const uint8_t*>(P.wpack);
-            for (uint32_t o = t * 16u; o < p.w_bytes; o += NPROD * 16u) cp_async16(sW + o, wsrc + o, 16u);
+            for (uint32_t o = t * 16u; o < p.w_bytes; o += kBProducers * 16u) cp_async16(sW + o, wsrc + o, 16u);
             cp_async_mbar_arrive(wfull_bar);
         }
         const int ncg0 = P.c0p / 8, ncg = p.ncg;
@@ -142,197 +132,43 @@ __global__ void __launch_bounds__(band_threads(XF), 1) conv_band_kernel(const __
         const int per_plane = HY * HX * ncg;
         const uint32_t inv_hx = (1u << 20) / uint32_t(HX) + 1u;     // pos / HX == (pos * inv_hx) >> 20 for pos < HX*HY (no integer division in the loop)
         const int cg_shift = ncg == 2 ? 1 : 2;
-        if constexpr (XF) {
-            // The planes still arrive by cp.async (deep, register-free prefetch: the ring holds several planes in flight); the transform
-            // runs IN PLACE two planes behind the copies: every thread waits for its own copy group (cp.async.wait_group), rewrites the
-            // chunks it copied (no cross-thread dependency), makes them visible to the tensor-core proxy and only then arrives on the
-            // plane's full barrier.  A register-staged ld.global -> st.shared version kept ~2 loads per thread in flight and ran the
-            // layer 3x slower (latency-bound).
-            // this thread's chunks all belong to one channel group of one source (kBProducers is a multiple of ncg)
-            const int cg = t & (ncg - 1);
-            const bool from0 = cg < ncg0;
-            const SrcTransform& X = from0 ? P.xf[0] : P.xf[1];
-            const int cgl = from0 ? cg : cg - ncg0;
-            const bool xon = X.enabled != 0;
-            XfCoef kc;
-            if (xon) xf_coefs(X, cgl, kc);
-            else kc.act = 0;
-            const uint8_t* const sg = (from0 ? s0 : s1) + cgl * 16;
-            uint8_t* const wb = xon && X.writeback ? static_cast<uint8_t*>(X.writeback) + cgl * 16 : nullptr;
-            const uint32_t pitch = from0 ? pitch0 : pitch1;
-            const uint32_t dst_cg = uint32_t(cg * G) * uint32_t(ROWS);
-            // Per-thread chunk table, built once: the chunks a thread copies sit at the same place of every plane (slot offset) and at the
-            // same voxel offset from the plane origin, so the per-plane loops are a table walk (~8 instructions per copy) instead of the
-            // divide / range-test / address arithmetic of the generic loop -- the producers' instruction latency per plane is what limits
-            // this variant.  ent = (hy*W + hx) << 12 | 16-byte unit inside the slot.
-            constexpr int MAXC = KS == 1 ? 4 : (G == 4 ? 7 : 5);   // chunks per thread and plane: covers every tile conv_band_launch_one picks
-            static_assert(NPROD == 384, "MAXC is sized for 384 producer threads");
-            const int pos0 = t >> cg_shift, pos_step = NPROD >> cg_shift, npos = HY * HX;
-            uint32_t ent[MAXC];
-            uint32_t interior = 0u;
-            int nper = 0;
-#pragma unroll
-            for (int i = 0; i < MAXC; ++i) {
-                const int pos = pos0 + i * pos_step;
-                ent[i] = 0u;
-                if (pos < npos) {
-                    const int hy = int((uint32_t(pos) * inv_hx) >> 20);
-                    const int hx = pos - hy * HX;
-                    ent[i] = (uint32_t(hy * W + hx) << 12) | (dst_cg + uint32_t((hx & (G - 1)) * ROWS + hy * HQ + hx / G));
-                    if (hx >= 1 && hx <= p.TX && hy >= 1 && hy <= p.TY) interior |= 1u << i;
-                    nper = i + 1;
-                }
-            }
-            auto ok_mask = [&](int x0, int y0) {   // in-volume chunks of this thread for a tile column
-                uint32_t m = 0u;
-#pragma unroll
-                for (int i = 0; i < MAXC; ++i) {
-                    const int pos = pos0 + i * pos_step;
-                    if (pos < npos) {
-                        const int hy = int((uint32_t(pos) * inv_hx) >> 20);
-                        const int hx = pos - hy * HX;
-                        if ((unsigned)(x0 + hx) < (unsigned)W && (unsigned)(y0 + hy) < (unsigned)H) m |= 1u << i;
-                    }
-                }
-                return m;
-            };
-            struct Rec { uint32_t slot, ok; int vox0; };   // slot | (plane owned by this item) << 16; ok = 0 for a plane outside the volume; vox0: voxel index of the plane origin
-            auto issue = [&](const Rec& r) {
-                const uint32_t blk = sbase + (r.slot & 0xFFFFu) * p.slot_bytes;
-                const uint8_t* const base = sg + (long long)r.vox0 * (long long)pitch;
-#pragma unroll
-                for (int i = 0; i < MAXC; ++i) {
-                    if (i < nper) {
-                        const bool ok = (r.ok >> i) & 1u;
-                        const uint8_t* src = ok ? base + (unsigned long long)(ent[i] >> 12) * pitch : sg;
-                        cp_async16_ca(blk + (ent[i] & 0xFFFu) * 16u, src, ok ? 16u : 0u);
-                    }
-                }
-                cp_async_commit();
-            };
-            auto finish_t = [&](const Rec& r, auto act_c) {
-                constexpr int ACT = decltype(act_c)::value;   // the copies of this plane have landed (this thread's own)
-                if (xon) {
-                    const uint32_t blk = sbase + (r.slot & 0xFFFFu) * p.slot_bytes;
-                    uint8_t* const wbase = wb + (long long)r.vox0 * (long long)pitch;
-                    const uint32_t wmask = (wb != nullptr && (r.slot >> 16)) ? (interior & r.ok) : 0u;
-#pragma unroll
-                    for (int g0 = 0; g0 < MAXC; g0 += 4) {   // four chunks at a time, branch-free: loads, arithmetic, stores
-                        if (g0 >= nper) break;
-                        uint4 v[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (g0 + u < MAXC) v[u] = lds16_if(blk + (ent[g0 + u] & 0xFFFu) * 16u, (r.ok >> (g0 + u)) & 1u);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (g0 + u < MAXC) v[u] = xf_apply_c<ACT>(v[u], kc.sc, kc.sh);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (g0 + u < MAXC) {
-                                sts16_if(blk + (ent[g0 + u] & 0xFFFu) * 16u, v[u], (r.ok >> (g0 + u)) & 1u);
-                                if (wb != nullptr)
-                                    stg16_if(wbase + (unsigned long long)(ent[g0 + u] >> 12) * pitch, v[u], (wmask >> (g0 + u)) & 1u);
-                            }
-                        }
-                    }
-                    // no fence.proxy.async here: it would wait for this thread's cp.async copies of the NEXT planes (the full DRAM
-                    // latency, every plane).  The MMA issuer fences after it has acquired the plane's full barrier, as it does for the
-                    // copy-written planes of the plain variant.
-                }
-                // ONE arrival per warp: 256 thread arrivals on one barrier word serialise (~30 clk each = more than the plane's MMAs)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(r.slot & 0xFFFFu));
-            };
-            auto finish = [&](const Rec& r) { xf_dispatch_act(kc.act, [&](auto act_c) { finish_t(r, act_c); }); };
-            // One loop, one call site each for issue / finish (inlined, the tables stay in registers).  Per step: finish the oldest
-            // copied plane (its copies had a plane time to land), or ALL copied planes when the ring is full and the thread is about
-            // to block on the MMAs (so that the transform never sits between a freed slot and the next MMA batch) or the work is done;
-            // then copy the next plane.
-            Rec ra{}, rb{};     // planes copied but not yet finished (ra older)
-            int npend = 0;
-            uint32_t cnt = 0;
-            int item = blockIdx.x, gz = 0, z0 = 0, z1 = -1, x0 = 0, y0 = 0;
-            uint32_t okm = 0u;
-            bool have = item < p.total_items;
-            auto decode = [&]() {
-                int rem = item;
-                const int zc = rem % p.zchunks; rem /= p.zchunks;
-                const int tx = rem % p.tiles_x;
-                const int ty = rem / p.tiles_x;
-                x0 = tx * p.TX - 1; y0 = ty * p.TY - 1;
-                z0 = zc * p.zlen; z1 = min(D, z0 + p.zlen);
-                gz = z0 - 1;
-                okm = ok_mask(x0, y0);
-            };
-            if (have) decode();
-            for (;;) {
-                const uint32_t slot = qmod(cnt), par = ((qdiv(cnt)) & 1) ^ 1;
-                int nfin = 0;
-                if (!have || (npend > 0 && !mbar_try_wait(empty_bar(slot), par))) nfin = npend;
-                else if (npend == 2) nfin = 1;
-                if (nfin > 0) {
-                    if (nfin == npend) cp_async_wait<0>();
-                    else cp_async_wait<1>();
-                    for (; nfin > 0; --nfin, --npend) {
-                        finish(ra);
-                        ra = rb;
-                    }
-                }
-                if (!have) break;
-                Rec r;
+        uint32_t cnt = 0;   // planes loaded by this CTA so far (ring position)
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int rem = item;
+            const int zc = rem % p.zchunks; rem /= p.zchunks;
+            const int tx = rem % p.tiles_x;
+            const int ty = rem / p.tiles_x;
+            const int x0 = tx * p.TX - 1, y0 = ty * p.TY - 1;
+            const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
+            for (int gz = z0 - 1; gz <= z1; ++gz, ++cnt) {
+                const uint32_t slot = qmod(cnt);
+                mbar_wait(empty_bar(slot), ((qdiv(cnt)) & 1) ^ 1, 0x2100u | slot);
+                const uint32_t blk = sbase + slot * p.slot_bytes;
                 const bool zok = (unsigned)gz < (unsigned)D;
-                r.slot = slot | ((gz >= z0 && gz < z1) ? 0x10000u : 0u); r.ok = zok ? okm : 0u;
-                r.vox0 = ((zok ? gz : 0) * H + y0) * W + x0;
-                mbar_wait(empty_bar(slot), par, 0x2100u | slot);
-                issue(r);
-                if (npend == 0) ra = r; else rb = r;
-                ++npend;
-                ++cnt;
-                if (++gz > z1) {
-                    item += gridDim.x;
-                    have = item < p.total_items;
-                    if (have) decode();
-                }
-            }
-        } else {
-            uint32_t cnt = 0;   // planes loaded by this CTA so far (ring position)
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                int rem = item;
-                const int zc = rem % p.zchunks; rem /= p.zchunks;
-                const int tx = rem % p.tiles_x;
-                const int ty = rem / p.tiles_x;
-                const int x0 = tx * p.TX - 1, y0 = ty * p.TY - 1;
-                const int z0 = zc * p.zlen, z1 = min(D, z0 + p.zlen);
-                for (int gz = z0 - 1; gz <= z1; ++gz, ++cnt) {
-                    const uint32_t slot = qmod(cnt);
-                    mbar_wait(empty_bar(slot), ((qdiv(cnt)) & 1) ^ 1, 0x2100u | slot);
-                    const uint32_t blk = sbase + slot * p.slot_bytes;
-                    const bool zok = (unsigned)gz < (unsigned)D;
-                    // plane origin (gz, y0, x0); only offsets of in-range voxels are ever added to it
-                    const long long vox0 = ((long long)(zok ? gz : 0) * H + y0) * W + x0;
-                    const uint8_t* const p0 = s0 + vox0 * (long long)pitch0;
-                    const uint8_t* const p1 = s1 + vox0 * (long long)pitch1;
-                    // consecutive lanes: the 16-byte chunks of one voxel, then the next voxel along x (coalesced)
+                // plane origin (gz, y0, x0); only offsets of in-range voxels are ever added to it
+                const long long vox0 = ((long long)(zok ? gz : 0) * H + y0) * W + x0;
+                const uint8_t* const p0 = s0 + vox0 * (long long)pitch0;
+                const uint8_t* const p1 = s1 + vox0 * (long long)pitch1;
+                // consecutive lanes: the 16-byte chunks of one voxel, then the next voxel along x (coalesced)
 #pragma unroll 2
-                    for (int idx = t; idx < per_plane; idx += NPROD) {
-                        const int cg = idx & (ncg - 1);
-                        const uint32_t pos = uint32_t(idx) >> cg_shift;
-                        const int hy = int((pos * inv_hx) >> 20);
-                        const int hx = int(pos) - hy * HX;
-                        const bool ok = zok && (unsigned)(x0 + hx) < (unsigned)W && (unsigned)(y0 + hy) < (unsigned)H;
-                        const int off = hy * W + hx;
-                        const uint8_t* src;
-                        if (cg < ncg0) src = ok ? p0 + (long long)off * pitch0 + cg * 16 : s0;
-                        else src = ok ? p1 + (long long)off * pitch1 + (cg - ncg0) * 16 : s1;
-                        const int r = hx & (G - 1), hq = hx / G;
-                        cp_async16_ca(blk + uint32_t((cg * G + r) * ROWS + hy * HQ + hq) * 16u, src, ok ? 16u : 0u);
-                    }
-                    cp_async_mbar_arrive(full_bar(slot));
+                for (int idx = t; idx < per_plane; idx += kBProducers) {
+                    const int cg = idx & (ncg - 1);
+                    const uint32_t pos = uint32_t(idx) >> cg_shift;
+                    const int hy = int((pos * inv_hx) >> 20);
+                    const int hx = int(pos) - hy * HX;
+                    const bool ok = zok && (unsigned)(x0 + hx) < (unsigned)W && (unsigned)(y0 + hy) < (unsigned)H;
+                    const int off = hy * W + hx;
+                    const uint8_t* src;
+                    if (cg < ncg0) src = ok ? p0 + (long long)off * pitch0 + cg * 16 : s0;
+                    else src = ok ? p1 + (long long)off * pitch1 + (cg - ncg0) * 16 : s1;
+                    const int r = hx & (G - 1), hq = hx / G;
+                    cp_async16_ca(blk + uint32_t((cg * G + r) * ROWS + hy * HQ + hq) * 16u, src, ok ? 16u : 0u);
                 }
+                cp_async_mbar_arrive(full_bar(slot));
             }
         }
         cp_async_wait<0>();
-    } else if (warp >= IW) {
+    } else if (warp >= 12) {
         // ===================================== MMA issuers ===================================
         // Two issuing threads: issuer wi owns TMEM accumulator wi and every output plane whose running index has parity wi.  A single
         // thread sustains one MMA per ~87 clk in this loop (ncu: it never waits, it is issue-bound), the hardware accepts one per ~40.
@@ -340,7 +176,7 @@ __global__ void __launch_bounds__(band_threads(XF), 1) conv_band_kernel(const __
         // output that reads q (outputs q-2, q-1, q of its parity); planes it never reads are released as soon as they are resident.
         // The WHOLE warp runs the loop: under `if (lane == 0)` the compiler cannot prove the descriptors uniform and feeds every
         // tcgen05.mma through an R2UR / vote loop; with uniform control flow they stay in uniform registers and one elected lane issues.
-        const uint32_t wi = uint32_t(warp - IW);
+        const uint32_t wi = uint32_t(warp - 12);
         {
             const int HQ = p.HQ, ROWS = p.ROWS;
             const uint32_t lbo_a = uint32_t(G * ROWS) * 16u;             // next channel group of 8
@@ -548,7 +384,7 @@ __global__ void __launch_bounds__(band_threads(XF), 1) conv_band_kernel(const __
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == IW) tmem_dealloc(tmem_base, 4 * N);
+    if (warp == 12) tmem_dealloc(tmem_base, 4 * N);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -879,7 +715,6 @@ bool conv_band_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch&
     if (probs.size() == 2) {   // two-pass split of a 32 + 32 channel concat layer
         if (probs[0].band_pass != 1 || probs[1].band_pass != 2 || cfg.epi != EPI_STORE16) return false;
         if (probs[0].c0p != 32 || probs[0].c1p != 32) return false;
-        if (probs[1].xf[1].enabled) return false;   // pass 2 is the read-add-store instantiation
     } else if (probs.size() != 1 || probs[0].band_pass != 0)
         return false;
     ConvProblem P = probs[0];
@@ -893,26 +728,21 @@ bool conv_band_eligible(const std::vector<ConvProblem>& probs, const ConvLaunch&
     return true;
 }
 
-template <int G, int CO, int KS, bool ACC, bool XF>
+template <int G, int CO, int KS, bool ACC>
 static int launch_band_ta(const BParams& bp, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<G, CO, KS, ACC, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_band_kernel<G, CO, KS, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    conv_band_kernel<G, CO, KS, ACC, XF><<<grid, band_threads(XF), smem, stream>>>(bp);
+    conv_band_kernel<G, CO, KS, ACC><<<grid, kBThreads, smem, stream>>>(bp);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 template <int G, int CO, int KS>
 static int launch_band_t(const BParams& bp, int grid, size_t smem, cudaStream_t stream) {
-    const bool xf = bp.P.xf[0].enabled || bp.P.xf[1].enabled;
-    if (bp.epi == EPI_ACCUM16) {
-        if (xf) { set_error("conv_band_launch: a source transform cannot be combined with the read-add-store epilogue"); return 1; }
-        return launch_band_ta<G, CO, KS, true, false>(bp, grid, smem, stream);
-    }
-    if (xf) return launch_band_ta<G, CO, KS, false, true>(bp, grid, smem, stream);
-    return launch_band_ta<G, CO, KS, false, false>(bp, grid, smem, stream);
+    if (bp.epi == EPI_ACCUM16) return launch_band_ta<G, CO, KS, true>(bp, grid, smem, stream);
+    return launch_band_ta<G, CO, KS, false>(bp, grid, smem, stream);
 }
 
 static int conv_band_launch_one(const ConvProblem& P, const ConvLaunch& cfg, bool stats, cudaStream_t stream);
@@ -922,8 +752,6 @@ int conv_band_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cf
         ConvProblem A = probs[0], B = probs[1];
         A.c1p = 0; A.nch1 = 0; A.src1 = nullptr;
         B.src0 = B.src1; B.c0p = B.c1p; B.nch0 = B.nch1; B.c1p = 0; B.nch1 = 0; B.src1 = nullptr; B.bias = nullptr;
-        A.xf[1].enabled = 0;
-        B.xf[0] = B.xf[1]; B.xf[1].enabled = 0;
         ConvLaunch c1 = cfg, c2 = cfg;
         c1.epi = EPI_STORE16; c1.stats_partials = nullptr; c1.stats_grid_out = nullptr;
         c2.epi = EPI_ACCUM16;
@@ -982,7 +810,7 @@ static int conv_band_launch_one(const ConvProblem& Pin, const ConvLaunch& cfg, b
     bp.slot_bytes = uint32_t(bp.ncg * bp.G * bp.ROWS * 16);
     // experimental, opt-in (U3D_ZBAND=1): parity green, but 206 us vs 156 us per 16 -> 16 layer at 160x192x160 (see the kernel's header)
     static const bool use_zband = std::getenv("U3D_ZBAND") != nullptr;
-    const bool zband = use_zband && bp.CO == 16 && bp.KS == 1 && P.c1p == 0 && !P.xf[0].enabled;
+    const bool zband = use_zband && bp.CO == 16 && bp.KS == 1 && P.c1p == 0;
     bp.w_bytes = zband ? kZWBytes : uint32_t(9 * bp.KS * 2 * bp.NB * 16);
     const uint32_t stats_bytes = uint32_t((zband ? 17 : 9) * bp.CO * 4);
     bp.nslots = int(std::min<size_t>(kMaxSlots, (size_t(222) * 1024 - bp.w_bytes - stats_bytes) / bp.slot_bytes));

@@ -18,7 +18,6 @@
 
 #include "common.cuh"
 #include "u3d.h"
-#include "xform.cuh"
 
 namespace u3d {
 namespace {
@@ -51,8 +50,7 @@ __device__ __forceinline__ void halve_step_s(float (&a)[16], float (&q)[16], int
     }
 }
 
-// XF: planes staged through registers with the source's norm + activation applied (SrcTransform, as conv_band.cu)
-template <int KS, int NCH, bool XF>   // K chunks of 16 input channels, output column chunks of 16
+template <int KS, int NCH>   // K chunks of 16 input channels, output column chunks of 16
 __global__ void __launch_bounds__(kSThreads, 1) conv_s2_kernel(const __grid_constant__ SParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int N = NCH * 16;
@@ -72,7 +70,7 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_s2_kernel(const __grid_cons
     constexpr uint32_t TCOLS = 2 * N < 32 ? 32 : 2 * N;
 
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < kSSlots; ++s) { mbar_init(full_bar(s), XF ? kSProducers / 32 : kSProducers); mbar_init(empty_bar(s), 1); }
+        for (uint32_t s = 0; s < kSSlots; ++s) { mbar_init(full_bar(s), kSProducers); mbar_init(empty_bar(s), 1); }
         for (uint32_t a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
         mbar_init(wfull_bar, kSProducers);
         fence_barrier_init();
@@ -105,125 +103,33 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_s2_kernel(const __grid_cons
         const int per_plane = HY * HX * ncg;
         const uint32_t inv_hx = (1u << 20) / uint32_t(HX) + 1u;
         const int cg_shift = ncg == 2 ? 1 : 2;
-        if constexpr (XF) {
-            // cp.async copies as below, the transform in place two planes behind them (see conv_band.cu)
-            const int cg = t & (ncg - 1);
-            const SrcTransform& X = P.xf[0];
-            const bool xon = X.enabled != 0;
-            XfCoef kc;
-            if (xon) xf_coefs(X, cg, kc);
-            else kc.act = 0;
-            const uint8_t* const sg = s0 + cg * 16;
-            uint8_t* const wb = xon && X.writeback ? static_cast<uint8_t*>(X.writeback) + cg * 16 : nullptr;
-            const int pos0 = t >> cg_shift, pos_step = kSProducers >> cg_shift, npos = HY * HX;
-            struct Rec { uint32_t slot; int gz, x0, y0; bool zin; };
-            auto issue = [&](const Rec& r) {
-                const uint32_t blk = sbase + r.slot * p.slot_bytes;
-                const bool zok = (unsigned)r.gz < (unsigned)D;
-                const long long vox0 = ((long long)(zok ? r.gz : 0) * H + r.y0) * W + r.x0;
+        uint32_t cnt = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int rem = item;
+            const int zc = rem % p.zchunks; rem /= p.zchunks;
+            const int tx = rem % p.tiles_x;
+            const int ty = rem / p.tiles_x;
+            const int x0 = 2 * tx * p.OTX - 1, y0 = 2 * ty * p.OTY - 1;     // input coordinate of halo position (0, 0)
+            const int z0 = zc * p.zlen, z1 = min(OD, z0 + p.zlen);
+            for (int gz = 2 * z0 - 1; gz <= 2 * (z1 - 1) + 1; ++gz, ++cnt) {
+                const uint32_t slot = cnt % kSSlots;
+                mbar_wait(empty_bar(slot), ((cnt / kSSlots) & 1) ^ 1, 0x4100u | slot);
+                const uint32_t blk = sbase + slot * p.slot_bytes;
+                const bool zok = (unsigned)gz < (unsigned)D;
+                const long long vox0 = ((long long)(zok ? gz : 0) * H + y0) * W + x0;
+                const uint8_t* const p0 = s0 + vox0 * (long long)pitch0;
 #pragma unroll 2
-                for (int pos = pos0; pos < npos; pos += pos_step) {
-                    const int hy = int((uint32_t(pos) * inv_hx) >> 20);
-                    const int hx = pos - hy * HX;
-                    const bool ok = zok && (unsigned)(r.x0 + hx) < (unsigned)W && (unsigned)(r.y0 + hy) < (unsigned)H;
-                    const uint8_t* src = ok ? sg + (vox0 + hy * W + hx) * (long long)pitch0 : sg;
+                for (int idx = t; idx < per_plane; idx += kSProducers) {
+                    const int cg = idx & (ncg - 1);
+                    const uint32_t pos = uint32_t(idx) >> cg_shift;
+                    const int hy = int((pos * inv_hx) >> 20);
+                    const int hx = int(pos) - hy * HX;
+                    const bool ok = zok && (unsigned)(x0 + hx) < (unsigned)W && (unsigned)(y0 + hy) < (unsigned)H;
+                    const uint8_t* src = ok ? p0 + (long long)(hy * W + hx) * pitch0 + cg * 16 : s0;
                     const int plane = (cg * 2 + (hy & 1)) * 2 + (hx & 1);
                     cp_async16_ca(blk + uint32_t(plane * ROWS + (hy >> 1) * HQ + (hx >> 1)) * 16u, src, ok ? 16u : 0u);
                 }
-                cp_async_commit();
-            };
-            auto finish_t = [&](const Rec& r, auto act_c) {
-                constexpr int ACT = decltype(act_c)::value;
-                if (xon) {
-                    const uint32_t blk = sbase + r.slot * p.slot_bytes;
-                    const bool zok = (unsigned)r.gz < (unsigned)D;
-                    const long long vox0 = ((long long)(zok ? r.gz : 0) * H + r.y0) * W + r.x0;
-                    if (zok) {
-#pragma unroll 2
-                        for (int pos = pos0; pos < npos; pos += pos_step) {
-                            const int hy = int((uint32_t(pos) * inv_hx) >> 20);
-                            const int hx = pos - hy * HX;
-                            if ((unsigned)(r.x0 + hx) >= (unsigned)W || (unsigned)(r.y0 + hy) >= (unsigned)H) continue;
-                            const int plane = (cg * 2 + (hy & 1)) * 2 + (hx & 1);
-                            const uint32_t dst = blk + uint32_t(plane * ROWS + (hy >> 1) * HQ + (hx >> 1)) * 16u;
-                            const uint4 v = xf_apply_c<ACT>(lds16(dst), kc.sc, kc.sh);
-                            sts16(dst, v);
-                            if (wb != nullptr && r.zin && hx >= 1 && hx <= 2 * p.OTX && hy >= 1 && hy <= 2 * p.OTY)
-                                *reinterpret_cast<uint4*>(wb + (vox0 + hy * W + hx) * (long long)pitch0) = v;
-                        }
-                    }
-                    // no fence.proxy.async here: it would wait for this thread's cp.async copies of the NEXT planes (the full DRAM
-                    // latency, every plane).  The MMA issuer fences after it has acquired the plane's full barrier, as it does for the
-                    // copy-written planes of the plain variant.
-                }
-                // ONE arrival per warp: 256 thread arrivals on one barrier word serialise (~30 clk each = more than the plane's MMAs)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(r.slot));
-            };
-            auto finish = [&](const Rec& r) { xf_dispatch_act(kc.act, [&](auto act_c) { finish_t(r, act_c); }); };
-            Rec ra{}, rb{};
-            int npend = 0;
-            uint32_t cnt = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                int rem = item;
-                const int zc = rem % p.zchunks; rem /= p.zchunks;
-                const int tx = rem % p.tiles_x;
-                const int ty = rem / p.tiles_x;
-                const int x0 = 2 * tx * p.OTX - 1, y0 = 2 * ty * p.OTY - 1;
-                const int z0 = zc * p.zlen, z1 = min(OD, z0 + p.zlen);
-                for (int gz = 2 * z0 - 1; gz <= 2 * (z1 - 1) + 1; ++gz, ++cnt) {
-                    Rec r;
-                    r.slot = cnt % kSSlots; r.gz = gz; r.x0 = x0; r.y0 = y0; r.zin = gz >= 2 * z0 && gz < 2 * z1;
-                    if (npend > 0 && !mbar_try_wait(empty_bar(r.slot), ((cnt / kSSlots) & 1) ^ 1)) {   // ring full: finish what is copied first
-                        cp_async_wait<0>();
-                        finish(ra);
-                        if (npend == 2) finish(rb);
-                        npend = 0;
-                    }
-                    mbar_wait(empty_bar(r.slot), ((cnt / kSSlots) & 1) ^ 1, 0x4100u | r.slot);
-                    issue(r);
-                    if (npend == 2) {
-                        cp_async_wait<2>();
-                        finish(ra);
-                        ra = rb; rb = r;
-                    } else {
-                        if (npend == 0) ra = r; else rb = r;
-                        ++npend;
-                    }
-                }
-            }
-            cp_async_wait<0>();
-            if (npend >= 1) finish(ra);
-            if (npend == 2) finish(rb);
-        } else {
-            uint32_t cnt = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                int rem = item;
-                const int zc = rem % p.zchunks; rem /= p.zchunks;
-                const int tx = rem % p.tiles_x;
-                const int ty = rem / p.tiles_x;
-                const int x0 = 2 * tx * p.OTX - 1, y0 = 2 * ty * p.OTY - 1;     // input coordinate of halo position (0, 0)
-                const int z0 = zc * p.zlen, z1 = min(OD, z0 + p.zlen);
-                for (int gz = 2 * z0 - 1; gz <= 2 * (z1 - 1) + 1; ++gz, ++cnt) {
-                    const uint32_t slot = cnt % kSSlots;
-                    mbar_wait(empty_bar(slot), ((cnt / kSSlots) & 1) ^ 1, 0x4100u | slot);
-                    const uint32_t blk = sbase + slot * p.slot_bytes;
-                    const bool zok = (unsigned)gz < (unsigned)D;
-                    const long long vox0 = ((long long)(zok ? gz : 0) * H + y0) * W + x0;
-                    const uint8_t* const p0 = s0 + vox0 * (long long)pitch0;
-#pragma unroll 2
-                    for (int idx = t; idx < per_plane; idx += kSProducers) {
-                        const int cg = idx & (ncg - 1);
-                        const uint32_t pos = uint32_t(idx) >> cg_shift;
-                        const int hy = int((pos * inv_hx) >> 20);
-                        const int hx = int(pos) - hy * HX;
-                        const bool ok = zok && (unsigned)(x0 + hx) < (unsigned)W && (unsigned)(y0 + hy) < (unsigned)H;
-                        const uint8_t* src = ok ? p0 + (long long)(hy * W + hx) * pitch0 + cg * 16 : s0;
-                        const int plane = (cg * 2 + (hy & 1)) * 2 + (hx & 1);
-                        cp_async16_ca(blk + uint32_t(plane * ROWS + (hy >> 1) * HQ + (hx >> 1)) * 16u, src, ok ? 16u : 0u);
-                    }
-                    cp_async_mbar_arrive(full_bar(slot));
-                }
+                cp_async_mbar_arrive(full_bar(slot));
             }
         }
         cp_async_wait<0>();
@@ -379,21 +285,16 @@ __global__ void __launch_bounds__(kSThreads, 1) conv_s2_kernel(const __grid_cons
     if (warp == 12) tmem_dealloc(tmem_base, TCOLS);
 }
 
-template <int KS, int NCH, bool XF>
-int launch_s2_tx(const SParams& sp, int grid, size_t smem, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_s2_kernel<KS, NCH, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    conv_s2_kernel<KS, NCH, XF><<<grid, kSThreads, smem, stream>>>(sp);
-    U3D_CUDA_CHECK(cudaGetLastError());
-    return 0;
-}
 template <int KS, int NCH>
 int launch_s2_t(const SParams& sp, int grid, size_t smem, cudaStream_t stream) {
-    if (sp.P.xf[0].enabled) return launch_s2_tx<KS, NCH, true>(sp, grid, smem, stream);
-    return launch_s2_tx<KS, NCH, false>(sp, grid, smem, stream);
+    static bool attr_set = false;
+    if (!attr_set) {
+        U3D_CUDA_CHECK(cudaFuncSetAttribute(conv_s2_kernel<KS, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    conv_s2_kernel<KS, NCH><<<grid, kSThreads, smem, stream>>>(sp);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace
@@ -482,8 +383,9 @@ int conv_s2_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg,
     if (KS == 1 && nch == 1) return launch_s2_t<1, 1>(sp, grid, smem, stream);
     if (KS == 1 && nch == 2) return launch_s2_t<1, 2>(sp, grid, smem, stream);
     if (KS == 1) return launch_s2_t<1, 4>(sp, grid, smem, stream);
-    set_error("conv_s2_launch: 16 padded input channels only");
-    return 1;
+    if (nch == 1) return launch_s2_t<2, 1>(sp, grid, smem, stream);
+    if (nch == 2) return launch_s2_t<2, 2>(sp, grid, smem, stream);
+    return launch_s2_t<2, 4>(sp, grid, smem, stream);
 }
 
 }  // namespace u3d

@@ -13,20 +13,8 @@ int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cu
     if (conv_band_eligible(probs, cfg)) return conv_band_launch(probs, cfg, stream);
     if (!probs.empty() && probs[0].banded) { set_error("conv_launch: banded weight pack but the problem is not eligible for conv_band"); return 1; }
     if (conv_s2_eligible(probs, cfg)) return conv_s2_launch(probs, cfg, stream);
-    for (const auto& P : probs)
-        if (P.xf[0].enabled || P.xf[1].enabled) { set_error("conv_launch: source transform on a kernel that does not stage through registers"); return 1; }
     if (conv_tma_eligible(probs, cfg)) return conv_tma_launch(probs, cfg, stream);
     return conv_igemm_launch(probs, cfg, nullptr, stream);
-}
-
-// May source `src` of this problem set carry a SrcTransform?  Only the kernels whose producers are threads (conv_band, conv_s2) can
-// transform while they stage; the copy-engine-fed kernels need the materialised tensor.
-bool conv_supports_xf(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, int src) {
-    static const bool disabled = std::getenv("U3D_NO_XF") != nullptr;
-    if (disabled) return false;
-    if (conv_band_eligible(probs, cfg)) return !(probs.size() == 2 && src == 1) && cfg.epi == EPI_STORE16;
-    if (probs.empty() || probs[0].banded) return false;
-    return conv_s2_eligible(probs, cfg) && src == 0;
 }
 
 // profile family of the kernel conv_launch picks: 0 conv_igemm, 2 conv_s2, 4 conv_tma, 5 conv_band

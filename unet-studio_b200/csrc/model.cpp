@@ -787,38 +787,23 @@ int Model::ensure_plan() {
             M_CHECK(alloc(reinterpret_cast<void**>(&s.idx), tens[s.out].V() * tens[s.out].Cp * sizeof(int)));
         }
     }
-    // Norm + activation folded into the consumers: when every reader of an activated tensor is a kernel whose producers
-    // are threads (conv_band, conv_s2, head_fwd), the norm_act_fwd pass is dropped; the readers take the raw tensor and apply
-    // scale/shift/activation while staging.  In training the first reader also stores the activated voxels, because the weight
-    // gradients (copy-engine fed) and the fused head backward read the materialised tensor.
-    for (size_t ni = 0; ni < steps.size(); ++ni) {
+    // Norm + activation folded into the output head: when the only reader of an activated tensor is the CUDA-core head
+    // kernel, the norm_act_fwd pass over that full-resolution tensor is dropped; head_fwd takes the raw conv output and applies
+    // scale/shift/activation itself (in training it also stores the activated voxels: the fused head backward reads them).
+    // The same fold into the tensor-core consumers (conv_band / conv_s2 producers) was built and measured slower than the separate pass
+    // -- those kernels are bound by shared-memory operand fetch and producer latency, see DESIGN.md 10.
+    static const bool no_xf = std::getenv("U3D_NO_XF") != nullptr;
+    for (size_t ni = 0; ni < steps.size() && !no_xf; ++ni) {
         Step& n = steps[ni];
         if (n.kind != Step::NORMACT) continue;
-        bool ok = true;
-        std::vector<std::pair<size_t, int>> readers;
-        for (size_t ci = 0; ci < steps.size() && ok; ++ci) {
-            Step& c = steps[ci];
-            if (c.in0 != n.out && c.in1 != n.out) continue;
-            if (c.kind != Step::CONV || (c.in0 == n.out && c.in1 == n.out)) { ok = false; break; }
-            const int src = c.in0 == n.out ? 0 : 1;
-            if (c.head_level >= 0) ok = c.head_fwd_fused;
-            else {
-                ConvLaunch cfg{};
-                cfg.kc = c.fkc;
-                cfg.epi = EPI_STORE16;
-                ok = conv_supports_xf(c.fprobs, cfg, src);
-            }
-            readers.push_back({ci, src});
-        }
-        if (!ok || readers.empty()) continue;
+        int reader = -1, nreaders = 0;
+        for (size_t ci = 0; ci < steps.size(); ++ci)
+            if (steps[ci].in0 == n.out || steps[ci].in1 == n.out) { reader = int(ci); ++nreaders; }
+        if (nreaders != 1) continue;
+        Step& c = steps[reader];
+        if (c.kind != Step::CONV || c.head_level < 0 || !c.head_fwd_fused || c.in0 != n.out) continue;
         n.elided = true;
-        for (size_t r = 0; r < readers.size(); ++r) {
-            Step& c = steps[readers[r].first];
-            const int src = readers[r].second;
-            c.xf_from[src] = int(ni);
-            c.xf_write[src] = tr && r == 0;
-            for (auto& P : c.fprobs) (src == 0 ? P.src0 : P.src1) = tens[n.in0].p;
-        }
+        c.xf_from = int(ni);
     }
     {   // concat convs whose source 0 (the skip tensor) is also consumed by another conv: their skip gradient can be deferred
         skip_has_other_consumer.assign(steps.size(), 0);
@@ -898,29 +883,28 @@ int Model::run_forward(int levels_wanted, bool bn_eval) {
     for (auto& s : steps) {
         if (s.kind == Step::CONV) {
             if (s.head_level >= levels_wanted) continue;
-            SrcTransform xf[2] = {};
-            for (int src = 0; src < 2; ++src) {
-                if (s.xf_from[src] < 0) continue;
-                const Step& n = steps[s.xf_from[src]];
-                xf[src].enabled = 1;
-                xf[src].C = tens[n.in0].C;
-                xf[src].has_norm = n.cur_has_norm;
-                xf[src].act = n.act;
-                xf[src].mean = n.cur_mean;
-                xf[src].rstd = n.cur_rstd;
-                xf[src].gamma = n.norm ? param_ptr(n.p_g) : nullptr;
-                xf[src].beta = n.norm ? param_ptr(n.p_g + 1) : nullptr;
-                xf[src].writeback = s.xf_write[src] ? tens[n.out].p : nullptr;
-            }
             if (s.head_fwd_fused) {
                 const Ten& a = tens[s.in0];
-                const void* x = s.xf_from[0] >= 0 ? tens[steps[s.xf_from[0]].in0].p : a.p;
+                SrcTransform xf{};
+                const void* x = a.p;
+                if (s.xf_from >= 0) {
+                    const Step& n = steps[s.xf_from];
+                    xf.enabled = 1;
+                    xf.C = tens[n.in0].C;
+                    xf.has_norm = n.cur_has_norm;
+                    xf.act = n.act;
+                    xf.mean = n.cur_mean;
+                    xf.rstd = n.cur_rstd;
+                    xf.gamma = n.norm ? param_ptr(n.p_g) : nullptr;
+                    xf.beta = n.norm ? param_ptr(n.p_g + 1) : nullptr;
+                    xf.writeback = training ? a.p : nullptr;
+                    x = tens[n.in0].p;
+                }
                 M_CHECK(head_fwd_launch(x, a.C, a.Cp, param_ptr(s.p_w), param_ptr(s.p_b), logits[s.head_level], s.g.cout, a.V(), stream,
-                                        s.xf_from[0] >= 0 ? &xf[0] : nullptr));
+                                        s.xf_from >= 0 ? &xf : nullptr));
                 ++launches;
                 continue;
             }
-            for (auto& P : s.fprobs) { P.xf[0] = xf[0]; P.xf[1] = xf[1]; }
             ConvLaunch cfg{};
             cfg.kc = s.fkc;
             cfg.epi = s.head_level >= 0 ? EPI_PLANAR32 : EPI_STORE16;

@@ -61,8 +61,8 @@ struct Step {
     std::vector<WgradProblem> wg;
     std::vector<void*> pack_bufs;  // owned device blobs (fwd then dgrad)
     double flops = 0;              // algorithmic 2*Cin*Cout*k^3*V_out of this layer
-    int xf_from[2] = {-1, -1};     // source i is the output of an ELIDED norm/activation step: read its raw input and transform on the fly
-    bool xf_write[2] = {false, false};   // ... and store the activated voxels (training: the weight gradients read them)
+    int xf_from = -1;              // fused head: its input is the output of an ELIDED norm/activation step -- read that step's raw input and
+                                   // apply scale/shift/activation in head_fwd_kernel (SrcTransform)
     // NORMACT
     int norm = 0;              // 0 none, 1 InstanceNorm3d (eps 1e-5), 2 BatchNorm3d (eps 0)
     int act = ACT_NONE;
@@ -71,7 +71,7 @@ struct Step {
     float* rstd = nullptr;
     int buf0 = -1;
     bool stats_from_conv = false;
-    bool elided = false;       // every consumer applies scale/shift/activation while it stages its operand (SrcTransform): statistics only
+    bool elided = false;       // the only reader is the fused head, which applies scale/shift/activation itself (SrcTransform): statistics only
     const float* cur_mean = nullptr;   // coefficients of the current forward pass (mode dependent), read by the consumers of an elided step
     const float* cur_rstd = nullptr;
     int cur_has_norm = 0;

@@ -35,9 +35,9 @@ enum EpiMode : int {
     EPI_PLANAR32 = 2,   // fp32 planar [n][lattice voxel] store (+bias): logits in reference NCDHW order
 };
 
-// Optional on-the-fly normalisation + activation of a conv source (conv_band.cu / conv_s2.cu producers, head_fwd_kernel): the source
-// pointer is the RAW output of the layer in front and the consumer applies y = act(gamma*rstd*(x - mean) + beta) while it stages the
-// operand, exactly the arithmetic of norm_act_fwd_kernel (unet.cpp:74-98) -- that kernel's HBM round trip disappears.
+// Optional on-the-fly normalisation + activation of the input of head_fwd_kernel (loss.cu): the pointer it gets is the RAW output of
+// the last conv and it applies y = act(gamma*rstd*(x - mean) + beta) itself, exactly the arithmetic of norm_act_fwd_kernel
+// (unet.cpp:74-98) -- that kernel's HBM round trip over the full-resolution tensor disappears.
 struct SrcTransform {
     int enabled;
     int C;                 // real channels of the source (padded channels stay 0)
@@ -46,13 +46,12 @@ struct SrcTransform {
     const float* rstd;     // nullptr = 1
     const float* gamma;
     const float* beta;
-    void* writeback;       // training: the consumer also stores the activated voxels it owns (same pitch as the source) for the weight gradient
+    void* writeback;       // training: the activated voxels are also stored (same pitch) for the fused head backward
 };
 
 struct ConvProblem {
     const void* src0;
     const void* src1;
-    SrcTransform xf[2];    // per source; honoured by the kernels conv_supports_xf() names, rejected by conv_launch otherwise
     int c0p, c1p;          // channel pitch (elements) of each source tensor
     int coff0, coff1;      // first channel used in each source
     int nch0, nch1;        // number of kc-wide K chunks taken from each source
@@ -132,7 +131,6 @@ int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch&
                       cudaStream_t stream);
 
 int conv_launch(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, cudaStream_t stream);  // band, s2, TMA or gather kernel (dispatch.cpp)
-bool conv_supports_xf(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg, int src);
 int conv_kernel_kind(const std::vector<ConvProblem>& probs, const ConvLaunch& cfg);  // profile family conv_launch will use: 0 igemm, 2 s2, 4 tma, 5 band
 bool conv_band_wants(int k_channels_padded, int n_channels_padded, long long voxels);
 bool conv_s2_wants_kc16(int ks, int stride, int transposed, int cin_padded, int n_sources, int cout_padded, long long out_voxels);
