@@ -147,26 +147,31 @@ __global__ void loss_reduce_kernel(const LossLevel L) {
     }
 }
 
-__global__ void loss_finalize_kernel(const LossLevel L, int rows) {
+__global__ void __launch_bounds__(1024) loss_finalize_kernel(const LossLevel L, int rows) {
     const int Cc = L.collapse_before ? L.C - L.collapse_before + 1 : L.C;
-    // fixed-order double sum over the per-block partial rows: thread (g, i) walks rows g, g+G, ... of accumulator i (coalesced rows,
-    // independent loads), then thread i adds the G group sums in order
+    // fixed-order double sum over the per-block partial rows.  The 1024 threads form G groups of NI lanes (NI = the accumulator count
+    // rounded up to a power of two: 8 for a binary head, so G = 128): thread (g, i) walks rows g, g+G, ... of accumulator i, then a
+    // fixed-shape tree over the groups.  (With a fixed 10 x 96 split only 70 of 960 threads worked: 23 us per level on the critical
+    // path between the forward and the backward pass.)
     __shared__ double tot[kAccN];
-    __shared__ double grp[10][96];
-    const int i = threadIdx.x % 96, g = threadIdx.x / 96;
+    __shared__ double grp[1024];
     const int nacc = 3 + 2 * Cc;
+    int NI = 8;
+    while (NI < nacc) NI <<= 1;          // <= 128 (kAccN = 67)
+    const int G = 1024 / NI;
+    const int i = threadIdx.x % NI, g = threadIdx.x / NI;
     double t = 0;
-    if (g < 10 && i < nacc) {
-#pragma unroll 8
-        for (int r = g; r < rows; r += 10) t += double(L.part[size_t(r) * kAccN + i]);
-    }
-    if (g < 10) grp[g][i] = t;
+    if (i < nacc)
+        for (int r = g; r < rows; r += G) t += double(L.part[size_t(r) * kAccN + i]);
+    grp[g * NI + i] = t;
     __syncthreads();
+    for (int half = G >> 1; half > 0; half >>= 1) {   // G is a power of two
+        if (g < half) grp[g * NI + i] += grp[(g + half) * NI + i];
+        __syncthreads();
+    }
     if (g == 0 && i < nacc) {
-        double a = 0;
-        for (int k = 0; k < 10; ++k) a += grp[k][i];
-        tot[i] = a;
-        L.acc[i] = a;
+        tot[i] = grp[i];
+        L.acc[i] = grp[i];
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
@@ -288,44 +293,62 @@ __global__ void loss_grad_kernel(const LossLevel L) {
 // ---- 1x1 output head fused with the loss gradient (levels whose head input has <= 32 channels: bandwidth-bound) ----
 // forward: logits[c][v] = b[c] + sum_k W[c][k] x[v][k]            (unet.cpp:186-187, Conv3d k1 of the output token)
 // xf.enabled: x is the RAW output of the last conv; its norm + activation is applied here (and the activated voxels stored to
-// xf.writeback for the backward pass) -- see SrcTransform in u3d.h
-template <int XCP>
+// xf.writeback for the backward pass) -- see SrcTransform in u3d.h.
+// One thread per (voxel, group of 8 input channels): a warp's loads (and write-back stores) are contiguous 16-byte chunks; the
+// XCP/8 partial dot products of a voxel are combined by shuffles in a fixed order and lane g writes the classes c = g, g + GP, ...
+// ACT = -1: plain input; otherwise the activation of the folded norm step as a compile-time constant
+template <int XCP, int ACT>
 __global__ void head_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                 float* __restrict__ logits, int C, int xc, long long nv, const SrcTransform xf) {
+    constexpr int GP = XCP / 8;
     __shared__ float sw[kMaxC * XCP];
     __shared__ float sb[kMaxC];
     __shared__ float ssc[XCP], ssh[XCP];
-    if (xf.enabled)
-        for (int i = threadIdx.x; i < XCP; i += blockDim.x) xf_coef1(xf, i, ssc[i], ssh[i]);
-    uint4* const wb = xf.enabled ? static_cast<uint4*>(xf.writeback) : nullptr;
     for (int i = threadIdx.x; i < C * XCP; i += blockDim.x) {
         const int c = i / XCP, k = i % XCP;
         sw[i] = k < xc ? w[c * xc + k] : 0.f;
     }
     for (int i = threadIdx.x; i < C; i += blockDim.x) sb[i] = b[i];
+    if (ACT >= 0)
+        for (int i = threadIdx.x; i < XCP; i += blockDim.x) xf_coef1(xf, i, ssc[i], ssh[i]);
+    uint4* const wb = ACT >= 0 ? static_cast<uint4*>(xf.writeback) : nullptr;
     __syncthreads();
-    for (long long vox = blockIdx.x * (long long)blockDim.x + threadIdx.x; vox < nv; vox += (long long)gridDim.x * blockDim.x) {
-        float xv[XCP];
+    const int g = int(threadIdx.x) % GP;
+    const long long total = nv * GP;
+    // whole warps stay in the loop (the shuffles need all GP lanes of a voxel; GP divides 32 and the stride); two chunks per thread
+    // and iteration so that two loads are in flight
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = blockIdx.x * (long long)blockDim.x; base < total; base += 2 * stride) {
+        const long long i0 = base + threadIdx.x, i1 = i0 + stride;
+        const bool on0 = i0 < total, on1 = i1 < total;
+        uint4 q[2];
+        q[0] = on0 ? x[i0] : make_uint4(0u, 0u, 0u, 0u);
+        q[1] = on1 ? x[i1] : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int g = 0; g < XCP / 8; ++g) {
-            uint4 q = x[vox * (XCP / 8) + g];
-            if (xf.enabled) {
-                q = xf_apply(q, ssc + g * 8, ssh + g * 8, xf.act);
-                if (wb != nullptr) wb[vox * (XCP / 8) + g] = q;
+        for (int h = 0; h < 2; ++h) {
+            const long long i = h ? i1 : i0;
+            const bool on = h ? on1 : on0;
+            if (ACT >= 0) {
+                q[h] = xf_apply_c<(ACT < 0 ? 0 : ACT)>(q[h], ssc + g * 8, ssh + g * 8);
+                if (wb != nullptr && on) wb[i] = q[h];
             }
-            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t u[4] = {q[h].x, q[h].y, q[h].z, q[h].w};
+            float xv[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 f = unpack2<false>(u[j]);
-                xv[g * 8 + 2 * j] = f.x;
-                xv[g * 8 + 2 * j + 1] = f.y;
+                xv[2 * j] = f.x;
+                xv[2 * j + 1] = f.y;
             }
-        }
-        for (int c = 0; c < C; ++c) {
-            float acc = sb[c];
+            const long long vox = i / GP;
+            for (int c = 0; c < C; ++c) {
+                float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < XCP; ++k) acc = fmaf(sw[c * XCP + k], xv[k], acc);
-            logits[c * nv + vox] = acc;
+                for (int k = 0; k < 8; ++k) acc = fmaf(sw[c * XCP + g * 8 + k], xv[k], acc);
+#pragma unroll
+                for (int o = 1; o < GP; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (on && (c % GP) == g) logits[c * nv + vox] = acc + sb[c];
+            }
         }
     }
 }
@@ -333,7 +356,7 @@ __global__ void head_fwd_kernel(const uint4* __restrict__ x, const float* __rest
 // backward: dlogits stay in registers; dx[v][k] = sum_c dl[c] W[c][k] (fp16, store or accumulate), dW[c][k] += dl[c] x[v][k],
 // db[c] += dl[c].  Replaces loss_grad + the head's dgrad / wgrad / bias-gradient launches and the dlogits round trip.
 template <int CT, int XCP>
-__global__ void __launch_bounds__(128, (CT * XCP <= 64 ? 5 : 3)) loss_grad_head_kernel(const LossLevel L, const HeadFuse Hd) {
+__global__ void __launch_bounds__(128, (CT * XCP <= 32 ? 5 : CT * XCP <= 64 ? 4 : 3)) loss_grad_head_kernel(const LossLevel L, const HeadFuse Hd) {
     const long long nv = (long long)L.d * L.h * L.w;
     const int cb = L.collapse_before;
     const int Cc = cb ? L.C - cb + 1 : L.C;
@@ -356,11 +379,14 @@ __global__ void __launch_bounds__(128, (CT * XCP <= 64 ? 5 : 3)) loss_grad_head_
     const float invZ = 1.f / float(Cc - 1 > 1 ? Cc - 1 : 1);
     const uint4* xin = static_cast<const uint4*>(Hd.x);
     uint4* dxo = static_cast<uint4*>(Hd.dx);
-    // one thread per (voxel, group of 8 head-input channels): the XCP/8 threads of a voxel evaluate its softmax gradient redundantly
-    // (a few classes) but each owns 16 bytes of x / dx, so a warp's loads and stores are contiguous and a thread carries CT*8 weight-
-    // gradient accumulators instead of CT*XCP (the one-thread-per-voxel form needed 167 registers: 19 % occupancy, 2.1 TB/s)
+    // A warp takes 32 voxels per iteration.  Phase A: lane l evaluates the softmax gradient of voxel l (once per voxel; logits and
+    // labels are read as contiguous 128-byte rows).  Phase B: the 32*GP 16-byte chunks of those voxels (GP = XCP/8 channel groups)
+    // are processed in GP rounds of 32 contiguous chunks; a lane gets the gradient of its round's voxel by shuffle and owns 16 bytes
+    // of x / dx, so it carries CT*8 weight-gradient accumulators.  (One thread per voxel needed 167 registers: 19 % occupancy; one
+    // thread per chunk with the gradient evaluated redundantly by the GP lanes of a voxel was instruction-bound at 176 us.)
     constexpr int GP = XCP / 8;
-    const int g = int(threadIdx.x) % GP;
+    const int lane = int(threadIdx.x) & 31;
+    const int g = lane % GP;
     float aw[CT][8], ab[CT];
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
@@ -368,50 +394,71 @@ __global__ void __launch_bounds__(128, (CT * XCP <= 64 ? 5 : 3)) loss_grad_head_
 #pragma unroll
         for (int k = 0; k < 8; ++k) aw[c][k] = 0.f;
     }
-    const long long vstride = (long long)gridDim.x * (blockDim.x / GP);
-    for (long long vox = blockIdx.x * (long long)(blockDim.x / GP) + threadIdx.x / GP; vox < nv; vox += vstride) {
-        int x = 0, y = 0, z = 0;
-        if (L.shift != 0) {   // level 0 reads label[vox] directly; deeper levels need (x,y,z) (32-bit: a level has < 2^31 voxels)
-            const unsigned uv = unsigned(vox);
-            x = int(uv % unsigned(L.w));
-            const unsigned q = uv / unsigned(L.w);
-            y = int(q % unsigned(L.h));
-            z = int(q / unsigned(L.h));
-        }
-        const uint4 qx = xin[vox * GP + g];
-        uint4 qd = make_uint4(0u, 0u, 0u, 0u);
-        if (Hd.dx_accum) qd = dxo[vox * GP + g];
-        Voxel<CT> o;
-        eval_voxel<CT>(L, vox, x, y, z, o);
-        float dlo[CT];
-        voxel_grad<CT>(L, o, sI, sK, inv_n, invZ, dlo);
-        const uint32_t u[4] = {qx.x, qx.y, qx.z, qx.w};
-        const uint32_t ud[4] = {qd.x, qd.y, qd.z, qd.w};
-        float xv[8], dv[8];
+    const long long wstride = (long long)gridDim.x * (blockDim.x / 32) * 32;
+    for (long long v0 = (blockIdx.x * (long long)(blockDim.x / 32) + threadIdx.x / 32) * 32; v0 < nv; v0 += wstride) {
+        // the x rows of both rounds first: their latency overlaps phase A
+        uint4 qx[GP], qd[GP];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack2<false>(u[j]);
-            xv[2 * j] = f.x;
-            xv[2 * j + 1] = f.y;
-            const float2 fd = unpack2<false>(ud[j]);
-            dv[2 * j] = fd.x;
-            dv[2 * j + 1] = fd.y;
-        }
-#pragma unroll
-        for (int c = 0; c < CT; ++c) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                dv[k] = fmaf(dlo[c], sw[c * XCP + g * 8 + k], dv[k]);
-                aw[c][k] = fmaf(dlo[c], xv[k], aw[c][k]);
+        for (int r = 0; r < GP; ++r) {
+            const long long vox = v0 + r * (32 / GP) + lane / GP;
+            qx[r] = qd[r] = make_uint4(0u, 0u, 0u, 0u);
+            if (vox < nv) {
+                qx[r] = xin[vox * GP + g];
+                if (Hd.dx_accum) qd[r] = dxo[vox * GP + g];
             }
         }
-        uint4 qo;
-        qo.x = pack2<false>(dv[0], dv[1]); qo.y = pack2<false>(dv[2], dv[3]);
-        qo.z = pack2<false>(dv[4], dv[5]); qo.w = pack2<false>(dv[6], dv[7]);
-        dxo[vox * GP + g] = qo;
-        if (g == 0) {
+        float dlo[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) dlo[c] = 0.f;
+        const long long va = v0 + lane;
+        if (va < nv) {
+            int x = 0, y = 0, z = 0;
+            if (L.shift != 0) {   // level 0 reads label[vox] directly; deeper levels need (x,y,z) (32-bit: a level has < 2^31 voxels)
+                const unsigned uv = unsigned(va);
+                x = int(uv % unsigned(L.w));
+                const unsigned q = uv / unsigned(L.w);
+                y = int(q % unsigned(L.h));
+                z = int(q / unsigned(L.h));
+            }
+            Voxel<CT> o;
+            eval_voxel<CT>(L, va, x, y, z, o);
+            voxel_grad<CT>(L, o, sI, sK, inv_n, invZ, dlo);
 #pragma unroll
             for (int c = 0; c < CT; ++c) ab[c] += dlo[c];
+        }
+#pragma unroll
+        for (int r = 0; r < GP; ++r) {
+            const int vl = r * (32 / GP) + lane / GP;
+            const long long vox = v0 + vl;
+            float d[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) d[c] = __shfl_sync(0xffffffffu, dlo[c], vl);
+            const uint32_t u[4] = {qx[r].x, qx[r].y, qx[r].z, qx[r].w};
+            const uint32_t ud[4] = {qd[r].x, qd[r].y, qd[r].z, qd[r].w};
+            float xv[8], dv[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2<false>(u[j]);
+                xv[2 * j] = f.x;
+                xv[2 * j + 1] = f.y;
+                const float2 fd = unpack2<false>(ud[j]);
+                dv[2 * j] = fd.x;
+                dv[2 * j + 1] = fd.y;
+            }
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    dv[k] = fmaf(d[c], sw[c * XCP + g * 8 + k], dv[k]);
+                    aw[c][k] = fmaf(d[c], xv[k], aw[c][k]);      // x = 0 beyond the volume: no contribution
+                }
+            }
+            if (vox < nv) {
+                uint4 qo;
+                qo.x = pack2<false>(dv[0], dv[1]); qo.y = pack2<false>(dv[2], dv[3]);
+                qo.z = pack2<false>(dv[4], dv[5]); qo.w = pack2<false>(dv[6], dv[7]);
+                dxo[vox * GP + g] = qo;
+            }
         }
     }
     // lanes with the same channel group: lane % GP == g  ->  butterfly over the lane bits above log2(GP)
@@ -453,10 +500,29 @@ int head_fwd_launch(const void* x, int xc, int xcp, const float* w, const float*
     SrcTransform xf{};
     if (xfp) xf = *xfp;
     if (!head_fwd_supported(C, xcp)) { set_error("head_fwd_launch: unsupported shape"); return 1; }
-    long long g = (nv + 255) / 256;
+    long long g = (nv * (xcp / 8) + 255) / 256;
     const int grid = int(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
-    if (xcp == 16) head_fwd_kernel<16><<<grid, 256, 0, s>>>(static_cast<const uint4*>(x), w, b, logits, C, xc, nv, xf);
-    else head_fwd_kernel<32><<<grid, 256, 0, s>>>(static_cast<const uint4*>(x), w, b, logits, C, xc, nv, xf);
+    const uint4* xp = static_cast<const uint4*>(x);
+    const int act = xf.enabled ? xf.act : -1;
+#define U3D_HEAD_FWD(XCP_, ACT_) head_fwd_kernel<XCP_, ACT_><<<grid, 256, 0, s>>>(xp, w, b, logits, C, xc, nv, xf)
+    if (xcp == 16) {
+        switch (act) {
+            case ACT_NONE: U3D_HEAD_FWD(16, ACT_NONE); break;
+            case ACT_RELU: U3D_HEAD_FWD(16, ACT_RELU); break;
+            case ACT_LEAKY: U3D_HEAD_FWD(16, ACT_LEAKY); break;
+            case ACT_ELU: U3D_HEAD_FWD(16, ACT_ELU); break;
+            default: U3D_HEAD_FWD(16, -1); break;
+        }
+    } else {
+        switch (act) {
+            case ACT_NONE: U3D_HEAD_FWD(32, ACT_NONE); break;
+            case ACT_RELU: U3D_HEAD_FWD(32, ACT_RELU); break;
+            case ACT_LEAKY: U3D_HEAD_FWD(32, ACT_LEAKY); break;
+            case ACT_ELU: U3D_HEAD_FWD(32, ACT_ELU); break;
+            default: U3D_HEAD_FWD(32, -1); break;
+        }
+    }
+#undef U3D_HEAD_FWD
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -476,12 +542,15 @@ int loss_level_launch(const LossLevel& L, const HeadFuse* Hd, cudaStream_t s) {
     const long long nv = (long long)L.d * L.h * L.w;
     long long g = (nv + 255) / 256;
     const int grid = int(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
-    if (L.C <= 8) loss_reduce_kernel<8><<<grid, 256, 0, s>>>(L);
+    // the class loops are unrolled to the template bound: the binary / few-class heads must not pay for 8
+    if (L.C <= 2) loss_reduce_kernel<2><<<grid, 256, 0, s>>>(L);
+    else if (L.C <= 4) loss_reduce_kernel<4><<<grid, 256, 0, s>>>(L);
+    else if (L.C <= 8) loss_reduce_kernel<8><<<grid, 256, 0, s>>>(L);
     else loss_reduce_kernel<kMaxC><<<grid, 256, 0, s>>>(L);
-    loss_finalize_kernel<<<1, 960, 0, s>>>(L, grid);
+    loss_finalize_kernel<<<1, 1024, 0, s>>>(L, grid);
     if (Hd != nullptr) {
         if (!head_bwd_supported(L.C, Hd->xcp)) { set_error("loss_level_launch: unsupported fused head shape"); return 1; }
-        long long gh = (nv * (Hd->xcp / 8) + 127) / 128;
+        long long gh = (nv + 127) / 128;   // a warp takes 32 voxels per iteration
         const int gridh = int(gh < 1 ? 1 : (gh > 148 * 16 ? 148 * 16 : gh));
         const int ct = L.C <= 2 ? 2 : L.C <= 4 ? 4 : 8;
         if (ct == 2 && Hd->xcp == 16) loss_grad_head_kernel<2, 16><<<gridh, 128, 0, s>>>(L, *Hd);

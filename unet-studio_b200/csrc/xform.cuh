@@ -8,23 +8,24 @@
 
 namespace u3d {
 
-__device__ __forceinline__ float xf_act(float z, int act) {
-    switch (act) {
-        case ACT_RELU: return fmaxf(z, 0.f);
-        case ACT_LEAKY: return z > 0.f ? z : 0.01f * z;
-        case ACT_ELU: return z > 0.f ? z : expm1f(z);
-        default: return z;
-    }
+// activation known at compile time: branch-free, 1-2 instructions per element (with a run-time switch inside an unrolled chunk loop
+// the compiler inlines the ELU path 8 times: ~370 instructions per 16-byte chunk).  Same results as act_fwd of elementwise.cu:
+// max(z, 0.01 z) == (z > 0 ? z : 0.01 z) for every z incl. -0 / NaN.
+template <int ACT>
+__device__ __forceinline__ float xf_act_c(float z) {
+    if constexpr (ACT == ACT_RELU) return fmaxf(z, 0.f);
+    else if constexpr (ACT == ACT_LEAKY) return fmaxf(z, 0.01f * z);
+    else if constexpr (ACT == ACT_ELU) return z > 0.f ? z : expm1f(z);
+    else return z;
 }
-
-// sc / sh: the 8 coefficients of the chunk's channel group (registers or shared memory)
-__device__ __forceinline__ uint4 xf_apply(const uint4& q, const float* sc, const float* sh, int act) {
+template <int ACT>
+__device__ __forceinline__ uint4 xf_apply_c(const uint4& q, const float* sc, const float* sh) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float2 t = unpack2<false>(w[j]);
-        o[j] = pack2<false>(xf_act(sc[2 * j] * t.x + sh[2 * j], act), xf_act(sc[2 * j + 1] * t.y + sh[2 * j + 1], act));
+        o[j] = pack2<false>(xf_act_c<ACT>(sc[2 * j] * t.x + sh[2 * j]), xf_act_c<ACT>(sc[2 * j + 1] * t.y + sh[2 * j + 1]));
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
