@@ -36,6 +36,7 @@ struct WBParams {
     int tiles_x, tiles_y, zchunks, zlen, total_items;
     int ngo, npairs, cpp;      // channel-group pairs (gi, go) of a wide layer: CTA b owns pair b % npairs and every cpp-th tile of it
     uint32_t x_slot_bytes, y_slot_bytes, off_y, off_bars;
+    float* scratch;            // != nullptr: the epilogue stores the CTA's gradient block [CO][NCG*8][27] here (wgrad_band_sum_kernel adds them up)
 };
 
 template <int NCG, int CO>
@@ -203,29 +204,77 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
         const int r = threadIdx.x;
         mbar_wait(done_bar, 0, 0x3400u);
         tc_fence_after();
-        const int a = r / (NCG * 8);
-        const int ci = gi * NCG * 8 + r % (NCG * 8);
-        const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
+        constexpr int CIG = NCG * 8;
+        constexpr int RUN = CIG * 27;                 // floats per output channel of this CTA's block
+        const int a = r / CIG;
+        const int cil = r % CIG;
         const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
-        const bool ci_ok = ci < P.t_creal;
+        if (p.scratch != nullptr) {
+            // Partial-block mode.  Every launch ends in ~4 M fp32 atomics (27*Cin*Cout elements x the CTAs that share them), and the L2
+            // atomic units make that the ~50 us floor of the deep-level launches, however the atomics are arranged (scattered from the
+            // registers, or staged and issued as contiguous 128-byte rows: measured slower, the rows serialise on one L2 slice).
+            // Here the block is laid out in shared memory (the rings are free once done_bar has fired) in the gradient's own order
+            // [co][ci][27 taps] and stored, coalesced, to this CTA's slot of the scratch buffer; wgrad_band_sum_kernel adds the slots.
+            float* const stage = reinterpret_cast<float*>(smem);
+            if constexpr (R > 1) {
+                for (int i = r; i < CO * RUN; i += 128) stage[i] = 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
 #pragma unroll 1
-        for (int dz = 0; dz < 3; ++dz) {
+            for (int dz = 0; dz < 3; ++dz) {
 #pragma unroll 1
-            for (int b = 0; b < R; ++b) {
-                const int dyi = a - b;   // = dy + 1
-                const bool ok = ci_ok && dyi >= 0 && dyi <= 2;
+                for (int b = 0; b < R; ++b) {
+                    const int dyi = a - b;   // = dy + 1
+                    const bool ok = dyi >= 0 && dyi <= 2;
 #pragma unroll 1
-                for (int dxc = 0; dxc < 3; ++dxc) {
-                    const int tap = (dz * 3 + dyi) * 3 + dxc;
-                    float* dwrow = P.dw + size_t(P.w_moff + ci) * P.w_ktaps + tap;
+                    for (int dxc = 0; dxc < 3; ++dxc) {
+                        const int tap = (dz * 3 + dyi) * 3 + dxc;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < CO; c0 += 16) {
-                        float v[16];
-                        tmem_ld16(t_row + uint32_t(dz * N + (b * 3 + dxc) * CO + c0), v);
-                        if (ok) {
+                        for (int c0 = 0; c0 < CO; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(t_row + uint32_t(dz * N + (b * 3 + dxc) * CO + c0), v);
+                            if (ok) {
+                                // (lanes = consecutive ci: stride 27 floats, conflict-free); several (a, b) pairs share a tap when R > 1
+                                float* const sp = &stage[c0 * RUN + cil * 27 + tap];
+                                if constexpr (R == 1) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (go * CO + c0 + j < P.u_creal) atomicAdd(dwrow + size_t(P.w_noff + go * CO + c0 + j) * nstride, v[j]);
+                                    for (int j = 0; j < 16; ++j) sp[j * RUN] = v[j];
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) atomicAdd(sp + j * RUN, v[j]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float4* const dst = reinterpret_cast<float4*>(p.scratch + size_t(blockIdx.x) * (CO * RUN));
+            const float4* const src = reinterpret_cast<const float4*>(stage);
+            for (int i = r; i < CO * RUN / 4; i += 128) dst[i] = src[i];
+        } else {
+            const int ci = gi * CIG + cil;
+            const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
+            const bool ci_ok = ci < P.t_creal;
+#pragma unroll 1
+            for (int dz = 0; dz < 3; ++dz) {
+#pragma unroll 1
+                for (int b = 0; b < R; ++b) {
+                    const int dyi = a - b;   // = dy + 1
+                    const bool ok = ci_ok && dyi >= 0 && dyi <= 2;
+#pragma unroll 1
+                    for (int dxc = 0; dxc < 3; ++dxc) {
+                        const int tap = (dz * 3 + dyi) * 3 + dxc;
+                        float* dwrow = P.dw + size_t(P.w_moff + ci) * P.w_ktaps + tap;
+#pragma unroll 1
+                        for (int c0 = 0; c0 < CO; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(t_row + uint32_t(dz * N + (b * 3 + dxc) * CO + c0), v);
+                            if (ok) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (go * CO + c0 + j < P.u_creal) atomicAdd(dwrow + size_t(P.w_noff + go * CO + c0 + j) * nstride, v[j]);
+                            }
                         }
                     }
                 }
@@ -235,6 +284,29 @@ __global__ void __launch_bounds__(kWThreads, 1) conv_wgrad_band_kernel(const __g
     tc_fence_before();
     __syncthreads();
     if (warp == 12) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// Adds the per-CTA blocks of partial-block mode into the gradient.  CTA index of the main kernel = rank * npairs + pair; block
+// (pair, co) of this kernel owns the contiguous run [ci][27 taps] of output channel co of channel-group pair `pair`; blockIdx.y cuts
+// the ranks into slices of 16 (fixed-order sums inside a slice; with more than one slice the slices meet in fp32 atomics -- 16x fewer
+// than before -- otherwise the add is a plain read-modify-write and the layer's weight gradient is deterministic).
+__global__ void wgrad_band_sum_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int npairs, int ngo, int nranks, int co_grp,
+                                      int ci_grp, int t_creal, int u_creal, int w_mtot, int w_moff, int w_noff) {
+    const int pair = blockIdx.x / co_grp, co = blockIdx.x % co_grp;
+    const int gi = pair / ngo, go = pair % ngo;
+    const int run_all = ci_grp * 27;
+    const int ci_real = min(ci_grp, t_creal - gi * ci_grp);
+    const int run = ci_real > 0 ? ci_real * 27 : 0;
+    if (go * co_grp + co >= u_creal) return;
+    const int r0 = blockIdx.y * 16, r1 = min(nranks, r0 + 16);
+    const size_t slot = size_t(co_grp) * run_all;
+    float* const dst = dw + (size_t(w_noff + go * co_grp + co) * w_mtot + w_moff + gi * ci_grp) * 27;
+    for (int i = threadIdx.x; i < run; i += blockDim.x) {
+        float acc = 0.f;
+        for (int rk = r0; rk < r1; ++rk) acc += scratch[(size_t(rk) * npairs + pair) * slot + size_t(co) * run_all + i];
+        if (gridDim.y > 1) atomicAdd(dst + i, acc);
+        else dst[i] += acc;
+    }
 }
 
 template <int NCG, int CO>
@@ -271,7 +343,9 @@ bool conv_wgrad_band_eligible(const WgradProblem& P) {
     return true;
 }
 
-int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream) {
+size_t conv_wgrad_band_scratch_bytes() { return size_t(device_sm_count()) * 32 * 32 * 27 * 4; }
+
+int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream, float* partial_scratch, size_t partial_scratch_bytes) {
     WBParams wp;
     std::memset(&wp, 0, sizeof(wp));
     wp.P = P;
@@ -321,14 +395,29 @@ int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream) {
     wp.y_slot_bytes = uint32_t(TY * 3 * ncgy * kRunB + 127) & ~127u;
     wp.off_y = kXSlots * wp.x_slot_bytes;
     wp.off_bars = wp.off_y + kYSlots * wp.y_slot_bytes;
+    {   // the epilogue stages the CTA's gradient block [ucg][tcg][27] fp32 over the (then idle) rings
+        const uint32_t stage_bytes = uint32_t(ucg) * uint32_t(tcg) * 27u * 4u;
+        if (wp.off_bars < stage_bytes) wp.off_bars = (stage_bytes + 127u) & ~127u;
+    }
     const size_t smem = wp.off_bars + 8 * (2 * kXSlots + 2 * kYSlots + 1) + 16;
     if (smem > 227 * 1024) { set_error("conv_wgrad_band_launch: tile does not fit in shared memory"); return 1; }
     wp.cpp = std::max(1, std::min(wp.total_items, sms));
     const int grid = wp.cpp * wp.npairs;
-    if (ncg == 2 && ucg == 16) return launch_wband_t<2, 16>(wp, grid, smem, stream);
-    if (ncg == 2) return launch_wband_t<2, 32>(wp, grid, smem, stream);
-    if (ucg == 16) return launch_wband_t<4, 16>(wp, grid, smem, stream);
-    return launch_wband_t<4, 32>(wp, grid, smem, stream);
+    static const bool no_partial = std::getenv("U3D_WBAND_ATOMICS") != nullptr;
+    const size_t slot_bytes = size_t(ucg) * tcg * 27 * 4;
+    if (!no_partial && partial_scratch != nullptr && size_t(grid) * slot_bytes <= partial_scratch_bytes) wp.scratch = partial_scratch;
+    int rc;
+    if (ncg == 2 && ucg == 16) rc = launch_wband_t<2, 16>(wp, grid, smem, stream);
+    else if (ncg == 2) rc = launch_wband_t<2, 32>(wp, grid, smem, stream);
+    else if (ucg == 16) rc = launch_wband_t<4, 16>(wp, grid, smem, stream);
+    else rc = launch_wband_t<4, 32>(wp, grid, smem, stream);
+    if (rc || wp.scratch == nullptr) return rc;
+    const int nranks = std::min(wp.cpp, wp.total_items);   // CTAs of rank >= total_items had no work and wrote nothing
+    const dim3 sgrid(unsigned(wp.npairs * ucg), unsigned((nranks + 15) / 16));
+    wgrad_band_sum_kernel<<<sgrid, 256, 0, stream>>>(wp.scratch, P.dw, wp.npairs, ngo, nranks, ucg, tcg, P.t_creal, P.u_creal, P.w_mtot, P.w_moff,
+                                                     P.w_noff);
+    U3D_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace u3d

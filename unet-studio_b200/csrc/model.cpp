@@ -373,6 +373,7 @@ void Model::free_plan() {
     d_in_f32 = d_label = d_partials = d_sums = nullptr;
     d_pack_descs = nullptr; d_pack_first = nullptr; n_pack_jobs = n_pack_blocks = 0;
     d_scratch = nullptr;
+    d_wgrad_partial = nullptr; wgrad_partial_bytes = 0;
     d_splitk = nullptr;
     splitk_bytes = 0;
     planned = false;
@@ -694,6 +695,8 @@ int Model::ensure_plan() {
     if (tr) {
         M_CHECK(alloc(&d_scratch, max_bytes));
         scratch_bytes = max_bytes;
+        wgrad_partial_bytes = conv_wgrad_band_scratch_bytes();
+        M_CHECK(alloc(reinterpret_cast<void**>(&d_wgrad_partial), wgrad_partial_bytes));
     }
     splitk_bytes = size_t(96) << 20;   // 16 slices x (< 74 boxes x 120 voxels) x 256 channels x 4 B fits with room to spare
     M_CHECK(alloc(reinterpret_cast<void**>(&d_splitk), splitk_bytes));
@@ -1184,6 +1187,7 @@ int Model::run_backward() {
             // weight gradient on the side stream: it only reads x and dy (both final here) and adds into this layer's slice of the
             // flat gradient, so it can overlap the data gradient below (the small deep-level launches fill the SMs the other leaves idle)
             WgradLaunch wc{};
+            wc.partial_scratch = d_wgrad_partial; wc.partial_scratch_bytes = wgrad_partial_bytes;
             bool all_rows = !s.wg.empty(), all_quad = !s.wg.empty();
             for (const auto& wp : s.wg) {
                 all_quad = all_quad && conv_wgrad_quad_eligible(wp);

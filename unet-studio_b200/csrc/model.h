@@ -238,6 +238,8 @@ class Model {
     float* d_partials = nullptr;
     float* d_sums = nullptr;
     void* d_scratch = nullptr;       // gradient staging for multi-consumer tensors
+    float* d_wgrad_partial = nullptr;   // per-CTA weight-gradient blocks of conv_wgrad_band (partial-block mode)
+    size_t wgrad_partial_bytes = 0;
     float* d_splitk = nullptr;       // fp32 slices of the deterministic split-K convs of the deep levels (conv_tma.cu)
     size_t splitk_bytes = 0;
     size_t scratch_bytes = 0;

@@ -126,6 +126,8 @@ struct WgradProblem {
 };
 struct WgradLaunch {
     int t_bf16, u_bf16;
+    float* partial_scratch;        // optional: conv_wgrad_band writes per-CTA gradient blocks here and a second kernel sums them into the
+    size_t partial_scratch_bytes;  // gradient (an order of magnitude fewer fp32 atomics); nullptr = atomics straight from the accumulators
 };
 int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch& cfg, WgradProblem* dev_scratch,
                       cudaStream_t stream);
@@ -150,7 +152,8 @@ bool conv_wgrad_quad_eligible(const WgradProblem& P);   // 16 x 16 channels, k3 
 int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream);
 unsigned int read_device_error_wquad();
 bool conv_wgrad_band_eligible(const WgradProblem& P);
-int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream);
+int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream, float* partial_scratch = nullptr, size_t partial_scratch_bytes = 0);
+size_t conv_wgrad_band_scratch_bytes();   // enough for any problem
 unsigned int read_device_error_wband();
 // N-stacked band kernel per eligible problem, generic kernel for the rest; *launches = kernels launched
 int conv_wgrad_dispatch(const std::vector<WgradProblem>& probs, const WgradLaunch& cfg, cudaStream_t stream, int* launches);
