@@ -168,6 +168,13 @@ def test_fallback_kernels_under_the_debug_switches():
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+    # the weight-gradient kernels reduce across CTAs through per-CTA blocks in a scratch buffer + a summing kernel; without the scratch
+    # (or with these switches) they add straight from the accumulators with fp32 atomics
+    env = dict(os.environ, U3D_WBAND_ATOMICS="1", U3D_WGRAD_ATOMICS="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k", "test_conv_backward and (" + pick + " or big_16_16 or k3s1_32_32)"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
     # and with only the TMA kernel removed the banded / s2 kernels keep running next to the gather fallback
     env = dict(os.environ, U3D_NO_TMA="1")
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k", "test_conv_forward and (k3s1_64_64 or k3s2_128_256 or ct_256_256 or s2_32_64_tma)"],

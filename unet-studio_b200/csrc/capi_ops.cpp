@@ -213,6 +213,8 @@ extern "C" int u3d_op_conv_backward(int transposed, int ks, int stride, int cin0
             wprobs.push_back(W);
         }
         WgradLaunch wc{};
+        DevBuf dpart;   // the partial-block scratch the model gives its weight gradients (U3D_WBAND_ATOMICS / U3D_WGRAD_ATOMICS fall back to atomics)
+        if (!dpart.alloc(size_t(64) << 20)) { wc.partial_scratch = static_cast<float*>(dpart.p); wc.partial_scratch_bytes = size_t(64) << 20; }
         OP_CHECK(conv_wgrad_dispatch(wprobs, wc, s, nullptr));
         OP_CHECK(finish(s));
         OP_CUDA(cudaMemcpy(gw, dgw.p, wcount * 4, cudaMemcpyDeviceToHost));

@@ -14,6 +14,7 @@
 // results are reduced across K splits with fp32 atomics straight into the reference-layout
 // gradient tensor (summation order across CTAs is not fixed; see DESIGN.md "determinism").
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -26,6 +27,7 @@ namespace {
 constexpr int kThreads = 288;
 constexpr int kMaxProb = 8;
 constexpr int kKB = 64;  // voxels per stage
+constexpr int kMinPartialSplits = 4;   // partial-tile mode (scratch + sum kernel) from this many K splits on
 
 struct WParams {
     WgradProblem probs[kMaxProb];
@@ -36,6 +38,9 @@ struct WParams {
     int ntile_max;
     int tmem_cols;
     uint32_t off_b, off_bars;
+    float* scratch;      // != nullptr: every work item stores its 128 x ntile accumulator tile to slot `item` ([n][128 rows]) and
+                         // conv_wgrad_sum_kernel reduces the K splits (instead of 128 x ntile fp32 atomics per item)
+    int nsum_blocks;
 };
 
 struct WItem {
@@ -255,11 +260,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
             float* dwrow = nullptr;
             if (rv) dwrow = P.dw + size_t(P.w_moff + c) * P.w_ktaps + P.tap_ref[tap0 + tl];
             const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
+            // (a problem with few K splits keeps the direct atomics: its sum kernel would do the same scattered read-modify-writes)
+            float* const slot = (p.scratch && P.ksplit >= kMinPartialSplits) ? p.scratch + size_t(item) * (128u * size_t(p.ntile_max)) + r : nullptr;
 #pragma unroll 1
             for (int c0 = 0; c0 < P.ntile; c0 += 16) {
                 float v[16];
                 tmem_ld16(t_row + c0, v);
-                if (rv) {
+                if (slot != nullptr) {   // column-major tile: the lanes (consecutive rows) write consecutive floats
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) slot[size_t(c0 + j) * 128] = v[j];
+                } else if (rv) {
                     const int n0 = w.nt * P.ntile + c0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -274,6 +284,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// Partial-tile mode, second kernel: block = (problem, M tile, N tile, 8 output channels, slice of 16 K splits); thread = tile row
+// (tap-in-group, input channel).  Fixed-order sum inside a slice; more than one slice -> the slices meet in fp32 atomics (16x fewer
+// than the one-kernel form), otherwise a plain read-modify-write (deterministic).
+__global__ void __launch_bounds__(128) conv_wgrad_sum_kernel(const __grid_constant__ WParams p) {
+    int b = blockIdx.x, pi = 0;
+    for (; pi < p.nprob; ++pi) {
+        const WgradProblem& Q = p.probs[pi];
+        const int nb = Q.ksplit >= kMinPartialSplits ? Q.mtiles * Q.ntiles * (Q.ntile / 8) * ((Q.ksplit + 15) / 16) : 0;
+        if (b < nb) break;
+        b -= nb;
+    }
+    if (pi >= p.nprob) return;
+    const WgradProblem& P = p.probs[pi];
+    const int nsl = (P.ksplit + 15) / 16;
+    const int sl = b % nsl; b /= nsl;
+    const int n8 = b % (P.ntile / 8); b /= (P.ntile / 8);
+    const int nt = b % P.ntiles, mt = b / P.ntiles;
+    const int r = threadIdx.x;
+    const int cpt = cpt_of(P);
+    const int ctiles = (P.t_c + cpt - 1) / cpt;
+    const int tapgrp = mt / ctiles, ctile = mt % ctiles;
+    const int tap0 = tapgrp * P.tg;
+    const int ntap_here = min(P.tg, P.ntaps - tap0);
+    const int tl = r / cpt;
+    const int c = r - tl * cpt + ctile * 128;
+    if (!(tl < ntap_here && c < P.t_creal)) return;
+    float* const dwrow = P.dw + size_t(P.w_moff + c) * P.w_ktaps + P.tap_ref[tap0 + tl];
+    const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
+    const size_t slot = 128u * size_t(p.ntile_max);
+    const int item0 = P.item_base + (mt * P.ntiles + nt) * P.ksplit;
+    const int k0 = sl * 16, k1 = min(P.ksplit, k0 + 16);
+#pragma unroll 1
+    for (int jn = 0; jn < 8; ++jn) {
+        const int n = n8 * 8 + jn;
+        const int n_abs = nt * P.ntile + n;
+        if (n_abs >= P.u_creal) break;
+        float acc = 0.f;
+        for (int ks = k0; ks < k1; ++ks) acc += p.scratch[size_t(item0 + ks) * slot + size_t(n) * 128 + r];
+        float* const dst = dwrow + size_t(P.w_noff + n_abs) * nstride;
+        if (nsl > 1) atomicAdd(dst, acc);
+        else *dst += acc;
+    }
 }
 
 }  // namespace
@@ -348,9 +402,21 @@ int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch&
         attr_set = true;
     }
     const int grid = std::max(1, std::min(items, sms));
+    static const bool no_partial = std::getenv("U3D_WGRAD_ATOMICS") != nullptr;
+    if (!no_partial && cfg.partial_scratch != nullptr && size_t(items) * 128 * ntile_max * 4 <= cfg.partial_scratch_bytes) {
+        kp.scratch = cfg.partial_scratch;
+        for (int i = 0; i < kp.nprob; ++i) {
+            const WgradProblem& P = kp.probs[i];
+            if (P.ksplit >= kMinPartialSplits) kp.nsum_blocks += P.mtiles * P.ntiles * (P.ntile / 8) * ((P.ksplit + 15) / 16);
+        }
+    }
     if (stages >= 8) conv_wgrad_kernel<6><<<grid, kThreads, smem, stream>>>(kp);
     else conv_wgrad_kernel<2><<<grid, kThreads, smem, stream>>>(kp);
     U3D_CUDA_CHECK(cudaGetLastError());
+    if (kp.scratch != nullptr && kp.nsum_blocks > 0) {
+        conv_wgrad_sum_kernel<<<kp.nsum_blocks, 128, 0, stream>>>(kp);
+        U3D_CUDA_CHECK(cudaGetLastError());
+    }
     return 0;
 }
 

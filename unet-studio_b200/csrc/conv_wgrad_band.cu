@@ -413,8 +413,12 @@ int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream, float* pa
     else rc = launch_wband_t<4, 32>(wp, grid, smem, stream);
     if (rc || wp.scratch == nullptr) return rc;
     const int nranks = std::min(wp.cpp, wp.total_items);   // CTAs of rank >= total_items had no work and wrote nothing
-    const dim3 sgrid(unsigned(wp.npairs * ucg), unsigned((nranks + 15) / 16));
-    wgrad_band_sum_kernel<<<sgrid, 256, 0, stream>>>(wp.scratch, P.dw, wp.npairs, ngo, nranks, ucg, tcg, P.t_creal, P.u_creal, P.w_mtot, P.w_moff,
+    return wgrad_block_sum_launch(wp.scratch, P, wp.npairs, ngo, nranks, ucg, tcg, stream);
+}
+
+int wgrad_block_sum_launch(const float* scratch, const WgradProblem& P, int npairs, int ngo, int nranks, int co_grp, int ci_grp, cudaStream_t stream) {
+    const dim3 sgrid(unsigned(npairs * co_grp), unsigned((nranks + 15) / 16));
+    wgrad_band_sum_kernel<<<sgrid, 256, 0, stream>>>(scratch, P.dw, npairs, ngo, nranks, co_grp, ci_grp, P.t_creal, P.u_creal, P.w_mtot, P.w_moff,
                                                      P.w_noff);
     U3D_CUDA_CHECK(cudaGetLastError());
     return 0;

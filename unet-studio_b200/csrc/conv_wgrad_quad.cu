@@ -54,6 +54,7 @@ struct WQParams {
     int xt;                    // voxels per tile along x (multiple of 16)
     uint32_t row_b;            // bytes of one atom row = xt * 32
     uint32_t xslot_b, yslot_b, off_y, off_bars;
+    float* scratch;            // != nullptr: the epilogue stores the CTA's gradient block [16 co][16 ci][27] here (wgrad_block_sum_launch adds them)
 };
 
 __device__ __forceinline__ uint64_t desc_sw32_mn(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -231,6 +232,13 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
         const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
         const uint32_t t_row = tmem_base + (uint32_t(warp * 32) << 16);
         const bool ci_ok = ci < P.t_creal;
+        // partial-block mode (see conv_wgrad_band.cu): the 36 useful (x row, g row) blocks are summed per tap in shared memory (the rings
+        // are idle once done_bar has fired) in the gradient's order [co][ci][27] and stored to this CTA's slot of the scratch buffer
+        float* const stage = reinterpret_cast<float*>(smem);
+        if (p.scratch != nullptr) {
+            for (int i = m; i < 16 * 16 * 27; i += 128) stage[i] = 0.f;
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
 #pragma unroll 1
         for (int acc = 0; acc < 2; ++acc) {
             const int ay = acc * 2 + ayp;
@@ -245,13 +253,24 @@ __global__ void __launch_bounds__(kQThreads, 1) conv_wgrad_quad_kernel(const __g
                     tmem_ld16(t_row + uint32_t(acc * 256 + (dxc * 4 + rw) * 16), v);   // warp-collective: every lane takes part
                     if (ok) {
                         const int tap = (dzi * 3 + dyi) * 3 + dxc;
-                        float* dwrow = P.dw + size_t(P.w_moff + ci) * P.w_ktaps + tap;
+                        if (p.scratch != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < P.u_creal) atomicAdd(dwrow + size_t(P.w_noff + j) * nstride, v[j]);
+                            for (int j = 0; j < 16; ++j) atomicAdd(&stage[(j * 16 + ci) * 27 + tap], v[j]);
+                        } else {
+                            float* dwrow = P.dw + size_t(P.w_moff + ci) * P.w_ktaps + tap;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < P.u_creal) atomicAdd(dwrow + size_t(P.w_noff + j) * nstride, v[j]);
+                        }
                     }
                 }
             }
+        }
+        if (p.scratch != nullptr) {
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            float4* const dst = reinterpret_cast<float4*>(p.scratch + size_t(blockIdx.x) * (16 * 16 * 27));
+            const float4* const src = reinterpret_cast<const float4*>(stage);
+            for (int i = m; i < 16 * 16 * 27 / 4; i += 128) dst[i] = src[i];
         }
     }
     tc_fence_before();
@@ -310,7 +329,7 @@ bool conv_wgrad_quad_eligible(const WgradProblem& P) {
     return true;
 }
 
-int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream) {
+int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream, float* partial_scratch, size_t partial_scratch_bytes) {
     WQParams wp;
     std::memset(&wp, 0, sizeof(wp));
     wp.P = P;
@@ -364,8 +383,11 @@ int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream) {
     if (encode_rows(&maps.x, P.T, P.t_coff, P.t_cp, P.t_w, P.t_h, P.t_d, kQXT, 4)) return 1;
     if (encode_rows(&maps.g, P.U, P.u_coff, P.u_cp, P.lw, P.lh, P.ld, kQXT, 2)) return 1;
     if (encode_rows(&maps.gh, P.U, P.u_coff, P.u_cp, P.lw, P.lh, P.ld, 1, 2)) return 1;
+    static const bool no_partial = std::getenv("U3D_WBAND_ATOMICS") != nullptr;
+    if (!no_partial && partial_scratch != nullptr && size_t(grid) * 16 * 16 * 27 * 4 <= partial_scratch_bytes) wp.scratch = partial_scratch;
     conv_wgrad_quad_kernel<<<grid, kQThreads, kQSmem, stream>>>(wp, maps);
     U3D_CUDA_CHECK(cudaGetLastError());
+    if (wp.scratch != nullptr) return wgrad_block_sum_launch(wp.scratch, P, 1, 1, grid, 16, 16, stream);
     return 0;
 }
 

@@ -37,7 +37,7 @@ int conv_wgrad_dispatch(const std::vector<WgradProblem>& probs, const WgradLaunc
     int n = 0;
     for (const auto& P : probs) {
         if (conv_wgrad_quad_eligible(P)) {
-            if (conv_wgrad_quad_launch(P, stream)) return 1;
+            if (conv_wgrad_quad_launch(P, stream, cfg.partial_scratch, cfg.partial_scratch_bytes)) return 1;
             ++n;
         } else if (conv_wgrad_band_eligible(P)) {
             if (conv_wgrad_band_launch(P, stream, cfg.partial_scratch, cfg.partial_scratch_bytes)) return 1;

@@ -695,7 +695,7 @@ int Model::ensure_plan() {
     if (tr) {
         M_CHECK(alloc(&d_scratch, max_bytes));
         scratch_bytes = max_bytes;
-        wgrad_partial_bytes = conv_wgrad_band_scratch_bytes();
+        wgrad_partial_bytes = std::max(conv_wgrad_band_scratch_bytes(), size_t(64) << 20);   // (the generic kernel: items x 128 x ntile x 4 bytes)
         M_CHECK(alloc(reinterpret_cast<void**>(&d_wgrad_partial), wgrad_partial_bytes));
     }
     splitk_bytes = size_t(96) << 20;   // 16 slices x (< 74 boxes x 120 voxels) x 256 channels x 4 B fits with room to spare

@@ -149,7 +149,9 @@ unsigned int read_device_error_tma();
 bool conv_band_wants_kc16(int ks, int stride, int transposed, int k_channels_padded, int n_channels_padded, long long voxels);
 
 bool conv_wgrad_quad_eligible(const WgradProblem& P);   // 16 x 16 channels, k3 s1, big volume: 2 x 2 g rows per MMA pair (conv_wgrad_quad.cu)
-int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream);
+int conv_wgrad_quad_launch(const WgradProblem& P, cudaStream_t stream, float* partial_scratch = nullptr, size_t partial_scratch_bytes = 0);
+// sums per-CTA gradient blocks [co_grp][ci_grp][27] (CTA index = rank * npairs + pair, pair = gi * ngo + go) into P.dw (conv_wgrad_band.cu)
+int wgrad_block_sum_launch(const float* scratch, const WgradProblem& P, int npairs, int ngo, int nranks, int co_grp, int ci_grp, cudaStream_t stream);
 unsigned int read_device_error_wquad();
 bool conv_wgrad_band_eligible(const WgradProblem& P);
 int conv_wgrad_band_launch(const WgradProblem& P, cudaStream_t stream, float* partial_scratch = nullptr, size_t partial_scratch_bytes = 0);
