@@ -317,16 +317,22 @@ __global__ void __launch_bounds__(128) conv_wgrad_sum_kernel(const __grid_consta
     const size_t slot = 128u * size_t(p.ntile_max);
     const int item0 = P.item_base + (mt * P.ntiles + nt) * P.ksplit;
     const int k0 = sl * 16, k1 = min(P.ksplit, k0 + 16);
-#pragma unroll 1
+#pragma unroll 2
     for (int jn = 0; jn < 8; ++jn) {
         const int n = n8 * 8 + jn;
         const int n_abs = nt * P.ntile + n;
         if (n_abs >= P.u_creal) break;
-        float acc = 0.f;
-        for (int ks = k0; ks < k1; ++ks) acc += p.scratch[size_t(item0 + ks) * slot + size_t(n) * 128 + r];
+        float v[16];   // all loads of the slice in flight before the first add
+        const float* const src = p.scratch + size_t(item0) * slot + size_t(n) * 128 + r;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = k0 + k < k1 ? __ldcs(src + size_t(k0 + k) * slot) : 0.f;
         float* const dst = dwrow + size_t(P.w_noff + n_abs) * nstride;
+        const float old = nsl > 1 ? 0.f : *dst;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += v[k];
         if (nsl > 1) atomicAdd(dst, acc);
-        else *dst += acc;
+        else *dst = old + acc;
     }
 }
 

@@ -302,10 +302,17 @@ __global__ void wgrad_band_sum_kernel(const float* __restrict__ scratch, float* 
     const size_t slot = size_t(co_grp) * run_all;
     float* const dst = dw + (size_t(w_noff + go * co_grp + co) * w_mtot + w_moff + gi * ci_grp) * 27;
     for (int i = threadIdx.x; i < run; i += blockDim.x) {
+        // all loads of the slice are issued before the first add (a dependent load-add chain made this kernel 15 - 34 us per launch)
+        float v[16];
+        const float* const src = scratch + size_t(pair) * slot + size_t(co) * run_all + i;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = r0 + k < r1 ? __ldcs(src + size_t(r0 + k) * npairs * slot) : 0.f;
+        const float old = gridDim.y > 1 ? 0.f : dst[i];
         float acc = 0.f;
-        for (int rk = r0; rk < r1; ++rk) acc += scratch[(size_t(rk) * npairs + pair) * slot + size_t(co) * run_all + i];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += v[k];
         if (gridDim.y > 1) atomicAdd(dst + i, acc);
-        else dst[i] += acc;
+        else dst[i] = old + acc;
     }
 }
 
