@@ -35,19 +35,21 @@ bool conv_band_wants_kc16(int ks, int stride, int transposed, int k_channels_pad
 int conv_wgrad_dispatch(const std::vector<WgradProblem>& probs, const WgradLaunch& cfg, cudaStream_t stream, int* launches) {
     std::vector<WgradProblem> rest;
     int n = 0;
+    static const bool block_atomics = std::getenv("U3D_WBAND_ATOMICS") != nullptr, tile_atomics = std::getenv("U3D_WGRAD_ATOMICS") != nullptr;
+    const int per_block_launch = (cfg.partial_scratch != nullptr && !block_atomics) ? 2 : 1;   // main kernel + summing kernel
     for (const auto& P : probs) {
         if (conv_wgrad_quad_eligible(P)) {
             if (conv_wgrad_quad_launch(P, stream, cfg.partial_scratch, cfg.partial_scratch_bytes)) return 1;
-            ++n;
+            n += per_block_launch;
         } else if (conv_wgrad_band_eligible(P)) {
             if (conv_wgrad_band_launch(P, stream, cfg.partial_scratch, cfg.partial_scratch_bytes)) return 1;
-            ++n;
+            n += per_block_launch;
         } else
             rest.push_back(P);
     }
     if (!rest.empty()) {
         if (conv_wgrad_launch(rest, cfg, nullptr, stream)) return 1;
-        ++n;
+        n += (cfg.partial_scratch != nullptr && !tile_atomics) ? 2 : 1;   // (the summing kernel is skipped when no problem has enough K splits)
     }
     if (launches) *launches = n;
     return 0;
