@@ -23,7 +23,7 @@ def main(trace_path, csv_path, title, step_index=1):
         if "trace_marker" in k["name"]:
             cur = []
             groups.append(cur)
-        elif cur is not None and any(t in k["name"] for t in ("conv_band", "conv_tma", "conv_s2", "conv_wgrad", "conv_igemm", "conv_zband", "splitk")):
+        elif cur is not None and any(t in k["name"] for t in ("conv_band", "conv_tma", "conv_s2", "conv_wgrad", "conv_igemm", "conv_zband", "splitk", "wgrad_band_sum")):
             cur.append(k)
     n = min(len(groups), len(trace))
     # one training step = the entries between two "encode0.0.weight fwd" lines
@@ -40,7 +40,7 @@ def main(trace_path, csv_path, title, step_index=1):
         name, pas, family, nprob, flops, shape = trace[i]
         g = groups[i]
         t = sum(k.get("gpu__time_duration.sum", 0.0) for k in g) / 1e3
-        main_k = [k for k in g if "splitk" not in k["name"]]
+        main_k = [k for k in g if "splitk" not in k["name"] and "_sum_kernel" not in k["name"]]
         tp = (sum(k.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * k.get("gpu__time_duration.sum", 0.0) for k in main_k) /
               max(sum(k.get("gpu__time_duration.sum", 0.0) for k in main_k), 1e-9))
         fl = float(flops)

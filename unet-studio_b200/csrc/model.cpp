@@ -299,6 +299,7 @@ Model::~Model() {
     cudaFree(d_counter);
     cudaFree(d_chunks); cudaFree(d_status); cudaFree(d_loss_acc); cudaFree(d_loss_part); cudaFree(d_losses);
     if (stream3) { cudaStreamSynchronize(stream3); cudaStreamDestroy(stream3); }
+    for (cudaEvent_t e : ev_slabs) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { if (ev_sample[i]) cudaEventDestroy(ev_sample[i]); if (pf_in[i]) cudaFree(pf_in[i]); }
     for (int i = 0; i < 2; ++i) { if (ew_in[i]) cudaFree(ew_in[i]); if (ew_out[i]) cudaFree(ew_out[i]); }
     if (ev_buf) cudaFree(ev_buf);
@@ -1099,23 +1100,49 @@ int Model::evaluate_volume(const float* volume, int vw, int vh, int vd, int sx, 
     float* d_fg = d_cnt + VV;
     uint8_t* d_lab = reinterpret_cast<uint8_t*>(d_fg + VV);
     const float* vol = volume;
+    const std::vector<int> ox = window_origins(vw, ww, sx), oy = window_origins(vh, wh, sy), oz = window_origins(vd, wd, sz);
+    // Host volume: uploaded in z slabs on the copy stream, one slab per window z-origin (the slab ends where that origin's windows end),
+    // so the first windows run while the rest of the volume is still on its way (the 131 MB of a 320^3 volume are 5 ms of PCIe time).
+    std::vector<int> slab_end;        // exclusive z end of slab k (ascending); windows at oz[k] read z < slab_end[k]
     if (where == 0) {
-        M_CUDA(cudaMemcpyAsync(d_vol, volume, size_t(in_count) * VV * 4, cudaMemcpyHostToDevice, stream));
+        if (!stream3) M_CUDA(cudaStreamCreateWithFlags(&stream3, cudaStreamNonBlocking));
+        while (ev_slabs.size() < oz.size()) {
+            cudaEvent_t e;
+            M_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev_slabs.push_back(e);
+        }
+        M_CUDA(cudaEventRecord(ev_fork, stream));             // the previous call's kernels have finished with the volume buffer
+        M_CUDA(cudaStreamWaitEvent(stream3, ev_fork, 0));
+        int z0 = 0;
+        for (size_t k = 0; k < oz.size(); ++k) {
+            const int z1 = k + 1 == oz.size() ? vd : std::min(vd, std::max(z0, oz[k] + wd));
+            if (z1 > z0)
+                M_CUDA(cudaMemcpy2DAsync(d_vol + size_t(z0) * vh * vw, size_t(VV) * 4, volume + size_t(z0) * vh * vw, size_t(VV) * 4,
+                                         size_t(z1 - z0) * vh * vw * 4, size_t(in_count), cudaMemcpyHostToDevice, stream3));
+            M_CUDA(cudaEventRecord(ev_slabs[k], stream3));
+            slab_end.push_back(z1);
+            z0 = z1;
+        }
         vol = d_vol;
     }
     M_CUDA(cudaMemsetAsync(d_acc, 0, (size_t(C) + 1) * VV * 4, stream));
-    const std::vector<int> ox = window_origins(vw, ww, sx), oy = window_origins(vh, wh, sy), oz = window_origins(vd, wd, sz);
     int n = 0;
-    for (int z : oz)
+    for (size_t zi = 0; zi < oz.size(); ++zi) {
+        const int z = oz[zi];
+        if (where == 0) M_CUDA(cudaStreamWaitEvent(stream, ev_slabs[zi], 0));
         for (int y : oy)
             for (int x : ox) {
                 M_CHECK(crop_window_launch(vol, d_win, in_count, vw, vh, vd, ww, wh, wd, x, y, z, stream));
-                M_CHECK(pack_act_launch(d_win, tens[0].p, in_count, tens[0].Cp, WV, false, stream, split_input ? 1 : 0));
-                M_CHECK(run_forward(1));
+                // pack + forward of the window buffer: the same launches for every window, replayed as a graph from the second one on
+                M_CHECK(graph_run({4u, uint64_t(reinterpret_cast<uintptr_t>(d_win)), uint64_t(bn_running ? 1 : 0)}, [&]() -> int {
+                    M_CHECK(pack_act_launch(d_win, tens[0].p, in_count, tens[0].Cp, WV, false, stream, split_input ? 1 : 0));
+                    return run_forward(1);
+                }));
                 M_CHECK(softmax_accumulate_launch(logits[0], d_acc, d_cnt, C, vw, vh, vd, ww, wh, wd, x, y, z, stream));
                 launches += 3;
                 ++n;
             }
+    }
     M_CHECK(mask_argmax_launch(d_acc, d_cnt, d_lab, d_fg, C, VV, threshold, prob_out != nullptr, stream));
     ++launches;
     if (n_windows_out) *n_windows_out = n;

@@ -124,6 +124,7 @@ class Model {
     cudaEvent_t ev_ar_ready = nullptr, ev_ar_done = nullptr;
     int attach_comm(void* comm, int microbatches_per_step);
     cudaStream_t stream3 = nullptr;
+    std::vector<cudaEvent_t> ev_slabs;   // evaluate_volume: one per z slab of the host volume upload
     cudaEvent_t ev_sample[2] = {nullptr, nullptr};
     float* pf_in[2] = {nullptr, nullptr};
     float* pf_label[2] = {nullptr, nullptr};
