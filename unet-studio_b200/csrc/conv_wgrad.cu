@@ -27,7 +27,8 @@ namespace {
 constexpr int kThreads = 288;
 constexpr int kMaxProb = 8;
 constexpr int kKB = 64;  // voxels per stage
-constexpr int kMinPartialSplits = 4;   // partial-tile mode (scratch + sum kernel) from this many K splits on
+// partial-tile mode (scratch + sum kernel) for every problem with a real N: the 2-channel output heads keep their (few) direct atomics
+__host__ __device__ inline bool use_partial(const WgradProblem& P) { return P.u_creal >= 8; }
 
 struct WParams {
     WgradProblem probs[kMaxProb];
@@ -260,8 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
             float* dwrow = nullptr;
             if (rv) dwrow = P.dw + size_t(P.w_moff + c) * P.w_ktaps + P.tap_ref[tap0 + tl];
             const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
-            // (a problem with few K splits keeps the direct atomics: its sum kernel would do the same scattered read-modify-writes)
-            float* const slot = (p.scratch && P.ksplit >= kMinPartialSplits) ? p.scratch + size_t(item) * (128u * size_t(p.ntile_max)) + r : nullptr;
+            float* const slot = (p.scratch && use_partial(P)) ? p.scratch + size_t(item) * (128u * size_t(p.ntile_max)) + r : nullptr;
 #pragma unroll 1
             for (int c0 = 0; c0 < P.ntile; c0 += 16) {
                 float v[16];
@@ -286,53 +286,68 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_kernel(const __grid_co
     if (warp == 8) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// Partial-tile mode, second kernel: block = (problem, M tile, N tile, 8 output channels, slice of 16 K splits); thread = tile row
-// (tap-in-group, input channel).  Fixed-order sum inside a slice; more than one slice -> the slices meet in fp32 atomics (16x fewer
-// than the one-kernel form), otherwise a plain read-modify-write (deterministic).
+// Partial-tile mode, second kernel.  For one output channel n the gradient's [ci][reference taps] block is ONE contiguous run of the
+// reference-layout tensor, but the accumulator tiles hold it scattered over the tap-group tiles (rows = (tap in group, ci)), and a
+// tile row is written 4 bytes at a time 108 bytes apart when it goes straight to the gradient.  Here block (problem, n, channel tile,
+// slice of 16 K splits) reads the rows of every tap-group tile for its n (thread = tile row: coalesced 512-byte rows of the
+// column-major scratch tiles), sums its K splits in a fixed order, transposes through shared memory and adds the run to the gradient
+// with contiguous accesses (plain read-modify-write for one slice = deterministic; fp32 atomics when slices meet).
 __global__ void __launch_bounds__(128) conv_wgrad_sum_kernel(const __grid_constant__ WParams p) {
+    __shared__ float srun[128 * 27];
     int b = blockIdx.x, pi = 0;
     for (; pi < p.nprob; ++pi) {
         const WgradProblem& Q = p.probs[pi];
-        const int nb = Q.ksplit >= kMinPartialSplits ? Q.mtiles * Q.ntiles * (Q.ntile / 8) * ((Q.ksplit + 15) / 16) : 0;
+        const int cpt_q = cpt_of(Q);
+        const int nb = use_partial(Q) ? Q.u_creal * ((Q.t_c + cpt_q - 1) / cpt_q) : 0;
         if (b < nb) break;
         b -= nb;
     }
     if (pi >= p.nprob) return;
     const WgradProblem& P = p.probs[pi];
-    const int nsl = (P.ksplit + 15) / 16;
-    const int sl = b % nsl; b /= nsl;
-    const int n8 = b % (P.ntile / 8); b /= (P.ntile / 8);
-    const int nt = b % P.ntiles, mt = b / P.ntiles;
-    const int r = threadIdx.x;
     const int cpt = cpt_of(P);
     const int ctiles = (P.t_c + cpt - 1) / cpt;
-    const int tapgrp = mt / ctiles, ctile = mt % ctiles;
-    const int tap0 = tapgrp * P.tg;
-    const int ntap_here = min(P.tg, P.ntaps - tap0);
-    const int tl = r / cpt;
-    const int c = r - tl * cpt + ctile * 128;
-    if (!(tl < ntap_here && c < P.t_creal)) return;
-    float* const dwrow = P.dw + size_t(P.w_moff + c) * P.w_ktaps + P.tap_ref[tap0 + tl];
-    const size_t nstride = size_t(P.w_mtot) * P.w_ktaps;
+    const int ctile = b % ctiles, n_abs = b / ctiles;
+    const int nt = n_abs / P.ntile, n = n_abs % P.ntile;
+    const int nsl = (P.ksplit + 15) / 16;                  // slices of THIS problem (the grid is sized for the largest)
+    const int k0 = blockIdx.y * 16, k1 = min(P.ksplit, k0 + 16);
+    const int r = threadIdx.x;
+    const int tl = r / cpt, cl = r - tl * cpt;            // tap in group, channel in tile
+    const int c = cl + ctile * 128;
+    const int creal = min(cpt, P.t_creal - ctile * 128);  // real channels of this tile
+    const int ktaps = P.w_ktaps;
     const size_t slot = 128u * size_t(p.ntile_max);
-    const int item0 = P.item_base + (mt * P.ntiles + nt) * P.ksplit;
-    const int k0 = sl * 16, k1 = min(P.ksplit, k0 + 16);
-#pragma unroll 2
-    for (int jn = 0; jn < 8; ++jn) {
-        const int n = n8 * 8 + jn;
-        const int n_abs = nt * P.ntile + n;
-        if (n_abs >= P.u_creal) break;
-        float v[16];   // all loads of the slice in flight before the first add
-        const float* const src = p.scratch + size_t(item0) * slot + size_t(n) * 128 + r;
+    if (k0 < k1) {
+        const int ngroups = (P.ntaps + P.tg - 1) / P.tg;
+        for (int tapgrp = 0; tapgrp < ngroups; ++tapgrp) {
+            const int t = tapgrp * P.tg + tl;
+            const int mt = tapgrp * ctiles + ctile;
+            const float* const src = p.scratch + size_t(P.item_base + (mt * P.ntiles + nt) * P.ksplit) * slot + size_t(n) * 128 + r;
+            float v[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = k0 + k < k1 ? __ldcs(src + size_t(k0 + k) * slot) : 0.f;
-        float* const dst = dwrow + size_t(P.w_noff + n_abs) * nstride;
-        const float old = nsl > 1 ? 0.f : *dst;
-        float acc = 0.f;
+            for (int k = 0; k < 16; ++k) v[k] = k0 + k < k1 ? __ldcs(src + size_t(k0 + k) * slot) : 0.f;
+            float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc += v[k];
-        if (nsl > 1) atomicAdd(dst, acc);
-        else *dst = old + acc;
+            for (int k = 0; k < 16; ++k) acc += v[k];
+            if (t < P.ntaps && tl < P.tg && c < P.t_creal) srun[cl * ktaps + P.tap_ref[t]] = acc;
+        }
+    }
+    __syncthreads();
+    if (k0 >= k1 || creal <= 0) return;
+    float* const dst = P.dw + (size_t(P.w_noff + n_abs) * P.w_mtot + P.w_moff + ctile * 128) * ktaps;
+    const int run = creal * ktaps;
+    // (taps the problem does not cover -- none for the layers of this network -- are left untouched)
+    if (P.ntaps == ktaps) {
+        for (int i = r; i < run; i += 128) {
+            if (nsl > 1) atomicAdd(dst + i, srun[i]);
+            else dst[i] += srun[i];
+        }
+    } else {
+        for (int t = 0; t < P.ntaps; ++t)
+            for (int cc = r; cc < creal; cc += 128) {
+                const int i = cc * ktaps + P.tap_ref[t];
+                if (nsl > 1) atomicAdd(dst + i, srun[i]);
+                else dst[i] += srun[i];
+            }
     }
 }
 
@@ -409,18 +424,23 @@ int conv_wgrad_launch(const std::vector<WgradProblem>& probs, const WgradLaunch&
     }
     const int grid = std::max(1, std::min(items, sms));
     static const bool no_partial = std::getenv("U3D_WGRAD_ATOMICS") != nullptr;
+    int max_ksplit = 1;
     if (!no_partial && cfg.partial_scratch != nullptr && size_t(items) * 128 * ntile_max * 4 <= cfg.partial_scratch_bytes) {
         kp.scratch = cfg.partial_scratch;
         for (int i = 0; i < kp.nprob; ++i) {
             const WgradProblem& P = kp.probs[i];
-            if (P.ksplit >= kMinPartialSplits) kp.nsum_blocks += P.mtiles * P.ntiles * (P.ntile / 8) * ((P.ksplit + 15) / 16);
+            const int cpt = P.t_c <= 128 ? P.t_c : 128;
+            if (use_partial(P)) {
+                kp.nsum_blocks += P.u_creal * ((P.t_c + cpt - 1) / cpt);
+                max_ksplit = std::max(max_ksplit, P.ksplit);
+            }
         }
     }
     if (stages >= 8) conv_wgrad_kernel<6><<<grid, kThreads, smem, stream>>>(kp);
     else conv_wgrad_kernel<2><<<grid, kThreads, smem, stream>>>(kp);
     U3D_CUDA_CHECK(cudaGetLastError());
     if (kp.scratch != nullptr && kp.nsum_blocks > 0) {
-        conv_wgrad_sum_kernel<<<kp.nsum_blocks, 128, 0, stream>>>(kp);
+        conv_wgrad_sum_kernel<<<dim3(unsigned(kp.nsum_blocks), unsigned((max_ksplit + 15) / 16)), 128, 0, stream>>>(kp);
         U3D_CUDA_CHECK(cudaGetLastError());
     }
     return 0;
